@@ -1,0 +1,150 @@
+/*
+ * hsv.h — C-ABI of the B200 (sm_100a) waveform-generation kernels.
+ *
+ * The reference (liuhuang31/Megatts2_HierSpeechpp) is pure Python/PyTorch and
+ * has no FFI for this path; its "operator interface" is the set of ATen calls
+ * made by the nn.Modules on the hot path.  Each entry point below replaces one
+ * such call group and cites it (paths relative to the reference root).  The
+ * Python host side (megatts2_hierspeechpp_b200/) binds these with ctypes and
+ * mirrors the reference's nn.Module classes on top.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless
+ *     named host_*; the caller (PyTorch) owns every buffer, nothing is
+ *     allocated or freed here;
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on
+ *     that stream, does no host synchronisation and is CUDA-graph capturable;
+ *   - return value 0 = success, negative = error (hsv_last_error() gives the
+ *     message, thread-local);
+ *   - activations are fp32, layout [B, C, L] contiguous ("NCL", the
+ *     reference's layout) unless stated otherwise;
+ *   - "blk16" is the tensor-core operand layout produced by the activation
+ *     kernel and consumed by hsv_conv1d_umma: fp16 [B][C/8][Lp][8] with
+ *     Lp = HSV_BLK_PAD + roundup(L,128) + HSV_BLK_PAD rows per (b, 8-channel
+ *     chunk); rows outside [HSV_BLK_PAD, HSV_BLK_PAD+L) must be zero (they
+ *     implement the conv's zero padding) and are never written.
+ */
+#ifndef HSV_H_
+#define HSV_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HSV_VERSION 100
+#define HSV_BLK_PAD 32          /* zero rows before/after each blk16 sequence */
+#define HSV_UMMA_TILE_M 128     /* output time rows per CTA of the tcgen05 conv */
+
+/* error codes */
+#define HSV_OK 0
+#define HSV_ERR_ARG (-1)        /* bad argument / unsupported shape */
+#define HSV_ERR_CUDA (-2)       /* CUDA runtime error at launch */
+
+int hsv_version(void);
+const char *hsv_last_error(void);
+/* 1 if the running device is compute capability 10.x (tcgen05 capable). */
+int hsv_device_supported(void);
+
+/* Rows per (b, chunk) of a blk16 buffer for sequence length L. */
+int64_t hsv_blk16_rows(int64_t L);
+
+/* ---- Activation1d(SnakeBeta): alias_free_torch/act.py:23-27 =
+ * UpSample1d (resample.py:25-32) o SnakeBeta (activations.py:107-119, log-scale
+ * alpha/beta) o DownSample1d (resample.py:46-48 -> filter.py:86-94), with the
+ * fixed 12-tap kaiser-sinc filter (filter.py:28-57) — ONE fused kernel.
+ *   x      [B,C,L] fp32
+ *   alpha, beta [C] fp32 (log scale, as stored in the state_dict)
+ *   out_mode 0: out = fp32 [B,C,L]
+ *   out_mode 1: out = fp16 blk16 (C % 8 == 0), rows per chunk = hsv_blk16_rows(L)
+ */
+int hsv_act1d_snakebeta(const float *x, void *out, const float *alpha, const float *beta,
+                        int B, int C, int64_t L, int out_mode, void *stream);
+
+/* ---- weight norm fold: torch._weight_norm(v, g, dim=0) as applied by the
+ * forward pre-hook of torch.nn.utils.weight_norm on every conv of the path
+ * (hierspeechpp_speechsynthesizer.py:401,406,349-364; speechsr.py:21-36,73).
+ *   v [n0, inner], g [n0]  ->  w [n0, inner] = v * g / ||v||_2(row)
+ */
+int hsv_weight_norm_fold(const float *v, const float *g, float *w, int n0, int inner, void *stream);
+
+/* ---- pack a folded Conv1d weight [Cout,Cin,k] fp32 into the tcgen05 B-operand
+ * stream: fp16 [Cout/n_tile][k*Cin/16][2][n_tile][8] (K-major core matrices).
+ * Cin % 16 == 0, Cout % n_tile == 0, n_tile % 16 == 0, n_tile <= 256.
+ */
+int hsv_pack_conv_weight(const float *w, void *packed, int Cout, int Cin, int k, int n_tile, void *stream);
+
+/* ---- dilated 'same' Conv1d as a tcgen05/TMEM implicit GEMM:
+ * the AMPBlock convs (hierspeechpp_speechsynthesizer.py:349-364,380-384;
+ * speechsr24k/speechsr.py:21-36,52-56): F.conv1d(x, w, b, dilation=d,
+ * padding=(k*d-d)/2), fp16 operands, fp32 accumulation, fused epilogue.
+ *   a_blk16   fp16 blk16 activations [B][Cin/8][Lp][8]
+ *   w_packed  from hsv_pack_conv_weight (same n_tile)
+ *   bias      [Cout] fp32 or NULL
+ *   residual  [B,Cout,L] fp32 or NULL     (v = acc + bias + residual)
+ *   out       [B,Cout,L] fp32 or NULL     (out = v; may alias residual)
+ *   acc       [B,Cout,L] fp32 or NULL, acc_mode: 0 none, 1 acc = v,
+ *             2 acc += v, 3 acc = (acc + v) / acc_div   (mean over resblocks,
+ *             hierspeechpp_speechsynthesizer.py:440-446)
+ */
+int hsv_conv1d_umma(const void *a_blk16, const void *w_packed, const float *bias,
+                    const float *residual, float *out, float *acc, int acc_mode, float acc_div,
+                    int B, int Cin, int Cout, int64_t L, int k, int d, int n_tile, void *stream);
+
+/* ---- generic fp32 Conv1d (stride 1, zero padding `pad`, dilation d) on CUDA
+ * cores, for the small/odd-shaped convs of the path: conv_pre, cond, proj,
+ * DBlock convs, conv_post (+tanh) (hierspeechpp_speechsynthesizer.py:401,
+ * 421-426,430,437,449-450; speechsr.py:106-107).
+ *   x [B,Cin,Lin], w [Cout,Cin,k], bias [Cout] or NULL -> out [B,Cout,Lout],
+ *   Lout = Lin + 2*pad - d*(k-1).
+ *   flags: HSV_CONV_LRELU_IN  apply leaky_relu(0.1) to x first (DBlock :336-337)
+ *          HSV_CONV_TANH      tanh on the result (Generator :450)
+ *          HSV_CONV_ADD_OUT   out += result instead of out = result
+ */
+#define HSV_CONV_LRELU_IN 1
+#define HSV_CONV_TANH 2
+#define HSV_CONV_ADD_OUT 4
+int hsv_conv1d_direct(const float *x, const float *w, const float *bias, float *out,
+                      int B, int Cin, int Cout, int64_t Lin, int64_t Lout, int k, int d, int pad,
+                      int flags, void *stream);
+
+/* ---- ConvTranspose1d (ups[i], hierspeechpp_speechsynthesizer.py:404-408,434):
+ *   x [B,Cin,Lin], w [Cin,Cout,k] (folded), bias [Cout] -> out [B,Cout,u*Lin],
+ *   stride u, padding (k-u)/2, output_padding 0.  add [B,Cout,u*Lin] or NULL is
+ *   added to the result (proj(pitch) at stage 0, :436-438).
+ */
+int hsv_conv_transpose1d_direct(const float *x, const float *w, const float *bias, const float *add,
+                                float *out, int B, int Cin, int Cout, int64_t Lin, int k, int u,
+                                void *stream);
+
+/* ---- SpeechSR front end: conv_pre (Cin=1, k=7, pad 3; speechsr.py:90) followed
+ * by F.interpolate(mode='linear', align_corners=False) to Lout (speechsr.py:96),
+ * fused.  x [B,1,Lin], w [C,1,7], bias [C] -> out [B,C,Lout].
+ * Source index math in fp32 exactly as ATen's CUDA kernel.
+ */
+int hsv_sr_pre_interp(const float *x, const float *w, const float *bias, float *out,
+                      int B, int C, int64_t Lin, int64_t Lout, void *stream);
+
+/* Index probe for the bit-exact part of the parity contract: writes, for each
+ * dst in [0,Lout): i0, i1 (int32) and lambda (fp32) of the linear interpolation. */
+int hsv_interp_linear_table(int64_t Lin, int64_t Lout, int32_t *i0, int32_t *i1, float *lam, void *stream);
+
+/* ---- nearest-neighbour down-sampling gather of DBlock
+ * (F.interpolate(x, size=L//factor), hierspeechpp_speechsynthesizer.py:329-334):
+ * out[b,c,t] = x[b,c,min(floor(t*scale), Lin-1)], scale = (float)Lin/Lout. */
+int hsv_nearest_gather(const float *x, float *out, int rows, int64_t Lin, int64_t Lout, void *stream);
+
+/* out[i] = a[i] + b[i] + c[row(i)] ... small fused adds used at the stage-0 join
+ * (x = conv_pre(x) + downs(pitch) + cond(g), :430): out = a + b + bc[b,c,0]. */
+int hsv_add3_bcast(const float *a, const float *b, const float *bc, float *out,
+                   int rows, int64_t L, void *stream);
+
+/* fp32 [B,C,L] -> fp16 blk16 (optional leaky_relu(0.1) first); C % 8 == 0. */
+int hsv_pack_blk16(const float *x, void *out, int B, int C, int64_t L, int lrelu, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HSV_H_ */

@@ -1,0 +1,227 @@
+// Fused anti-aliased activation: UpSample1d(x2 kaiser-sinc) -> SnakeBeta -> DownSample1d(x2).
+//
+// Replaces alias_free_torch/act.py:23-27 (9 ATen kernels and three 2x-rate
+// temporaries per call in the reference) with ONE kernel that reads x once and
+// writes the result once.  Closed form, f = 12 symmetric taps:
+//   y[2m-1] = 2*sum_i f[2i]  *x[clamp(m+2-i)]      (odd 2x sample)
+//   y[2m]   = 2*sum_i f[2i+1]*x[clamp(m+2-i)]      (even 2x sample)
+//   z[n]    = y[n] + 1/(exp(beta)+1e-9) * sin(y[n]*exp(alpha))^2
+//   out[t]  = sum_j f[j]*z[clamp2L(2t+j-5)]
+// x is edge-replicated on the 1x grid, z on the 2x grid (the *activated* edge
+// sample is replicated, resample.py:28 / filter.py:90).
+//
+// Mapping: a CTA owns ROWS=8 channel rows x TILE=RUNS*R time steps.  The x tile
+// (+-5 halo, clamped) is staged in shared memory with coalesced loads; each
+// thread then walks a run of R consecutive outputs with the 2x signal living
+// only in registers (a ring of six (odd,even) z pairs), so no 2x-rate value
+// ever touches shared or global memory.  R is odd and the row pitch is
+// 4 (mod 32) words, which makes every shared access of the walk conflict-free.
+// Results are staged in shared memory and written back coalesced, either as
+// fp32 [B,C,L] or as the fp16 "blk16" tensor-core operand layout.
+#include "hsv_common.cuh"
+
+namespace {
+
+constexpr int ROWS = 8;
+constexpr int RUNS = 16;
+constexpr int NT = ROWS * RUNS;  // 128 threads
+
+template <int R>
+struct Cfg {
+  static constexpr int TILE = RUNS * R;
+  static constexpr int XW = TILE + 10;
+  // pitch == 4 (mod 32) words -> (row*PITCH + R*run + j) hits 32 distinct banks per warp
+  static constexpr int PITCH = ((XW + 27) / 32) * 32 + 4;
+  static constexpr int OPITCH = ((TILE + 27) / 32) * 32 + 4;
+};
+
+__device__ __forceinline__ float snake(float y, float a, float ib) {
+  // activations.py:119  x + 1/(beta+eps) * sin(x*alpha)^2 ; MUFU sine of the fp32 product
+  const float s = __sinf(y * a);
+  return fmaf(ib * s, s, y);
+}
+
+struct ZPair {
+  float o, e;  // z[2m-1], z[2m]
+};
+
+__device__ __forceinline__ ZPair up_snake(const float w0, const float w1, const float w2, const float w3,
+                                          const float w4, const float w5, float a, float ib) {
+  // taps pre-doubled (ratio*conv_transpose, resample.py:29; x2 is exact)
+  constexpr float G0 = 2.f * HSV_F0, G1 = 2.f * HSV_F1, G2 = 2.f * HSV_F2, G3 = 2.f * HSV_F3,
+                  G4 = 2.f * HSV_F4, G5 = 2.f * HSV_F5;
+  float yo = G0 * w5;
+  float ye = G0 * w0;
+  yo = fmaf(G1, w0, yo);
+  ye = fmaf(G1, w5, ye);
+  yo = fmaf(G2, w4, yo);
+  ye = fmaf(G2, w1, ye);
+  yo = fmaf(G3, w1, yo);
+  ye = fmaf(G3, w4, ye);
+  yo = fmaf(G4, w3, yo);
+  ye = fmaf(G4, w2, ye);
+  yo = fmaf(G5, w2, yo);
+  ye = fmaf(G5, w3, ye);
+  ZPair z;
+  z.o = snake(yo, a, ib);
+  z.e = snake(ye, a, ib);
+  return z;
+}
+
+__device__ __forceinline__ float down6(const ZPair &p0, const ZPair &p1, const ZPair &p2, const ZPair &p3,
+                                       const ZPair &p4, const ZPair &p5) {
+  // out[t] = f0 zo(t-2) + f1 ze(t-2) + f2 zo(t-1) + f3 ze(t-1) + f4 zo(t) + f5 ze(t)
+  //        + f5 zo(t+1) + f4 ze(t+1) + f3 zo(t+2) + f2 ze(t+2) + f1 zo(t+3) + f0 ze(t+3)
+  float s0 = HSV_F0 * (p0.o + p5.e);
+  float s1 = HSV_F1 * (p0.e + p5.o);
+  s0 = fmaf(HSV_F2, p1.o + p4.e, s0);
+  s1 = fmaf(HSV_F3, p1.e + p4.o, s1);
+  s0 = fmaf(HSV_F4, p2.o + p3.e, s0);
+  s1 = fmaf(HSV_F5, p2.e + p3.o, s1);
+  return s0 + s1;
+}
+
+template <int R, bool EDGE>
+__device__ __forceinline__ void walk(const float *__restrict__ xw, float *__restrict__ outv, float a, float ib,
+                                     int64_t ta, int64_t L, float zL, float zR) {
+  // xw[0 .. R+9] = x[ta-5 .. ta+R+4] (already clamped);  outv[0..R-1] = out[ta .. ta+R-1]
+  ZPair ring[6];
+  float w0 = xw[0], w1 = xw[1], w2 = xw[2], w3 = xw[3], w4 = xw[4];
+  const int64_t n_last = 2 * L - 1;
+#pragma unroll
+  for (int s = 0; s < R + 5; ++s) {
+    const float w5 = xw[s + 5];
+    ZPair z = up_snake(w0, w1, w2, w3, w4, w5, a, ib);
+    if (EDGE) {
+      const int64_t m = ta - 2 + s;
+      const int64_t no = 2 * m - 1, ne = 2 * m;
+      z.o = no < 0 ? zL : (no > n_last ? zR : z.o);
+      z.e = ne < 0 ? zL : (ne > n_last ? zR : z.e);
+    }
+    ring[s % 6] = z;
+    if (s >= 5) {
+      outv[s - 5] = down6(ring[(s - 5) % 6], ring[(s - 4) % 6], ring[(s - 3) % 6], ring[(s - 2) % 6],
+                          ring[(s - 1) % 6], ring[s % 6]);
+    }
+    w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5;
+  }
+}
+
+template <int R, int OUT_MODE>
+__global__ void __launch_bounds__(NT) act1d_kernel(const float *__restrict__ x, void *__restrict__ outp,
+                                                   const float *__restrict__ alpha,
+                                                   const float *__restrict__ beta, int C, int64_t L,
+                                                   int64_t nrows, int ntiles, int64_t Lp) {
+  using K = Cfg<R>;
+  __shared__ float x_s[ROWS * K::PITCH];
+  __shared__ __align__(16) float o_s[OUT_MODE == 0 ? ROWS * K::OPITCH : K::TILE * 4];
+
+  const int tid = threadIdx.x;
+  const int tile = blockIdx.x % ntiles;
+  const int64_t rowgrp = blockIdx.x / ntiles;
+  const int64_t row0 = rowgrp * ROWS;
+  const int64_t t0 = (int64_t)tile * K::TILE;
+
+  // ---- stage x tile (replicate-clamped on the 1x grid) ----
+  for (int idx = tid; idx < ROWS * K::XW; idx += NT) {
+    const int c = idx / K::XW, p = idx - c * K::XW;
+    const int64_t row = row0 + c;
+    float v = 0.f;
+    if (row < nrows) {
+      int64_t t = t0 - 5 + p;
+      t = t < 0 ? 0 : (t > L - 1 ? L - 1 : t);
+      v = __ldg(x + row * L + t);
+    }
+    x_s[c * K::PITCH + p] = v;
+  }
+  __syncthreads();
+
+  const int c = tid % ROWS, run = tid / ROWS;
+  const int64_t row = row0 + c;
+  const int64_t ta = t0 + (int64_t)run * R;
+  float outv[R];
+  const bool active = row < nrows && ta < L;
+  if (active) {
+    const int ch = (int)(row % C);
+    const float a = expf(__ldg(alpha + ch));
+    const float ib = 1.0f / (expf(__ldg(beta + ch)) + 0.000000001f);
+    const float *xw = x_s + c * K::PITCH + run * R;
+    const bool edge = (2 * ta - 5 < 0) || (2 * (ta + R - 1) + 6 > 2 * L - 1);
+    if (!edge) {
+      walk<R, false>(xw, outv, a, ib, ta, L, 0.f, 0.f);
+    } else {
+      // z[0] (m=0, even) and z[2L-1] (m=L, odd) from clamped global x
+      const float *xr = x + row * L;
+      float wl[6], wr[6];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        int64_t tl = -3 + q, tr = L - 3 + q;
+        tl = tl < 0 ? 0 : (tl > L - 1 ? L - 1 : tl);
+        tr = tr < 0 ? 0 : (tr > L - 1 ? L - 1 : tr);
+        wl[q] = __ldg(xr + tl);
+        wr[q] = __ldg(xr + tr);
+      }
+      const float zL = up_snake(wl[0], wl[1], wl[2], wl[3], wl[4], wl[5], a, ib).e;
+      const float zR = up_snake(wr[0], wr[1], wr[2], wr[3], wr[4], wr[5], a, ib).o;
+      walk<R, true>(xw, outv, a, ib, ta, L, zL, zR);
+    }
+  }
+
+  // ---- stage results, write back coalesced ----
+  if (OUT_MODE == 0) {
+    if (active) {
+      float *o = o_s + c * K::OPITCH + run * R;
+#pragma unroll
+      for (int j = 0; j < R; ++j) o[j] = outv[j];
+    }
+    __syncthreads();
+    float *out = reinterpret_cast<float *>(outp);
+    for (int idx = tid; idx < ROWS * K::TILE; idx += NT) {
+      const int cc = idx / K::TILE, p = idx - cc * K::TILE;
+      const int64_t r = row0 + cc, t = t0 + p;
+      if (r < nrows && t < L) out[r * L + t] = o_s[cc * K::OPITCH + p];
+    }
+  } else {
+    __half *o_h = reinterpret_cast<__half *>(o_s);  // [TILE][8]
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < R; ++j) o_h[(run * R + j) * 8 + c] = __float2half_rn(outv[j]);
+    }
+    __syncthreads();
+    // rows row0..row0+7 are one 8-channel chunk of one batch item (C % 8 == 0)
+    const int64_t chunk = row0 / 8;  // == b*(C/8) + q
+    uint4 *dst = reinterpret_cast<uint4 *>(outp) + chunk * Lp + HSV_BLK_PAD + t0;
+    const uint4 *src = reinterpret_cast<const uint4 *>(o_s);
+    for (int p = tid; p < K::TILE; p += NT) {
+      if (t0 + p < L) dst[p] = src[p];
+    }
+  }
+}
+
+template <int R, int OUT_MODE>
+int launch(const float *x, void *out, const float *alpha, const float *beta, int B, int C, int64_t L,
+           cudaStream_t st) {
+  using K = Cfg<R>;
+  const int64_t nrows = (int64_t)B * C;
+  const int64_t ntiles = (L + K::TILE - 1) / K::TILE;
+  const int64_t ngrp = (nrows + ROWS - 1) / ROWS;
+  const int64_t nblk = ntiles * ngrp;
+  HSV_REQUIRE(nblk < (1ll << 31) && ntiles < (1ll << 31), "act1d: grid too large");
+  act1d_kernel<R, OUT_MODE><<<(unsigned)nblk, NT, 0, st>>>(x, out, alpha, beta, C, L, nrows, (int)ntiles,
+                                                          hsv::blk16_rows(L));
+  return hsv::check_launch("act1d_snakebeta");
+}
+
+}  // namespace
+
+extern "C" int hsv_act1d_snakebeta(const float *x, void *out, const float *alpha, const float *beta, int B,
+                                   int C, int64_t L, int out_mode, void *stream) {
+  HSV_REQUIRE(x && out && alpha && beta, "act1d: null pointer");
+  HSV_REQUIRE(B >= 0 && C > 0 && L >= 0, "act1d: bad shape B=%d C=%d L=%lld", B, C, (long long)L);
+  HSV_REQUIRE(out_mode == 0 || out_mode == 1, "act1d: out_mode must be 0 (fp32 NCL) or 1 (fp16 blk16)");
+  if (B == 0 || L == 0) return HSV_OK;
+  cudaStream_t st = hsv::as_stream(stream);
+  if (out_mode == 0) return launch<17, 0>(x, out, alpha, beta, B, C, L, st);
+  HSV_REQUIRE(C % 8 == 0, "act1d: blk16 output needs C %% 8 == 0 (C=%d)", C);
+  return launch<17, 1>(x, out, alpha, beta, B, C, L, st);
+}

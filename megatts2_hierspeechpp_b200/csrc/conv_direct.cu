@@ -1,0 +1,438 @@
+// fp32 CUDA-core kernels for the small / odd-shaped ops of the path:
+//   conv1d_direct            conv_pre, cond, proj, DBlock convs, conv_post(+tanh)
+//   conv_transpose1d_direct  ups[i] as u polyphase stride-1 convs
+//   sr_pre_interp            SpeechSR conv_pre (Cin=1) fused with the linear interpolation
+//   nearest_gather, add3_bcast, weight_norm_fold, pack_blk16, interp_linear_table
+// These carry < 6 % of the path's FLOPs; the dense AMP convs run on tcgen05
+// (conv_umma.cu).
+#include "hsv_common.cuh"
+
+namespace {
+
+constexpr int CI = 8;        // input channels per shared-memory chunk
+constexpr int KMAX = 16;     // max taps
+constexpr int HALO_MAX = 64; // max (k-1)*d
+
+// ------------------------------------------------------------------------------------------
+// tiled conv1d: CTA = TCO out channels x TT time steps, thread = 4 co x 4 t
+// ------------------------------------------------------------------------------------------
+template <int TCO, int TT>
+__global__ void __launch_bounds__((TCO / 4) * (TT / 4))
+conv1d_tiled_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias,
+                    float *__restrict__ out, int Cin, int Cout, int64_t Lin, int64_t Lout, int k, int d,
+                    int pad, int flags) {
+  constexpr int NTHR = (TCO / 4) * (TT / 4);
+  constexpr int LT = TT / 4;  // lanes along time
+  __shared__ float x_s[CI][TT + HALO_MAX];
+  __shared__ float w_s[CI * KMAX][TCO + 1];
+
+  const int tid = threadIdx.x;
+  const int tt = tid % LT, tco = tid / LT;
+  const int64_t t0 = (int64_t)blockIdx.x * TT;
+  const int co0 = blockIdx.y * TCO;
+  const int b = blockIdx.z;
+  const int span = TT + (k - 1) * d;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[i][q] = 0.f;
+
+  for (int ci0 = 0; ci0 < Cin; ci0 += CI) {
+    for (int idx = tid; idx < CI * span; idx += NTHR) {
+      const int ci = idx / span, pp = idx - ci * span;
+      const int64_t t = t0 - pad + pp;
+      float v = 0.f;
+      if (ci0 + ci < Cin && t >= 0 && t < Lin) {
+        v = __ldg(x + ((int64_t)b * Cin + ci0 + ci) * Lin + t);
+        if (flags & HSV_CONV_LRELU_IN) v = v > 0.f ? v : 0.1f * v;
+      }
+      x_s[ci][pp] = v;
+    }
+    const int cik = CI * k;
+    for (int idx = tid; idx < TCO * cik; idx += NTHR) {
+      const int co = idx / cik, r = idx - co * cik;  // r = ci*k + j, contiguous in global
+      const int ci = r / k;
+      float v = 0.f;
+      if (co0 + co < Cout && ci0 + ci < Cin) v = __ldg(w + ((int64_t)(co0 + co) * Cin + ci0) * k + r);
+      w_s[r][co] = v;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int ci = 0; ci < CI; ++ci) {
+      for (int j = 0; j < k; ++j) {
+        float wv[4], xv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) wv[i] = w_s[ci * k + j][tco * 4 + i];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) xv[q] = x_s[ci][tt + LT * q + j * d];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[i][q] = fmaf(wv[i], xv[q], acc[i][q]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int co = co0 + tco * 4 + i;
+    if (co >= Cout) continue;
+    const float bv = bias ? __ldg(bias + co) : 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int64_t t = t0 + tt + LT * q;
+      if (t >= Lout) continue;
+      float v = acc[i][q] + bv;
+      if (flags & HSV_CONV_TANH) v = tanhf(v);
+      float *o = out + ((int64_t)b * Cout + co) * Lout + t;
+      if (flags & HSV_CONV_ADD_OUT) v += *o;
+      *o = v;
+    }
+  }
+}
+
+// thin conv for Cout <= 4 (conv_post): one thread per (b, t), weights through the read-only cache
+__global__ void conv1d_thin_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                                   const float *__restrict__ bias, float *__restrict__ out, int B, int Cin,
+                                   int Cout, int64_t Lin, int64_t Lout, int k, int d, int pad, int flags) {
+  const int64_t n = (int64_t)B * Lout;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / Lout);
+    const int64_t t = i - (int64_t)b * Lout;
+    for (int co = 0; co < Cout; ++co) {
+      float acc = 0.f;
+      for (int ci = 0; ci < Cin; ++ci) {
+        const float *xr = x + ((int64_t)b * Cin + ci) * Lin;
+        const float *wr = w + ((int64_t)co * Cin + ci) * k;
+        for (int j = 0; j < k; ++j) {
+          const int64_t ts = t - pad + (int64_t)j * d;
+          if (ts >= 0 && ts < Lin) {
+            float v = __ldg(xr + ts);
+            if (flags & HSV_CONV_LRELU_IN) v = v > 0.f ? v : 0.1f * v;
+            acc = fmaf(__ldg(wr + j), v, acc);
+          }
+        }
+      }
+      if (bias) acc += __ldg(bias + co);
+      if (flags & HSV_CONV_TANH) acc = tanhf(acc);
+      float *o = out + ((int64_t)b * Cout + co) * Lout + t;
+      if (flags & HSV_CONV_ADD_OUT) acc += *o;
+      *o = acc;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// ConvTranspose1d, polyphase: output phase rho = o mod u is a stride-1 conv over the input rows
+//   o = u*q + rho,  r = (rho+p) mod u,  c = (rho+p) div u,  taps j = r + i*u reading x[q + c - i]
+// ------------------------------------------------------------------------------------------
+template <int TCO, int TT>
+__global__ void __launch_bounds__((TCO / 4) * (TT / 4))
+conv_transpose1d_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                        const float *__restrict__ bias, const float *__restrict__ add,
+                        float *__restrict__ out, int Cin, int Cout, int64_t Lin, int k, int u, int nco_tiles) {
+  constexpr int NTHR = (TCO / 4) * (TT / 4);
+  constexpr int LT = TT / 4;
+  constexpr int XH = 8;  // taps per phase <= ceil(k/u) <= 4; window halo
+  __shared__ float x_s[CI][TT + 2 * XH];
+  __shared__ float w_s[CI * 4][TCO + 1];
+
+  const int tid = threadIdx.x;
+  const int tt = tid % LT, tco = tid / LT;
+  const int64_t q0 = (int64_t)blockIdx.x * TT;
+  const int rho = blockIdx.y / nco_tiles;
+  const int co0 = (blockIdx.y % nco_tiles) * TCO;
+  const int b = blockIdx.z;
+  const int p = (k - u) / 2;
+  const int r = (rho + p) % u, c = (rho + p) / u;
+  const int ntaps = (k - r + u - 1) / u;  // taps j = r + i*u < k
+  const int64_t Lout = (int64_t)u * Lin;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq) acc[i][qq] = 0.f;
+
+  for (int ci0 = 0; ci0 < Cin; ci0 += CI) {
+    // x_s[ci][pp] = x[q0 - XH + pp]
+    for (int idx = tid; idx < CI * (TT + 2 * XH); idx += NTHR) {
+      const int ci = idx / (TT + 2 * XH), pp = idx - ci * (TT + 2 * XH);
+      const int64_t t = q0 - XH + pp;
+      float v = 0.f;
+      if (ci0 + ci < Cin && t >= 0 && t < Lin) v = __ldg(x + ((int64_t)b * Cin + ci0 + ci) * Lin + t);
+      x_s[ci][pp] = v;
+    }
+    // w_s[ci*ntaps + i][co] = W[ci0+ci][co0+co][r + i*u]      (W is [Cin, Cout, k])
+    for (int idx = tid; idx < CI * ntaps * TCO; idx += NTHR) {
+      const int i = idx % ntaps;
+      const int co = (idx / ntaps) % TCO;
+      const int ci = idx / (ntaps * TCO);
+      float v = 0.f;
+      if (ci0 + ci < Cin && co0 + co < Cout)
+        v = __ldg(w + ((int64_t)(ci0 + ci) * Cout + co0 + co) * k + r + i * u);
+      w_s[ci * ntaps + i][co] = v;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int ci = 0; ci < CI; ++ci) {
+      for (int i = 0; i < ntaps; ++i) {
+        float wv[4], xv[4];
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) wv[ii] = w_s[ci * ntaps + i][tco * 4 + ii];
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) xv[qq] = x_s[ci][XH + tt + LT * qq + c - i];
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) acc[ii][qq] = fmaf(wv[ii], xv[qq], acc[ii][qq]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int ii = 0; ii < 4; ++ii) {
+    const int co = co0 + tco * 4 + ii;
+    if (co >= Cout) continue;
+    const float bv = bias ? __ldg(bias + co) : 0.f;
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq) {
+      const int64_t q = q0 + tt + LT * qq;
+      if (q >= Lin) continue;
+      const int64_t off = ((int64_t)b * Cout + co) * Lout + q * u + rho;
+      float v = acc[ii][qq] + bv;
+      if (add) v += __ldg(add + off);
+      out[off] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// SpeechSR front: conv_pre (Cin=1,k=7,pad=3) + linear interpolation (align_corners=False)
+// ATen upsample_linear1d (CUDA): src = scale*(dst+0.5)-0.5 clamped at 0, evaluated in fp32 with
+// nvcc's default contraction (one FMA);  out = (1-lam)*v[i0] + lam*v[i1].
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void lin_src(int64_t dst, float scale, int64_t Lin, int &i0, int &i1, float &lam) {
+  float src = __fmaf_rn(scale, (float)dst + 0.5f, -0.5f);
+  src = src < 0.f ? 0.f : src;
+  int a = (int)src;
+  if (a > Lin - 1) a = (int)(Lin - 1);
+  i0 = a;
+  i1 = a + (a < Lin - 1 ? 1 : 0);
+  lam = src - (float)a;
+}
+
+__global__ void sr_pre_interp_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                                     const float *__restrict__ bias, float *__restrict__ out, int B, int C,
+                                     int64_t Lin, int64_t Lout, float scale) {
+  const int64_t n = (int64_t)B * Lout;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / Lout);
+    const int64_t t = i - (int64_t)b * Lout;
+    int i0, i1;
+    float lam;
+    lin_src(t, scale, Lin, i0, i1, lam);
+    const float *xr = x + (int64_t)b * Lin;
+    float xa[7], xb[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      const int64_t ta = (int64_t)i0 - 3 + j, tb = (int64_t)i1 - 3 + j;
+      xa[j] = (ta >= 0 && ta < Lin) ? __ldg(xr + ta) : 0.f;
+      xb[j] = (tb >= 0 && tb < Lin) ? __ldg(xr + tb) : 0.f;
+    }
+    const float w0 = 1.0f - lam, w1 = lam;
+    for (int c = 0; c < C; ++c) {
+      float va = 0.f, vb = 0.f;
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        const float wj = __ldg(w + c * 7 + j);
+        va = fmaf(wj, xa[j], va);
+        vb = fmaf(wj, xb[j], vb);
+      }
+      const float bv = bias ? __ldg(bias + c) : 0.f;
+      va += bv;
+      vb += bv;
+      out[((int64_t)b * C + c) * Lout + t] = w0 * va + w1 * vb;
+    }
+  }
+}
+
+__global__ void interp_table_kernel(int64_t Lin, int64_t Lout, float scale, int32_t *__restrict__ i0,
+                                    int32_t *__restrict__ i1, float *__restrict__ lam) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < Lout; t += (int64_t)gridDim.x * blockDim.x) {
+    int a, b;
+    float l;
+    lin_src(t, scale, Lin, a, b, l);
+    i0[t] = a;
+    i1[t] = b;
+    lam[t] = l;
+  }
+}
+
+__global__ void nearest_gather_kernel(const float *__restrict__ x, float *__restrict__ out, int64_t rows,
+                                      int64_t Lin, int64_t Lout, float scale) {
+  const int64_t n = rows * Lout;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / Lout, t = i - r * Lout;
+    int64_t s = (int64_t)floorf((float)t * scale);
+    if (s > Lin - 1) s = Lin - 1;
+    out[i] = __ldg(x + r * Lin + s);
+  }
+}
+
+__global__ void add3_bcast_kernel(const float *__restrict__ a, const float *__restrict__ b,
+                                  const float *__restrict__ bc, float *__restrict__ out, int64_t rows, int64_t L) {
+  const int64_t n = rows * L;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = a[i];
+    if (b) v += b[i];
+    if (bc) v += __ldg(bc + i / L);
+    out[i] = v;
+  }
+}
+
+// w[r, :] = v[r, :] * (g[r] / ||v[r, :]||_2)   one CTA per row
+__global__ void weight_norm_fold_kernel(const float *__restrict__ v, const float *__restrict__ g,
+                                        float *__restrict__ w, int inner) {
+  __shared__ float red[32];
+  const int r = blockIdx.x;
+  const float *vr = v + (int64_t)r * inner;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < inner; i += blockDim.x) {
+    const float t = vr[i];
+    s = fmaf(t, t, s);
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) red[0] = g[r] / sqrtf(s);
+  }
+  __syncthreads();
+  const float sc = red[0];
+  for (int i = threadIdx.x; i < inner; i += blockDim.x) w[(int64_t)r * inner + i] = vr[i] * sc;
+}
+
+// fp32 [B,C,L] -> fp16 blk16; one thread per (b, chunk, t)
+__global__ void pack_blk16_kernel(const float *__restrict__ x, uint4 *__restrict__ out, int B, int C, int64_t L,
+                                  int64_t Lp, int lrelu) {
+  const int nch = C >> 3;
+  const int64_t n = (int64_t)B * nch * L;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t bq = i / L, t = i - bq * L;
+    const float *xr = x + bq * 8 * L + t;  // (b*C + 8q) * L + t
+    __half2 h[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float v0 = __ldg(xr + (2 * e) * L), v1 = __ldg(xr + (2 * e + 1) * L);
+      if (lrelu) {
+        v0 = v0 > 0.f ? v0 : 0.1f * v0;
+        v1 = v1 > 0.f ? v1 : 0.1f * v1;
+      }
+      h[e] = __floats2half2_rn(v0, v1);
+    }
+    out[bq * Lp + HSV_BLK_PAD + t] = *reinterpret_cast<uint4 *>(h);
+  }
+}
+
+inline int grid_for(int64_t n, int threads) {
+  int64_t b = (n + threads - 1) / threads;
+  const int64_t cap = 148 * 32;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+
+extern "C" int hsv_conv1d_direct(const float *x, const float *w, const float *bias, float *out, int B, int Cin,
+                                 int Cout, int64_t Lin, int64_t Lout, int k, int d, int pad, int flags,
+                                 void *stream) {
+  HSV_REQUIRE(x && w && out, "conv1d_direct: null pointer");
+  HSV_REQUIRE(Cin > 0 && Cout > 0 && k >= 1 && k <= KMAX && d >= 1, "conv1d_direct: bad shape");
+  HSV_REQUIRE((k - 1) * d <= HALO_MAX, "conv1d_direct: (k-1)*d=%d exceeds %d", (k - 1) * d, HALO_MAX);
+  HSV_REQUIRE(Lout == Lin + 2 * (int64_t)pad - (int64_t)d * (k - 1), "conv1d_direct: Lout mismatch");
+  if (B == 0 || Lout <= 0) return HSV_OK;
+  cudaStream_t st = hsv::as_stream(stream);
+  if (Cout <= 4) {
+    conv1d_thin_kernel<<<grid_for((int64_t)B * Lout, 256), 256, 0, st>>>(x, w, bias, out, B, Cin, Cout, Lin,
+                                                                        Lout, k, d, pad, flags);
+  } else {
+    constexpr int TCO = 32, TT = 64;
+    HSV_REQUIRE(B <= 65535 && (Cout + TCO - 1) / TCO <= 65535, "conv1d_direct: grid too large");
+    dim3 grid((unsigned)((Lout + TT - 1) / TT), (unsigned)((Cout + TCO - 1) / TCO), (unsigned)B);
+    conv1d_tiled_kernel<TCO, TT><<<grid, (TCO / 4) * (TT / 4), 0, st>>>(x, w, bias, out, Cin, Cout, Lin, Lout, k,
+                                                                       d, pad, flags);
+  }
+  return hsv::check_launch("conv1d_direct");
+}
+
+extern "C" int hsv_conv_transpose1d_direct(const float *x, const float *w, const float *bias, const float *add,
+                                           float *out, int B, int Cin, int Cout, int64_t Lin, int k, int u,
+                                           void *stream) {
+  HSV_REQUIRE(x && w && out, "conv_transpose1d: null pointer");
+  HSV_REQUIRE(Cin > 0 && Cout > 0 && u >= 1 && k >= u && k <= KMAX, "conv_transpose1d: bad shape k=%d u=%d", k, u);
+  HSV_REQUIRE((k + u - 1) / u <= 4, "conv_transpose1d: more than 4 taps per phase");
+  // L_out = (Lin-1)*u - 2p + k must equal u*Lin  (true for all five (k,u) pairs of the path)
+  HSV_REQUIRE(k - 2 * ((k - u) / 2) == u, "conv_transpose1d: (k,u)=(%d,%d) does not give L_out = u*L_in", k, u);
+  if (B == 0 || Lin == 0) return HSV_OK;
+  constexpr int TCO = 32, TT = 64;
+  const int nco = (Cout + TCO - 1) / TCO;
+  HSV_REQUIRE(B <= 65535 && (int64_t)nco * u <= 65535, "conv_transpose1d: grid too large");
+  dim3 grid((unsigned)((Lin + TT - 1) / TT), (unsigned)(nco * u), (unsigned)B);
+  conv_transpose1d_kernel<TCO, TT><<<grid, (TCO / 4) * (TT / 4), 0, hsv::as_stream(stream)>>>(
+      x, w, bias, add, out, Cin, Cout, Lin, k, u, nco);
+  return hsv::check_launch("conv_transpose1d_direct");
+}
+
+extern "C" int hsv_sr_pre_interp(const float *x, const float *w, const float *bias, float *out, int B, int C,
+                                 int64_t Lin, int64_t Lout, void *stream) {
+  HSV_REQUIRE(x && w && out, "sr_pre_interp: null pointer");
+  HSV_REQUIRE(C > 0 && Lin > 0 && Lout > 0, "sr_pre_interp: bad shape");
+  if (B == 0) return HSV_OK;
+  const float scale = (float)Lin / (float)Lout;  // ATen area_pixel_compute_scale, align_corners=False
+  sr_pre_interp_kernel<<<grid_for((int64_t)B * Lout, 256), 256, 0, hsv::as_stream(stream)>>>(x, w, bias, out, B,
+                                                                                            C, Lin, Lout, scale);
+  return hsv::check_launch("sr_pre_interp");
+}
+
+extern "C" int hsv_interp_linear_table(int64_t Lin, int64_t Lout, int32_t *i0, int32_t *i1, float *lam,
+                                       void *stream) {
+  HSV_REQUIRE(i0 && i1 && lam && Lin > 0 && Lout > 0, "interp_linear_table: bad argument");
+  const float scale = (float)Lin / (float)Lout;
+  interp_table_kernel<<<grid_for(Lout, 256), 256, 0, hsv::as_stream(stream)>>>(Lin, Lout, scale, i0, i1, lam);
+  return hsv::check_launch("interp_linear_table");
+}
+
+extern "C" int hsv_nearest_gather(const float *x, float *out, int rows, int64_t Lin, int64_t Lout, void *stream) {
+  HSV_REQUIRE(x && out && rows >= 0 && Lin > 0 && Lout > 0, "nearest_gather: bad argument");
+  if (rows == 0) return HSV_OK;
+  const float scale = (float)Lin / (float)Lout;  // ATen compute_scales_value
+  nearest_gather_kernel<<<grid_for((int64_t)rows * Lout, 256), 256, 0, hsv::as_stream(stream)>>>(x, out, rows,
+                                                                                                 Lin, Lout, scale);
+  return hsv::check_launch("nearest_gather");
+}
+
+extern "C" int hsv_add3_bcast(const float *a, const float *b, const float *bc, float *out, int rows, int64_t L,
+                              void *stream) {
+  HSV_REQUIRE(a && out && rows >= 0 && L >= 0, "add3_bcast: bad argument");
+  if (rows == 0 || L == 0) return HSV_OK;
+  add3_bcast_kernel<<<grid_for((int64_t)rows * L, 256), 256, 0, hsv::as_stream(stream)>>>(a, b, bc, out, rows, L);
+  return hsv::check_launch("add3_bcast");
+}
+
+extern "C" int hsv_weight_norm_fold(const float *v, const float *g, float *w, int n0, int inner, void *stream) {
+  HSV_REQUIRE(v && g && w && n0 > 0 && inner > 0, "weight_norm_fold: bad argument");
+  weight_norm_fold_kernel<<<n0, 256, 0, hsv::as_stream(stream)>>>(v, g, w, inner);
+  return hsv::check_launch("weight_norm_fold");
+}
+
+extern "C" int hsv_pack_blk16(const float *x, void *out, int B, int C, int64_t L, int lrelu, void *stream) {
+  HSV_REQUIRE(x && out && C > 0 && C % 8 == 0, "pack_blk16: C %% 8 != 0 (C=%d)", C);
+  if (B == 0 || L == 0) return HSV_OK;
+  pack_blk16_kernel<<<grid_for((int64_t)B * (C / 8) * L, 256), 256, 0, hsv::as_stream(stream)>>>(
+      x, reinterpret_cast<uint4 *>(out), B, C, L, hsv::blk16_rows(L), lrelu);
+  return hsv::check_launch("pack_blk16");
+}

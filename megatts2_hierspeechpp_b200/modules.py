@@ -1,0 +1,630 @@
+"""Drop-in nn.Module mirror of the reference's waveform-generation blocks.
+
+Same class names, constructor signatures, forward signatures and ``state_dict``
+keys as the reference, so a reference checkpoint
+loads ``strict=True`` and the reference's own callers
+(``SynthesizerTrn.infer/voice_conversion*`` in hierspeechpp_speechsynthesizer.py
+:648-649,670-671,696-697; inference_speechsr.py:38) can use these classes
+unchanged.  All arithmetic runs in the sm_100a kernels of ``libhsv.so``:
+
+* ``Activation1d``     -> one fused kernel (alias_free_torch/act.py:23-27)
+* AMP block convs      -> tcgen05/TMEM implicit GEMM, fp16 operands, fp32 accumulate,
+                          weight-norm folded once per checkpoint (not per forward)
+* everything else      -> small fp32 CUDA-core kernels
+
+Inference only (the reference never trains these modules in this repository,
+SURVEY.md §2): outputs carry no autograd graph.  CUDA tensors only.
+"""
+from __future__ import annotations
+
+import math
+import warnings
+from typing import List, Optional, Sequence
+
+import torch
+from torch import nn
+from torch.nn import Conv1d, ConvTranspose1d
+
+from . import ops
+
+LRELU_SLOPE = 0.1  # modules.py:17
+
+# 12-tap kaiser-sinc taps (cutoff 0.25, half-width 0.3) as stored in the reference checkpoints
+FILTER_TAPS = (0.0020289647, 0.0093894657, -0.0255434588, -0.0576573834, 0.1285725832, 0.4432097971,
+               0.4432097971, 0.1285725832, -0.0576573834, -0.0255434588, 0.0093894657, 0.0020289647)
+
+
+def get_padding(kernel_size: int, dilation: int = 1) -> int:
+    """commons.py:14-15."""
+    return int((kernel_size * dilation - dilation) / 2)
+
+
+# Derived tensors (folded / packed weights, the filter check) are cached per module and keyed on the
+# parameters' (data_ptr, _version) plus this epoch, which every load_state_dict bumps.  In-place edits
+# through ``.data`` bypass autograd's version counter: call ``invalidate_caches()`` after such edits.
+_CACHE_EPOCH = [0]
+
+
+def invalidate_caches():
+    _CACHE_EPOCH[0] += 1
+
+
+def _bump_on_load(module: nn.Module):
+    module.register_load_state_dict_post_hook(lambda m, incompatible_keys: invalidate_caches())
+
+
+def _weight_norm(m: nn.Module) -> nn.Module:
+    # old-style weight norm: parameters weight_g / weight_v (the reference's state_dict layout)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return torch.nn.utils.weight_norm(m)
+
+
+def kaiser_sinc_filter1d(cutoff: float, half_width: float, kernel_size: int) -> torch.Tensor:
+    """alias_free_torch/filter.py:28-57 — host-side, constructor only; returns [1,1,k] fp32."""
+    even = kernel_size % 2 == 0
+    half_size = kernel_size // 2
+    delta_f = 4 * half_width
+    A = 2.285 * (half_size - 1) * math.pi * delta_f + 7.95
+    if A > 50.0:
+        beta = 0.1102 * (A - 8.7)
+    elif A >= 21.0:
+        beta = 0.5842 * (A - 21) ** 0.4 + 0.07886 * (A - 21.0)
+    else:
+        beta = 0.0
+    window = torch.kaiser_window(kernel_size, beta=beta, periodic=False)
+    time = (torch.arange(-half_size, half_size) + 0.5) if even else (torch.arange(kernel_size) - half_size)
+    if cutoff == 0:
+        return torch.zeros(1, 1, kernel_size)
+    filt = 2 * cutoff * window * torch.sinc(2 * cutoff * time)
+    filt = filt / filt.sum()
+    return filt.view(1, 1, kernel_size)
+
+
+# ----------------------------------------------------------------------------------------------
+# alias_free_torch / activations
+# ----------------------------------------------------------------------------------------------
+class SnakeBeta(nn.Module):
+    """activations.py:62-119.  Parameter holder: the arithmetic lives in the fused Activation1d kernel."""
+
+    def __init__(self, in_features, alpha=1.0, alpha_trainable=True, alpha_logscale=False):
+        super().__init__()
+        self.in_features = in_features
+        self.alpha_logscale = alpha_logscale
+        if alpha_logscale:
+            self.alpha = nn.Parameter(torch.zeros(in_features) * alpha)
+            self.beta = nn.Parameter(torch.zeros(in_features) * alpha)
+        else:
+            self.alpha = nn.Parameter(torch.ones(in_features) * alpha)
+            self.beta = nn.Parameter(torch.ones(in_features) * alpha)
+        self.alpha.requires_grad = alpha_trainable
+        self.beta.requires_grad = alpha_trainable
+        self.no_div_by_zero = 0.000000001
+
+    def forward(self, x):
+        raise RuntimeError("SnakeBeta is evaluated inside the fused Activation1d kernel on this path; "
+                           "wrap it in Activation1d (as every use in the reference does)")
+
+
+class LowPassFilter1d(nn.Module):
+    """alias_free_torch/filter.py:60-94 (buffer holder)."""
+
+    def __init__(self, cutoff=0.5, half_width=0.6, stride: int = 1, padding: bool = True,
+                 padding_mode: str = "replicate", kernel_size: int = 12):
+        super().__init__()
+        if cutoff < -0.0:
+            raise ValueError("Minimum cutoff must be larger than zero.")
+        if cutoff > 0.5:
+            raise ValueError("A cutoff above 0.5 does not make sense.")
+        self.kernel_size = kernel_size
+        self.even = kernel_size % 2 == 0
+        self.pad_left = kernel_size // 2 - int(self.even)
+        self.pad_right = kernel_size // 2
+        self.stride = stride
+        self.padding = padding
+        self.padding_mode = padding_mode
+        self.register_buffer("filter", kaiser_sinc_filter1d(cutoff, half_width, kernel_size))
+
+
+class UpSample1d(nn.Module):
+    """alias_free_torch/resample.py:10-22 (buffer holder)."""
+
+    def __init__(self, ratio=2, kernel_size=None):
+        super().__init__()
+        self.ratio = ratio
+        self.kernel_size = int(6 * ratio // 2) * 2 if kernel_size is None else kernel_size
+        self.stride = ratio
+        self.pad = self.kernel_size // ratio - 1
+        self.pad_left = self.pad * self.stride + (self.kernel_size - self.stride) // 2
+        self.pad_right = self.pad * self.stride + (self.kernel_size - self.stride + 1) // 2
+        self.register_buffer("filter", kaiser_sinc_filter1d(0.5 / ratio, 0.6 / ratio, self.kernel_size))
+
+
+class DownSample1d(nn.Module):
+    """alias_free_torch/resample.py:36-44 (buffer holder)."""
+
+    def __init__(self, ratio=2, kernel_size=None):
+        super().__init__()
+        self.ratio = ratio
+        self.kernel_size = int(6 * ratio // 2) * 2 if kernel_size is None else kernel_size
+        self.lowpass = LowPassFilter1d(cutoff=0.5 / ratio, half_width=0.6 / ratio, stride=ratio,
+                                       kernel_size=self.kernel_size)
+
+
+class Activation1d(nn.Module):
+    """alias_free_torch/act.py:8-27: x2 kaiser-sinc upsample -> SnakeBeta -> x2 low-pass downsample,
+    as ONE fused kernel (``hsv_act1d_snakebeta``)."""
+
+    def __init__(self, activation, up_ratio: int = 2, down_ratio: int = 2, up_kernel_size: int = 12,
+                 down_kernel_size: int = 12):
+        super().__init__()
+        if (up_ratio, down_ratio, up_kernel_size, down_kernel_size) != (2, 2, 12, 12):
+            raise NotImplementedError("the fused kernel implements the configuration the reference uses: "
+                                      "ratio 2/2, 12-tap filters")
+        if not isinstance(activation, SnakeBeta) or not activation.alpha_logscale:
+            raise NotImplementedError("the fused kernel implements SnakeBeta(alpha_logscale=True), the only "
+                                      "activation on the reference's waveform path")
+        self.up_ratio = up_ratio
+        self.down_ratio = down_ratio
+        self.act = activation
+        self.upsample = UpSample1d(up_ratio, up_kernel_size)
+        self.downsample = DownSample1d(down_ratio, down_kernel_size)
+        self._filter_key = None
+        _bump_on_load(self)
+
+    def check_filters(self):
+        """The kernel constant-folds the taps; the state_dict buffers must equal them."""
+        fu, fd = self.upsample.filter, self.downsample.lowpass.filter
+        key = (fu._version, fd._version, fu.data_ptr(), fd.data_ptr(), _CACHE_EPOCH[0])
+        if key == self._filter_key:
+            return
+        ref = torch.tensor(FILTER_TAPS, dtype=torch.float32)
+        for name, f in (("upsample.filter", fu), ("downsample.lowpass.filter", fd)):
+            if f.numel() != 12 or (f.detach().flatten().cpu().float() - ref).abs().max().item() > 1e-7:
+                raise ValueError(f"{name} differs from kaiser_sinc_filter1d(0.25, 0.3, 12); the fused kernel "
+                                 "constant-folds those taps")
+        self._filter_key = key
+
+    def params(self):
+        return self.act.alpha.detach(), self.act.beta.detach()
+
+    def forward(self, x):
+        self.check_filters()
+        x = _as_input(x)
+        a, b = self.params()
+        return ops.act1d(x, a, b)
+
+
+def _as_input(x: torch.Tensor) -> torch.Tensor:
+    if not x.is_cuda:
+        raise RuntimeError(f"expected a CUDA tensor (no CPU fallback), got device {x.device}")
+    if x.dtype != torch.float32:
+        raise ValueError(f"expected float32 input, got {x.dtype}")
+    return x.detach().contiguous()
+
+
+# ----------------------------------------------------------------------------------------------
+# folded-weight cache (weight norm is folded once per checkpoint instead of every forward)
+# ----------------------------------------------------------------------------------------------
+class _Folded:
+    """Derived tensors of one conv: folded fp32 weight and, on demand, the packed tcgen05 operand."""
+
+    def __init__(self, conv: nn.Module):
+        self.conv = conv
+        self.key = None
+        self.w = None
+        self.packed = None
+        self.n_tile = None
+
+    def _params(self):
+        c = self.conv
+        if hasattr(c, "weight_g"):
+            return (c.weight_g, c.weight_v)
+        return (c.weight,)
+
+    def weight(self) -> torch.Tensor:
+        ps = self._params()
+        key = tuple((p.data_ptr(), p._version) for p in ps) + (_CACHE_EPOCH[0],)
+        if key != self.key:
+            if len(ps) == 2:
+                g, v = ps
+                self.w = ops.weight_norm_fold(v.detach().contiguous(), g.detach().contiguous())
+            else:
+                self.w = ps[0].detach().contiguous()
+            self.packed = None
+            self.key = key
+        return self.w
+
+    def packed_weight(self):
+        w = self.weight()
+        if self.packed is None:
+            self.n_tile = ops.pick_n_tile(w.shape[0])
+            self.packed = ops.pack_conv_weight(w, self.n_tile)
+        return self.packed, self.n_tile
+
+    def bias(self):
+        b = getattr(self.conv, "bias", None)
+        return None if b is None else b.detach()
+
+
+# ----------------------------------------------------------------------------------------------
+# AMP block
+# ----------------------------------------------------------------------------------------------
+class AMPBlock1(nn.Module):
+    """hierspeechpp_speechsynthesizer.py:344-392 (AMPBlock0 of speechsr.py:16-64 is identical)."""
+
+    def __init__(self, channels, kernel_size=3, dilation=(1, 3, 5), activation=None):
+        super().__init__()
+        self.channels = channels
+        self.kernel_size = kernel_size
+        self.dilation = tuple(dilation)
+        self.convs1 = nn.ModuleList([
+            _weight_norm(Conv1d(channels, channels, kernel_size, 1, dilation=d, padding=get_padding(kernel_size, d)))
+            for d in self.dilation])
+        self.convs2 = nn.ModuleList([
+            _weight_norm(Conv1d(channels, channels, kernel_size, 1, dilation=1, padding=get_padding(kernel_size, 1)))
+            for _ in self.dilation])
+        self.num_layers = len(self.convs1) + len(self.convs2)
+        self.activations = nn.ModuleList([
+            Activation1d(activation=SnakeBeta(channels, alpha_logscale=True)) for _ in range(self.num_layers)])
+        self._f1 = [_Folded(c) for c in self.convs1]
+        self._f2 = [_Folded(c) for c in self.convs2]
+        _bump_on_load(self)
+
+    def run(self, x: torch.Tensor, slot: int = 0, acc: Optional[torch.Tensor] = None, acc_mode: int = ops.ACC_NONE,
+            acc_div: float = 1.0, before_final=None) -> Optional[torch.Tensor]:
+        """x fp32 [B,C,L] (not modified).  Returns the block output, or None when the result is only
+        accumulated into ``acc`` (mean over resblocks).  ``before_final`` is called right before the
+        last conv is enqueued (used to order accumulation across streams)."""
+        B, C, L = x.shape
+        if C != self.channels or C % 16:
+            raise ValueError(f"AMP block expects {self.channels} channels (multiple of 16), got {C}")
+        k = self.kernel_size
+        buf = ops.blk16_buffer(B, C, L, x.device, slot)
+        xt = torch.empty_like(x)
+        cur = x
+        nl = len(self.dilation)
+        for i, d in enumerate(self.dilation):
+            a1, a2 = self.activations[2 * i], self.activations[2 * i + 1]
+            a1.check_filters(); a2.check_filters()
+            w1, nt1 = self._f1[i].packed_weight()
+            w2, nt2 = self._f2[i].packed_weight()
+            ops.act1d_blk16(cur, *a1.params(), buf)
+            ops.conv1d_umma(buf, w1, self._f1[i].bias(), L, C, C, k, d, nt1, out=xt)
+            ops.act1d_blk16(xt, *a2.params(), buf)
+            last = i == nl - 1
+            if last and before_final is not None:
+                before_final()
+            if last and acc_mode != ops.ACC_NONE:
+                ops.conv1d_umma(buf, w2, self._f2[i].bias(), L, C, C, k, 1, nt2, residual=cur, acc=acc,
+                                acc_mode=acc_mode, acc_div=acc_div, want_out=False)
+                return None
+            out = torch.empty_like(x) if cur is x else cur
+            ops.conv1d_umma(buf, w2, self._f2[i].bias(), L, C, C, k, 1, nt2, residual=cur, out=out)
+            cur = out
+        return cur
+
+    def forward(self, x):
+        return self.run(_as_input(x))
+
+    def remove_weight_norm(self):
+        for l in list(self.convs1) + list(self.convs2):
+            torch.nn.utils.remove_weight_norm(l)
+        self._f1 = [_Folded(c) for c in self.convs1]
+        self._f2 = [_Folded(c) for c in self.convs2]
+
+
+AMPBlock0 = AMPBlock1
+
+
+def mean_of_blocks(x: torch.Tensor, blocks: Sequence[AMPBlock1], parallel: bool = False) -> torch.Tensor:
+    """xs = sum_j resblock_j(x) / num_kernels (hierspeechpp_speechsynthesizer.py:440-446); the sum and
+    the division are fused into the epilogue of each block's last conv."""
+    nk = len(blocks)
+    if nk == 1:
+        return blocks[0].run(x)
+    xs = torch.empty_like(x)
+    modes = [ops.ACC_SET] + [ops.ACC_ADD] * (nk - 2) + [ops.ACC_MEAN]
+    if not parallel:
+        for j, blk in enumerate(blocks):
+            blk.run(x, slot=0, acc=xs, acc_mode=modes[j], acc_div=float(nk))
+        return xs
+    # one stream per resblock; the accumulating epilogues are chained with events
+    main = torch.cuda.current_stream()
+    fork = torch.cuda.Event()
+    fork.record(main)
+    streams = _side_streams(x.device, nk)
+    done = [torch.cuda.Event() for _ in range(nk)]
+    for j, blk in enumerate(blocks):
+        s = streams[j]
+        s.wait_event(fork)
+        with torch.cuda.stream(s):
+            prev = done[j - 1] if j > 0 else None
+            blk.run(x, slot=j, acc=xs, acc_mode=modes[j], acc_div=float(nk),
+                    before_final=(lambda p=prev, st=s: st.wait_event(p)) if prev is not None else None)
+            done[j].record(s)
+    for ev in done:
+        main.wait_event(ev)
+    return xs
+
+
+_streams = {}
+
+
+def _side_streams(device, n):
+    key = (torch.device(device).index, n)
+    if key not in _streams:
+        _streams[key] = [torch.cuda.Stream(device=device) for _ in range(n)]
+    return _streams[key]
+
+
+# ----------------------------------------------------------------------------------------------
+# HierSpeech++ vocoder blocks
+# ----------------------------------------------------------------------------------------------
+class DBlock(nn.Module):
+    """hierspeechpp_speechsynthesizer.py:317-342."""
+
+    def __init__(self, input_size, hidden_size, factor):
+        super().__init__()
+        self.factor = factor
+        self.residual_dense = _weight_norm(Conv1d(input_size, hidden_size, 1))
+        self.conv = nn.ModuleList([
+            _weight_norm(Conv1d(input_size, hidden_size, 3, dilation=1, padding=1)),
+            _weight_norm(Conv1d(hidden_size, hidden_size, 3, dilation=2, padding=2)),
+            _weight_norm(Conv1d(hidden_size, hidden_size, 3, dilation=4, padding=4)),
+        ])
+        self._fr = _Folded(self.residual_dense)
+        self._fc = [_Folded(c) for c in self.conv]
+        _bump_on_load(self)
+
+    def forward(self, x):
+        x = _as_input(x)
+        size = x.shape[-1] // self.factor
+        # nearest down-sampling commutes with the 1x1 conv: gather first (4x less work, same values)
+        xd = ops.nearest_gather(x, size)
+        out = ops.conv1d_direct(xd, self._fr.weight(), self._fr.bias())
+        h = xd
+        for i, d in enumerate((1, 2, 4)):
+            last = i == 2
+            h = ops.conv1d_direct(h, self._fc[i].weight(), self._fc[i].bias(), d=d, pad=d,
+                                  flags=ops.CONV_LRELU_IN | (ops.CONV_ADD_OUT if last else 0),
+                                  out=out if last else None)
+        return h
+
+    def remove_weight_norm(self):
+        for l in self.conv:
+            torch.nn.utils.remove_weight_norm(l)
+        self._fc = [_Folded(c) for c in self.conv]
+
+
+class _VocoderBase(nn.Module):
+    parallel_blocks = False
+
+    def __init__(self):
+        super().__init__()
+        _bump_on_load(self)
+
+    def _stage(self, x, i):
+        nk = self.num_kernels
+        return mean_of_blocks(x, [self.resblocks[i * nk + j] for j in range(nk)], self.parallel_blocks)
+
+
+class SourceNetwork(_VocoderBase):
+    """hierspeechpp_speechsynthesizer.py:251-308."""
+
+    def __init__(self, upsample_initial_channel=256):
+        super().__init__()
+        resblock_kernel_sizes = [3, 5, 7]
+        upsample_rates = [2, 2]
+        initial_channel = 192
+        upsample_kernel_sizes = [4, 4]
+        resblock_dilation_sizes = [[1, 3, 5], [1, 3, 5], [1, 3, 5]]
+        self.num_kernels = len(resblock_kernel_sizes)
+        self.num_upsamples = len(upsample_rates)
+        self.upsample_rates = upsample_rates
+        self.conv_pre = _weight_norm(Conv1d(initial_channel, upsample_initial_channel, 7, 1, padding=3))
+        self.ups = nn.ModuleList()
+        for i, (u, k) in enumerate(zip(upsample_rates, upsample_kernel_sizes)):
+            self.ups.append(_weight_norm(ConvTranspose1d(upsample_initial_channel // (2 ** i),
+                                                         upsample_initial_channel // (2 ** (i + 1)), k, u,
+                                                         padding=(k - u) // 2)))
+        self.resblocks = nn.ModuleList()
+        ch = upsample_initial_channel
+        for i in range(len(self.ups)):
+            ch = upsample_initial_channel // (2 ** (i + 1))
+            for k, d in zip(resblock_kernel_sizes, resblock_dilation_sizes):
+                self.resblocks.append(AMPBlock1(ch, k, d, activation="snakebeta"))
+        self.activation_post = Activation1d(activation=SnakeBeta(ch, alpha_logscale=True))
+        self.conv_post = Conv1d(ch, 1, 7, 1, padding=3, bias=False)
+        self.cond = Conv1d(256, upsample_initial_channel, 1)
+        self._f_pre = _Folded(self.conv_pre)
+        self._f_ups = [_Folded(u) for u in self.ups]
+        self._f_post = _Folded(self.conv_post)
+        self._f_cond = _Folded(self.cond)
+
+    def forward(self, x, g):
+        x, g = _as_input(x), _as_input(g)
+        xp = ops.conv1d_direct(x, self._f_pre.weight(), self._f_pre.bias(), pad=3)
+        cg = ops.conv1d_direct(g, self._f_cond.weight(), self._f_cond.bias())
+        x = ops.add3_bcast(xp, None, cg, out=xp)
+        for i in range(self.num_upsamples):
+            x = ops.conv_transpose1d(x, self._f_ups[i].weight(), self._f_ups[i].bias(), self.upsample_rates[i])
+            x = self._stage(x, i)
+        self.activation_post.check_filters()
+        x = ops.act1d(x, *self.activation_post.params())
+        x_ = ops.conv1d_direct(x, self._f_post.weight(), None, pad=3)
+        return x, x_
+
+
+class Generator(_VocoderBase):
+    """HierSpeech++ BigVGAN-style generator, hierspeechpp_speechsynthesizer.py:394-461."""
+
+    def __init__(self, initial_channel, resblock_kernel_sizes, resblock_dilation_sizes, upsample_rates,
+                 upsample_initial_channel, upsample_kernel_sizes, gin_channels=256):
+        super().__init__()
+        self.num_kernels = len(resblock_kernel_sizes)
+        self.num_upsamples = len(upsample_rates)
+        self.upsample_rates = list(upsample_rates)
+        self.conv_pre = _weight_norm(Conv1d(initial_channel, upsample_initial_channel, 7, 1, padding=3))
+        self.ups = nn.ModuleList()
+        for i, (u, k) in enumerate(zip(upsample_rates, upsample_kernel_sizes)):
+            self.ups.append(_weight_norm(ConvTranspose1d(upsample_initial_channel // (2 ** i),
+                                                         upsample_initial_channel // (2 ** (i + 1)), k, u,
+                                                         padding=(k - u) // 2)))
+        self.resblocks = nn.ModuleList()
+        ch = upsample_initial_channel
+        for i in range(len(self.ups)):
+            ch = upsample_initial_channel // (2 ** (i + 1))
+            for k, d in zip(resblock_kernel_sizes, resblock_dilation_sizes):
+                self.resblocks.append(AMPBlock1(ch, k, d, activation="snakebeta"))
+        self.activation_post = Activation1d(activation=SnakeBeta(ch, alpha_logscale=True))
+        self.conv_post = Conv1d(ch, 1, 7, 1, padding=3, bias=False)
+        if gin_channels != 0:
+            self.cond = nn.Conv1d(gin_channels, upsample_initial_channel, 1)
+        self.downs = DBlock(upsample_initial_channel // 8, upsample_initial_channel, 4)
+        self.proj = Conv1d(upsample_initial_channel // 8, upsample_initial_channel // 2, 7, 1, padding=3)
+        self._f_pre = _Folded(self.conv_pre)
+        self._f_ups = [_Folded(u) for u in self.ups]
+        self._f_post = _Folded(self.conv_post)
+        self._f_cond = _Folded(self.cond) if gin_channels != 0 else None
+        self._f_proj = _Folded(self.proj)
+
+    def forward(self, x, pitch, g=None):
+        x, pitch = _as_input(x), _as_input(pitch)
+        xp = ops.conv1d_direct(x, self._f_pre.weight(), self._f_pre.bias(), pad=3)
+        dn = self.downs(pitch)
+        if g is None:
+            # the reference evaluates self.cond(g) unconditionally (:430) and fails on g=None
+            raise ValueError("Generator.forward needs the speaker embedding g")
+        cg = ops.conv1d_direct(_as_input(g), self._f_cond.weight(), self._f_cond.bias())
+        x = ops.add3_bcast(xp, dn, cg, out=xp)
+        for i in range(self.num_upsamples):
+            add = None
+            if i == 0:
+                add = ops.conv1d_direct(pitch, self._f_proj.weight(), self._f_proj.bias(), pad=3)
+            x = ops.conv_transpose1d(x, self._f_ups[i].weight(), self._f_ups[i].bias(), self.upsample_rates[i],
+                                     add=add)
+            x = self._stage(x, i)
+        self.activation_post.check_filters()
+        x = ops.act1d(x, *self.activation_post.params())
+        return ops.conv1d_direct(x, self._f_post.weight(), None, pad=3, flags=ops.CONV_TANH)
+
+    def remove_weight_norm(self):
+        for l in self.ups:
+            torch.nn.utils.remove_weight_norm(l)
+        for l in self.resblocks:
+            l.remove_weight_norm()
+        self.downs.remove_weight_norm()
+        torch.nn.utils.remove_weight_norm(self.conv_pre)
+        self._f_pre = _Folded(self.conv_pre)
+        self._f_ups = [_Folded(u) for u in self.ups]
+
+
+# ----------------------------------------------------------------------------------------------
+# SpeechSR
+# ----------------------------------------------------------------------------------------------
+class SpeechSRGenerator(_VocoderBase):
+    """speechsr24k/speechsr.py:67-115 (scale 1.5) and speechsr48k/speechsr.py:67-114 (scale 3).
+
+    The reference hard-codes the ratio in ``forward`` (:96); ``upsample_rates`` only sets the loop
+    count.  ``scale`` selects the twin."""
+
+    scale = 1.5
+
+    def __init__(self, initial_channel, resblock, resblock_kernel_sizes, resblock_dilation_sizes, upsample_rates,
+                 upsample_initial_channel, upsample_kernel_sizes, gin_channels=0):
+        super().__init__()
+        self.num_kernels = len(resblock_kernel_sizes)
+        self.num_upsamples = len(upsample_rates)
+        if self.num_upsamples != 1:
+            raise NotImplementedError("the reference builds resblocks for exactly one stage (speechsr.py:77)")
+        if initial_channel != 1:
+            raise NotImplementedError("SpeechSR conv_pre takes the mono waveform (speechsr.py:242)")
+        self.conv_pre = _weight_norm(Conv1d(initial_channel, upsample_initial_channel, 7, 1, padding=3))
+        self.resblocks = nn.ModuleList()
+        ch = upsample_initial_channel
+        for k, d in zip(resblock_kernel_sizes, resblock_dilation_sizes):
+            self.resblocks.append(AMPBlock0(ch, k, d, activation="snakebeta"))
+        self.activation_post = Activation1d(activation=SnakeBeta(ch, alpha_logscale=True))
+        self.conv_post = Conv1d(ch, 1, 7, 1, padding=3, bias=False)
+        if gin_channels != 0:
+            self.cond = nn.Conv1d(gin_channels, upsample_initial_channel, 1)
+        self._f_pre = _Folded(self.conv_pre)
+        self._f_post = _Folded(self.conv_post)
+
+    def forward(self, x, g=None):
+        if g is not None:
+            raise NotImplementedError("SpeechSR is unconditional in the reference (gin_channels=0)")
+        x = _as_input(x)
+        L = x.shape[-1]
+        x = ops.sr_pre_interp(x, self._f_pre.weight(), self._f_pre.bias(), int(L * self.scale))
+        x = self._stage(x, 0)
+        self.activation_post.check_filters()
+        x = ops.act1d(x, *self.activation_post.params())
+        return ops.conv1d_direct(x, self._f_post.weight(), None, pad=3, flags=ops.CONV_TANH)
+
+    def remove_weight_norm(self):
+        for l in self.resblocks:
+            l.remove_weight_norm()
+        torch.nn.utils.remove_weight_norm(self.conv_pre)
+        self._f_pre = _Folded(self.conv_pre)
+
+
+class SpeechSR24Generator(SpeechSRGenerator):
+    scale = 1.5
+
+
+class SpeechSR48Generator(SpeechSRGenerator):
+    scale = 3
+
+
+class _SpeechSRSynthesizer(nn.Module):
+    """SynthesizerTrn of speechsr24k/speechsr.py:215-252 (inference part: ``dec`` only)."""
+
+    _gen_cls = SpeechSR24Generator
+
+    def __init__(self, spec_channels, segment_size, resblock, resblock_kernel_sizes, resblock_dilation_sizes,
+                 upsample_rates, upsample_initial_channel, upsample_kernel_sizes, **kwargs):
+        super().__init__()
+        self.spec_channels = spec_channels
+        self.resblock = resblock
+        self.resblock_kernel_sizes = resblock_kernel_sizes
+        self.resblock_dilation_sizes = resblock_dilation_sizes
+        self.upsample_rates = upsample_rates
+        self.upsample_initial_channel = upsample_initial_channel
+        self.upsample_kernel_sizes = upsample_kernel_sizes
+        self.segment_size = segment_size
+        self.dec = self._gen_cls(1, resblock, resblock_kernel_sizes, resblock_dilation_sizes, upsample_rates,
+                                 upsample_initial_channel, upsample_kernel_sizes)
+
+    def forward(self, x):
+        return self.dec(x)
+
+    @torch.no_grad()
+    def infer(self, x, max_len=None):
+        return self.dec(x[:, :, :max_len])
+
+
+class SpeechSR24(_SpeechSRSynthesizer):
+    _gen_cls = SpeechSR24Generator
+
+
+class SpeechSR48(_SpeechSRSynthesizer):
+    _gen_cls = SpeechSR48Generator
+
+
+class Vocoder(nn.Module):
+    """The ``sn`` -> ``dec`` pair as ``SynthesizerTrn`` owns it (hierspeechpp_speechsynthesizer.py:624-625,
+    648-649): ``forward(z, g)`` returns the 16 kHz waveform [B,1,320*T]."""
+
+    def __init__(self, **cfg):
+        super().__init__()
+        from .config import HIER_CFG
+        c = dict(HIER_CFG)
+        c.update(cfg)
+        self.dec = Generator(**c)
+        self.sn = SourceNetwork(c["upsample_initial_channel"] // 2)
+
+    def forward(self, z, g):
+        e, _ = self.sn(z, g)
+        return self.dec(z, e, g=g)

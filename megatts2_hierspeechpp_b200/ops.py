@@ -1,0 +1,266 @@
+"""Tensor-level wrappers over the hsv C-ABI (``include/hsv.h``).
+
+PyTorch is used only for device memory and streams: every function here checks
+its arguments, takes raw device pointers and launches a hand-written sm_100a
+kernel on ``torch.cuda.current_stream()``.  No function has a CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+
+BLK_PAD = 32
+TILE_M = 128
+
+CONV_LRELU_IN = 1
+CONV_TANH = 2
+CONV_ADD_OUT = 4
+
+ACC_NONE, ACC_SET, ACC_ADD, ACC_MEAN = 0, 1, 2, 3
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _req(t: torch.Tensor, name: str, dtype=torch.float32, ndim: Optional[int] = None):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (no CPU fallback), got device {t.device}")
+    if t.dtype != dtype:
+        raise ValueError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: expected a contiguous tensor")
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError(f"{name}: expected {ndim} dims, got shape {tuple(t.shape)}")
+
+
+def blk16_rows(L: int) -> int:
+    return 2 * BLK_PAD + ((L + TILE_M - 1) // TILE_M) * TILE_M
+
+
+_blk_pool: Dict[Tuple, torch.Tensor] = {}
+
+
+def blk16_buffer(B: int, C: int, L: int, device, slot: int = 0) -> torch.Tensor:
+    """Zero-initialised fp16 [B, C/8, Lp, 8] operand buffer, cached per shape.
+
+    Producers only ever write rows [BLK_PAD, BLK_PAD+L), so the zero rows that
+    implement the conv's zero padding survive reuse."""
+    dev = torch.device(device)
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device(), B, C, L, slot)
+    buf = _blk_pool.get(key)
+    if buf is None:
+        if C % 8:
+            raise ValueError(f"blk16 needs C % 8 == 0 (C={C})")
+        buf = torch.zeros(B, C // 8, blk16_rows(L), 8, dtype=torch.float16, device=dev)
+        _blk_pool[key] = buf
+    return buf
+
+
+def clear_workspace():
+    _blk_pool.clear()
+
+
+def act1d(x: torch.Tensor, alpha: torch.Tensor, beta: torch.Tensor, out: Optional[torch.Tensor] = None):
+    """Fused Activation1d(SnakeBeta): fp32 [B,C,L] -> fp32 [B,C,L]."""
+    _req(x, "x", ndim=3); _req(alpha, "alpha"); _req(beta, "beta")
+    B, C, L = x.shape
+    if alpha.numel() != C or beta.numel() != C:
+        raise ValueError(f"alpha/beta must have {C} elements")
+    if out is None:
+        out = torch.empty_like(x)
+    else:
+        _req(out, "out", ndim=3)
+    lib = _lib.load()
+    _lib.check(lib.hsv_act1d_snakebeta(_p(x), _p(out), _p(alpha), _p(beta), B, C, L, 0, _stream()), "hsv_act1d_snakebeta")
+    return out
+
+
+def act1d_blk16(x: torch.Tensor, alpha: torch.Tensor, beta: torch.Tensor, buf: torch.Tensor):
+    """Fused Activation1d(SnakeBeta): fp32 [B,C,L] -> fp16 blk16 operand (written into ``buf``)."""
+    _req(x, "x", ndim=3); _req(alpha, "alpha"); _req(beta, "beta"); _req(buf, "buf", torch.float16, 4)
+    B, C, L = x.shape
+    if tuple(buf.shape) != (B, C // 8, blk16_rows(L), 8):
+        raise ValueError(f"blk16 buffer shape {tuple(buf.shape)} does not match x {tuple(x.shape)}")
+    lib = _lib.load()
+    _lib.check(lib.hsv_act1d_snakebeta(_p(x), _p(buf), _p(alpha), _p(beta), B, C, L, 1, _stream()), "hsv_act1d_snakebeta")
+    return buf
+
+
+def pack_blk16(x: torch.Tensor, buf: torch.Tensor, lrelu: bool = False):
+    _req(x, "x", ndim=3); _req(buf, "buf", torch.float16, 4)
+    B, C, L = x.shape
+    if tuple(buf.shape) != (B, C // 8, blk16_rows(L), 8):
+        raise ValueError("blk16 buffer shape mismatch")
+    lib = _lib.load()
+    _lib.check(lib.hsv_pack_blk16(_p(x), _p(buf), B, C, L, int(lrelu), _stream()), "hsv_pack_blk16")
+    return buf
+
+
+def weight_norm_fold(v: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
+    """w = v * g/||v|| (norm over all dims but 0) == torch._weight_norm(v, g, 0)."""
+    _req(v, "weight_v"); _req(g, "weight_g")
+    n0 = v.shape[0]
+    if g.numel() != n0:
+        raise ValueError("weight_g must have one element per dim-0 slice of weight_v")
+    w = torch.empty_like(v)
+    lib = _lib.load()
+    _lib.check(lib.hsv_weight_norm_fold(_p(v), _p(g), _p(w), n0, v.numel() // n0, _stream()), "hsv_weight_norm_fold")
+    return w
+
+
+def pick_n_tile(cout: int) -> int:
+    if cout <= 128:
+        return cout
+    if cout % 128 == 0:
+        return 128
+    for n in range(256, 15, -16):
+        if cout % n == 0:
+            return n
+    raise ValueError(f"Cout={cout} not a multiple of 16")
+
+
+def pack_conv_weight(w: torch.Tensor, n_tile: int) -> torch.Tensor:
+    _req(w, "w", ndim=3)
+    cout, cin, k = w.shape
+    out = torch.empty(cout * cin * k, dtype=torch.float16, device=w.device)
+    lib = _lib.load()
+    _lib.check(lib.hsv_pack_conv_weight(_p(w), _p(out), cout, cin, k, n_tile, _stream()), "hsv_pack_conv_weight")
+    return out
+
+
+def conv1d_umma(a_blk: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], L: int, cin: int,
+                cout: int, k: int, d: int, n_tile: int, residual: Optional[torch.Tensor] = None,
+                out: Optional[torch.Tensor] = None, acc: Optional[torch.Tensor] = None, acc_mode: int = ACC_NONE,
+                acc_div: float = 1.0, want_out: bool = True):
+    """tcgen05 implicit-GEMM Conv1d.  Returns ``out`` (fp32 [B,Cout,L]) or None if want_out=False."""
+    _req(a_blk, "a_blk16", torch.float16, 4); _req(w_packed, "w_packed", torch.float16)
+    B = a_blk.shape[0]
+    if tuple(a_blk.shape) != (B, cin // 8, blk16_rows(L), 8):
+        raise ValueError(f"a_blk16 shape {tuple(a_blk.shape)} does not match Cin={cin}, L={L}")
+    if w_packed.numel() != cout * cin * k:
+        raise ValueError("w_packed size mismatch")
+    for t, n in ((bias, "bias"), (residual, "residual"), (out, "out"), (acc, "acc")):
+        if t is not None:
+            _req(t, n)
+    if residual is not None and tuple(residual.shape) != (B, cout, L):
+        raise ValueError("residual shape mismatch")
+    if out is None and want_out:
+        out = torch.empty(B, cout, L, dtype=torch.float32, device=a_blk.device)
+    if out is not None and tuple(out.shape) != (B, cout, L):
+        raise ValueError("out shape mismatch")
+    if acc is not None and tuple(acc.shape) != (B, cout, L):
+        raise ValueError("acc shape mismatch")
+    lib = _lib.load()
+    _lib.check(lib.hsv_conv1d_umma(_p(a_blk), _p(w_packed), _p(bias), _p(residual), _p(out), _p(acc), acc_mode,
+                                   float(acc_div), B, cin, cout, L, k, d, n_tile, _stream()), "hsv_conv1d_umma")
+    return out
+
+
+def conv1d_direct(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], d: int = 1, pad: int = 0,
+                  flags: int = 0, out: Optional[torch.Tensor] = None):
+    _req(x, "x", ndim=3); _req(w, "w", ndim=3)
+    if bias is not None:
+        _req(bias, "bias")
+    B, cin, Lin = x.shape
+    cout, cin_w, k = w.shape
+    if cin_w != cin:
+        raise ValueError(f"weight Cin {cin_w} != input Cin {cin}")
+    Lout = Lin + 2 * pad - d * (k - 1)
+    if out is None:
+        if flags & CONV_ADD_OUT:
+            raise ValueError("CONV_ADD_OUT needs an out tensor")
+        out = torch.empty(B, cout, Lout, dtype=torch.float32, device=x.device)
+    else:
+        _req(out, "out", ndim=3)
+        if tuple(out.shape) != (B, cout, Lout):
+            raise ValueError("out shape mismatch")
+    lib = _lib.load()
+    _lib.check(lib.hsv_conv1d_direct(_p(x), _p(w), _p(bias), _p(out), B, cin, cout, Lin, Lout, k, d, pad, flags,
+                                     _stream()), "hsv_conv1d_direct")
+    return out
+
+
+def conv_transpose1d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], u: int,
+                     add: Optional[torch.Tensor] = None):
+    _req(x, "x", ndim=3); _req(w, "w", ndim=3)
+    B, cin, Lin = x.shape
+    cin_w, cout, k = w.shape
+    if cin_w != cin:
+        raise ValueError(f"weight Cin {cin_w} != input Cin {cin}")
+    out = torch.empty(B, cout, u * Lin, dtype=torch.float32, device=x.device)
+    if add is not None:
+        _req(add, "add", ndim=3)
+        if add.shape != out.shape:
+            raise ValueError("add shape mismatch")
+    if bias is not None:
+        _req(bias, "bias")
+    lib = _lib.load()
+    _lib.check(lib.hsv_conv_transpose1d_direct(_p(x), _p(w), _p(bias), _p(add), _p(out), B, cin, cout, Lin, k, u,
+                                               _stream()), "hsv_conv_transpose1d_direct")
+    return out
+
+
+def sr_pre_interp(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], Lout: int):
+    _req(x, "x", ndim=3); _req(w, "w", ndim=3)
+    B, one, Lin = x.shape
+    C = w.shape[0]
+    if one != 1 or tuple(w.shape[1:]) != (1, 7):
+        raise ValueError("sr_pre_interp expects x [B,1,L] and w [C,1,7]")
+    out = torch.empty(B, C, Lout, dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    _lib.check(lib.hsv_sr_pre_interp(_p(x), _p(w), _p(bias), _p(out), B, C, Lin, Lout, _stream()), "hsv_sr_pre_interp")
+    return out
+
+
+def interp_linear_table(Lin: int, Lout: int, device):
+    i0 = torch.empty(Lout, dtype=torch.int32, device=device)
+    i1 = torch.empty(Lout, dtype=torch.int32, device=device)
+    lam = torch.empty(Lout, dtype=torch.float32, device=device)
+    if not i0.is_cuda:
+        raise RuntimeError("interp_linear_table: CUDA device required")
+    lib = _lib.load()
+    _lib.check(lib.hsv_interp_linear_table(Lin, Lout, _p(i0), _p(i1), _p(lam), _stream()), "hsv_interp_linear_table")
+    return i0, i1, lam
+
+
+def nearest_gather(x: torch.Tensor, Lout: int):
+    _req(x, "x", ndim=3)
+    B, C, Lin = x.shape
+    out = torch.empty(B, C, Lout, dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    _lib.check(lib.hsv_nearest_gather(_p(x), _p(out), B * C, Lin, Lout, _stream()), "hsv_nearest_gather")
+    return out
+
+
+def add3_bcast(a: torch.Tensor, b: Optional[torch.Tensor], bc: Optional[torch.Tensor], out: Optional[torch.Tensor] = None):
+    """out = a + b + bc (bc is [B,C,1], broadcast along L)."""
+    _req(a, "a", ndim=3)
+    B, C, L = a.shape
+    if b is not None:
+        _req(b, "b", ndim=3)
+        if b.shape != a.shape:
+            raise ValueError("b shape mismatch")
+    if bc is not None:
+        _req(bc, "bc")
+        if bc.numel() != B * C:
+            raise ValueError("bc must be [B,C,1]")
+    if out is None:
+        out = torch.empty_like(a)
+    lib = _lib.load()
+    _lib.check(lib.hsv_add3_bcast(_p(a), _p(b), _p(bc), _p(out), B * C, L, _stream()), "hsv_add3_bcast")
+    return out
+
+
+def set_umma_debug(flags: int):
+    _lib.load().hsv_set_umma_debug(int(flags))

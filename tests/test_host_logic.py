@@ -1,0 +1,107 @@
+"""Host-side logic: state_dict layout, config, sharding (incl. a world_size-2 gloo run)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, golden
+import megatts2_hierspeechpp_b200 as hsv
+from megatts2_hierspeechpp_b200.runtime import bucket_by_length, shard_utterances
+from oracle import synth
+
+
+def _manifest(name):
+    return [s.split(":") for s in golden("state_dict_manifest.npz")[name].tolist()]
+
+
+@pytest.mark.parametrize("name,factory", [
+    ("dec", lambda: hsv.Generator(**hsv.HIER_CFG)),
+    ("sn", lambda: hsv.SourceNetwork(256)),
+    ("sr", lambda: hsv.SpeechSR24(100, 40, **hsv.SR_CFG)),
+])
+def test_state_dict_matches_reference_manifest(name, factory):
+    m = factory()
+    sd = m.state_dict()
+    man = _manifest(name)
+    assert [k for k, _ in man] == list(sd.keys())
+    for k, shp in man:
+        assert ",".join(map(str, sd[k].shape)) == shp, k
+
+
+def test_synthetic_checkpoints_load_strict():
+    v = hsv.Vocoder()
+    v.load_state_dict(synth.vocoder_sd(1234), strict=True)
+    hsv.SpeechSR48(128, 40, **hsv.SR_CFG).load_state_dict(synth.speechsr_sd(), strict=True)
+    n_dec = sum(p.numel() for p in v.dec.parameters())
+    n_sn = sum(p.numel() for p in v.sn.parameters())
+    assert n_dec == 15165152 and n_sn == 2432384      # SURVEY.md §0.4 [measured on the reference]
+
+
+def test_real_checkpoint_loads_and_filters_check():
+    sd = {k: torch.from_numpy(v.copy()) for k, v in golden("speechsr24_state.npz").items()}
+    m = hsv.SpeechSR24(100, 40, **hsv.SR_CFG)
+    m.load_state_dict(sd, strict=True)
+    m.dec.activation_post.check_filters()
+    with torch.no_grad():
+        m.dec.activation_post.upsample.filter[0, 0, 3] += 1e-3
+    with pytest.raises(ValueError, match="constant-folds"):
+        m.dec.activation_post.check_filters()
+
+
+def test_kaiser_sinc_filter_matches_checkpoint_taps():
+    f = hsv.kaiser_sinc_filter1d(0.25, 0.3, 12).flatten()
+    assert (f - torch.tensor(hsv.modules.FILTER_TAPS)).abs().max() < 5e-8
+    assert hsv.get_padding(11, 5) == 25 and hsv.get_padding(3, 1) == 1
+
+
+def test_cpu_forward_fails_loudly():
+    m = hsv.SpeechSR24(100, 40, **hsv.SR_CFG)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 1, 64))
+
+
+def test_sharding_is_a_balanced_partition():
+    rng = np.random.RandomState(0)
+    lengths = rng.randint(100, 1500, size=101).tolist()
+    for ws in (1, 2, 4, 8):
+        parts = [shard_utterances(lengths, ws, r) for r in range(ws)]
+        assert sorted(i for p in parts for i in p) == list(range(101))
+        counts = [len(p) for p in parts]
+        assert max(counts) - min(counts) <= 1
+        tot = [sum(lengths[i] for i in p) for p in parts]
+        assert max(tot) - min(tot) <= 1500
+    b = bucket_by_length(list(range(10)), [5, 5, 5, 7, 7, 5, 5, 5, 5, 7], 4)
+    assert all(len(set([5, 5, 5, 7, 7, 5, 5, 5, 5, 7][i] for i in mb)) == 1 and len(mb) <= 4 for mb in b)
+    assert sorted(i for mb in b for i in mb) == list(range(10))
+
+
+def test_two_rank_gloo_shard_and_gather(tmp_path):
+    """world_size-2 job on CPU/gloo: each rank takes its shard, 'processes' it, rank 0 gathers everything."""
+    script = tmp_path / "job.py"
+    script.write_text(
+        "import os, sys, torch, torch.distributed as dist\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "from megatts2_hierspeechpp_b200.runtime import shard_utterances, gather_waveforms\n"
+        "dist.init_process_group('gloo')\n"
+        "r, ws = dist.get_rank(), dist.get_world_size()\n"
+        "lengths = [10 + (7 * i) % 13 for i in range(9)]\n"
+        "mine = shard_utterances(lengths, ws, r)\n"
+        "local = {i: torch.full((1, lengths[i] * 320), float(i)) for i in mine}\n"
+        "dist.barrier()\n"
+        "allw = gather_waveforms(local, dst=0)\n"
+        "if r == 0:\n"
+        "    assert sorted(allw) == list(range(9)), sorted(allw)\n"
+        "    assert all(allw[i].shape == (1, lengths[i] * 320) and float(allw[i][0, 0]) == i for i in allw)\n"
+        "    print('GATHER_OK', len(allw))\n"
+        "else:\n"
+        "    assert allw is None\n"
+        "dist.destroy_process_group()\n")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29617", str(script)],
+                       capture_output=True, text=True, env=env, timeout=240)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "GATHER_OK 9" in r.stdout

@@ -1,0 +1,89 @@
+"""Pin the oracle against the REAL reference modules (authoring container only; skipped on the GPU box)."""
+import pytest
+import torch
+
+from oracle import functional as OF
+from oracle import refload, synth
+
+pytestmark = pytest.mark.skipif(not refload.available(), reason="/root/reference not present")
+
+
+def test_vocoder_bit_exact_vs_reference():
+    ref = refload.load()
+    sd = synth.vocoder_sd(1234)
+    G = ref.H.Generator(**synth.HIER_CFG)
+    S = ref.H.SourceNetwork(256)
+    G.load_state_dict({k[4:]: v for k, v in sd.items() if k.startswith("dec.")}, strict=True)
+    S.load_state_dict({k[3:]: v for k, v in sd.items() if k.startswith("sn.")}, strict=True)
+    G.eval(); S.eval()
+    z, g = synth.vocoder_inputs(2, 12, seed=5)
+    with torch.no_grad():
+        e, e_ = S(z, g)
+        o = G(z, e, g)
+    e2, e2_ = OF.source_network(sd, "sn.", z, g)
+    o2 = OF.hier_generator(sd, "dec.", z, e2, g)
+    assert torch.equal(e, e2) and torch.equal(e_, e2_) and torch.equal(o, o2)
+
+
+@pytest.mark.parametrize("which", [24, 48])
+def test_speechsr_bit_exact_vs_reference(which):
+    m = refload.load_speechsr(which)
+    x = refload.example_wav()[:, :, 4000:9000]
+    with torch.no_grad():
+        a = m(x)
+    b = OF.speechsr(m.state_dict(), x, which)
+    assert a.shape[-1] == OF.speechsr_out_len(5000, which)
+    assert torch.equal(a, b)
+
+
+def test_synthetic_speechsr_sd_loads_strict():
+    ref = refload.load()
+    sd = synth.speechsr_sd()
+    m = ref.sr24.SynthesizerTrn(100, 40, **synth.SR_CFG)
+    m.load_state_dict(sd, strict=True)
+
+
+def test_b200_modules_are_drop_in_for_reference_state_dicts():
+    """Every key/shape of the reference modules' state_dict exists in the B200 modules and vice versa."""
+    import megatts2_hierspeechpp_b200 as hsv
+    ref = refload.load()
+    pairs = [
+        (ref.H.Generator(**synth.HIER_CFG), hsv.Generator(**hsv.HIER_CFG)),
+        (ref.H.SourceNetwork(256), hsv.SourceNetwork(256)),
+        (ref.sr24.SynthesizerTrn(100, 40, **synth.SR_CFG), hsv.SpeechSR24(100, 40, **hsv.SR_CFG)),
+        (ref.sr48.SynthesizerTrn(128, 40, **synth.SR_CFG), hsv.SpeechSR48(128, 40, **hsv.SR_CFG)),
+        (ref.H.AMPBlock1(32, 7, (1, 3, 5), activation="snakebeta"), hsv.AMPBlock1(32, 7, (1, 3, 5))),
+        (ref.H.DBlock(64, 512, 4), hsv.DBlock(64, 512, 4)),
+    ]
+    for r, m in pairs:
+        rs, ms = r.state_dict(), m.state_dict()
+        assert list(rs.keys()) == list(ms.keys()), type(r).__name__
+        for k in rs:
+            assert rs[k].shape == ms[k].shape, k
+        m.load_state_dict(rs, strict=True)
+        r.load_state_dict(m.state_dict(), strict=True)
+
+
+def test_patch_reference_swaps_classes():
+    import megatts2_hierspeechpp_b200 as hsv
+    ref = refload.load()
+    saved = {n: getattr(ref.H, n) for n in ("Generator", "SourceNetwork", "AMPBlock1", "DBlock", "Activation1d")}
+    saved_sr = {n: getattr(ref.sr24, n) for n in ("Generator", "AMPBlock0", "Activation1d")}
+    saved_sr48 = {n: getattr(ref.sr48, n) for n in ("Generator", "AMPBlock0", "Activation1d")}
+    try:
+        patched = hsv.patch_reference()
+        assert "hierspeechpp_speechsynthesizer.Generator" in patched
+        assert ref.H.Generator is hsv.Generator and ref.sr24.Generator is hsv.SpeechSR24Generator
+        m = ref.sr24.SynthesizerTrn(100, 40, **synth.SR_CFG)          # the reference's own SynthesizerTrn
+        assert isinstance(m.dec, hsv.SpeechSR24Generator)
+        m.load_state_dict(refload.load_speechsr(24).state_dict(), strict=True)
+    finally:
+        for n, v in saved.items():
+            setattr(ref.H, n, v)
+        for n, v in saved_sr.items():
+            setattr(ref.sr24, n, v)
+        for n, v in saved_sr48.items():
+            setattr(ref.sr48, n, v)
+        import importlib, sys
+        for modname in ("alias_free_torch", "activations"):
+            importlib.reload(sys.modules[modname])
