@@ -1,0 +1,446 @@
+#!/usr/bin/env python
+"""Benchmark of the waveform-generation hot path (BASELINE.json metric: vocoder audio-sec/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--workload vocoder|speechsr48|speechsr24] [--batch B] [--seconds S]
+
+Default workload = BASELINE.json configs[1]: HierSpeech++ SourceNetwork + Generator (libritts960 arch,
+seeded random init), B=1 x 10 s (z [1,192,500], g [1,256,1]) -> 16 kHz wav [1,1,160000], one GPU.
+A "step" is one pass of the hot path over one batch.  N>1 (torchrun, one rank per GPU): every rank
+runs its own utterances (weak scaling, no data-path collective); NCCL is used for the barrier and the
+max-over-ranks of the device time only.
+
+`--impl reference` times the reference's CPU implementation of the same step (the oracle port: the
+reference's own ATen op sequence, fp32, all host threads) and prints the same JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HBM_FALLBACK_GBS = 6650.0
+TENSOR_FALLBACK_TFLOPS = 1590.0
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "measured"
+    return HBM_FALLBACK_GBS, TENSOR_FALLBACK_TFLOPS, "fallback"
+
+
+# ----------------------------------------------------------------------------------------------
+# workloads
+# ----------------------------------------------------------------------------------------------
+def make_workload(args, rank):
+    """Returns dict(name, sd, host_inputs(list of CPU tensors), audio_seconds, which)."""
+    from oracle import synth
+    import numpy as np
+
+    if args.workload == "vocoder":
+        T = int(round(args.seconds * 50))
+        z, g = synth.vocoder_inputs(args.batch, T, seed=1111 + rank)
+        return dict(name=f"hierspeechpp_vocoder_sn+dec_B{args.batch}x{args.seconds:g}s", kind="vocoder",
+                    sd=synth.vocoder_sd(1234), host_inputs=[z, g], audio_seconds=args.batch * T / 50.0,
+                    data="synthetic z~N(0,1) [B,192,T], g~N(0,1) [B,256,1] (seed 1111+rank); "
+                         "random-init weights (seed 1234, SnakeBeta alpha~U(-0.5,1), beta~U(-0.5,0.8))")
+    which = 48 if args.workload == "speechsr48" else 24
+    L = int(round(args.seconds * 16000))
+    x = synth.speechsr_input(args.batch, L, seed=1111 + rank)
+    gpath = os.path.join(ROOT, "tests", "golden", f"speechsr{which}_state.npz")
+    sd = {k: torch.from_numpy(v.copy()) for k, v in np.load(gpath).items()}
+    return dict(name=f"speechsr{which}_B{args.batch}x{args.seconds:g}s", kind=f"sr{which}", sd=sd, host_inputs=[x],
+                audio_seconds=args.batch * L / 16000.0, which=which,
+                data=f"synthetic 0.1*N(0,1) [B,1,L] (seed 1111+rank); bundled speechsr{which}k checkpoint weights")
+
+
+def oracle_forward(wl):
+    from oracle import functional as OF
+
+    sd = wl["sd"]
+    if wl["kind"] == "vocoder":
+        z, g = wl["host_inputs"]
+        return lambda: OF.vocoder(sd, z, g)
+    x = wl["host_inputs"][0]
+    return lambda: OF.speechsr(sd, x, wl["which"])
+
+
+def time_cpu(fn, steps, warmup):
+    with torch.no_grad():
+        for _ in range(warmup):
+            fn()
+        ts = []
+        for _ in range(steps):
+            t = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t)
+    return ts
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampler
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [c.strip() for c in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm (CPU)
+# ----------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = make_workload(args, 0)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample = f"{wl['name']} (the full step)"
+    if wl["audio_seconds"] > 40:          # bound each CPU step (cost is linear in batch x duration)
+        a2 = argparse.Namespace(**vars(args))
+        a2.batch, a2.seconds = 1, min(args.seconds, 10.0)
+        wl = make_workload(a2, 0)
+        sample = f"{wl['name']} (slice of the workload; CPU cost is linear in batch x duration)"
+    ts = time_cpu(oracle_forward(wl), args.steps, args.warmup)
+    ms = 1e3 * sum(ts) / len(ts)
+    val = wl["audio_seconds"] / (ms / 1e3)
+    sample += f", {args.steps} timed steps after {args.warmup} warm-up, mean"
+    line = {
+        "impl": "reference", "metric": "vocoder audio-sec/sec (RTF^-1)", "value": val, "unit": "audio-s/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": wl["data"],
+        "config": {"workload": wl["name"], "device": "cpu", "threads": cores,
+                   "note": "reference CPU path = oracle port (same ATen op sequence as the reference modules; "
+                           "the reference is pure Python and has no installable package)"},
+        "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------
+def build_model(wl, device):
+    import megatts2_hierspeechpp_b200 as hsv
+
+    if wl["kind"] == "vocoder":
+        m = hsv.Vocoder()
+    else:
+        m = (hsv.SpeechSR48 if wl["which"] == 48 else hsv.SpeechSR24)(100, 40, **hsv.SR_CFG)
+    m.load_state_dict(wl["sd"], strict=True)
+    return m.to(device).eval()
+
+
+def kernel_roofline(model, dev_inputs, hbm_peak, tensor_peak, peak_kind, flush):
+    """Time every hsv launch of one eager forward with its own CUDA-event pair (L2 flushed before each
+    timed launch) and aggregate per kernel family.  Reports the dominant family against its roofline."""
+    from megatts2_hierspeechpp_b200 import ops
+
+    records = []
+    originals = {}
+
+    def wrap(name, bytes_fn=None, flops_fn=None):
+        fn = getattr(ops, name)
+        originals[name] = fn
+
+        def timed(*a, **k):
+            if flush is not None:
+                flush()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*a, **k)
+            e1.record()
+            records.append((name, e0, e1, bytes_fn(*a, **k) if bytes_fn else 0.0, flops_fn(*a, **k) if flops_fn else 0.0))
+            return out
+
+        setattr(ops, name, timed)
+
+    # algorithmic bytes / flops per launch
+    wrap("act1d", bytes_fn=lambda x, *a, **k: 8.0 * x.numel())                 # fp32 in + fp32 out
+    wrap("act1d_blk16", bytes_fn=lambda x, *a, **k: 6.0 * x.numel())           # fp32 in + fp16 out
+
+    def umma_bytes(a_blk, w, bias, L, cin, cout, k, d, n_tile, residual=None, out=None, acc=None, acc_mode=0, **kw):
+        B = a_blk.shape[0]
+        b = 2.0 * B * cin * L + 2.0 * cout * cin * k           # fp16 operand + packed weights
+        if residual is not None:
+            b += 4.0 * B * cout * L
+        if out is not None or kw.get("want_out", True):
+            b += 4.0 * B * cout * L
+        if acc_mode == 1:
+            b += 4.0 * B * cout * L
+        elif acc_mode in (2, 3):
+            b += 8.0 * B * cout * L
+        return b
+
+    wrap("conv1d_umma", bytes_fn=umma_bytes,
+         flops_fn=lambda a_blk, w, bias, L, cin, cout, k, d, n_tile, **kw: 2.0 * a_blk.shape[0] * cin * cout * k * L)
+    wrap("conv1d_direct",
+         flops_fn=lambda x, w, *a, **k: 2.0 * x.shape[0] * w.shape[0] * w.shape[1] * w.shape[2] * x.shape[2])
+    wrap("conv_transpose1d",
+         flops_fn=lambda x, w, *a, **k: 2.0 * x.shape[0] * w.shape[0] * w.shape[1] * w.shape[2] * x.shape[2])
+    for n in ("sr_pre_interp", "nearest_gather", "add3_bcast"):
+        wrap(n)
+    try:
+        with torch.no_grad():
+            model(*dev_inputs)
+        torch.cuda.synchronize()
+    finally:
+        for n, fn in originals.items():
+            setattr(ops, n, fn)
+    fam = {}
+    for name, e0, e1, nbytes, flops in records:
+        f = fam.setdefault(name, {"launches": 0, "ms": 0.0, "bytes": 0.0, "flops": 0.0})
+        f["launches"] += 1
+        f["ms"] += e0.elapsed_time(e1)
+        f["bytes"] += nbytes
+        f["flops"] += flops
+    total_ms = sum(f["ms"] for f in fam.values())
+    for f in fam.values():
+        f["share"] = f["ms"] / total_ms if total_ms else 0.0
+    # activation kernels (both output modes) are one family for the headline roofline
+    act = {"launches": 0, "ms": 0.0, "bytes": 0.0}
+    for n in ("act1d", "act1d_blk16"):
+        if n in fam:
+            for key in act:
+                act[key] += fam[n][key]
+    ach = act["bytes"] / (act["ms"] * 1e-3) / 1e9 if act["ms"] else 0.0
+    roof = {"kernel": "act1d_kernel (fused Activation1d/SnakeBeta, fp32 in, fp32|fp16 out)", "bound": "hbm",
+            "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+            "peak_kind": peak_kind, "launches_per_step": act["launches"],
+            "avg_launch_us": 1e3 * act["ms"] / max(1, act["launches"]),
+            "share_of_step_kernel_time": act["ms"] / total_ms if total_ms else None,
+            "note": "algorithmic bytes (read x once, write result once) summed over all activation launches of "
+                    "one step / summed CUDA-event durations, L2 flushed before each timed launch"}
+    extra = {}
+    if "conv1d_umma" in fam:
+        u = fam["conv1d_umma"]
+        tf = u["flops"] / (u["ms"] * 1e-3) / 1e12 if u["ms"] else 0.0
+        extra["conv1d_umma"] = {"bound": "tensor", "achieved": tf, "peak": tensor_peak, "unit": "TFLOP/s",
+                                "frac": tf / tensor_peak, "hbm_GBps": u["bytes"] / (u["ms"] * 1e-3) / 1e9,
+                                "launches_per_step": u["launches"], "share_of_step_kernel_time": u["share"]}
+    shares = {n: {"launches": f["launches"], "ms": round(f["ms"], 4), "share": round(f["share"], 4)} for n, f in fam.items()}
+    return roof, extra, shares
+
+
+def run_b200(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: the B200 arm needs a CUDA device (no CPU fallback); use --impl reference for the CPU baseline")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import megatts2_hierspeechpp_b200 as hsv
+    from megatts2_hierspeechpp_b200 import _lib, build
+
+    build.build()
+    hbm_peak, tensor_peak, peak_kind = peaks()
+    wl = make_workload(args, rank)
+    model = build_model(wl, dev)
+    if args.parallel_blocks:
+        for m in model.modules():
+            if hasattr(m, "parallel_blocks"):
+                m.parallel_blocks = True
+    host_in = [t.contiguous().pin_memory() for t in wl["host_inputs"]]
+    dev_in = [t.to(dev) for t in host_in]
+    runner = hsv.CudaGraphRunner(model) if not args.no_graph else None
+    fwd = (lambda *a: runner(*a)) if runner else (lambda *a: model(*a))
+
+    flush_buf = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 256 MB > 126 MB L2
+
+    def flush():
+        flush_buf.fill_(1.0)
+
+    with torch.no_grad():
+        n0 = _lib.LAUNCHES[0]
+        model(*dev_in)                      # eager once: folds weights, counts launches per step
+        launches_per_step = _lib.LAUNCHES[0] - n0
+        n0 = _lib.LAUNCHES[0]
+        model(*dev_in)
+        launches_per_step = _lib.LAUNCHES[0] - n0      # steady state (no fold/pack launches)
+        out = fwd(*dev_in)
+        static_in = runner.static_inputs(*dev_in) if runner else dev_in
+        host_out = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+        torch.cuda.synchronize()
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        # ---------------- device-resident timing ----------------
+        for _ in range(args.warmup):
+            flush(); fwd(*static_in)
+        sampler = ClockSampler(local)
+        barrier()
+        sampler.start()
+        evs = []
+        for _ in range(args.steps):
+            flush()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fwd(*static_in); e1.record()
+            evs.append((e0, e1))
+        barrier()
+        step_ms = [a.elapsed_time(b) for a, b in evs]
+        dev_ms = sum(step_ms)
+
+        # ---------------- end to end: pinned host -> device -> host ----------------
+        h2d = sum(t.numel() * t.element_size() for t in host_in)
+        d2h = host_out.numel() * host_out.element_size()
+
+        def e2e_step():
+            for s, h in zip(static_in, host_in):
+                s.copy_(h, non_blocking=True)
+            o = fwd(*static_in)
+            host_out.copy_(o, non_blocking=True)
+
+        for _ in range(max(3, args.warmup)):
+            e2e_step()
+        barrier()
+        evs = []
+        for _ in range(args.steps):
+            flush()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); e2e_step(); e1.record()
+            evs.append((e0, e1))
+        barrier()
+        clocks = sampler.stop()
+        e2e_ms = sum(a.elapsed_time(b) for a, b in evs)
+
+        t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms = float(t[0]), float(t[1])
+
+        roof = extra = shares = cpu = None
+        if rank == 0:
+            par = [m for m in model.modules() if getattr(m, "parallel_blocks", False)]
+            for m in par:
+                m.parallel_blocks = False          # per-kernel timing wants one stream
+            roof, extra, shares = kernel_roofline(model, dev_in, hbm_peak, tensor_peak, peak_kind, flush)
+            for m in par:
+                m.parallel_blocks = True
+            if world == 1 and not args.no_cpu_baseline:
+                cores = os.cpu_count() or 1
+                torch.set_num_threads(cores)
+                cwl = wl
+                sample = f"{wl['name']} (the full step)"
+                if wl["audio_seconds"] > 40:      # bound the CPU sample to ~10-30 s of work
+                    a2 = argparse.Namespace(**vars(args))
+                    a2.batch, a2.seconds = 1, min(args.seconds, 10.0)
+                    cwl = make_workload(a2, 0)
+                    sample = f"{cwl['name']} (slice of the workload; CPU cost is linear in batch x duration)"
+                ts = time_cpu(oracle_forward(cwl), 3, 1)
+                cpu = {"value": cwl["audio_seconds"] / min(ts), "unit": "audio-s/s", "cores": cores, "kind": "port",
+                       "sample": sample + ", oracle port of the reference's CPU path, 1 warm-up + best of 3"}
+
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    total_audio = wl["audio_seconds"] * world * args.steps
+    line = {
+        "metric": "vocoder audio-sec/sec (RTF^-1)", "value": total_audio / (dev_ms / 1e3), "unit": "audio-s/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 residual stream + f16 tensor-core operands, f32 accumulate", "data": wl["data"],
+        "config": {"workload": wl["name"], "per_gpu_batch": args.batch, "seconds_per_utterance": args.seconds,
+                   "cuda_graph": not args.no_graph, "parallel_resblocks": bool(args.parallel_blocks),
+                   "l2": "flushed (256 MB fill) before every timed step", "parallelism": f"utterance-sharded x{world}"},
+        "e2e": {"value": total_audio / (e2e_ms / 1e3), "unit": "audio-s/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": launches_per_step * args.steps,
+        "launches_per_step": launches_per_step,
+        "clocks": clocks, "roofline": roof, "roofline_other": extra, "kernel_shares": shares, "cpu_baseline": cpu,
+        "step_ms_min_med_max": [min(step_ms), statistics.median(step_ms), max(step_ms)],
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="vocoder", choices=["vocoder", "speechsr48", "speechsr24"])
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--seconds", type=float, default=10.0)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--parallel-blocks", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        args.steps = args.steps if args.steps is not None else 5
+        args.warmup = args.warmup if args.warmup is not None else 1
+        run_reference(args)
+    else:
+        args.steps = args.steps if args.steps is not None else 50
+        args.warmup = max(3, args.warmup if args.warmup is not None else 5)
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

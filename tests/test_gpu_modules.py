@@ -1,0 +1,159 @@
+"""Module-level parity on the GPU: drop-in modules vs golden vectors / the CPU oracle.
+
+Contract (BASELINE.json north_star): max-abs <= 2e-3 and SNR >= 40 dB against the fp32 reference
+forward on identical inputs and weights."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import MAX_ABS_TOL, SNR_DB_MIN, golden, golden_sd
+from oracle import closed_form as CF
+from oracle import functional as OF
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _check(name, got, ref, max_abs=MAX_ABS_TOL, snr_min=SNR_DB_MIN):
+    got = got.detach().cpu().numpy() if torch.is_tensor(got) else got
+    ref = ref.detach().cpu().numpy() if torch.is_tensor(ref) else ref
+    assert got.shape == ref.shape, (name, got.shape, ref.shape)
+    ma, snr = CF.max_abs(ref, got), CF.snr_db(ref, got)
+    print(f"[parity] {name}: max_abs={ma:.3e} snr={snr:.1f} dB")
+    assert ma <= max_abs, (name, ma)
+    assert snr >= snr_min, (name, snr)
+    return ma, snr
+
+
+@pytest.fixture(scope="module")
+def vocoder(hsv):
+    m = hsv.Vocoder()
+    m.load_state_dict(synth.vocoder_sd(1234), strict=True)
+    return m.to(DEV).eval()
+
+
+def test_ampblock_golden(hsv):
+    g = golden("ampblock_c16_k7.npz")
+    gen = torch.Generator().manual_seed(11)
+    sd = {}
+    synth._amp_block(sd, "", gen, 16, 7)
+    blk = hsv.AMPBlock1(16, 7, (1, 3, 5))
+    blk.load_state_dict(sd, strict=True)
+    blk.to(DEV)
+    y = blk(torch.from_numpy(g["x"]).to(DEV))
+    _check("AMPBlock1 c16 k7", y, g["y"], max_abs=2e-3, snr_min=50.0)
+
+
+def test_dblock_golden(hsv):
+    g = golden("dblock_L83.npz")
+    sd = synth.hier_generator_sd(1234, "")
+    db = hsv.DBlock(64, 512, 4)
+    db.load_state_dict({k[len("downs."):]: v for k, v in sd.items() if k.startswith("downs.")}, strict=True)
+    db.to(DEV)
+    y = db(torch.from_numpy(g["x"]).to(DEV))
+    _check("DBlock L83", y, g["y"], max_abs=1e-4, snr_min=80.0)      # fp32 path
+
+
+def test_vocoder_golden_T20(vocoder):
+    g = golden("vocoder_T20.npz")
+    z, gg = synth.vocoder_inputs(1, 20, seed=1111)
+    e, e_ = vocoder.sn(z.to(DEV), gg.to(DEV))
+    _check("SourceNetwork e", e, g["e"], max_abs=5e-3, snr_min=SNR_DB_MIN)
+    wav = vocoder(z.to(DEV), gg.to(DEV))
+    assert wav.shape == (1, 1, 6400)
+    _check("vocoder wav T=20", wav, g["wav"])
+
+
+def test_vocoder_config2_10s_vs_oracle(vocoder):
+    """Config #2: B=1 x 10 s (T=500), seed-1111 inputs, seed-1234 weights, vs the CPU oracle."""
+    z, gg = synth.vocoder_inputs(1, 500, seed=1111)
+    sd = synth.vocoder_sd(1234)
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    ref = OF.vocoder(sd, z, gg)
+    wav = vocoder(z.to(DEV), gg.to(DEV))
+    assert wav.shape == (1, 1, 160000)
+    _check("vocoder wav 10 s", wav, ref)
+    assert wav.abs().max().item() <= 1.0
+
+
+def test_vocoder_batch_and_graph_consistency(hsv, vocoder):
+    z, gg = synth.vocoder_inputs(3, 40, seed=3)
+    z, gg = z.to(DEV), gg.to(DEV)
+    full = vocoder(z, gg)
+    one = vocoder(z[1:2].contiguous(), gg[1:2].contiguous())
+    assert torch.equal(full[1:2], one)                       # utterances are independent -> shardable
+    runner = hsv.CudaGraphRunner(vocoder)
+    g1 = runner(z, gg).clone()
+    g2 = runner(z, gg).clone()
+    assert torch.equal(g1, full) and torch.equal(g2, full)   # graph replay == eager, deterministic
+    vocoder.dec.parallel_blocks = vocoder.sn.parallel_blocks = True
+    try:
+        par = vocoder(z, gg)
+        torch.cuda.synchronize()
+        assert torch.equal(par, full)                        # 3-stream resblocks == single stream
+    finally:
+        vocoder.dec.parallel_blocks = vocoder.sn.parallel_blocks = False
+
+
+@pytest.mark.parametrize("which", [24, 48])
+def test_speechsr_real_checkpoint_example(hsv, which):
+    """Config #1 (SR24 on example/reference_1.wav, bundled G_340000.pth) and the 48k twin (1 s)."""
+    sd = golden_sd(f"speechsr{which}_state.npz")
+    g = golden(f"speechsr{which}_example.npz")
+    cls = hsv.SpeechSR24 if which == 24 else hsv.SpeechSR48
+    m = cls(100, 40, **hsv.SR_CFG)
+    m.load_state_dict(sd, strict=True)
+    m.to(DEV).eval()
+    x = torch.from_numpy(g["x_int16"].astype(np.float32) / 32768.0).view(1, 1, -1).to(DEV)
+    y = m(x)
+    assert y.shape[-1] == OF.speechsr_out_len(x.shape[-1], which)
+    _check(f"SpeechSR{which} example", y, g["y"])
+    y2 = m.infer(x, max_len=8000)
+    assert y2.shape[-1] == OF.speechsr_out_len(8000, which)
+
+
+def test_speechsr48_batch_vs_oracle(hsv):
+    """Config #3 shape family at a size the CPU oracle finishes quickly: B=2 x 1 s, real weights."""
+    sd = golden_sd("speechsr48_state.npz")
+    m = hsv.SpeechSR48(128, 40, **hsv.SR_CFG)
+    m.load_state_dict(sd, strict=True)
+    m.to(DEV).eval()
+    x = synth.speechsr_input(2, 16000, seed=1111)
+    ref = OF.speechsr(sd, x, 48)
+    y = m(x.to(DEV))
+    _check("SpeechSR48 B=2 x 1 s", y, ref)
+    assert torch.equal(y[:1], m(x[:1].to(DEV)))
+
+
+def test_speechsr48_config3_slice_properties(hsv):
+    """Config #3 per-utterance size (10 s -> 480000 samples), B=4: batch independence + window parity."""
+    sd = golden_sd("speechsr48_state.npz")
+    m = hsv.SpeechSR48(128, 40, **hsv.SR_CFG)
+    m.load_state_dict(sd, strict=True)
+    m.to(DEV).eval()
+    x = synth.speechsr_input(4, 160000, seed=1111)
+    y = m(x.to(DEV))
+    assert y.shape == (4, 1, 480000) and y.abs().max().item() <= 1.0
+    assert torch.equal(y[2:3], m(x[2:3].to(DEV)))
+    # a window far from the edges depends only on nearby input: compare with the oracle on a crop
+    a, b = 60000, 64000                                  # input samples
+    ref = OF.speechsr(sd, x[1:2, :, a:b], 48)            # [1,1,12000]
+    got = y[1:2, :, 3 * a:3 * b].cpu()
+    cut = 1500                                           # > receptive field (3x rate)
+    _check("SpeechSR48 10 s window", got[..., cut:-cut], ref[..., cut:-cut])
+
+
+def test_weight_cache_invalidation(hsv):
+    m = hsv.SpeechSR24(100, 40, **hsv.SR_CFG)
+    sd = golden_sd("speechsr24_state.npz")
+    m.load_state_dict(sd, strict=True)
+    m.to(DEV).eval()
+    x = synth.speechsr_input(1, 2000).to(DEV)
+    y1 = m(x).clone()
+    sd2 = {k: (v * 1.5 if k.endswith("conv_post.weight") else v) for k, v in sd.items()}
+    m.load_state_dict(sd2, strict=True)                  # must refold / repack, not reuse stale weights
+    y2 = m(x)
+    ref = OF.speechsr(sd2, x.cpu(), 24)
+    _check("SpeechSR24 after reload", y2, ref)
+    assert not torch.equal(y1, y2)

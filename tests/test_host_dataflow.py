@@ -1,0 +1,80 @@
+"""Host-side dataflow of the drop-in modules, run on CPU with the kernels EMULATED (tests/emu_ops.py).
+
+Checks what the Python layer is responsible for: op order, epilogue modes (residual / mean over
+resblocks), buffer reuse, DBlock's gather-before-1x1 rewrite, weight-cache invalidation.  The real
+kernels are checked on the GPU (tests/test_gpu_*.py)."""
+import numpy as np
+import torch
+
+import emu_ops
+from conftest import golden, golden_sd
+import megatts2_hierspeechpp_b200 as hsv
+from oracle import closed_form as CF
+from oracle import functional as OF
+from oracle import synth
+
+
+def test_vocoder_dataflow_matches_oracle(monkeypatch):
+    emu_ops.install(monkeypatch)
+    g = golden("vocoder_T20.npz")
+    m = hsv.Vocoder()
+    m.load_state_dict(synth.vocoder_sd(1234), strict=True)
+    z, gg = synth.vocoder_inputs(1, 20, seed=1111)
+    e, e_ = m.sn(z, gg)
+    wav = m(z, gg)
+    assert wav.shape == (1, 1, 6400)
+    # fp16 operand rounding (emulated) keeps the result inside the parity contract
+    assert CF.max_abs(g["wav"], wav.numpy()) <= 2e-3 and CF.snr_db(g["wav"], wav.numpy()) >= 40.0
+    assert CF.snr_db(g["e"], e.numpy()) >= 40.0
+    assert e_.shape == (1, 1, 80)
+
+
+def test_speechsr_dataflow_matches_golden(monkeypatch):
+    emu_ops.install(monkeypatch)
+    for which, cls in ((24, hsv.SpeechSR24), (48, hsv.SpeechSR48)):
+        sd = golden_sd(f"speechsr{which}_state.npz")
+        g = golden(f"speechsr{which}_example.npz")
+        m = cls(100, 40, **hsv.SR_CFG)
+        m.load_state_dict(sd, strict=True)
+        x = torch.from_numpy(g["x_int16"][:4000].astype(np.float32) / 32768.0).view(1, 1, -1)
+        y = m(x).numpy()
+        n = y.shape[-1]
+        ref = g["y"][..., :n]
+        assert CF.max_abs(ref[..., :n - 1500], y[..., :n - 1500]) <= 2e-3
+        assert CF.snr_db(ref[..., :n - 1500], y[..., :n - 1500]) >= 40.0
+
+
+def test_dblock_and_ampblock_dataflow(monkeypatch):
+    emu_ops.install(monkeypatch)
+    g = golden("dblock_L83.npz")
+    sd = synth.hier_generator_sd(1234, "")
+    db = hsv.DBlock(64, 512, 4)
+    db.load_state_dict({k[len("downs."):]: v for k, v in sd.items() if k.startswith("downs.")}, strict=True)
+    y = db(torch.from_numpy(g["x"]))
+    assert np.abs(y.numpy() - g["y"]).max() <= 1e-5           # gather-then-1x1 == 1x1-then-gather
+    ga = golden("ampblock_c16_k7.npz")
+    gen = torch.Generator().manual_seed(11)
+    bsd = {}
+    synth._amp_block(bsd, "", gen, 16, 7)
+    blk = hsv.AMPBlock1(16, 7, (1, 3, 5))
+    blk.load_state_dict(bsd, strict=True)
+    x = torch.from_numpy(ga["x"])
+    x0 = x.clone()
+    y = blk(x)
+    assert torch.equal(x, x0)                                  # the input (shared by 3 resblocks) is not modified
+    assert CF.snr_db(ga["y"], y.numpy()) >= 50.0
+
+
+def test_mean_of_blocks_and_cache_invalidation(monkeypatch):
+    emu_ops.install(monkeypatch)
+    sd = synth.speechsr_sd(7)
+    m = hsv.SpeechSR24(100, 40, **hsv.SR_CFG)
+    m.load_state_dict(sd, strict=True)
+    x = synth.speechsr_input(2, 600)
+    y1 = m(x)
+    ref1 = OF.speechsr(sd, x, 24)
+    assert CF.snr_db(ref1.numpy(), y1.numpy()) >= 40.0
+    sd2 = synth.speechsr_sd(8)
+    m.load_state_dict(sd2, strict=True)
+    y2 = m(x)
+    assert CF.snr_db(OF.speechsr(sd2, x, 24).numpy(), y2.numpy()) >= 40.0   # refolded, not stale
