@@ -327,20 +327,27 @@ extern "C" int hsv_conv1d_umma(const void *a_blk16, const void *w_packed, const 
     p.stages--;
     smem = a_bytes + (size_t)p.stages * G * kstep_bytes;
   }
-  HSV_REQUIRE(smem <= 227 * 1024, "conv1d_umma: shared memory %zu B exceeds 227 KB (Cin=%d k=%d d=%d)", smem,
-              Cin, k, d);
-  static bool configured[64] = {false};
+  // opt-in dynamic shared memory: 227 KB per block minus the kernel's static shared memory
+  static int max_dyn[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev >= 0 && dev < 64 && !configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(conv1d_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(227 * 1024));
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (max_dyn[dev] == 0) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, conv1d_umma_kernel);
+    int want = 227 * 1024 - (e == cudaSuccess ? (int)fa.sharedSizeBytes : 1024);
+    want &= ~1023;
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv1d_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
     if (e != cudaSuccess) {
-      hsv::set_error("conv1d_umma: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      cudaGetLastError();  // clear
+      hsv::set_error("conv1d_umma: cudaFuncSetAttribute(%d): %s", want, cudaGetErrorString(e));
       return HSV_ERR_CUDA;
     }
-    configured[dev] = true;
+    max_dyn[dev] = want;
   }
+  HSV_REQUIRE(smem <= (size_t)max_dyn[dev], "conv1d_umma: shared memory %zu B exceeds %d B (Cin=%d k=%d d=%d)",
+              smem, max_dyn[dev], Cin, k, d);
   dim3 grid((unsigned)((L + TILE_M - 1) / TILE_M), (unsigned)(Cout / n_tile), (unsigned)B);
   conv1d_umma_kernel<<<grid, 128, smem, hsv::as_stream(stream)>>>(p);
   return hsv::check_launch("conv1d_umma");

@@ -168,7 +168,7 @@ def test_linear_interp_indices_bit_exact(hsv, Lin, Lout):
     # and against torch's own CUDA kernel on an arange probe (value = i0 + lam)
     ar = torch.arange(Lin, dtype=torch.float32, device=DEV).view(1, 1, -1)
     probe = F.interpolate(ar, Lout, mode="linear").view(-1).cpu().numpy()
-    mine = (e0 + el.astype(np.float64))
+    mine = (1.0 - el.astype(np.float64)) * e0 + el.astype(np.float64) * e1   # i1 == i0 at the clamped end
     assert np.abs(probe - mine).max() <= 1e-6 * max(Lin, 16) + 1e-6
 
 

@@ -136,12 +136,20 @@ def test_speechsr48_config3_slice_properties(hsv):
     y = m(x.to(DEV))
     assert y.shape == (4, 1, 480000) and y.abs().max().item() <= 1.0
     assert torch.equal(y[2:3], m(x[2:3].to(DEV)))
-    # a window far from the edges depends only on nearby input: compare with the oracle on a crop
-    a, b = 60000, 64000                                  # input samples
-    ref = OF.speechsr(sd, x[1:2, :, a:b], 48)            # [1,1,12000]
-    got = y[1:2, :, 3 * a:3 * b].cpu()
-    cut = 1500                                           # > receptive field (3x rate)
-    _check("SpeechSR48 10 s window", got[..., cut:-cut], ref[..., cut:-cut])
+    # full-length parity against the reference op sequence run by torch on the SAME device in strict fp32
+    # (no TF32).  A CPU/cropped oracle is not comparable here: at source index ~1.6e5 the fp32 ulp is
+    # 0.016, so the reference's own interpolation weights depend on the device's rounding of
+    # scale*(dst+0.5)-0.5; the CUDA formula is the oracle of record for the indices.
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        sd_dev = {k: v.to(DEV) for k, v in sd.items()}
+        with torch.no_grad():
+            ref = OF.speechsr(sd_dev, x[1:2].to(DEV), 48)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    _check("SpeechSR48 10 s (torch-CUDA fp32 oracle)", y[1:2], ref)
 
 
 def test_weight_cache_invalidation(hsv):

@@ -68,7 +68,7 @@ if __name__ == "__main__":
                 r = subprocess.run([sys.executable, __file__, *map(str, c)], capture_output=True, text=True, env=env,
                                    timeout=120)
                 out = [l for l in r.stdout.splitlines() if l.startswith("PROBE")]
-                print(out[0] if out else f"FAIL {c[0]} rc={r.returncode} {r.stdout[-300:]} {r.stderr[-600:]}", flush=True)
+                print(out[0] if out else f"FAIL {c[0]} rc={r.returncode} {r.stdout[-200:]} {r.stderr[-300:]}", flush=True)
                 if out and json.loads(out[0][6:])["max_err"] < 1e-3:
                     n_ok += 1
             except subprocess.TimeoutExpired:
