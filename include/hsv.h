@@ -93,6 +93,19 @@ int hsv_conv1d_umma(const void *a_blk16, const void *w_packed, const float *bias
                     const float *residual, float *out, float *acc, int acc_mode, float acc_div,
                     int B, int Cin, int Cout, int64_t L, int k, int d, int n_tile, void *stream);
 
+/* ---- ConvTranspose1d (ups[i], hierspeechpp_speechsynthesizer.py:404-408,434) on the same
+ * tcgen05 kernel: the u output phases are u stride-1 convolutions over the input rows
+ * (SURVEY.md §A.3), each an N-tile group of one launch.
+ *   hsv_pack_convT_weight: w [Cin,Cout,k] fp32 (folded) -> fp16 [phase][Cout/n_tile][taps*Cin/16][2][n_tile][8]
+ *   hsv_conv_transpose1d_umma: a_blk16 [B][Cin/8][Lp(Lin)][8] -> out [B,Cout,u*Lin] fp32,
+ *   out = convT + bias (+ add, same shape as out: proj(pitch) at stage 0, :436-438).
+ *   stride u <= 8, padding (k-u)/2, k - 2*((k-u)/2) == u (true for every (k,u) on the path).
+ */
+int hsv_pack_convT_weight(const float *w, void *packed, int Cin, int Cout, int k, int u, int n_tile, void *stream);
+int hsv_conv_transpose1d_umma(const void *a_blk16, const void *w_packed, const float *bias, const float *add,
+                              float *out, int B, int Cin, int Cout, int64_t Lin, int k, int u, int n_tile,
+                              void *stream);
+
 /* ---- generic fp32 Conv1d (stride 1, zero padding `pad`, dilation d) on CUDA
  * cores, for the small/odd-shaped convs of the path: conv_pre, cond, proj,
  * DBlock convs, conv_post (+tanh) (hierspeechpp_speechsynthesizer.py:401,

@@ -29,7 +29,8 @@ constexpr int NT = ROWS * RUNS;  // 128 threads
 template <int R>
 struct Cfg {
   static constexpr int TILE = RUNS * R;
-  static constexpr int XW = TILE + 10;
+  static constexpr int XOFF = 8;             // staged halo (>= 5), multiple of 4 for 16-byte TMA alignment
+  static constexpr int XW = TILE + 2 * XOFF;
   // pitch == 4 (mod 32) words -> (row*PITCH + R*run + j) hits 32 distinct banks per warp
   static constexpr int PITCH = ((XW + 27) / 32) * 32 + 4;
   static constexpr int OPITCH = ((TILE + 27) / 32) * 32 + 4;
@@ -113,8 +114,10 @@ __global__ void __launch_bounds__(NT) act1d_kernel(const float *__restrict__ x, 
                                                    const float *__restrict__ beta, int C, int64_t L,
                                                    int64_t nrows, int ntiles, int64_t Lp) {
   using K = Cfg<R>;
-  __shared__ float x_s[ROWS * K::PITCH];
+  // x_s[c][p] holds x[row0+c][t0 - XOFF + p]; XOFF = 8 keeps the tile start 16-byte aligned for TMA
+  __shared__ __align__(16) float x_s[ROWS * K::PITCH];
   __shared__ __align__(16) float o_s[OUT_MODE == 0 ? ROWS * K::OPITCH : K::TILE * 4];
+  __shared__ __align__(8) uint64_t bar;
 
   const int tid = threadIdx.x;
   const int tile = blockIdx.x % ntiles;
@@ -122,19 +125,57 @@ __global__ void __launch_bounds__(NT) act1d_kernel(const float *__restrict__ x, 
   const int64_t row0 = rowgrp * ROWS;
   const int64_t t0 = (int64_t)tile * K::TILE;
 
-  // ---- stage x tile (replicate-clamped on the 1x grid) ----
-  for (int idx = tid; idx < ROWS * K::XW; idx += NT) {
-    const int c = idx / K::XW, p = idx - c * K::XW;
-    const int64_t row = row0 + c;
-    float v = 0.f;
-    if (row < nrows) {
-      int64_t t = t0 - 5 + p;
-      t = t < 0 ? 0 : (t > L - 1 ? L - 1 : t);
-      v = __ldg(x + row * L + t);
+  // ---- stage the x tile ----
+  // interior tiles of 16-byte-aligned rows: one 1-D bulk TMA copy per row (no issue slots, no registers);
+  // edge tiles / unaligned rows: plain loads with the replicate clamp of the 1x grid.
+  const bool fast = ((L & 3) == 0) && t0 >= K::XOFF && t0 + K::TILE + K::XOFF <= L && row0 + ROWS <= nrows &&
+                    ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  if (fast) {
+    const uint32_t bar_a = static_cast<uint32_t>(__cvta_generic_to_shared(&bar));
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    x_s[c * K::PITCH + p] = v;
+    __syncthreads();
+    constexpr uint32_t ROW_BYTES = (K::TILE + 2 * K::XOFF) * 4;
+    if (tid == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(ROW_BYTES * ROWS)
+                   : "memory");
+    if (tid < ROWS) {
+      const float *src = x + (row0 + tid) * L + (t0 - K::XOFF);
+      const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(x_s + tid * K::PITCH));
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                   "l"(src), "r"(ROW_BYTES), "r"(bar_a)
+                   : "memory");
+    }
+    uint32_t ok = 0;
+    while (!ok) {
+      asm volatile(
+          "{\n\t"
+          ".reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t"
+          "}"
+          : "=r"(ok)
+          : "r"(bar_a)
+          : "memory");
+    }
+  } else {
+    const int Lm1 = (int)(L - 1);
+#pragma unroll 1
+    for (int c = 0; c < ROWS; ++c) {
+      const int64_t row = row0 + c;
+      const float *xr = x + row * L;
+      const bool rv = row < nrows;
+#pragma unroll 3
+      for (int p = tid; p < K::TILE + 2 * K::XOFF; p += NT) {
+        int64_t t = t0 - K::XOFF + p;
+        const int tc = t < 0 ? 0 : (t > Lm1 ? Lm1 : (int)t);
+        x_s[c * K::PITCH + p] = rv ? __ldg(xr + tc) : 0.f;
+      }
+    }
+    __syncthreads();
   }
-  __syncthreads();
 
   const int c = tid % ROWS, run = tid / ROWS;
   const int64_t row = row0 + c;
@@ -145,7 +186,7 @@ __global__ void __launch_bounds__(NT) act1d_kernel(const float *__restrict__ x, 
     const int ch = (int)(row % C);
     const float a = expf(__ldg(alpha + ch));
     const float ib = 1.0f / (expf(__ldg(beta + ch)) + 0.000000001f);
-    const float *xw = x_s + c * K::PITCH + run * R;
+    const float *xw = x_s + c * K::PITCH + run * R + (K::XOFF - 5);
     const bool edge = (2 * ta - 5 < 0) || (2 * (ta + R - 1) + 6 > 2 * L - 1);
     if (!edge) {
       walk<R, false>(xw, outv, a, ib, ta, L, 0.f, 0.f);

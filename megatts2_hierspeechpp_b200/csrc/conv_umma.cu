@@ -1,38 +1,53 @@
-// Dilated 'same' Conv1d as a tcgen05 / TMEM implicit GEMM (sm_100a).
+// Dense Conv1d / ConvTranspose1d as a tcgen05 / TMEM implicit GEMM (sm_100a).
 //
-// Replaces the weight-normed AMPBlock convs of the reference
-// (hierspeechpp_speechsynthesizer.py:349-364,380-384; speechsr24k/speechsr.py:21-36,52-56):
-//   out[b,co,t] = bias[co] + sum_{ci,j} W[co,ci,j] * a[b,ci,t + (j-(k-1)/2)*d]      (zero padded)
-// GEMM view per CTA:  D[M=128 time rows, N=n_tile out channels] = sum over taps j and 16-channel
-// K-steps of  A_j[128 x 16] * W_j[16 x n_tile],  fp16 operands, fp32 accumulation in TMEM.
+// Replaces the weight-normed convolutions of the reference's waveform path
+//   * AMPBlock convs    hierspeechpp_speechsynthesizer.py:349-364,380-384; speechsr24k/speechsr.py:21-36,52-56
+//   * conv_pre / proj / DBlock convs   hierspeechpp_speechsynthesizer.py:401,426,321-325
+//   * ups[i] ConvTranspose1d           hierspeechpp_speechsynthesizer.py:404-408,434
+// with one kernel.  Both are "sum over taps of a row-shifted [rows x Cin] x [Cin x Cout] product":
+//   conv1d      out[t]       = b + sum_j  W[:, :, j]        a[t + (j-(k-1)/2) d]
+//   convT phase out[u q + r] = b + sum_i  W[:, :, r' + i u] a[q + c - i]      (r' = (r+p) mod u, c = (r+p) div u)
+// GEMM view per CTA:  D[M = 128 rows, N = n_tile out channels] += A_tap[128 x 16] * W_tap[16 x n_tile]
+// over all taps and 16-channel K-steps; fp16 operands, fp32 accumulation in TMEM.
 //
-// Operand staging.  The activation operand arrives in the "blk16" layout written by the fused
-// activation kernel: fp16 [B][Cin/8][Lp][8], i.e. for each 8-channel chunk the time rows are
-// contiguous 16-byte records.  A time tile (+halo) of one chunk is therefore ONE contiguous span,
-// fetched with a 1-D bulk TMA copy (cp.async.bulk) straight into shared memory as
-// [chunk][row][8 halves].  That is exactly the tcgen05 K-major SWIZZLE_NONE canonical layout with
-// SBO = 128 B (8 rows x 16 B) and LBO = rows*16 B, in which consecutive rows of one K-chunk are
-// uniformly 16 B apart -- so the operand of tap j is the SAME shared tile with the descriptor start
-// address advanced by j*d rows.  The halo is loaded once and reused by all k taps; zero padding
-// comes from the zero rows the blk16 layout keeps around every sequence.
-// Weights are pre-packed (hsv_pack_conv_weight) as [n_tile block][K-step][2][n_tile][8] fp16 so a
-// group of K-steps is again one contiguous span, streamed through a ring of shared stages by bulk
-// TMA copies with mbarrier completion.
+// Operand staging.  Activations arrive in the "blk16" layout written by the fused activation kernel
+// (or hsv_pack_blk16): fp16 [B][Cin/8][Lp][8] -- per 8-channel chunk the time rows are consecutive
+// 16-byte records with zero rows around every sequence.  A time tile (+halo) of one chunk is ONE
+// contiguous span, fetched with a 1-D bulk TMA copy into shared memory as [chunk][row][8 halves].
+// That is tcgen05's K-major SWIZZLE_NONE canonical layout with SBO = 128 B (8 rows x 16 B) and
+// LBO = rows*16 B, in which rows of one K-chunk are uniformly 16 B apart -- so the operand of a tap is
+// the SAME shared tile with the descriptor start address advanced by the tap's row offset.  The halo is
+// loaded once and reused by all taps; zero padding comes from the zero rows of the blk16 layout.
+// Weights are pre-packed as [phase][n-tile][K-step][2][n_tile][8] fp16 so a group of K-steps is one
+// contiguous span, streamed through a ring of shared stages by bulk TMA copies (mbarrier full/empty).
 //
-// Roles (128 threads): warp0/lane0 TMA producer, warp1/lane0 MMA issuer, warp2 TMEM alloc/free,
-// then all four warps run the epilogue: tcgen05.ld (lane = time row), + bias, + residual, store
-// fp32 [B,C,L] (a warp stores 32 consecutive time steps of one channel: 128 B coalesced) and
-// optionally accumulate the mean over resblocks.
+// Roles (128 threads): warp0/lane0 TMA producer, warp1/lane0 MMA issuer, warp2 TMEM alloc/free, then all
+// four warps run the epilogue: tcgen05.ld (lane = row), + bias, + residual, store fp32 [B,C,L] (for
+// stride-1 outputs a warp stores 32 consecutive time steps of one channel = 128 B coalesced) and
+// optionally accumulate the mean over resblocks.  Residual loads are batched per 16-column chunk and
+// prefetched one chunk ahead (out may alias residual, so the compiler cannot do this itself).
 #include "hsv_common.cuh"
 
 namespace {
 
 constexpr int TILE_M = HSV_UMMA_TILE_M;  // 128
 constexpr int MAX_STAGES = 4;
+constexpr int MAX_PHASES = 8;
+constexpr int MAX_TAPS = 16;
+
+struct TapTable {
+  int nphase;
+  int out_stride;
+  int ntaps[MAX_PHASES];
+  int out_off[MAX_PHASES];
+  int8_t row_off[MAX_PHASES][MAX_TAPS];  // input row offset of the tap relative to the output row
+  int8_t wj[MAX_PHASES][MAX_TAPS];       // which tap of the weight tensor
+  int h_lo, h_hi;                        // rows needed before / after the tile
+};
 
 struct Params {
-  const uint4 *a;      // blk16 activations, 16-byte records
-  const uint4 *w;      // packed weights
+  const uint4 *a;   // blk16 activations, 16-byte records
+  const uint4 *w;   // packed weights
   const float *bias;
   const float *residual;
   float *out;
@@ -40,47 +55,48 @@ struct Params {
   int acc_mode;
   float acc_div;
   int Cin, Cout;
-  int64_t L, Lp;
-  int k, d, n_tile;
-  int R;             // rows per chunk in the shared A tile = 128 + (k-1)*d
-  int ksteps;        // k * Cin/16
-  int G;             // K-steps per weight block
-  int nblocks;       // ceil(ksteps / G)
+  int64_t L, Lp, Lout;
+  int n_tile, nco_tiles;
+  int R;        // rows per chunk in the shared A tile = 128 + h_lo + h_hi
+  int G;        // K-steps per weight block
   int stages;
   uint32_t tmem_cols;
   int debug;
+  TapTable tt;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
-
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  // try_wait suspends in hardware; the clock bound turns a protocol bug into a trap instead of a hang
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
   uint32_t ok;
-  const long long t_start = clock64();
-  do {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (!ok && clock64() - t_start > 4000000000ll) {
-      printf("hsv conv1d_umma: mbarrier wait timed out (block %d,%d,%d thread %d bar %u parity %u)\n", blockIdx.x,
-             blockIdx.y, blockIdx.z, threadIdx.x, bar, parity);
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  // try_wait suspends in hardware for a bounded time; the iteration bound turns a protocol bug into a
+  // trap instead of a hang
+  for (uint32_t it = 0; !mbar_try(bar, parity); ++it) {
+    if (it > (1u << 26)) {
+      printf("hsv conv_umma: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y,
+             blockIdx.z, threadIdx.x);
       __trap();
     }
-  } while (!ok);
+  }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
   asm volatile(
@@ -123,16 +139,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(128) conv1d_umma_kernel(const Params p) {
+__global__ void __launch_bounds__(128, 4) conv_umma_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bars[2 + 2 * MAX_STAGES];  // a_full, acc_full, w_full[S], w_empty[S]
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x, nt = blockIdx.y, b = blockIdx.z;
+  const int tile = blockIdx.x, b = blockIdx.z;
+  const int ph = blockIdx.y / p.nco_tiles, nt = blockIdx.y - ph * p.nco_tiles;
   const int nchunks = p.Cin >> 3;
   const int KC = p.Cin >> 4;
-  const int h = ((p.k - 1) >> 1) * p.d;
+  const int ntaps = p.tt.ntaps[ph];
+  const int ksteps = ntaps * KC;
+  const int nblocks = (ksteps + p.G - 1) / p.G;
   const uint32_t a_bytes_chunk = (uint32_t)p.R * 16u;
   const uint32_t a_bytes = a_bytes_chunk * nchunks;
   const uint32_t kstep_bytes = 32u * p.n_tile;
@@ -166,17 +185,21 @@ __global__ void __launch_bounds__(128) conv1d_umma_kernel(const Params p) {
 
   if (warp == 0 && lane == 0) {
     // ---------------- TMA producer ----------------
-    const int64_t row0 = (int64_t)HSV_BLK_PAD + (int64_t)tile * TILE_M - h;
+    const int64_t row0 = (int64_t)HSV_BLK_PAD + (int64_t)tile * TILE_M - p.tt.h_lo;
     mbar_expect_tx(bar_a, a_bytes);
     for (int q = 0; q < nchunks; ++q) {
       const uint4 *src = p.a + ((int64_t)b * nchunks + q) * p.Lp + row0;
       bulk_g2s(a_s + q * a_bytes_chunk, src, a_bytes_chunk, bar_a);
     }
-    const uint4 *wsrc = p.w + (int64_t)nt * p.ksteps * (kstep_bytes >> 4);
-    for (int blk = 0; blk < p.nblocks; ++blk) {
+    // K-step offset of (phase, n-tile) in the packed weight stream
+    int64_t ks0 = 0;
+    for (int q = 0; q < ph; ++q) ks0 += (int64_t)p.tt.ntaps[q] * KC * p.nco_tiles;
+    ks0 += (int64_t)nt * ksteps;
+    const uint4 *wsrc = p.w + ks0 * (kstep_bytes >> 4);
+    for (int blk = 0; blk < nblocks; ++blk) {
       const int s = blk % p.stages;
       if (blk >= p.stages) mbar_wait(bar_we + 8 * s, ((blk / p.stages) - 1) & 1);
-      const int nk = min(p.G, p.ksteps - blk * p.G);
+      const int nk = min(p.G, ksteps - blk * p.G);
       const uint32_t bytes = kstep_bytes * nk;
       mbar_expect_tx(bar_wf + 8 * s, bytes);
       bulk_g2s(w_s + s * wblk_bytes, wsrc + (int64_t)blk * (wblk_bytes >> 4), bytes, bar_wf + 8 * s);
@@ -188,15 +211,16 @@ __global__ void __launch_bounds__(128) conv1d_umma_kernel(const Params p) {
     const bool swap = p.debug & 1;
     mbar_wait(bar_a, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    for (int blk = 0; blk < p.nblocks; ++blk) {
+    for (int blk = 0; blk < nblocks; ++blk) {
       const int s = blk % p.stages;
       mbar_wait(bar_wf + 8 * s, (blk / p.stages) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int nk = min(p.G, p.ksteps - blk * p.G);
+      const int nk = min(p.G, ksteps - blk * p.G);
       for (int g = 0; g < nk; ++g) {
         const int ks = blk * p.G + g;
         const int j = ks / KC, kc = ks - j * KC;
-        const uint32_t a_addr = a_s + (uint32_t)(2 * kc * p.R + j * p.d) * 16u;
+        const int row = p.tt.row_off[ph][j] + p.tt.h_lo;
+        const uint32_t a_addr = a_s + (uint32_t)(2 * kc * p.R + row) * 16u;
         const uint32_t b_addr = w_s + s * wblk_bytes + g * kstep_bytes;
         const uint32_t a_lbo = a_bytes_chunk, b_lbo = 16u * p.n_tile, sbo = 128u;
         const uint64_t ad = swap ? make_desc(a_addr, sbo, a_lbo) : make_desc(a_addr, a_lbo, sbo);
@@ -213,24 +237,59 @@ __global__ void __launch_bounds__(128) conv1d_umma_kernel(const Params p) {
   mbar_wait(bar_acc, 0);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   __syncwarp();
-  const int64_t t = (int64_t)tile * TILE_M + warp * 32 + lane;
+  const int64_t t = (int64_t)tile * TILE_M + warp * 32 + lane;  // GEMM row = input time step
   const bool valid = t < p.L;
+  const int64_t o = (int64_t)p.tt.out_stride * t + p.tt.out_off[ph];
+  const int co0 = nt * p.n_tile;
+  const int64_t base = ((int64_t)b * p.Cout + co0) * p.Lout + o;
+  const float *resp = p.residual ? p.residual + base : nullptr;
+  float *outp = p.out ? p.out + base : nullptr;
+  float *accp = p.acc ? p.acc + base : nullptr;
+  const int64_t cs = p.Lout;  // channel stride
   const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+
+  float res_n[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) res_n[c] = 0.f;
+  if (valid && resp) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) res_n[c] = resp[c * cs];
+  }
   for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
     uint32_t r[16];
     tmem_ld16(trow + c0, r);
     if (valid) {
+      float v[16];
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        const int co = nt * p.n_tile + c0 + c;
-        const int64_t off = ((int64_t)b * p.Cout + co) * p.L + t;
-        float v = __uint_as_float(r[c]);
-        if (p.bias) v += __ldg(p.bias + co);
-        if (p.residual) v += p.residual[off];
-        if (p.out) p.out[off] = v;
-        if (p.acc_mode == 1) p.acc[off] = v;
-        else if (p.acc_mode == 2) p.acc[off] += v;
-        else if (p.acc_mode == 3) p.acc[off] = (p.acc[off] + v) / p.acc_div;
+      for (int c = 0; c < 16; ++c) v[c] = __uint_as_float(r[c]);
+      if (p.bias) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) v[c] += __ldg(p.bias + co0 + c0 + c);
+      }
+#pragma unroll
+      for (int c = 0; c < 16; ++c) v[c] += res_n[c];  // (conv + bias) + residual: the reference's order
+      if (resp && c0 + 16 < p.n_tile) {  // prefetch the next chunk's residual before this chunk's stores
+#pragma unroll
+        for (int c = 0; c < 16; ++c) res_n[c] = resp[(int64_t)(c0 + 16 + c) * cs];
+      }
+      if (p.acc_mode >= 2) {
+        float a[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) a[c] = accp[(int64_t)(c0 + c) * cs];
+        if (p.acc_mode == 2) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) accp[(int64_t)(c0 + c) * cs] = a[c] + v[c];
+        } else {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) accp[(int64_t)(c0 + c) * cs] = (a[c] + v[c]) / p.acc_div;
+        }
+      } else if (p.acc_mode == 1) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) accp[(int64_t)(c0 + c) * cs] = v[c];
+      }
+      if (outp) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) outp[(int64_t)(c0 + c) * cs] = v[c];
       }
     }
   }
@@ -242,79 +301,93 @@ __global__ void __launch_bounds__(128) conv1d_umma_kernel(const Params p) {
   }
 }
 
+// out[ph][nt][s][c2][n][e] = W(co = nt*n_tile + n, ci = 16*kc + 8*c2 + e, tap wj[ph][i]),  s = i*(Cin/16) + kc
+// element strides (s_co, s_ci) select Conv1d [Cout,Cin,k] or ConvTranspose1d [Cin,Cout,k] weights
 __global__ void pack_weight_kernel(const float *__restrict__ w, __half *__restrict__ out, int Cout, int Cin,
-                                   int k, int n_tile) {
-  // out[nt][s][c2][n][e] = w[co = nt*n_tile + n][ci = 16*kc + 8*c2 + e][j],  s = j*(Cin/16) + kc
-  const int64_t total = (int64_t)Cout * Cin * k;
+                                   int k, int n_tile, int64_t s_co, int64_t s_ci, const TapTable tt) {
   const int KC = Cin >> 4;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t r = i;
-    const int e = r % 8; r /= 8;
-    const int n = r % n_tile; r /= n_tile;
-    const int c2 = r % 2; r /= 2;
-    const int s = r % (k * KC); r /= (k * KC);
-    const int nt = (int)r;
-    const int j = s / KC, kc = s % KC;
-    const int co = nt * n_tile + n, ci = 16 * kc + 8 * c2 + e;
-    out[i] = __float2half_rn(w[((int64_t)co * Cin + ci) * k + j]);
+  const int nco = Cout / n_tile;
+  int64_t ph_base = 0;
+  for (int ph = 0; ph < tt.nphase; ++ph) {
+    const int64_t cnt = (int64_t)tt.ntaps[ph] * KC * nco * 2 * n_tile * 8;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < cnt; i += (int64_t)gridDim.x * blockDim.x) {
+      int64_t r = i;
+      const int e = r % 8; r /= 8;
+      const int n = r % n_tile; r /= n_tile;
+      const int c2 = r % 2; r /= 2;
+      const int s = r % (tt.ntaps[ph] * KC); r /= (tt.ntaps[ph] * KC);
+      const int nt = (int)r;
+      const int ti = s / KC, kc = s % KC;
+      const int co = nt * n_tile + n, ci = 16 * kc + 8 * c2 + e;
+      out[ph_base + i] = __float2half_rn(w[co * s_co + ci * s_ci + tt.wj[ph][ti]]);
+    }
+    ph_base += cnt;
   }
 }
 
-}  // namespace
-
-// bring-up aid only (bit0: swap LBO/SBO roles in the smem descriptors); not part of the drop-in contract
-static int g_host_debug = 0;
-extern "C" int hsv_set_umma_debug(int flags) {
-  g_host_debug = flags;
-  return HSV_OK;
+TapTable conv_taps(int k, int d) {
+  TapTable tt = {};
+  tt.nphase = 1;
+  tt.out_stride = 1;
+  tt.ntaps[0] = k;
+  const int h = ((k - 1) / 2) * d;
+  for (int j = 0; j < k; ++j) {
+    tt.row_off[0][j] = (int8_t)((j - (k - 1) / 2) * d);
+    tt.wj[0][j] = (int8_t)j;
+  }
+  tt.h_lo = h;
+  tt.h_hi = h;
+  return tt;
 }
 
-extern "C" int hsv_pack_conv_weight(const float *w, void *packed, int Cout, int Cin, int k, int n_tile,
-                                    void *stream) {
-  HSV_REQUIRE(w && packed, "pack_conv_weight: null pointer");
-  HSV_REQUIRE(Cin > 0 && Cin % 16 == 0, "pack_conv_weight: Cin %% 16 != 0 (Cin=%d)", Cin);
-  HSV_REQUIRE(n_tile >= 16 && n_tile <= 256 && n_tile % 16 == 0 && Cout % n_tile == 0,
-              "pack_conv_weight: bad n_tile=%d for Cout=%d", n_tile, Cout);
-  HSV_REQUIRE(k >= 1, "pack_conv_weight: k=%d", k);
-  const int64_t total = (int64_t)Cout * Cin * k;
-  const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-  pack_weight_kernel<<<blocks, 256, 0, hsv::as_stream(stream)>>>(w, reinterpret_cast<__half *>(packed), Cout,
-                                                                 Cin, k, n_tile);
-  return hsv::check_launch("pack_conv_weight");
+// ConvTranspose1d(k, stride u, padding p=(k-u)/2): output phase rho = o mod u reads input rows q + c - i
+// through taps j = r + i*u, r = (rho+p) mod u, c = (rho+p) div u   
+TapTable convT_taps(int k, int u) {
+  TapTable tt = {};
+  tt.nphase = u;
+  tt.out_stride = u;
+  const int p = (k - u) / 2;
+  int lo = 0, hi = 0;
+  for (int rho = 0; rho < u; ++rho) {
+    const int r = (rho + p) % u, c = (rho + p) / u;
+    int n = 0;
+    for (int j = r; j < k; j += u, ++n) {
+      tt.row_off[rho][n] = (int8_t)(c - n);
+      tt.wj[rho][n] = (int8_t)j;
+      if (c - n < lo) lo = c - n;
+      if (c - n > hi) hi = c - n;
+    }
+    tt.ntaps[rho] = n;
+    tt.out_off[rho] = rho;
+  }
+  tt.h_lo = -lo;
+  tt.h_hi = hi;
+  return tt;
 }
 
-extern "C" int hsv_conv1d_umma(const void *a_blk16, const void *w_packed, const float *bias,
-                               const float *residual, float *out, float *acc, int acc_mode, float acc_div,
-                               int B, int Cin, int Cout, int64_t L, int k, int d, int n_tile, void *stream) {
-  HSV_REQUIRE(a_blk16 && w_packed, "conv1d_umma: null operand");
-  HSV_REQUIRE(Cin > 0 && Cin % 16 == 0, "conv1d_umma: Cin %% 16 != 0 (Cin=%d)", Cin);
-  HSV_REQUIRE(n_tile >= 16 && n_tile <= 256 && n_tile % 16 == 0 && Cout % n_tile == 0,
-              "conv1d_umma: bad n_tile=%d for Cout=%d", n_tile, Cout);
-  HSV_REQUIRE(k >= 1 && (k & 1) && d >= 1, "conv1d_umma: k must be odd (k=%d d=%d)", k, d);
-  HSV_REQUIRE(((k - 1) / 2) * d <= HSV_BLK_PAD, "conv1d_umma: halo %d exceeds blk16 padding %d",
-              ((k - 1) / 2) * d, HSV_BLK_PAD);
-  HSV_REQUIRE(acc_mode >= 0 && acc_mode <= 3 && (acc_mode == 0 || acc), "conv1d_umma: bad acc_mode/acc");
-  HSV_REQUIRE(out || acc_mode, "conv1d_umma: no output");
-  if (B == 0 || L == 0) return HSV_OK;
-  HSV_REQUIRE(B <= 65535 && Cout / n_tile <= 65535, "conv1d_umma: grid too large");
+int g_host_debug = 0;
 
+int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const float *bias,
+           const float *residual, float *out, float *acc, int acc_mode, float acc_div, int B, int Cin, int Cout,
+           int64_t L, int64_t Lout, int n_tile, cudaStream_t st, const char *what) {
   Params p;
   p.a = reinterpret_cast<const uint4 *>(a_blk16);
   p.w = reinterpret_cast<const uint4 *>(w_packed);
   p.bias = bias; p.residual = residual; p.out = out; p.acc = acc;
   p.acc_mode = acc_mode; p.acc_div = acc_div;
-  p.Cin = Cin; p.Cout = Cout; p.L = L; p.Lp = hsv::blk16_rows(L);
-  p.k = k; p.d = d; p.n_tile = n_tile;
-  p.R = TILE_M + (k - 1) * d;
-  p.ksteps = k * (Cin / 16);
+  p.Cin = Cin; p.Cout = Cout; p.L = L; p.Lp = hsv::blk16_rows(L); p.Lout = Lout;
+  p.n_tile = n_tile; p.nco_tiles = Cout / n_tile;
+  p.R = TILE_M + tt.h_lo + tt.h_hi;
+  p.tt = tt;
+  int max_ksteps = 0;
+  for (int q = 0; q < tt.nphase; ++q) max_ksteps = tt.ntaps[q] * (Cin / 16) > max_ksteps ? tt.ntaps[q] * (Cin / 16) : max_ksteps;
   const int kstep_bytes = 32 * n_tile;
   int G = 32768 / kstep_bytes;
   if (G < 1) G = 1;
-  if (G > p.ksteps) G = p.ksteps;
+  if (G > max_ksteps) G = max_ksteps;
   p.G = G;
-  p.nblocks = (p.ksteps + G - 1) / G;
-  p.stages = p.nblocks < MAX_STAGES ? p.nblocks : MAX_STAGES;
+  const int nblocks = (max_ksteps + G - 1) / G;
+  p.stages = nblocks < MAX_STAGES ? nblocks : MAX_STAGES;
   uint32_t cols = 32;
   while ((int)cols < n_tile) cols <<= 1;
   p.tmem_cols = cols;
@@ -322,8 +395,7 @@ extern "C" int hsv_conv1d_umma(const void *a_blk16, const void *w_packed, const 
 
   const size_t a_bytes = ((size_t)p.R * 16 * (Cin / 8) + 127) & ~(size_t)127;
   size_t smem = a_bytes + (size_t)p.stages * G * kstep_bytes;
-  // shrink the weight ring if the A tile is large
-  while (smem > 200 * 1024 && p.stages > 2) {
+  while (smem > 200 * 1024 && p.stages > 2) {  // shrink the weight ring if the A tile is large
     p.stages--;
     smem = a_bytes + (size_t)p.stages * G * kstep_bytes;
   }
@@ -334,21 +406,90 @@ extern "C" int hsv_conv1d_umma(const void *a_blk16, const void *w_packed, const 
   if (dev < 0 || dev >= 64) dev = 0;
   if (max_dyn[dev] == 0) {
     cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, conv1d_umma_kernel);
+    cudaError_t e = cudaFuncGetAttributes(&fa, conv_umma_kernel);
     int want = 227 * 1024 - (e == cudaSuccess ? (int)fa.sharedSizeBytes : 1024);
     want &= ~1023;
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv1d_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
     if (e != cudaSuccess) {
       cudaGetLastError();  // clear
-      hsv::set_error("conv1d_umma: cudaFuncSetAttribute(%d): %s", want, cudaGetErrorString(e));
+      hsv::set_error("%s: cudaFuncSetAttribute(%d): %s", what, want, cudaGetErrorString(e));
       return HSV_ERR_CUDA;
     }
     max_dyn[dev] = want;
   }
-  HSV_REQUIRE(smem <= (size_t)max_dyn[dev], "conv1d_umma: shared memory %zu B exceeds %d B (Cin=%d k=%d d=%d)",
-              smem, max_dyn[dev], Cin, k, d);
-  dim3 grid((unsigned)((L + TILE_M - 1) / TILE_M), (unsigned)(Cout / n_tile), (unsigned)B);
-  conv1d_umma_kernel<<<grid, 128, smem, hsv::as_stream(stream)>>>(p);
-  return hsv::check_launch("conv1d_umma");
+  HSV_REQUIRE(smem <= (size_t)max_dyn[dev], "%s: shared memory %zu B exceeds %d B (Cin=%d)", what, smem,
+              max_dyn[dev], Cin);
+  HSV_REQUIRE(B <= 65535 && (int64_t)p.nco_tiles * tt.nphase <= 65535, "%s: grid too large", what);
+  dim3 grid((unsigned)((L + TILE_M - 1) / TILE_M), (unsigned)(p.nco_tiles * tt.nphase), (unsigned)B);
+  conv_umma_kernel<<<grid, 128, smem, st>>>(p);
+  return hsv::check_launch(what);
+}
+
+int check_common(const char *what, const void *a, const void *w, int Cin, int Cout, int n_tile) {
+  HSV_REQUIRE(a && w, "%s: null operand", what);
+  HSV_REQUIRE(Cin > 0 && Cin % 16 == 0, "%s: Cin %% 16 != 0 (Cin=%d)", what, Cin);
+  HSV_REQUIRE(n_tile >= 16 && n_tile <= 256 && n_tile % 16 == 0 && Cout % n_tile == 0,
+              "%s: bad n_tile=%d for Cout=%d", what, n_tile, Cout);
+  return HSV_OK;
+}
+
+int pack(const float *w, void *packed, int Cout, int Cin, int k, int n_tile, int64_t s_co, int64_t s_ci,
+         const TapTable &tt, cudaStream_t st, const char *what) {
+  const int64_t total = (int64_t)Cout * Cin * k;
+  const int blocks = (int)((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
+  pack_weight_kernel<<<blocks, 256, 0, st>>>(w, reinterpret_cast<__half *>(packed), Cout, Cin, k, n_tile, s_co,
+                                             s_ci, tt);
+  return hsv::check_launch(what);
+}
+
+}  // namespace
+
+// bring-up aid only (bit0: swap LBO/SBO roles in the smem descriptors); not part of the drop-in contract
+extern "C" int hsv_set_umma_debug(int flags) {
+  g_host_debug = flags;
+  return HSV_OK;
+}
+
+extern "C" int hsv_pack_conv_weight(const float *w, void *packed, int Cout, int Cin, int k, int n_tile,
+                                    void *stream) {
+  if (int rc = check_common("pack_conv_weight", w, packed, Cin, Cout, n_tile)) return rc;
+  HSV_REQUIRE(k >= 1 && k <= MAX_TAPS && (k & 1), "pack_conv_weight: k=%d (odd, <= %d)", k, MAX_TAPS);
+  return pack(w, packed, Cout, Cin, k, n_tile, (int64_t)Cin * k, k, conv_taps(k, 1), hsv::as_stream(stream),
+              "pack_conv_weight");
+}
+
+extern "C" int hsv_pack_convT_weight(const float *w, void *packed, int Cin, int Cout, int k, int u, int n_tile,
+                                     void *stream) {
+  if (int rc = check_common("pack_convT_weight", w, packed, Cin, Cout, n_tile)) return rc;
+  HSV_REQUIRE(u >= 1 && u <= MAX_PHASES && k >= u && k <= MAX_TAPS && k - 2 * ((k - u) / 2) == u,
+              "pack_convT_weight: unsupported (k,u)=(%d,%d)", k, u);
+  return pack(w, packed, Cout, Cin, k, n_tile, k, (int64_t)Cout * k, convT_taps(k, u), hsv::as_stream(stream),
+              "pack_convT_weight");
+}
+
+extern "C" int hsv_conv1d_umma(const void *a_blk16, const void *w_packed, const float *bias,
+                               const float *residual, float *out, float *acc, int acc_mode, float acc_div,
+                               int B, int Cin, int Cout, int64_t L, int k, int d, int n_tile, void *stream) {
+  if (int rc = check_common("conv1d_umma", a_blk16, w_packed, Cin, Cout, n_tile)) return rc;
+  HSV_REQUIRE(k >= 1 && k <= MAX_TAPS && (k & 1) && d >= 1, "conv1d_umma: k must be odd and <= %d (k=%d d=%d)",
+              MAX_TAPS, k, d);
+  HSV_REQUIRE(((k - 1) / 2) * d <= HSV_BLK_PAD, "conv1d_umma: halo %d exceeds blk16 padding %d",
+              ((k - 1) / 2) * d, HSV_BLK_PAD);
+  HSV_REQUIRE(acc_mode >= 0 && acc_mode <= 3 && (acc_mode == 0 || acc), "conv1d_umma: bad acc_mode/acc");
+  HSV_REQUIRE(out || acc_mode, "conv1d_umma: no output");
+  if (B == 0 || L == 0) return HSV_OK;
+  return launch(conv_taps(k, d), a_blk16, w_packed, bias, residual, out, acc, acc_mode, acc_div, B, Cin, Cout, L,
+                L, n_tile, hsv::as_stream(stream), "conv1d_umma");
+}
+
+extern "C" int hsv_conv_transpose1d_umma(const void *a_blk16, const void *w_packed, const float *bias,
+                                         const float *add, float *out, int B, int Cin, int Cout, int64_t Lin,
+                                         int k, int u, int n_tile, void *stream) {
+  if (int rc = check_common("conv_transpose1d_umma", a_blk16, w_packed, Cin, Cout, n_tile)) return rc;
+  HSV_REQUIRE(u >= 1 && u <= MAX_PHASES && k >= u && k <= MAX_TAPS && k - 2 * ((k - u) / 2) == u,
+              "conv_transpose1d_umma: unsupported (k,u)=(%d,%d)", k, u);
+  HSV_REQUIRE(out, "conv_transpose1d_umma: no output");
+  if (B == 0 || Lin == 0) return HSV_OK;
+  return launch(convT_taps(k, u), a_blk16, w_packed, bias, add, out, nullptr, 0, 1.f, B, Cin, Cout, Lin,
+                (int64_t)u * Lin, n_tile, hsv::as_stream(stream), "conv_transpose1d_umma");
 }

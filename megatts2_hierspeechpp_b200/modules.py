@@ -242,9 +242,51 @@ class _Folded:
             self.packed = ops.pack_conv_weight(w, self.n_tile)
         return self.packed, self.n_tile
 
+    def packedT_weight(self, u: int):
+        w = self.weight()
+        if self.packed is None:
+            self.n_tile = ops.pick_n_tile(w.shape[1])
+            self.packed = ops.pack_convT_weight(w, u, self.n_tile)
+        return self.packed, self.n_tile
+
     def bias(self):
         b = getattr(self.conv, "bias", None)
         return None if b is None else b.detach()
+
+
+_MAIN_SLOT = 3   # blk16 workspace slot of the main stream (slots 0..2 belong to the per-resblock streams)
+
+
+def _dense_conv(x: torch.Tensor, f: _Folded, k: int, d: int = 1, lrelu: bool = False,
+                residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """'same' Conv1d of an fp32 [B,C,L] tensor: tcgen05 path when both channel counts are multiples of
+    16 (pack to the fp16 operand layout, optional leaky_relu(0.1) fused into the pack), fp32 direct
+    kernel otherwise."""
+    B, C, L = x.shape
+    cout = f.conv.out_channels
+    if C % 16 == 0 and cout % 16 == 0 and ((k - 1) // 2) * d <= ops.BLK_PAD:
+        buf = ops.blk16_buffer(B, C, L, x.device, _MAIN_SLOT)
+        ops.pack_blk16(x, buf, lrelu)
+        wp, nt = f.packed_weight()
+        return ops.conv1d_umma(buf, wp, f.bias(), L, C, cout, k, d, nt, residual=residual)
+    pad = ((k - 1) // 2) * d
+    if residual is not None:
+        out = residual.clone()
+        return ops.conv1d_direct(x, f.weight(), f.bias(), d=d, pad=pad,
+                                 flags=(ops.CONV_LRELU_IN if lrelu else 0) | ops.CONV_ADD_OUT, out=out)
+    return ops.conv1d_direct(x, f.weight(), f.bias(), d=d, pad=pad, flags=ops.CONV_LRELU_IN if lrelu else 0)
+
+
+def _dense_convT(x: torch.Tensor, f: _Folded, k: int, u: int, add: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """ConvTranspose1d(k, stride u, padding (k-u)//2) of an fp32 [B,C,L] tensor (+ optional add)."""
+    B, C, L = x.shape
+    cout = f.conv.out_channels
+    if C % 16 == 0 and cout % 16 == 0:
+        buf = ops.blk16_buffer(B, C, L, x.device, _MAIN_SLOT)
+        ops.pack_blk16(x, buf)
+        wp, nt = f.packedT_weight(u)
+        return ops.conv_transpose1d_umma(buf, wp, f.bias(), L, C, cout, k, u, nt, add=add)
+    return ops.conv_transpose1d(x, f.weight(), f.bias(), u, add=add)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -382,13 +424,10 @@ class DBlock(nn.Module):
         size = x.shape[-1] // self.factor
         # nearest down-sampling commutes with the 1x1 conv: gather first (4x less work, same values)
         xd = ops.nearest_gather(x, size)
-        out = ops.conv1d_direct(xd, self._fr.weight(), self._fr.bias())
+        res = _dense_conv(xd, self._fr, 1)
         h = xd
         for i, d in enumerate((1, 2, 4)):
-            last = i == 2
-            h = ops.conv1d_direct(h, self._fc[i].weight(), self._fc[i].bias(), d=d, pad=d,
-                                  flags=ops.CONV_LRELU_IN | (ops.CONV_ADD_OUT if last else 0),
-                                  out=out if last else None)
+            h = _dense_conv(h, self._fc[i], 3, d, lrelu=True, residual=res if i == 2 else None)
         return h
 
     def remove_weight_norm(self):
@@ -444,11 +483,11 @@ class SourceNetwork(_VocoderBase):
 
     def forward(self, x, g):
         x, g = _as_input(x), _as_input(g)
-        xp = ops.conv1d_direct(x, self._f_pre.weight(), self._f_pre.bias(), pad=3)
+        xp = _dense_conv(x, self._f_pre, 7)
         cg = ops.conv1d_direct(g, self._f_cond.weight(), self._f_cond.bias())
         x = ops.add3_bcast(xp, None, cg, out=xp)
         for i in range(self.num_upsamples):
-            x = ops.conv_transpose1d(x, self._f_ups[i].weight(), self._f_ups[i].bias(), self.upsample_rates[i])
+            x = _dense_convT(x, self._f_ups[i], self.ups[i].kernel_size[0], self.upsample_rates[i])
             x = self._stage(x, i)
         self.activation_post.check_filters()
         x = ops.act1d(x, *self.activation_post.params())
@@ -491,7 +530,7 @@ class Generator(_VocoderBase):
 
     def forward(self, x, pitch, g=None):
         x, pitch = _as_input(x), _as_input(pitch)
-        xp = ops.conv1d_direct(x, self._f_pre.weight(), self._f_pre.bias(), pad=3)
+        xp = _dense_conv(x, self._f_pre, 7)
         dn = self.downs(pitch)
         if g is None:
             # the reference evaluates self.cond(g) unconditionally (:430) and fails on g=None
@@ -501,9 +540,8 @@ class Generator(_VocoderBase):
         for i in range(self.num_upsamples):
             add = None
             if i == 0:
-                add = ops.conv1d_direct(pitch, self._f_proj.weight(), self._f_proj.bias(), pad=3)
-            x = ops.conv_transpose1d(x, self._f_ups[i].weight(), self._f_ups[i].bias(), self.upsample_rates[i],
-                                     add=add)
+                add = _dense_conv(pitch, self._f_proj, 7)
+            x = _dense_convT(x, self._f_ups[i], self.ups[i].kernel_size[0], self.upsample_rates[i], add=add)
             x = self._stage(x, i)
         self.activation_post.check_filters()
         x = ops.act1d(x, *self.activation_post.params())

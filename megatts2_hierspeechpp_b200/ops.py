@@ -167,6 +167,38 @@ def conv1d_umma(a_blk: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torc
     return out
 
 
+def pack_convT_weight(w: torch.Tensor, u: int, n_tile: int) -> torch.Tensor:
+    """w: folded ConvTranspose1d weight [Cin, Cout, k] -> packed fp16 phase/tap stream."""
+    _req(w, "w", ndim=3)
+    cin, cout, k = w.shape
+    out = torch.empty(cout * cin * k, dtype=torch.float16, device=w.device)
+    lib = _lib.load()
+    _lib.check(lib.hsv_pack_convT_weight(_p(w), _p(out), cin, cout, k, u, n_tile, _stream()), "hsv_pack_convT_weight")
+    return out
+
+
+def conv_transpose1d_umma(a_blk: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], Lin: int,
+                          cin: int, cout: int, k: int, u: int, n_tile: int, add: Optional[torch.Tensor] = None):
+    """tcgen05 ConvTranspose1d (polyphase).  Returns fp32 [B, Cout, u*Lin]."""
+    _req(a_blk, "a_blk16", torch.float16, 4); _req(w_packed, "w_packed", torch.float16)
+    B = a_blk.shape[0]
+    if tuple(a_blk.shape) != (B, cin // 8, blk16_rows(Lin), 8):
+        raise ValueError(f"a_blk16 shape {tuple(a_blk.shape)} does not match Cin={cin}, L={Lin}")
+    if w_packed.numel() != cout * cin * k:
+        raise ValueError("w_packed size mismatch")
+    out = torch.empty(B, cout, u * Lin, dtype=torch.float32, device=a_blk.device)
+    if bias is not None:
+        _req(bias, "bias")
+    if add is not None:
+        _req(add, "add", ndim=3)
+        if add.shape != out.shape:
+            raise ValueError("add shape mismatch")
+    lib = _lib.load()
+    _lib.check(lib.hsv_conv_transpose1d_umma(_p(a_blk), _p(w_packed), _p(bias), _p(add), _p(out), B, cin, cout, Lin,
+                                             k, u, n_tile, _stream()), "hsv_conv_transpose1d_umma")
+    return out
+
+
 def conv1d_direct(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], d: int = 1, pad: int = 0,
                   flags: int = 0, out: Optional[torch.Tensor] = None):
     _req(x, "x", ndim=3); _req(w, "w", ndim=3)

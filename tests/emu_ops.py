@@ -83,6 +83,16 @@ def conv1d_umma(a_blk, wp, bias, L, cin, cout, k, d, n_tile, residual=None, out=
     return v if want_out else None
 
 
+def pack_convT_weight(w, u, n_tile):
+    return w.half().flatten().clone()
+
+
+def conv_transpose1d_umma(a_blk, wp, bias, Lin, cin, cout, k, u, n_tile, add=None):
+    x = _unpack(a_blk, Lin)
+    v = F.conv_transpose1d(x, wp.float().view(cin, cout, k), bias, stride=u, padding=(k - u) // 2)
+    return v if add is None else v + add
+
+
 def conv1d_direct(x, w, bias, d=1, pad=0, flags=0, out=None):
     xin = F.leaky_relu(x, 0.1) if flags & real.CONV_LRELU_IN else x
     v = F.conv1d(xin, w, bias, padding=pad, dilation=d)
@@ -121,7 +131,7 @@ def add3_bcast(a, b, bc, out=None):
     return v
 
 
-NAMES = ["blk16_buffer", "act1d", "act1d_blk16", "pack_blk16", "weight_norm_fold", "pack_conv_weight", "conv1d_umma",
+NAMES = ["blk16_buffer", "act1d", "act1d_blk16", "pack_blk16", "weight_norm_fold", "pack_conv_weight", "conv1d_umma", "pack_convT_weight", "conv_transpose1d_umma",
          "conv1d_direct", "conv_transpose1d", "sr_pre_interp", "nearest_gather", "add3_bcast"]
 
 

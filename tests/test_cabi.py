@@ -18,7 +18,7 @@ def lib():
 def _declared_symbols():
     src = open(os.path.join(ROOT, "include", "hsv.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(hsv_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(hsv_[A-Za-z0-9_]+)\s*\(", src)))
 
 
 def test_header_symbols_exported(lib):

@@ -226,6 +226,26 @@ def test_conv1d_umma_matrix(hsv, C, k, d, L):
     assert err <= 2e-4 * max(1.0, ref.abs().max().item()), (C, k, d, L, err)
 
 
+@pytest.mark.parametrize("cin,cout,k,u,L", [(512, 256, 8, 4, 37), (256, 128, 11, 5, 130), (128, 64, 8, 4, 300),
+                                            (64, 32, 4, 2, 257), (32, 16, 4, 2, 1000), (256, 128, 4, 2, 128)])
+def test_conv_transpose1d_umma(hsv, cin, cout, k, u, L):
+    gen = torch.Generator().manual_seed(cin + k + L)
+    x = torch.randn(2, cin, L, generator=gen)
+    w = torch.randn(cin, cout, k, generator=gen) / (cin * k / u) ** 0.5
+    b = torch.randn(cout, generator=gen)
+    add = torch.randn(2, cout, u * L, generator=gen)
+    ref = F.conv_transpose1d(x.half().double(), w.half().double(), b.double(), stride=u, padding=(k - u) // 2)
+    buf = hsv.ops.blk16_buffer(2, cin, L, DEV, slot=9)
+    hsv.ops.pack_blk16(x.to(DEV), buf)
+    nt = hsv.ops.pick_n_tile(cout)
+    wp = hsv.ops.pack_convT_weight(w.to(DEV), u, nt)
+    y = hsv.ops.conv_transpose1d_umma(buf, wp, b.to(DEV), L, cin, cout, k, u, nt).cpu().double()
+    assert y.shape == ref.shape == (2, cout, u * L)
+    assert (y - ref).abs().max().item() <= 2e-4 * max(1.0, ref.abs().max().item())
+    y2 = hsv.ops.conv_transpose1d_umma(buf, wp, b.to(DEV), L, cin, cout, k, u, nt, add=add.to(DEV)).cpu().double()
+    assert (y2 - (ref + add.double())).abs().max().item() <= 2e-4 * max(1.0, ref.abs().max().item())
+
+
 def test_conv1d_umma_rectangular_and_acc_modes(hsv):
     y, ref = _umma_case(hsv, 1, 64, 300, 3, 1, cout=256)
     assert (y - ref).abs().max().item() <= 2e-4 * max(1.0, ref.abs().max().item())

@@ -52,7 +52,7 @@ def test_dblock_golden(hsv):
     db.load_state_dict({k[len("downs."):]: v for k, v in sd.items() if k.startswith("downs.")}, strict=True)
     db.to(DEV)
     y = db(torch.from_numpy(g["x"]).to(DEV))
-    _check("DBlock L83", y, g["y"], max_abs=1e-4, snr_min=80.0)      # fp32 path
+    _check("DBlock L83", y, g["y"], max_abs=2e-3, snr_min=55.0)      # fp16 operands, fp32 accumulate
 
 
 def test_vocoder_golden_T20(vocoder):

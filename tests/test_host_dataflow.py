@@ -51,7 +51,7 @@ def test_dblock_and_ampblock_dataflow(monkeypatch):
     db = hsv.DBlock(64, 512, 4)
     db.load_state_dict({k[len("downs."):]: v for k, v in sd.items() if k.startswith("downs.")}, strict=True)
     y = db(torch.from_numpy(g["x"]))
-    assert np.abs(y.numpy() - g["y"]).max() <= 1e-5           # gather-then-1x1 == 1x1-then-gather
+    assert CF.snr_db(g["y"], y.numpy()) >= 55.0                # gather-then-1x1 == 1x1-then-gather (fp16 operands)
     ga = golden("ampblock_c16_k7.npz")
     gen = torch.Generator().manual_seed(11)
     bsd = {}
