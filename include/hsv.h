@@ -59,9 +59,11 @@ int64_t hsv_blk16_rows(int64_t L);
  *   alpha, beta [C] fp32 (log scale, as stored in the state_dict)
  *   out_mode 0: out = fp32 [B,C,L]
  *   out_mode 1: out = fp16 blk16 (C % 8 == 0), rows per chunk = hsv_blk16_rows(L)
+ *   in_scale    x is multiplied by this first (1/num_kernels: the "xs / self.num_kernels" of
+ *               hierspeechpp_speechsynthesizer.py:446 when x is the un-normalised sum over resblocks)
  */
 int hsv_act1d_snakebeta(const float *x, void *out, const float *alpha, const float *beta,
-                        int B, int C, int64_t L, int out_mode, void *stream);
+                        int B, int C, int64_t L, int out_mode, float in_scale, void *stream);
 
 /* ---- weight norm fold: torch._weight_norm(v, g, dim=0) as applied by the
  * forward pre-hook of torch.nn.utils.weight_norm on every conv of the path
@@ -72,7 +74,7 @@ int hsv_weight_norm_fold(const float *v, const float *g, float *w, int n0, int i
 
 /* ---- pack a folded Conv1d weight [Cout,Cin,k] fp32 into the tcgen05 B-operand
  * stream: fp16 [Cout/n_tile][k*Cin/16][2][n_tile][8] (K-major core matrices).
- * Cin % 16 == 0, Cout % n_tile == 0, n_tile % 16 == 0, n_tile <= 256.
+ * Cin % 16 == 0, Cout % n_tile == 0, n_tile % 16 == 0, n_tile <= 128.
  */
 int hsv_pack_conv_weight(const float *w, void *packed, int Cout, int Cin, int k, int n_tile, void *stream);
 
@@ -85,9 +87,9 @@ int hsv_pack_conv_weight(const float *w, void *packed, int Cout, int Cin, int k,
  *   bias      [Cout] fp32 or NULL
  *   residual  [B,Cout,L] fp32 or NULL     (v = acc + bias + residual)
  *   out       [B,Cout,L] fp32 or NULL     (out = v; may alias residual)
- *   acc       [B,Cout,L] fp32 or NULL, acc_mode: 0 none, 1 acc = v,
- *             2 acc += v, 3 acc = (acc + v) / acc_div   (mean over resblocks,
- *             hierspeechpp_speechsynthesizer.py:440-446)
+ *   acc       [B,Cout,L] fp32 or NULL, acc_mode: 0 none, 1 acc = v, 2 acc += v (sum over
+ *             resblocks, hierspeechpp_speechsynthesizer.py:440-445; the division by
+ *             num_kernels (:446) is the consumer's in_scale).  acc_div is reserved (pass 1).
  */
 int hsv_conv1d_umma(const void *a_blk16, const void *w_packed, const float *bias,
                     const float *residual, float *out, float *acc, int acc_mode, float acc_div,
@@ -154,8 +156,8 @@ int hsv_nearest_gather(const float *x, float *out, int rows, int64_t Lin, int64_
 int hsv_add3_bcast(const float *a, const float *b, const float *bc, float *out,
                    int rows, int64_t L, void *stream);
 
-/* fp32 [B,C,L] -> fp16 blk16 (optional leaky_relu(0.1) first); C % 8 == 0. */
-int hsv_pack_blk16(const float *x, void *out, int B, int C, int64_t L, int lrelu, void *stream);
+/* fp32 [B,C,L] * in_scale -> fp16 blk16 (optional leaky_relu(0.1) first); C % 8 == 0. */
+int hsv_pack_blk16(const float *x, void *out, int B, int C, int64_t L, int lrelu, float in_scale, void *stream);
 
 #ifdef __cplusplus
 }

@@ -20,7 +20,8 @@ SIGNATURES = {
     "hsv_last_error": (c_char_p, []),
     "hsv_device_supported": (c_int, []),
     "hsv_blk16_rows": (c_int64, [c_int64]),
-    "hsv_act1d_snakebeta": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_void_p]),
+    "hsv_act1d_snakebeta": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_float,
+                                    c_void_p]),
     "hsv_weight_norm_fold": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "hsv_pack_conv_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "hsv_conv1d_umma": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float,
@@ -36,12 +37,13 @@ SIGNATURES = {
     "hsv_interp_linear_table": (c_int, [c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hsv_nearest_gather": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p]),
     "hsv_add3_bcast": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p]),
-    "hsv_pack_blk16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_void_p]),
+    "hsv_pack_blk16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_float, c_void_p]),
 }
 
 # bring-up aids exported by the library but not part of the drop-in contract
 _EXTRA = {
     "hsv_set_umma_debug": (c_int, [c_int]),
+    "hsv_set_act_variant": (c_int, [c_int]),
 }
 
 _lib = None
@@ -70,6 +72,8 @@ def load() -> ctypes.CDLL:
         raise HsvError(f"libhsv.so version {lib.hsv_version()} does not match the Python binding (100)")
     if os.environ.get("HSV_UMMA_DEBUG"):
         lib.hsv_set_umma_debug(int(os.environ["HSV_UMMA_DEBUG"]))
+    if os.environ.get("HSV_ACT_VARIANT"):
+        lib.hsv_set_act_variant(int(os.environ["HSV_ACT_VARIANT"]))
     _lib = lib
     return lib
 

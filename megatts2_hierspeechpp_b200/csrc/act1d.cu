@@ -84,14 +84,14 @@ __device__ __forceinline__ float down6(const ZPair &p0, const ZPair &p1, const Z
 
 template <int R, bool EDGE>
 __device__ __forceinline__ void walk(const float *__restrict__ xw, float *__restrict__ outv, float a, float ib,
-                                     int64_t ta, int64_t L, float zL, float zR) {
+                                     int64_t ta, int64_t L, float zL, float zR, float sc) {
   // xw[0 .. R+9] = x[ta-5 .. ta+R+4] (already clamped);  outv[0..R-1] = out[ta .. ta+R-1]
   ZPair ring[6];
-  float w0 = xw[0], w1 = xw[1], w2 = xw[2], w3 = xw[3], w4 = xw[4];
+  float w0 = xw[0] * sc, w1 = xw[1] * sc, w2 = xw[2] * sc, w3 = xw[3] * sc, w4 = xw[4] * sc;
   const int64_t n_last = 2 * L - 1;
 #pragma unroll
   for (int s = 0; s < R + 5; ++s) {
-    const float w5 = xw[s + 5];
+    const float w5 = xw[s + 5] * sc;
     ZPair z = up_snake(w0, w1, w2, w3, w4, w5, a, ib);
     if (EDGE) {
       const int64_t m = ta - 2 + s;
@@ -108,11 +108,91 @@ __device__ __forceinline__ void walk(const float *__restrict__ xw, float *__rest
   }
 }
 
-template <int R, int OUT_MODE>
+// ---- packed-pair variant: Blackwell's FFMA2/FMUL2 (fma.rn.f32x2) process the (odd, even) 2x samples of
+// one step in one instruction; a scalar operand broadcasts for free, tap pairs live in uniform registers.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk(u64 v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+  u64 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+__device__ __forceinline__ u64 up_snake2(const float w0, const float w1, const float w2, const float w3,
+                                         const float w4, const float w5, u64 a2, u64 ib2) {
+  constexpr float G0 = 2.f * HSV_F0, G1 = 2.f * HSV_F1, G2 = 2.f * HSV_F2, G3 = 2.f * HSV_F3,
+                  G4 = 2.f * HSV_F4, G5 = 2.f * HSV_F5;
+  // lane lo = odd sample z[2m-1], lane hi = even sample z[2m]
+  u64 y = mul2(pk(w0, w0), pk(G1, G0));
+  y = fma2(pk(w5, w5), pk(G0, G1), y);
+  y = fma2(pk(w1, w1), pk(G3, G2), y);
+  y = fma2(pk(w4, w4), pk(G2, G3), y);
+  y = fma2(pk(w2, w2), pk(G5, G4), y);
+  y = fma2(pk(w3, w3), pk(G4, G5), y);
+  float to, te;
+  upk(mul2(y, a2), to, te);
+  const u64 s = pk(__sinf(to), __sinf(te));
+  return fma2(mul2(s, ib2), s, y);
+}
+
+__device__ __forceinline__ float down6_2(u64 p0, u64 p1, u64 p2, u64 p3, u64 p4, u64 p5) {
+  u64 acc = mul2(p0, pk(HSV_F0, HSV_F1));
+  acc = fma2(p5, pk(HSV_F1, HSV_F0), acc);
+  acc = fma2(p1, pk(HSV_F2, HSV_F3), acc);
+  acc = fma2(p4, pk(HSV_F3, HSV_F2), acc);
+  acc = fma2(p2, pk(HSV_F4, HSV_F5), acc);
+  acc = fma2(p3, pk(HSV_F5, HSV_F4), acc);
+  float lo, hi;
+  upk(acc, lo, hi);
+  return lo + hi;
+}
+
+template <int R, bool EDGE>
+__device__ __forceinline__ void walk2(const float *__restrict__ xw, float *__restrict__ outv, float a, float ib,
+                                      int64_t ta, int64_t L, float zL, float zR, float sc) {
+  u64 ring[6];
+  const u64 a2 = pk(a, a), ib2 = pk(ib, ib);
+  float w0 = xw[0] * sc, w1 = xw[1] * sc, w2 = xw[2] * sc, w3 = xw[3] * sc, w4 = xw[4] * sc;
+  const int64_t n_last = 2 * L - 1;
+#pragma unroll
+  for (int s = 0; s < R + 5; ++s) {
+    const float w5 = xw[s + 5] * sc;
+    u64 z = up_snake2(w0, w1, w2, w3, w4, w5, a2, ib2);
+    if (EDGE) {
+      const int64_t m = ta - 2 + s;
+      const int64_t no = 2 * m - 1, ne = 2 * m;
+      float zo, ze;
+      upk(z, zo, ze);
+      zo = no < 0 ? zL : (no > n_last ? zR : zo);
+      ze = ne < 0 ? zL : (ne > n_last ? zR : ze);
+      z = pk(zo, ze);
+    }
+    ring[s % 6] = z;
+    if (s >= 5) {
+      outv[s - 5] = down6_2(ring[(s - 5) % 6], ring[(s - 4) % 6], ring[(s - 3) % 6], ring[(s - 2) % 6],
+                            ring[(s - 1) % 6], ring[s % 6]);
+    }
+    w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5;
+  }
+}
+
+template <int R, int OUT_MODE, bool PACKED>
 __global__ void __launch_bounds__(NT) act1d_kernel(const float *__restrict__ x, void *__restrict__ outp,
                                                    const float *__restrict__ alpha,
                                                    const float *__restrict__ beta, int C, int64_t L,
-                                                   int64_t nrows, int ntiles, int64_t Lp) {
+                                                   int64_t nrows, int ntiles, int64_t Lp, float sc) {
   using K = Cfg<R>;
   // x_s[c][p] holds x[row0+c][t0 - XOFF + p]; XOFF = 8 keeps the tile start 16-byte aligned for TMA
   __shared__ __align__(16) float x_s[ROWS * K::PITCH];
@@ -124,6 +204,14 @@ __global__ void __launch_bounds__(NT) act1d_kernel(const float *__restrict__ x, 
   const int64_t rowgrp = blockIdx.x / ntiles;
   const int64_t row0 = rowgrp * ROWS;
   const int64_t t0 = (int64_t)tile * K::TILE;
+  const int c = tid % ROWS, run = tid / ROWS;
+  const int64_t row = row0 + c;
+  // per-channel parameters: issue these global loads before waiting for the tile
+  float al = 0.f, be = 0.f;
+  if (row < nrows) {
+    al = __ldg(alpha + (int)(row % C));
+    be = __ldg(beta + (int)(row % C));
+  }
 
   // ---- stage the x tile ----
   // interior tiles of 16-byte-aligned rows: one 1-D bulk TMA copy per row (no issue slots, no registers);
@@ -161,35 +249,39 @@ __global__ void __launch_bounds__(NT) act1d_kernel(const float *__restrict__ x, 
           : "memory");
     }
   } else {
+    // all loads of a thread are issued before the first store (one exposed memory latency, not one per row)
+    constexpr int NLD = (ROWS * K::XW + NT - 1) / NT;
     const int Lm1 = (int)(L - 1);
-#pragma unroll 1
-    for (int c = 0; c < ROWS; ++c) {
-      const int64_t row = row0 + c;
-      const float *xr = x + row * L;
-      const bool rv = row < nrows;
-#pragma unroll 3
-      for (int p = tid; p < K::TILE + 2 * K::XOFF; p += NT) {
-        int64_t t = t0 - K::XOFF + p;
-        const int tc = t < 0 ? 0 : (t > Lm1 ? Lm1 : (int)t);
-        x_s[c * K::PITCH + p] = rv ? __ldg(xr + tc) : 0.f;
-      }
+    float v[NLD];
+#pragma unroll
+    for (int i = 0; i < NLD; ++i) {
+      const int idx = tid + NT * i;
+      const int cc = idx / K::XW, p = idx - cc * K::XW;
+      const int64_t rw = row0 + cc;
+      const int64_t t = t0 - K::XOFF + p;
+      const int tc = t < 0 ? 0 : (t > Lm1 ? Lm1 : (int)t);
+      v[i] = (idx < ROWS * K::XW && rw < nrows) ? __ldg(x + rw * L + tc) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < NLD; ++i) {
+      const int idx = tid + NT * i;
+      const int cc = idx / K::XW, p = idx - cc * K::XW;
+      if (idx < ROWS * K::XW) x_s[cc * K::PITCH + p] = v[i];
     }
     __syncthreads();
   }
 
-  const int c = tid % ROWS, run = tid / ROWS;
-  const int64_t row = row0 + c;
   const int64_t ta = t0 + (int64_t)run * R;
   float outv[R];
   const bool active = row < nrows && ta < L;
   if (active) {
-    const int ch = (int)(row % C);
-    const float a = expf(__ldg(alpha + ch));
-    const float ib = 1.0f / (expf(__ldg(beta + ch)) + 0.000000001f);
+    const float a = expf(al);
+    const float ib = 1.0f / (expf(be) + 0.000000001f);
     const float *xw = x_s + c * K::PITCH + run * R + (K::XOFF - 5);
     const bool edge = (2 * ta - 5 < 0) || (2 * (ta + R - 1) + 6 > 2 * L - 1);
     if (!edge) {
-      walk<R, false>(xw, outv, a, ib, ta, L, 0.f, 0.f);
+      if (PACKED) walk2<R, false>(xw, outv, a, ib, ta, L, 0.f, 0.f, sc);
+      else walk<R, false>(xw, outv, a, ib, ta, L, 0.f, 0.f, sc);
     } else {
       // z[0] (m=0, even) and z[2L-1] (m=L, odd) from clamped global x
       const float *xr = x + row * L;
@@ -199,12 +291,13 @@ __global__ void __launch_bounds__(NT) act1d_kernel(const float *__restrict__ x, 
         int64_t tl = -3 + q, tr = L - 3 + q;
         tl = tl < 0 ? 0 : (tl > L - 1 ? L - 1 : tl);
         tr = tr < 0 ? 0 : (tr > L - 1 ? L - 1 : tr);
-        wl[q] = __ldg(xr + tl);
-        wr[q] = __ldg(xr + tr);
+        wl[q] = __ldg(xr + tl) * sc;
+        wr[q] = __ldg(xr + tr) * sc;
       }
       const float zL = up_snake(wl[0], wl[1], wl[2], wl[3], wl[4], wl[5], a, ib).e;
       const float zR = up_snake(wr[0], wr[1], wr[2], wr[3], wr[4], wr[5], a, ib).o;
-      walk<R, true>(xw, outv, a, ib, ta, L, zL, zR);
+      if (PACKED) walk2<R, true>(xw, outv, a, ib, ta, L, zL, zR, sc);
+      else walk<R, true>(xw, outv, a, ib, ta, L, zL, zR, sc);
     }
   }
 
@@ -239,8 +332,10 @@ __global__ void __launch_bounds__(NT) act1d_kernel(const float *__restrict__ x, 
   }
 }
 
+int g_act_variant = 1;  // 1: packed f32x2 math (default), 0: scalar math
+
 template <int R, int OUT_MODE>
-int launch(const float *x, void *out, const float *alpha, const float *beta, int B, int C, int64_t L,
+int launch(const float *x, void *out, const float *alpha, const float *beta, int B, int C, int64_t L, float sc,
            cudaStream_t st) {
   using K = Cfg<R>;
   const int64_t nrows = (int64_t)B * C;
@@ -248,21 +343,31 @@ int launch(const float *x, void *out, const float *alpha, const float *beta, int
   const int64_t ngrp = (nrows + ROWS - 1) / ROWS;
   const int64_t nblk = ntiles * ngrp;
   HSV_REQUIRE(nblk < (1ll << 31) && ntiles < (1ll << 31), "act1d: grid too large");
-  act1d_kernel<R, OUT_MODE><<<(unsigned)nblk, NT, 0, st>>>(x, out, alpha, beta, C, L, nrows, (int)ntiles,
-                                                          hsv::blk16_rows(L));
+  if (g_act_variant)
+    act1d_kernel<R, OUT_MODE, true><<<(unsigned)nblk, NT, 0, st>>>(x, out, alpha, beta, C, L, nrows, (int)ntiles,
+                                                                  hsv::blk16_rows(L), sc);
+  else
+    act1d_kernel<R, OUT_MODE, false><<<(unsigned)nblk, NT, 0, st>>>(x, out, alpha, beta, C, L, nrows, (int)ntiles,
+                                                                   hsv::blk16_rows(L), sc);
   return hsv::check_launch("act1d_snakebeta");
 }
 
 }  // namespace
 
+// bring-up aid (A/B of the packed-math variant); not part of the drop-in contract
+extern "C" int hsv_set_act_variant(int v) {
+  g_act_variant = v;
+  return HSV_OK;
+}
+
 extern "C" int hsv_act1d_snakebeta(const float *x, void *out, const float *alpha, const float *beta, int B,
-                                   int C, int64_t L, int out_mode, void *stream) {
+                                   int C, int64_t L, int out_mode, float in_scale, void *stream) {
   HSV_REQUIRE(x && out && alpha && beta, "act1d: null pointer");
   HSV_REQUIRE(B >= 0 && C > 0 && L >= 0, "act1d: bad shape B=%d C=%d L=%lld", B, C, (long long)L);
   HSV_REQUIRE(out_mode == 0 || out_mode == 1, "act1d: out_mode must be 0 (fp32 NCL) or 1 (fp16 blk16)");
   if (B == 0 || L == 0) return HSV_OK;
   cudaStream_t st = hsv::as_stream(stream);
-  if (out_mode == 0) return launch<17, 0>(x, out, alpha, beta, B, C, L, st);
+  if (out_mode == 0) return launch<17, 0>(x, out, alpha, beta, B, C, L, in_scale, st);
   HSV_REQUIRE(C % 8 == 0, "act1d: blk16 output needs C %% 8 == 0 (C=%d)", C);
-  return launch<17, 1>(x, out, alpha, beta, B, C, L, st);
+  return launch<17, 1>(x, out, alpha, beta, B, C, L, in_scale, st);
 }

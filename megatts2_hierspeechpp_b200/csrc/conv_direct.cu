@@ -319,7 +319,7 @@ __global__ void weight_norm_fold_kernel(const float *__restrict__ v, const float
 
 // fp32 [B,C,L] -> fp16 blk16; one thread per (b, chunk, t)
 __global__ void pack_blk16_kernel(const float *__restrict__ x, uint4 *__restrict__ out, int B, int C, int64_t L,
-                                  int64_t Lp, int lrelu) {
+                                  int64_t Lp, int lrelu, float sc) {
   const int nch = C >> 3;
   const int64_t n = (int64_t)B * nch * L;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -328,7 +328,7 @@ __global__ void pack_blk16_kernel(const float *__restrict__ x, uint4 *__restrict
     __half2 h[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      float v0 = __ldg(xr + (2 * e) * L), v1 = __ldg(xr + (2 * e + 1) * L);
+      float v0 = __ldg(xr + (2 * e) * L) * sc, v1 = __ldg(xr + (2 * e + 1) * L) * sc;
       if (lrelu) {
         v0 = v0 > 0.f ? v0 : 0.1f * v0;
         v1 = v1 > 0.f ? v1 : 0.1f * v1;
@@ -429,10 +429,11 @@ extern "C" int hsv_weight_norm_fold(const float *v, const float *g, float *w, in
   return hsv::check_launch("weight_norm_fold");
 }
 
-extern "C" int hsv_pack_blk16(const float *x, void *out, int B, int C, int64_t L, int lrelu, void *stream) {
+extern "C" int hsv_pack_blk16(const float *x, void *out, int B, int C, int64_t L, int lrelu, float in_scale,
+                              void *stream) {
   HSV_REQUIRE(x && out && C > 0 && C % 8 == 0, "pack_blk16: C %% 8 != 0 (C=%d)", C);
   if (B == 0 || L == 0) return HSV_OK;
   pack_blk16_kernel<<<grid_for((int64_t)B * (C / 8) * L, 256), 256, 0, hsv::as_stream(stream)>>>(
-      x, reinterpret_cast<uint4 *>(out), B, C, L, hsv::blk16_rows(L), lrelu);
+      x, reinterpret_cast<uint4 *>(out), B, C, L, hsv::blk16_rows(L), lrelu, in_scale);
   return hsv::check_launch("pack_blk16");
 }

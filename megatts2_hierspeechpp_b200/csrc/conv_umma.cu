@@ -139,7 +139,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(128, 4) conv_umma_kernel(const __grid_constant__ Params p) {
+template <int NMAX, int MINB>
+__global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bars[2 + 2 * MAX_STAGES];  // a_full, acc_full, w_full[S], w_empty[S]
   __shared__ uint32_t tmem_base_s;
@@ -234,9 +235,6 @@ __global__ void __launch_bounds__(128, 4) conv_umma_kernel(const __grid_constant
 
   // ---------------- epilogue: all 4 warps ----------------
   __syncwarp();
-  mbar_wait(bar_acc, 0);
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  __syncwarp();
   const int64_t t = (int64_t)tile * TILE_M + warp * 32 + lane;  // GEMM row = input time step
   const bool valid = t < p.L;
   const int64_t o = (int64_t)p.tt.out_stride * t + p.tt.out_off[ph];
@@ -246,50 +244,47 @@ __global__ void __launch_bounds__(128, 4) conv_umma_kernel(const __grid_constant
   float *outp = p.out ? p.out + base : nullptr;
   float *accp = p.acc ? p.acc + base : nullptr;
   const int64_t cs = p.Lout;  // channel stride
-  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-
-  float res_n[16];
+  // the residual does not depend on the accumulator: fetch ALL of it (NMAX registers) while the MMAs run,
+  // so the epilogue exposes one memory latency instead of one per 16-column chunk
+  float res[NMAX];
 #pragma unroll
-  for (int c = 0; c < 16; ++c) res_n[c] = 0.f;
+  for (int c = 0; c < NMAX; ++c) res[c] = 0.f;
   if (valid && resp) {
 #pragma unroll
-    for (int c = 0; c < 16; ++c) res_n[c] = resp[c * cs];
+    for (int c = 0; c < NMAX; ++c)
+      if (c < p.n_tile) res[c] = resp[c * cs];
   }
-  for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
-    uint32_t r[16];
-    tmem_ld16(trow + c0, r);
-    if (valid) {
-      float v[16];
+  mbar_wait(bar_acc, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  __syncwarp();
+  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
 #pragma unroll
-      for (int c = 0; c < 16; ++c) v[c] = __uint_as_float(r[c]);
-      if (p.bias) {
+  for (int c0 = 0; c0 < NMAX; c0 += 16) {
+    if (c0 < p.n_tile) {  // uniform
+      uint32_t r[16];
+      tmem_ld16(trow + c0, r);
+      if (valid) {
+        float v[16];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) v[c] += __ldg(p.bias + co0 + c0 + c);
-      }
+        for (int c = 0; c < 16; ++c) v[c] = __uint_as_float(r[c]);
+        if (p.bias) {
 #pragma unroll
-      for (int c = 0; c < 16; ++c) v[c] += res_n[c];  // (conv + bias) + residual: the reference's order
-      if (resp && c0 + 16 < p.n_tile) {  // prefetch the next chunk's residual before this chunk's stores
-#pragma unroll
-        for (int c = 0; c < 16; ++c) res_n[c] = resp[(int64_t)(c0 + 16 + c) * cs];
-      }
-      if (p.acc_mode >= 2) {
-        float a[16];
-#pragma unroll
-        for (int c = 0; c < 16; ++c) a[c] = accp[(int64_t)(c0 + c) * cs];
-        if (p.acc_mode == 2) {
-#pragma unroll
-          for (int c = 0; c < 16; ++c) accp[(int64_t)(c0 + c) * cs] = a[c] + v[c];
-        } else {
-#pragma unroll
-          for (int c = 0; c < 16; ++c) accp[(int64_t)(c0 + c) * cs] = (a[c] + v[c]) / p.acc_div;
+          for (int c = 0; c < 16; ++c) v[c] += __ldg(p.bias + co0 + c0 + c);
         }
-      } else if (p.acc_mode == 1) {
 #pragma unroll
-        for (int c = 0; c < 16; ++c) accp[(int64_t)(c0 + c) * cs] = v[c];
-      }
-      if (outp) {
+        for (int c = 0; c < 16; ++c) v[c] += res[c0 + c];  // (conv + bias) + residual: the reference's order
+        if (p.acc_mode == 1) {
 #pragma unroll
-        for (int c = 0; c < 16; ++c) outp[(int64_t)(c0 + c) * cs] = v[c];
+          for (int c = 0; c < 16; ++c) accp[(int64_t)(c0 + c) * cs] = v[c];
+        } else if (p.acc_mode == 2) {
+          // red.global.add: no read, one add per element per kernel -> deterministic given stream order
+#pragma unroll
+          for (int c = 0; c < 16; ++c) atomicAdd(accp + (int64_t)(c0 + c) * cs, v[c]);
+        }
+        if (outp) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) outp[(int64_t)(c0 + c) * cs] = v[c];
+        }
       }
     }
   }
@@ -367,6 +362,33 @@ TapTable convT_taps(int k, int u) {
 
 int g_host_debug = 0;
 
+template <int NMAX, int MINB>
+int launch_variant(const Params &p, dim3 grid, size_t smem, cudaStream_t st, const char *what) {
+  // opt-in dynamic shared memory: 227 KB per block minus the kernel's static shared memory
+  static int max_dyn[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (max_dyn[dev] == 0) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, conv_umma_kernel<NMAX, MINB>);
+    int want = 227 * 1024 - (e == cudaSuccess ? (int)fa.sharedSizeBytes : 1024);
+    want &= ~1023;
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_umma_kernel<NMAX, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+    if (e != cudaSuccess) {
+      cudaGetLastError();  // clear
+      hsv::set_error("%s: cudaFuncSetAttribute(%d): %s", what, want, cudaGetErrorString(e));
+      return HSV_ERR_CUDA;
+    }
+    max_dyn[dev] = want;
+  }
+  HSV_REQUIRE(smem <= (size_t)max_dyn[dev], "%s: shared memory %zu B exceeds %d B (Cin=%d)", what, smem,
+              max_dyn[dev], p.Cin);
+  conv_umma_kernel<NMAX, MINB><<<grid, 128, smem, st>>>(p);
+  return hsv::check_launch(what);
+}
+
 int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const float *bias,
            const float *residual, float *out, float *acc, int acc_mode, float acc_div, int B, int Cin, int Cout,
            int64_t L, int64_t Lout, int n_tile, cudaStream_t st, const char *what) {
@@ -399,36 +421,19 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
     p.stages--;
     smem = a_bytes + (size_t)p.stages * G * kstep_bytes;
   }
-  // opt-in dynamic shared memory: 227 KB per block minus the kernel's static shared memory
-  static int max_dyn[64] = {0};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64) dev = 0;
-  if (max_dyn[dev] == 0) {
-    cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, conv_umma_kernel);
-    int want = 227 * 1024 - (e == cudaSuccess ? (int)fa.sharedSizeBytes : 1024);
-    want &= ~1023;
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
-    if (e != cudaSuccess) {
-      cudaGetLastError();  // clear
-      hsv::set_error("%s: cudaFuncSetAttribute(%d): %s", what, want, cudaGetErrorString(e));
-      return HSV_ERR_CUDA;
-    }
-    max_dyn[dev] = want;
-  }
-  HSV_REQUIRE(smem <= (size_t)max_dyn[dev], "%s: shared memory %zu B exceeds %d B (Cin=%d)", what, smem,
-              max_dyn[dev], Cin);
   HSV_REQUIRE(B <= 65535 && (int64_t)p.nco_tiles * tt.nphase <= 65535, "%s: grid too large", what);
   dim3 grid((unsigned)((L + TILE_M - 1) / TILE_M), (unsigned)(p.nco_tiles * tt.nphase), (unsigned)B);
-  conv_umma_kernel<<<grid, 128, smem, st>>>(p);
-  return hsv::check_launch(what);
+  int rc;
+  if (n_tile <= 32) rc = launch_variant<32, 8>(p, grid, smem, st, what);
+  else if (n_tile <= 64) rc = launch_variant<64, 4>(p, grid, smem, st, what);
+  else rc = launch_variant<128, 2>(p, grid, smem, st, what);
+  return rc;
 }
 
 int check_common(const char *what, const void *a, const void *w, int Cin, int Cout, int n_tile) {
   HSV_REQUIRE(a && w, "%s: null operand", what);
   HSV_REQUIRE(Cin > 0 && Cin % 16 == 0, "%s: Cin %% 16 != 0 (Cin=%d)", what, Cin);
-  HSV_REQUIRE(n_tile >= 16 && n_tile <= 256 && n_tile % 16 == 0 && Cout % n_tile == 0,
+  HSV_REQUIRE(n_tile >= 16 && n_tile <= 128 && n_tile % 16 == 0 && Cout % n_tile == 0,
               "%s: bad n_tile=%d for Cout=%d", what, n_tile, Cout);
   return HSV_OK;
 }
@@ -475,7 +480,7 @@ extern "C" int hsv_conv1d_umma(const void *a_blk16, const void *w_packed, const 
               MAX_TAPS, k, d);
   HSV_REQUIRE(((k - 1) / 2) * d <= HSV_BLK_PAD, "conv1d_umma: halo %d exceeds blk16 padding %d",
               ((k - 1) / 2) * d, HSV_BLK_PAD);
-  HSV_REQUIRE(acc_mode >= 0 && acc_mode <= 3 && (acc_mode == 0 || acc), "conv1d_umma: bad acc_mode/acc");
+  HSV_REQUIRE(acc_mode >= 0 && acc_mode <= 2 && (acc_mode == 0 || acc), "conv1d_umma: bad acc_mode/acc");
   HSV_REQUIRE(out || acc_mode, "conv1d_umma: no output");
   if (B == 0 || L == 0) return HSV_OK;
   return launch(conv_taps(k, d), a_blk16, w_packed, bias, residual, out, acc, acc_mode, acc_div, B, Cin, Cout, L,

@@ -277,15 +277,18 @@ def _dense_conv(x: torch.Tensor, f: _Folded, k: int, d: int = 1, lrelu: bool = F
     return ops.conv1d_direct(x, f.weight(), f.bias(), d=d, pad=pad, flags=ops.CONV_LRELU_IN if lrelu else 0)
 
 
-def _dense_convT(x: torch.Tensor, f: _Folded, k: int, u: int, add: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """ConvTranspose1d(k, stride u, padding (k-u)//2) of an fp32 [B,C,L] tensor (+ optional add)."""
+def _dense_convT(x: torch.Tensor, f: _Folded, k: int, u: int, add: Optional[torch.Tensor] = None,
+                 scale: float = 1.0) -> torch.Tensor:
+    """ConvTranspose1d(k, stride u, padding (k-u)//2) of the fp32 [B,C,L] tensor ``x * scale`` (+ optional add)."""
     B, C, L = x.shape
     cout = f.conv.out_channels
     if C % 16 == 0 and cout % 16 == 0:
         buf = ops.blk16_buffer(B, C, L, x.device, _MAIN_SLOT)
-        ops.pack_blk16(x, buf)
+        ops.pack_blk16(x, buf, scale=scale)
         wp, nt = f.packedT_weight(u)
         return ops.conv_transpose1d_umma(buf, wp, f.bias(), L, C, cout, k, u, nt, add=add)
+    if scale != 1.0:
+        raise NotImplementedError("channel counts that are not multiples of 16 are not supported on this path")
     return ops.conv_transpose1d(x, f.weight(), f.bias(), u, add=add)
 
 
@@ -314,9 +317,9 @@ class AMPBlock1(nn.Module):
         _bump_on_load(self)
 
     def run(self, x: torch.Tensor, slot: int = 0, acc: Optional[torch.Tensor] = None, acc_mode: int = ops.ACC_NONE,
-            acc_div: float = 1.0, before_final=None) -> Optional[torch.Tensor]:
+            before_final=None) -> Optional[torch.Tensor]:
         """x fp32 [B,C,L] (not modified).  Returns the block output, or None when the result is only
-        accumulated into ``acc`` (mean over resblocks).  ``before_final`` is called right before the
+        accumulated into ``acc`` (sum over resblocks).  ``before_final`` is called right before the
         last conv is enqueued (used to order accumulation across streams)."""
         B, C, L = x.shape
         if C != self.channels or C % 16:
@@ -339,7 +342,7 @@ class AMPBlock1(nn.Module):
                 before_final()
             if last and acc_mode != ops.ACC_NONE:
                 ops.conv1d_umma(buf, w2, self._f2[i].bias(), L, C, C, k, 1, nt2, residual=cur, acc=acc,
-                                acc_mode=acc_mode, acc_div=acc_div, want_out=False)
+                                acc_mode=acc_mode, want_out=False)
                 return None
             out = torch.empty_like(x) if cur is x else cur
             ops.conv1d_umma(buf, w2, self._f2[i].bias(), L, C, C, k, 1, nt2, residual=cur, out=out)
@@ -359,18 +362,20 @@ class AMPBlock1(nn.Module):
 AMPBlock0 = AMPBlock1
 
 
-def mean_of_blocks(x: torch.Tensor, blocks: Sequence[AMPBlock1], parallel: bool = False) -> torch.Tensor:
-    """xs = sum_j resblock_j(x) / num_kernels (hierspeechpp_speechsynthesizer.py:440-446); the sum and
-    the division are fused into the epilogue of each block's last conv."""
+def sum_of_blocks(x: torch.Tensor, blocks: Sequence[AMPBlock1], parallel: bool = False):
+    """(xs, scale) with xs = sum_j resblock_j(x) and scale = 1/num_kernels
+    (hierspeechpp_speechsynthesizer.py:440-446).  The sum is accumulated in the epilogue of each block's
+    last conv (store, then red.add in stream order: deterministic); the division is applied by the
+    consumer of xs (``in_scale`` of the next activation / operand pack), so xs is never re-read."""
     nk = len(blocks)
     if nk == 1:
-        return blocks[0].run(x)
+        return blocks[0].run(x), 1.0
     xs = torch.empty_like(x)
-    modes = [ops.ACC_SET] + [ops.ACC_ADD] * (nk - 2) + [ops.ACC_MEAN]
+    modes = [ops.ACC_SET] + [ops.ACC_ADD] * (nk - 1)
     if not parallel:
         for j, blk in enumerate(blocks):
-            blk.run(x, slot=0, acc=xs, acc_mode=modes[j], acc_div=float(nk))
-        return xs
+            blk.run(x, slot=0, acc=xs, acc_mode=modes[j])
+        return xs, 1.0 / nk
     # one stream per resblock; the accumulating epilogues are chained with events
     main = torch.cuda.current_stream()
     fork = torch.cuda.Event()
@@ -382,12 +387,12 @@ def mean_of_blocks(x: torch.Tensor, blocks: Sequence[AMPBlock1], parallel: bool 
         s.wait_event(fork)
         with torch.cuda.stream(s):
             prev = done[j - 1] if j > 0 else None
-            blk.run(x, slot=j, acc=xs, acc_mode=modes[j], acc_div=float(nk),
+            blk.run(x, slot=j, acc=xs, acc_mode=modes[j],
                     before_final=(lambda p=prev, st=s: st.wait_event(p)) if prev is not None else None)
             done[j].record(s)
     for ev in done:
         main.wait_event(ev)
-    return xs
+    return xs, 1.0 / nk
 
 
 _streams = {}
@@ -445,7 +450,7 @@ class _VocoderBase(nn.Module):
 
     def _stage(self, x, i):
         nk = self.num_kernels
-        return mean_of_blocks(x, [self.resblocks[i * nk + j] for j in range(nk)], self.parallel_blocks)
+        return sum_of_blocks(x, [self.resblocks[i * nk + j] for j in range(nk)], self.parallel_blocks)
 
 
 class SourceNetwork(_VocoderBase):
@@ -486,11 +491,12 @@ class SourceNetwork(_VocoderBase):
         xp = _dense_conv(x, self._f_pre, 7)
         cg = ops.conv1d_direct(g, self._f_cond.weight(), self._f_cond.bias())
         x = ops.add3_bcast(xp, None, cg, out=xp)
+        sc = 1.0
         for i in range(self.num_upsamples):
-            x = _dense_convT(x, self._f_ups[i], self.ups[i].kernel_size[0], self.upsample_rates[i])
-            x = self._stage(x, i)
+            x = _dense_convT(x, self._f_ups[i], self.ups[i].kernel_size[0], self.upsample_rates[i], scale=sc)
+            x, sc = self._stage(x, i)
         self.activation_post.check_filters()
-        x = ops.act1d(x, *self.activation_post.params())
+        x = ops.act1d(x, *self.activation_post.params(), scale=sc)
         x_ = ops.conv1d_direct(x, self._f_post.weight(), None, pad=3)
         return x, x_
 
@@ -537,14 +543,16 @@ class Generator(_VocoderBase):
             raise ValueError("Generator.forward needs the speaker embedding g")
         cg = ops.conv1d_direct(_as_input(g), self._f_cond.weight(), self._f_cond.bias())
         x = ops.add3_bcast(xp, dn, cg, out=xp)
+        sc = 1.0
         for i in range(self.num_upsamples):
             add = None
             if i == 0:
                 add = _dense_conv(pitch, self._f_proj, 7)
-            x = _dense_convT(x, self._f_ups[i], self.ups[i].kernel_size[0], self.upsample_rates[i], add=add)
-            x = self._stage(x, i)
+            x = _dense_convT(x, self._f_ups[i], self.ups[i].kernel_size[0], self.upsample_rates[i], add=add,
+                             scale=sc)
+            x, sc = self._stage(x, i)
         self.activation_post.check_filters()
-        x = ops.act1d(x, *self.activation_post.params())
+        x = ops.act1d(x, *self.activation_post.params(), scale=sc)
         return ops.conv1d_direct(x, self._f_post.weight(), None, pad=3, flags=ops.CONV_TANH)
 
     def remove_weight_norm(self):
@@ -596,9 +604,9 @@ class SpeechSRGenerator(_VocoderBase):
         x = _as_input(x)
         L = x.shape[-1]
         x = ops.sr_pre_interp(x, self._f_pre.weight(), self._f_pre.bias(), int(L * self.scale))
-        x = self._stage(x, 0)
+        x, sc = self._stage(x, 0)
         self.activation_post.check_filters()
-        x = ops.act1d(x, *self.activation_post.params())
+        x = ops.act1d(x, *self.activation_post.params(), scale=sc)
         return ops.conv1d_direct(x, self._f_post.weight(), None, pad=3, flags=ops.CONV_TANH)
 
     def remove_weight_norm(self):

@@ -20,7 +20,7 @@ CONV_LRELU_IN = 1
 CONV_TANH = 2
 CONV_ADD_OUT = 4
 
-ACC_NONE, ACC_SET, ACC_ADD, ACC_MEAN = 0, 1, 2, 3
+ACC_NONE, ACC_SET, ACC_ADD = 0, 1, 2
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -71,8 +71,9 @@ def clear_workspace():
     _blk_pool.clear()
 
 
-def act1d(x: torch.Tensor, alpha: torch.Tensor, beta: torch.Tensor, out: Optional[torch.Tensor] = None):
-    """Fused Activation1d(SnakeBeta): fp32 [B,C,L] -> fp32 [B,C,L]."""
+def act1d(x: torch.Tensor, alpha: torch.Tensor, beta: torch.Tensor, out: Optional[torch.Tensor] = None,
+          scale: float = 1.0):
+    """Fused Activation1d(SnakeBeta) of ``x * scale``: fp32 [B,C,L] -> fp32 [B,C,L]."""
     _req(x, "x", ndim=3); _req(alpha, "alpha"); _req(beta, "beta")
     B, C, L = x.shape
     if alpha.numel() != C or beta.numel() != C:
@@ -82,28 +83,30 @@ def act1d(x: torch.Tensor, alpha: torch.Tensor, beta: torch.Tensor, out: Optiona
     else:
         _req(out, "out", ndim=3)
     lib = _lib.load()
-    _lib.check(lib.hsv_act1d_snakebeta(_p(x), _p(out), _p(alpha), _p(beta), B, C, L, 0, _stream()), "hsv_act1d_snakebeta")
+    _lib.check(lib.hsv_act1d_snakebeta(_p(x), _p(out), _p(alpha), _p(beta), B, C, L, 0, float(scale), _stream()),
+               "hsv_act1d_snakebeta")
     return out
 
 
-def act1d_blk16(x: torch.Tensor, alpha: torch.Tensor, beta: torch.Tensor, buf: torch.Tensor):
-    """Fused Activation1d(SnakeBeta): fp32 [B,C,L] -> fp16 blk16 operand (written into ``buf``)."""
+def act1d_blk16(x: torch.Tensor, alpha: torch.Tensor, beta: torch.Tensor, buf: torch.Tensor, scale: float = 1.0):
+    """Fused Activation1d(SnakeBeta) of ``x * scale``: fp32 [B,C,L] -> fp16 blk16 operand (into ``buf``)."""
     _req(x, "x", ndim=3); _req(alpha, "alpha"); _req(beta, "beta"); _req(buf, "buf", torch.float16, 4)
     B, C, L = x.shape
     if tuple(buf.shape) != (B, C // 8, blk16_rows(L), 8):
         raise ValueError(f"blk16 buffer shape {tuple(buf.shape)} does not match x {tuple(x.shape)}")
     lib = _lib.load()
-    _lib.check(lib.hsv_act1d_snakebeta(_p(x), _p(buf), _p(alpha), _p(beta), B, C, L, 1, _stream()), "hsv_act1d_snakebeta")
+    _lib.check(lib.hsv_act1d_snakebeta(_p(x), _p(buf), _p(alpha), _p(beta), B, C, L, 1, float(scale), _stream()),
+               "hsv_act1d_snakebeta")
     return buf
 
 
-def pack_blk16(x: torch.Tensor, buf: torch.Tensor, lrelu: bool = False):
+def pack_blk16(x: torch.Tensor, buf: torch.Tensor, lrelu: bool = False, scale: float = 1.0):
     _req(x, "x", ndim=3); _req(buf, "buf", torch.float16, 4)
     B, C, L = x.shape
     if tuple(buf.shape) != (B, C // 8, blk16_rows(L), 8):
         raise ValueError("blk16 buffer shape mismatch")
     lib = _lib.load()
-    _lib.check(lib.hsv_pack_blk16(_p(x), _p(buf), B, C, L, int(lrelu), _stream()), "hsv_pack_blk16")
+    _lib.check(lib.hsv_pack_blk16(_p(x), _p(buf), B, C, L, int(lrelu), float(scale), _stream()), "hsv_pack_blk16")
     return buf
 
 
@@ -124,7 +127,7 @@ def pick_n_tile(cout: int) -> int:
         return cout
     if cout % 128 == 0:
         return 128
-    for n in range(256, 15, -16):
+    for n in range(128, 15, -16):
         if cout % n == 0:
             return n
     raise ValueError(f"Cout={cout} not a multiple of 16")

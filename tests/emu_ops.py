@@ -36,20 +36,21 @@ def _pack_into(buf, y):
     buf[:, :, real.BLK_PAD:real.BLK_PAD + L, :] = y.half().view(B, C // 8, 8, L).permute(0, 1, 3, 2)
 
 
-def act1d(x, a, b, out=None):
-    y = _act(x, a, b)
+def act1d(x, a, b, out=None, scale=1.0):
+    y = _act(x * scale, a, b)
     if out is not None:
         out.copy_(y)
         return out
     return y
 
 
-def act1d_blk16(x, a, b, buf):
-    _pack_into(buf, _act(x, a, b))
+def act1d_blk16(x, a, b, buf, scale=1.0):
+    _pack_into(buf, _act(x * scale, a, b))
     return buf
 
 
-def pack_blk16(x, buf, lrelu=False):
+def pack_blk16(x, buf, lrelu=False, scale=1.0):
+    x = x * scale
     _pack_into(buf, F.leaky_relu(x, 0.1) if lrelu else x)
     return buf
 
@@ -75,8 +76,6 @@ def conv1d_umma(a_blk, wp, bias, L, cin, cout, k, d, n_tile, residual=None, out=
         acc.copy_(v)
     elif acc_mode == 2:
         acc.add_(v)
-    elif acc_mode == 3:
-        acc.copy_((acc + v) / acc_div)
     if out is not None:
         out.copy_(v)
         return out

@@ -43,10 +43,10 @@ def test_version_and_helpers(lib):
 
 def test_argument_errors_are_reported(lib):
     # argument validation happens before any CUDA call, so it is testable without a GPU
-    rc = lib.hsv_act1d_snakebeta(None, None, None, None, 1, 8, 16, 0, None)
+    rc = lib.hsv_act1d_snakebeta(None, None, None, None, 1, 8, 16, 0, 1.0, None)
     assert rc == -1 and b"null" in lib.hsv_last_error()
     one = ctypes.c_void_p(16)
-    rc = lib.hsv_act1d_snakebeta(one, one, one, one, 1, 12, 16, 1, None)
+    rc = lib.hsv_act1d_snakebeta(one, one, one, one, 1, 12, 16, 1, 1.0, None)
     assert rc == -1 and b"C % 8" in lib.hsv_last_error()
     rc = lib.hsv_conv1d_umma(one, one, None, None, one, None, 0, 1.0, 1, 24, 32, 100, 3, 1, 32, None)
     assert rc == -1 and b"Cin" in lib.hsv_last_error()

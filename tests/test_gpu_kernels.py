@@ -75,6 +75,20 @@ def test_act1d_blk16_output(hsv, B, C, L):
     assert buf[:, :, :ops.BLK_PAD].abs().max().item() == 0 and buf[:, :, ops.BLK_PAD + L:].abs().max().item() == 0
 
 
+def test_act1d_in_scale(hsv):
+    gen = torch.Generator().manual_seed(21)
+    x = torch.randn(2, 16, 700, generator=gen) * 3
+    al = torch.rand(16, generator=gen) - 0.5
+    be = torch.rand(16, generator=gen) - 0.5
+    ref = _act_oracle(x / 3, al, be)
+    y = hsv.ops.act1d(x.to(DEV), al.to(DEV), be.to(DEV), scale=1.0 / 3).cpu()
+    assert (y - ref).abs().max() <= 1e-5 * max(1.0, ref.abs().max().item())
+    buf = hsv.ops.blk16_buffer(2, 16, 700, DEV, slot=7)
+    hsv.ops.pack_blk16(x.to(DEV), buf, lrelu=True, scale=1.0 / 3)
+    yp = _unpack_blk16(buf, 700).cpu()
+    assert (yp - F.leaky_relu(x / 3, 0.1)).abs().max() <= 2e-3
+
+
 def test_act1d_full_size_properties(hsv):
     """Config-#2 stage-4 size [1,16,160000]: determinism, batch independence, shift structure."""
     gen = torch.Generator().manual_seed(1)
@@ -257,12 +271,12 @@ def test_conv1d_umma_rectangular_and_acc_modes(hsv):
     hsv.ops.pack_blk16(x.to(DEV), buf)
     acc = torch.empty(B, C, L, device=DEV)
     refs = []
-    for j, mode in enumerate((hsv.ops.ACC_SET, hsv.ops.ACC_ADD, hsv.ops.ACC_MEAN)):
+    for j, mode in enumerate((hsv.ops.ACC_SET, hsv.ops.ACC_ADD, hsv.ops.ACC_ADD)):
         w = torch.randn(C, C, k, generator=gen) / (C * k) ** 0.5
         refs.append(F.conv1d(x.half().double(), w.half().double(), None, padding=3))
         wp = hsv.ops.pack_conv_weight(w.to(DEV), 32)
-        hsv.ops.conv1d_umma(buf, wp, None, L, C, C, k, 1, 32, acc=acc, acc_mode=mode, acc_div=3.0, want_out=False)
-    ref = (refs[0] + refs[1] + refs[2]) / 3
+        hsv.ops.conv1d_umma(buf, wp, None, L, C, C, k, 1, 32, acc=acc, acc_mode=mode, want_out=False)
+    ref = refs[0] + refs[1] + refs[2]
     assert (acc.cpu().double() - ref).abs().max().item() <= 2e-4
 
 
