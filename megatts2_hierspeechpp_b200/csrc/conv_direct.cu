@@ -93,7 +93,54 @@ conv1d_tiled_kernel(const float *__restrict__ x, const float *__restrict__ w, co
   }
 }
 
-// thin conv for Cout <= 4 (conv_post): one thread per (b, t), weights through the read-only cache
+// thin conv for Cout <= 4 and d == 1 (conv_post 16|32|64 -> 1, k=7): each thread produces 4 consecutive
+// outputs of one (b, co) from a register window of k+3 inputs per input channel; weights are uniform loads.
+template <int K>
+__global__ void __launch_bounds__(256) conv1d_thin4_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                                                           const float *__restrict__ bias, float *__restrict__ out,
+                                                           int B, int Cin, int Cout, int64_t Lin, int64_t Lout,
+                                                           int pad, int flags) {
+  const int64_t nq = (Lout + 3) / 4;
+  const int64_t n = (int64_t)B * Cout * nq;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t q = i % nq;
+    const int co = (int)((i / nq) % Cout);
+    const int b = (int)(i / (nq * Cout));
+    const int64_t t0 = q * 4;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int ci = 0; ci < Cin; ++ci) {
+      const float *xr = x + ((int64_t)b * Cin + ci) * Lin;
+      const float *wr = w + ((int64_t)co * Cin + ci) * K;
+      float xv[K + 3];
+#pragma unroll
+      for (int j = 0; j < K + 3; ++j) {
+        const int64_t ts = t0 - pad + j;
+        float v = (ts >= 0 && ts < Lin) ? __ldg(xr + ts) : 0.f;
+        if (flags & HSV_CONV_LRELU_IN) v = v > 0.f ? v : 0.1f * v;
+        xv[j] = v;
+      }
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        const float wj = __ldg(wr + j);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[r] = fmaf(wj, xv[j + r], acc[r]);
+      }
+    }
+    const float bv = bias ? __ldg(bias + co) : 0.f;
+    float *o = out + ((int64_t)b * Cout + co) * Lout + t0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (t0 + r < Lout) {
+        float v = acc[r] + bv;
+        if (flags & HSV_CONV_TANH) v = tanhf(v);
+        if (flags & HSV_CONV_ADD_OUT) v += o[r];
+        o[r] = v;
+      }
+    }
+  }
+}
+
+// generic thin conv (any k, d): one thread per (b, t)
 __global__ void conv1d_thin_kernel(const float *__restrict__ x, const float *__restrict__ w,
                                    const float *__restrict__ bias, float *__restrict__ out, int B, int Cin,
                                    int Cout, int64_t Lin, int64_t Lout, int k, int d, int pad, int flags) {
@@ -121,6 +168,38 @@ __global__ void conv1d_thin_kernel(const float *__restrict__ x, const float *__r
       if (flags & HSV_CONV_ADD_OUT) acc += *o;
       *o = acc;
     }
+  }
+}
+
+// very short sequences (cond(g): Lin == Lout == 1): one warp per output element, lanes split the
+// Cin*k products, shuffle reduction
+__global__ void conv1d_rowdot_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                                     const float *__restrict__ bias, float *__restrict__ out, int B, int Cin,
+                                     int Cout, int64_t Lin, int64_t Lout, int k, int d, int pad, int flags) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nout = (int64_t)B * Cout * Lout;
+  const int64_t wid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (wid >= nout) return;
+  const int64_t t = wid % Lout;
+  const int co = (int)((wid / Lout) % Cout);
+  const int b = (int)(wid / (Lout * Cout));
+  float acc = 0.f;
+  for (int r = lane; r < Cin * k; r += 32) {
+    const int ci = r / k, j = r - ci * k;
+    const int64_t ts = t - pad + (int64_t)j * d;
+    if (ts >= 0 && ts < Lin) {
+      float v = __ldg(x + ((int64_t)b * Cin + ci) * Lin + ts);
+      if (flags & HSV_CONV_LRELU_IN) v = v > 0.f ? v : 0.1f * v;
+      acc = fmaf(__ldg(w + (int64_t)co * Cin * k + r), v, acc);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    if (bias) acc += __ldg(bias + co);
+    if (flags & HSV_CONV_TANH) acc = tanhf(acc);
+    float *o = out + ((int64_t)b * Cout + co) * Lout + t;
+    if (flags & HSV_CONV_ADD_OUT) acc += *o;
+    *o = acc;
   }
 }
 
@@ -356,7 +435,15 @@ extern "C" int hsv_conv1d_direct(const float *x, const float *w, const float *bi
   HSV_REQUIRE(Lout == Lin + 2 * (int64_t)pad - (int64_t)d * (k - 1), "conv1d_direct: Lout mismatch");
   if (B == 0 || Lout <= 0) return HSV_OK;
   cudaStream_t st = hsv::as_stream(stream);
-  if (Cout <= 4) {
+  if (Lout <= 8) {
+    const int64_t nwarps = (int64_t)B * Cout * Lout;
+    HSV_REQUIRE(nwarps * 32 / 256 + 1 < (1ll << 31), "conv1d_direct: grid too large");
+    conv1d_rowdot_kernel<<<(unsigned)((nwarps * 32 + 255) / 256), 256, 0, st>>>(x, w, bias, out, B, Cin, Cout, Lin,
+                                                                               Lout, k, d, pad, flags);
+  } else if (Cout <= 4 && d == 1 && k == 7) {
+    conv1d_thin4_kernel<7><<<grid_for((int64_t)B * Cout * ((Lout + 3) / 4), 256), 256, 0, st>>>(
+        x, w, bias, out, B, Cin, Cout, Lin, Lout, pad, flags);
+  } else if (Cout <= 4) {
     conv1d_thin_kernel<<<grid_for((int64_t)B * Lout, 256), 256, 0, st>>>(x, w, bias, out, B, Cin, Cout, Lin,
                                                                         Lout, k, d, pad, flags);
   } else {

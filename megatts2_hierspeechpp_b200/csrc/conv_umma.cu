@@ -57,6 +57,7 @@ struct Params {
   int Cin, Cout;
   int64_t L, Lp, Lout;
   int n_tile, nco_tiles;
+  int ntiles;   // real M-tiles (gridDim.x is rounded up to the cluster size; the extra CTAs only stream weights)
   int R;        // rows per chunk in the shared A tile = 128 + h_lo + h_hi
   int G;        // K-steps per weight block
   int stages;
@@ -103,6 +104,35 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
       "l"(src), "r"(bytes), "r"(bar)
       : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar,
+                                            uint16_t cta_mask) {
+  // multicast: the bytes land at the same shared offset of every CTA in cta_mask and complete_tx is
+  // signalled on the mbarrier at the same offset of each of them
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   // cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
@@ -163,12 +193,20 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
   const uint32_t bar_a = smem_u32(&bars[0]), bar_acc = smem_u32(&bars[1]);
   const uint32_t bar_wf = smem_u32(&bars[2]), bar_we = smem_u32(&bars[2 + MAX_STAGES]);
 
+  // Cluster of CL CTAs = CL consecutive M-tiles of the same (phase, n-tile, batch): they need the same
+  // weights, so every CTA fetches 1/CL of each weight block and multicasts it to the whole cluster
+  // (L2 -> SM weight traffic per SM drops by CL).  A stage is free again when all CL consumers released it.
+  const uint32_t CL = cluster_nctarank();
+  const uint32_t crank = cluster_ctarank();
+  const uint16_t cmask = (uint16_t)((1u << CL) - 1u);
+  const bool real_tile = tile < p.ntiles;
+
   if (threadIdx.x == 0) {
     mbar_init(bar_a, 1);
     mbar_init(bar_acc, 1);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(bar_wf + 8 * s, 1);
-      mbar_init(bar_we + 8 * s, 1);
+      mbar_init(bar_we + 8 * s, CL);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -181,16 +219,19 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // every CTA's barriers are initialised before any remote arrive / multicast
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_base_s;
 
   if (warp == 0 && lane == 0) {
     // ---------------- TMA producer ----------------
-    const int64_t row0 = (int64_t)HSV_BLK_PAD + (int64_t)tile * TILE_M - p.tt.h_lo;
-    mbar_expect_tx(bar_a, a_bytes);
-    for (int q = 0; q < nchunks; ++q) {
-      const uint4 *src = p.a + ((int64_t)b * nchunks + q) * p.Lp + row0;
-      bulk_g2s(a_s + q * a_bytes_chunk, src, a_bytes_chunk, bar_a);
+    if (real_tile) {
+      const int64_t row0 = (int64_t)HSV_BLK_PAD + (int64_t)tile * TILE_M - p.tt.h_lo;
+      mbar_expect_tx(bar_a, a_bytes);
+      for (int q = 0; q < nchunks; ++q) {
+        const uint4 *src = p.a + ((int64_t)b * nchunks + q) * p.Lp + row0;
+        bulk_g2s(a_s + q * a_bytes_chunk, src, a_bytes_chunk, bar_a);
+      }
     }
     // K-step offset of (phase, n-tile) in the packed weight stream
     int64_t ks0 = 0;
@@ -202,21 +243,27 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
       if (blk >= p.stages) mbar_wait(bar_we + 8 * s, ((blk / p.stages) - 1) & 1);
       const int nk = min(p.G, ksteps - blk * p.G);
       const uint32_t bytes = kstep_bytes * nk;
-      mbar_expect_tx(bar_wf + 8 * s, bytes);
-      bulk_g2s(w_s + s * wblk_bytes, wsrc + (int64_t)blk * (wblk_bytes >> 4), bytes, bar_wf + 8 * s);
+      mbar_expect_tx(bar_wf + 8 * s, bytes);  // the whole block lands here: own slice + the peers' multicasts
+      if (CL == 1) {
+        bulk_g2s(w_s + s * wblk_bytes, wsrc + (int64_t)blk * (wblk_bytes >> 4), bytes, bar_wf + 8 * s);
+      } else {
+        const uint32_t slice = bytes / CL;  // multiple of 16: kstep_bytes >= 2048 whenever CL > 1
+        bulk_g2s_mc(w_s + s * wblk_bytes + crank * slice,
+                    wsrc + (int64_t)blk * (wblk_bytes >> 4) + ((crank * slice) >> 4), slice, bar_wf + 8 * s, cmask);
+      }
     }
   } else if (warp == 1 && lane == 0) {
     // ---------------- MMA issuer ----------------
     // InstrDescriptor: D=F32 (1<<4), A=B=F16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
     const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
     const bool swap = p.debug & 1;
-    mbar_wait(bar_a, 0);
+    if (real_tile) mbar_wait(bar_a, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     for (int blk = 0; blk < nblocks; ++blk) {
       const int s = blk % p.stages;
       mbar_wait(bar_wf + 8 * s, (blk / p.stages) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int nk = min(p.G, ksteps - blk * p.G);
+      const int nk = real_tile ? min(p.G, ksteps - blk * p.G) : 0;
       for (int g = 0; g < nk; ++g) {
         const int ks = blk * p.G + g;
         const int j = ks / KC, kc = ks - j * KC;
@@ -228,7 +275,8 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
         const uint64_t bd = swap ? make_desc(b_addr, sbo, b_lbo) : make_desc(b_addr, b_lbo, sbo);
         umma_f16(tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
       }
-      umma_commit(bar_we + 8 * s);
+      if (CL == 1) umma_commit(bar_we + 8 * s);
+      else umma_commit_mc(bar_we + 8 * s, cmask);  // release this stage in every CTA of the cluster
     }
     umma_commit(bar_acc);
   }
@@ -236,7 +284,7 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
   // ---------------- epilogue: all 4 warps ----------------
   __syncwarp();
   const int64_t t = (int64_t)tile * TILE_M + warp * 32 + lane;  // GEMM row = input time step
-  const bool valid = t < p.L;
+  const bool valid = real_tile && t < p.L;
   const int64_t o = (int64_t)p.tt.out_stride * t + p.tt.out_off[ph];
   const int co0 = nt * p.n_tile;
   const int64_t base = ((int64_t)b * p.Cout + co0) * p.Lout + o;
@@ -294,6 +342,7 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(p.tmem_cols)
                  : "memory");
   }
+  if (CL > 1) cluster_sync_all();  // no CTA exits while peers may still multicast into it / arrive on its barriers
 }
 
 // out[ph][nt][s][c2][n][e] = W(co = nt*n_tile + n, ci = 16*kc + 8*c2 + e, tap wj[ph][i]),  s = i*(Cin/16) + kc
@@ -361,9 +410,10 @@ TapTable convT_taps(int k, int u) {
 }
 
 int g_host_debug = 0;
+int g_cluster_override = 0;  // bring-up aid: force the cluster size (0 = automatic)
 
 template <int NMAX, int MINB>
-int launch_variant(const Params &p, dim3 grid, size_t smem, cudaStream_t st, const char *what) {
+int launch_variant(const Params &p, dim3 grid, int cluster, size_t smem, cudaStream_t st, const char *what) {
   // opt-in dynamic shared memory: 227 KB per block minus the kernel's static shared memory
   static int max_dyn[64] = {0};
   int dev = 0;
@@ -385,7 +435,24 @@ int launch_variant(const Params &p, dim3 grid, size_t smem, cudaStream_t st, con
   }
   HSV_REQUIRE(smem <= (size_t)max_dyn[dev], "%s: shared memory %zu B exceeds %d B (Cin=%d)", what, smem,
               max_dyn[dev], p.Cin);
-  conv_umma_kernel<NMAX, MINB><<<grid, 128, smem, st>>>(p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(128);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<NMAX, MINB>, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    hsv::set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+    return HSV_ERR_CUDA;
+  }
   return hsv::check_launch(what);
 }
 
@@ -399,6 +466,7 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
   p.acc_mode = acc_mode; p.acc_div = acc_div;
   p.Cin = Cin; p.Cout = Cout; p.L = L; p.Lp = hsv::blk16_rows(L); p.Lout = Lout;
   p.n_tile = n_tile; p.nco_tiles = Cout / n_tile;
+  p.ntiles = (int)((L + TILE_M - 1) / TILE_M);
   p.R = TILE_M + tt.h_lo + tt.h_hi;
   p.tt = tt;
   int max_ksteps = 0;
@@ -422,11 +490,18 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
     smem = a_bytes + (size_t)p.stages * G * kstep_bytes;
   }
   HSV_REQUIRE(B <= 65535 && (int64_t)p.nco_tiles * tt.nphase <= 65535, "%s: grid too large", what);
-  dim3 grid((unsigned)((L + TILE_M - 1) / TILE_M), (unsigned)(p.nco_tiles * tt.nphase), (unsigned)B);
+  // weight multicast across a cluster of consecutive M-tiles pays when the weights are large
+  // (n_tile >= 64 -> K-step >= 2 KB) and there are at least two tiles to share them
+  int cluster = 1;
+  if (g_cluster_override > 0) cluster = g_cluster_override;
+  else if (n_tile >= 64) cluster = p.ntiles >= 8 ? 8 : (p.ntiles >= 4 ? 4 : (p.ntiles >= 2 ? 2 : 1));
+  if (n_tile < 64) cluster = 1;
+  const int gx = ((p.ntiles + cluster - 1) / cluster) * cluster;
+  dim3 grid((unsigned)gx, (unsigned)(p.nco_tiles * tt.nphase), (unsigned)B);
   int rc;
-  if (n_tile <= 32) rc = launch_variant<32, 8>(p, grid, smem, st, what);
-  else if (n_tile <= 64) rc = launch_variant<64, 4>(p, grid, smem, st, what);
-  else rc = launch_variant<128, 2>(p, grid, smem, st, what);
+  if (n_tile <= 32) rc = launch_variant<32, 8>(p, grid, cluster, smem, st, what);
+  else if (n_tile <= 64) rc = launch_variant<64, 4>(p, grid, cluster, smem, st, what);
+  else rc = launch_variant<128, 2>(p, grid, cluster, smem, st, what);
   return rc;
 }
 
@@ -451,7 +526,8 @@ int pack(const float *w, void *packed, int Cout, int Cin, int k, int n_tile, int
 
 // bring-up aid only (bit0: swap LBO/SBO roles in the smem descriptors); not part of the drop-in contract
 extern "C" int hsv_set_umma_debug(int flags) {
-  g_host_debug = flags;
+  g_host_debug = flags & 0xff;
+  g_cluster_override = (flags >> 8) & 0xff;  // bits 8..15: forced cluster size
   return HSV_OK;
 }
 
