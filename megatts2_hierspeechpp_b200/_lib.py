@@ -44,6 +44,7 @@ SIGNATURES = {
 _EXTRA = {
     "hsv_set_umma_debug": (c_int, [c_int]),
     "hsv_set_act_variant": (c_int, [c_int]),
+    "hsv_set_pdl": (c_int, [c_int]),
 }
 
 _lib = None
@@ -72,6 +73,8 @@ def load() -> ctypes.CDLL:
         raise HsvError(f"libhsv.so version {lib.hsv_version()} does not match the Python binding (100)")
     if os.environ.get("HSV_UMMA_DEBUG"):
         lib.hsv_set_umma_debug(int(os.environ["HSV_UMMA_DEBUG"]))
+    if os.environ.get("HSV_PDL"):
+        lib.hsv_set_pdl(int(os.environ["HSV_PDL"]))
     if os.environ.get("HSV_ACT_VARIANT"):
         lib.hsv_set_act_variant(int(os.environ["HSV_ACT_VARIANT"]))
     _lib = lib

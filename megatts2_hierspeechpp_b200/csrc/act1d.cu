@@ -206,12 +206,15 @@ __global__ void __launch_bounds__(NT) act1d_kernel(const float *__restrict__ x, 
   const int64_t t0 = (int64_t)tile * K::TILE;
   const int c = tid % ROWS, run = tid / ROWS;
   const int64_t row = row0 + c;
-  // per-channel parameters: issue these global loads before waiting for the tile
+  // PDL: let the next kernel start its prologue now; parameters are static, so load them before waiting
+  // for the producer of x
+  hsv::pdl_launch_dependents();
   float al = 0.f, be = 0.f;
   if (row < nrows) {
     al = __ldg(alpha + (int)(row % C));
     be = __ldg(beta + (int)(row % C));
   }
+  hsv::pdl_wait();
 
   // ---- stage the x tile ----
   // interior tiles of 16-byte-aligned rows: one 1-D bulk TMA copy per row (no issue slots, no registers);
@@ -343,12 +346,27 @@ int launch(const float *x, void *out, const float *alpha, const float *beta, int
   const int64_t ngrp = (nrows + ROWS - 1) / ROWS;
   const int64_t nblk = ntiles * ngrp;
   HSV_REQUIRE(nblk < (1ll << 31) && ntiles < (1ll << 31), "act1d: grid too large");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)nblk);
+  cfg.blockDim = dim3(NT);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = hsv::g_pdl ? 1 : 0;
+  const int nt_i = (int)ntiles;
+  const int64_t Lp = hsv::blk16_rows(L);
+  cudaError_t e;
   if (g_act_variant)
-    act1d_kernel<R, OUT_MODE, true><<<(unsigned)nblk, NT, 0, st>>>(x, out, alpha, beta, C, L, nrows, (int)ntiles,
-                                                                  hsv::blk16_rows(L), sc);
+    e = cudaLaunchKernelEx(&cfg, act1d_kernel<R, OUT_MODE, true>, x, out, alpha, beta, C, L, nrows, nt_i, Lp, sc);
   else
-    act1d_kernel<R, OUT_MODE, false><<<(unsigned)nblk, NT, 0, st>>>(x, out, alpha, beta, C, L, nrows, (int)ntiles,
-                                                                   hsv::blk16_rows(L), sc);
+    e = cudaLaunchKernelEx(&cfg, act1d_kernel<R, OUT_MODE, false>, x, out, alpha, beta, C, L, nrows, nt_i, Lp, sc);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    hsv::set_error("act1d_snakebeta: launch failed: %s", cudaGetErrorString(e));
+    return HSV_ERR_CUDA;
+  }
   return hsv::check_launch("act1d_snakebeta");
 }
 

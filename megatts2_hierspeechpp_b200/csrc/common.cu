@@ -4,6 +4,7 @@
 #include "hsv_common.cuh"
 
 namespace hsv {
+int g_pdl = 1;
 static thread_local char g_err[512] = "";
 
 void set_error(const char *fmt, ...) {
@@ -15,6 +16,12 @@ void set_error(const char *fmt, ...) {
 }  // namespace hsv
 
 extern "C" int hsv_version(void) { return HSV_VERSION; }
+
+// bring-up switch (not part of the drop-in contract): 0 disables programmatic dependent launch
+extern "C" int hsv_set_pdl(int on) {
+  hsv::g_pdl = on ? 1 : 0;
+  return HSV_OK;
+}
 
 extern "C" const char *hsv_last_error(void) { return hsv::g_err; }
 

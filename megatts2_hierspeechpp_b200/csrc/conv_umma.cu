@@ -120,6 +120,19 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) 
       "h"(cta_mask)
       : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  // one lane of the (converged) warp; lets the surrounding address arithmetic stay warp-uniform so the
+  // compiler keeps descriptors in uniform registers instead of moving them per MMA (R2UR)
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -153,6 +166,20 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                              uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -196,6 +223,7 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
   // Cluster of CL CTAs = CL consecutive M-tiles of the same (phase, n-tile, batch): they need the same
   // weights, so every CTA fetches 1/CL of each weight block and multicasts it to the whole cluster
   // (L2 -> SM weight traffic per SM drops by CL).  A stage is free again when all CL consumers released it.
+  hsv::pdl_launch_dependents();  // PDL: the next kernel may begin its prologue
   const uint32_t CL = cluster_nctarank();
   const uint32_t crank = cluster_ctarank();
   const uint16_t cmask = (uint16_t)((1u << CL) - 1u);
@@ -225,20 +253,12 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
 
   if (warp == 0 && lane == 0) {
     // ---------------- TMA producer ----------------
-    if (real_tile) {
-      const int64_t row0 = (int64_t)HSV_BLK_PAD + (int64_t)tile * TILE_M - p.tt.h_lo;
-      mbar_expect_tx(bar_a, a_bytes);
-      for (int q = 0; q < nchunks; ++q) {
-        const uint4 *src = p.a + ((int64_t)b * nchunks + q) * p.Lp + row0;
-        bulk_g2s(a_s + q * a_bytes_chunk, src, a_bytes_chunk, bar_a);
-      }
-    }
     // K-step offset of (phase, n-tile) in the packed weight stream
     int64_t ks0 = 0;
     for (int q = 0; q < ph; ++q) ks0 += (int64_t)p.tt.ntaps[q] * KC * p.nco_tiles;
     ks0 += (int64_t)nt * ksteps;
     const uint4 *wsrc = p.w + ks0 * (kstep_bytes >> 4);
-    for (int blk = 0; blk < nblocks; ++blk) {
+    auto load_w = [&](int blk) {
       const int s = blk % p.stages;
       if (blk >= p.stages) mbar_wait(bar_we + 8 * s, ((blk / p.stages) - 1) & 1);
       const int nk = min(p.G, ksteps - blk * p.G);
@@ -251,37 +271,76 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
         bulk_g2s_mc(w_s + s * wblk_bytes + crank * slice,
                     wsrc + (int64_t)blk * (wblk_bytes >> 4) + ((crank * slice) >> 4), slice, bar_wf + 8 * s, cmask);
       }
+    };
+    // weights are static: fill the ring before waiting for the kernel that produces the activations
+    const int npre = nblocks < p.stages ? nblocks : p.stages;
+    for (int blk = 0; blk < npre; ++blk) load_w(blk);
+    hsv::pdl_wait();
+    if (real_tile) {
+      const int64_t row0 = (int64_t)HSV_BLK_PAD + (int64_t)tile * TILE_M - p.tt.h_lo;
+      mbar_expect_tx(bar_a, a_bytes);
+      for (int q = 0; q < nchunks; ++q) {
+        const uint4 *src = p.a + ((int64_t)b * nchunks + q) * p.Lp + row0;
+        bulk_g2s(a_s + q * a_bytes_chunk, src, a_bytes_chunk, bar_a);
+      }
     }
+    for (int blk = npre; blk < nblocks; ++blk) load_w(blk);
   } else if (warp == 1 && lane == 0) {
     // ---------------- MMA issuer ----------------
+    // This loop runs on ONE thread, so every dependent scalar instruction per MMA is exposed latency.
+    // Weight blocks are tap-aligned (host picks G = whole taps, or a divisor of the K-steps of one tap),
+    // so the inner loop only bumps the two 14-bit address fields of the descriptors.
     // InstrDescriptor: D=F32 (1<<4), A=B=F16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
     const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
     const bool swap = p.debug & 1;
     if (real_tile) mbar_wait(bar_a, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t sbo16 = 128u >> 4, a_lbo16 = a_bytes_chunk >> 4, b_lbo16 = p.n_tile;  // 16-byte units
+    // SmemDescriptor hi word: SBO>>4 [0,14), version=1 at bit 14; lo word: addr>>4 [0,14), LBO>>4 [16,30)
+    const uint32_t a_hi = (swap ? a_lbo16 : sbo16) | (1u << 14);
+    const uint32_t b_hi = (swap ? b_lbo16 : sbo16) | (1u << 14);
+    const uint32_t a_lo0 = ((swap ? sbo16 : a_lbo16) << 16) | (a_s >> 4);   // + row + kc*2R
+    const uint32_t b_lo0 = ((swap ? sbo16 : b_lbo16) << 16) | (w_s >> 4);   // + stage*blk + g*kstep
+    const uint32_t a_kstep16 = 2u * (uint32_t)p.R, b_kstep16 = kstep_bytes >> 4, wblk16 = wblk_bytes >> 4;
+    const int G = p.G;
+    const bool whole_taps = KC <= G;            // block = m whole taps, else a tap = bpt blocks
+    const int m = whole_taps ? G / KC : 1;
+    const int bpt = whole_taps ? 1 : KC / G;
+    uint32_t acc_flag = 0;
+    int stage = 0;
+    uint32_t parity = 0;
     for (int blk = 0; blk < nblocks; ++blk) {
-      const int s = blk % p.stages;
-      mbar_wait(bar_wf + 8 * s, (blk / p.stages) & 1);
+      mbar_wait(bar_wf + 8 * stage, parity);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int nk = real_tile ? min(p.G, ksteps - blk * p.G) : 0;
-      for (int g = 0; g < nk; ++g) {
-        const int ks = blk * p.G + g;
-        const int j = ks / KC, kc = ks - j * KC;
-        const int row = p.tt.row_off[ph][j] + p.tt.h_lo;
-        const uint32_t a_addr = a_s + (uint32_t)(2 * kc * p.R + row) * 16u;
-        const uint32_t b_addr = w_s + s * wblk_bytes + g * kstep_bytes;
-        const uint32_t a_lbo = a_bytes_chunk, b_lbo = 16u * p.n_tile, sbo = 128u;
-        const uint64_t ad = swap ? make_desc(a_addr, sbo, a_lbo) : make_desc(a_addr, a_lbo, sbo);
-        const uint64_t bd = swap ? make_desc(b_addr, sbo, b_lbo) : make_desc(b_addr, b_lbo, sbo);
-        umma_f16(tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
+      if (real_tile) {
+        uint32_t b_lo = b_lo0 + (uint32_t)stage * wblk16;
+        const int j0 = whole_taps ? blk * m : blk / bpt;
+        const int nt_blk = whole_taps ? min(m, ntaps - j0) : 1;
+        const int kc0 = whole_taps ? 0 : (blk - j0 * bpt) * G;
+        const int nkc = whole_taps ? KC : G;
+        for (int tp = 0; tp < nt_blk; ++tp) {
+          uint32_t a_lo = a_lo0 + (uint32_t)(p.tt.row_off[ph][j0 + tp] + p.tt.h_lo) + (uint32_t)kc0 * a_kstep16;
+#pragma unroll 4
+          for (int kc = 0; kc < nkc; ++kc) {
+            umma_f16_lohi(tmem, a_lo, a_hi, b_lo, b_hi, idesc, acc_flag);
+            acc_flag = 1u;
+            a_lo += a_kstep16;
+            b_lo += b_kstep16;
+          }
+        }
       }
-      if (CL == 1) umma_commit(bar_we + 8 * s);
-      else umma_commit_mc(bar_we + 8 * s, cmask);  // release this stage in every CTA of the cluster
+      if (CL == 1) umma_commit(bar_we + 8 * stage);
+      else umma_commit_mc(bar_we + 8 * stage, cmask);  // release this stage in every CTA of the cluster
+      if (++stage == p.stages) {
+        stage = 0;
+        parity ^= 1u;
+      }
     }
     umma_commit(bar_acc);
   }
 
   // ---------------- epilogue: all 4 warps ----------------
+  hsv::pdl_wait();  // residual / out / acc belong to predecessor kernels
   __syncwarp();
   const int64_t t = (int64_t)tile * TILE_M + warp * 32 + lane;  // GEMM row = input time step
   const bool valid = real_tile && t < p.L;
@@ -440,13 +499,15 @@ int launch_variant(const Params &p, dim3 grid, int cluster, size_t smem, cudaStr
   cfg.blockDim = dim3(128);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cluster;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = hsv::g_pdl ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<NMAX, MINB>, p);
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -472,9 +533,22 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
   int max_ksteps = 0;
   for (int q = 0; q < tt.nphase; ++q) max_ksteps = tt.ntaps[q] * (Cin / 16) > max_ksteps ? tt.ntaps[q] * (Cin / 16) : max_ksteps;
   const int kstep_bytes = 32 * n_tile;
-  int G = 32768 / kstep_bytes;
-  if (G < 1) G = 1;
-  if (G > max_ksteps) G = max_ksteps;
+  // weight block = G K-steps (<= 32 KB), tap-aligned: whole taps if one tap fits, else a divisor of a tap
+  const int KC = Cin / 16;
+  int gmax = 32768 / kstep_bytes;
+  if (gmax < 1) gmax = 1;
+  int G;
+  if (KC <= gmax) {
+    G = KC * (gmax / KC);
+    if (G > max_ksteps) G = max_ksteps;  // max_ksteps is a multiple of KC
+  } else {
+    G = 1;
+    for (int q = gmax; q >= 1; --q)
+      if (KC % q == 0) {
+        G = q;
+        break;
+      }
+  }
   p.G = G;
   const int nblocks = (max_ksteps + G - 1) / G;
   p.stages = nblocks < MAX_STAGES ? nblocks : MAX_STAGES;

@@ -48,4 +48,12 @@ __host__ __device__ inline int64_t blk16_rows(int64_t L) {
 
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Programmatic dependent launch (PDL): a kernel launched with the attribute may start while its
+// predecessor in the stream is still running; it must execute pdl_wait() before touching any memory
+// the predecessor reads or writes.  Work that only depends on static data (weights, parameters,
+// barrier/TMEM set-up) goes before the wait and overlaps the predecessor's tail.
+extern int g_pdl;  // 0 = plain stream order (bring-up switch), 1 = PDL on the act/conv kernels
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 }  // namespace hsv

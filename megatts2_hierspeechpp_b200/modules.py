@@ -486,7 +486,9 @@ class SourceNetwork(_VocoderBase):
         self._f_post = _Folded(self.conv_post)
         self._f_cond = _Folded(self.cond)
 
-    def forward(self, x, g):
+    def forward(self, x, g, need_pred: bool = True):
+        """Returns (e, e_) like the reference (:290-308).  ``need_pred=False`` skips the f0 predictor
+        ``conv_post`` (e_ is returned as None): ``Generator`` only consumes the hidden state e."""
         x, g = _as_input(x), _as_input(g)
         xp = _dense_conv(x, self._f_pre, 7)
         cg = ops.conv1d_direct(g, self._f_cond.weight(), self._f_cond.bias())
@@ -497,7 +499,7 @@ class SourceNetwork(_VocoderBase):
             x, sc = self._stage(x, i)
         self.activation_post.check_filters()
         x = ops.act1d(x, *self.activation_post.params(), scale=sc)
-        x_ = ops.conv1d_direct(x, self._f_post.weight(), None, pad=3)
+        x_ = ops.conv1d_direct(x, self._f_post.weight(), None, pad=3) if need_pred else None
         return x, x_
 
 
@@ -672,5 +674,5 @@ class Vocoder(nn.Module):
         self.sn = SourceNetwork(c["upsample_initial_channel"] // 2)
 
     def forward(self, z, g):
-        e, _ = self.sn(z, g)
+        e, _ = self.sn(z, g, need_pred=False)
         return self.dec(z, e, g=g)
