@@ -59,6 +59,8 @@ struct Params {
   int n_tile, nco_tiles;
   int ntiles;   // real M-tiles (gridDim.x is rounded up to the cluster size; the extra CTAs only stream weights)
   int R;        // rows per chunk in the shared A tile = 128 + h_lo + h_hi
+  int Rs;       // row spacing of the chunks in shared memory (>= R; LBO_A = Rs*16 B)
+  int NB;       // rows per K-chunk of a packed weight K-step (>= n_tile; LBO_B = NB*16 B)
   int G;        // K-steps per weight block
   int stages;
   uint32_t tmem_cols;
@@ -210,13 +212,14 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
   const int ntaps = p.tt.ntaps[ph];
   const int ksteps = ntaps * KC;
   const int nblocks = (ksteps + p.G - 1) / p.G;
-  const uint32_t a_bytes_chunk = (uint32_t)p.R * 16u;
+  const uint32_t a_bytes_chunk = (uint32_t)p.R * 16u;     // bytes copied per chunk
+  const uint32_t a_pitch = (uint32_t)p.Rs * 16u;          // chunk spacing in shared memory
   const uint32_t a_bytes = a_bytes_chunk * nchunks;
-  const uint32_t kstep_bytes = 32u * p.n_tile;
+  const uint32_t kstep_bytes = 32u * p.NB;
   const uint32_t wblk_bytes = kstep_bytes * p.G;
 
   const uint32_t a_s = smem_u32(smem);
-  const uint32_t w_s = a_s + ((a_bytes + 127u) & ~127u);
+  const uint32_t w_s = a_s + ((a_pitch * nchunks + 127u) & ~127u);
   const uint32_t bar_a = smem_u32(&bars[0]), bar_acc = smem_u32(&bars[1]);
   const uint32_t bar_wf = smem_u32(&bars[2]), bar_we = smem_u32(&bars[2 + MAX_STAGES]);
 
@@ -281,7 +284,7 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
       mbar_expect_tx(bar_a, a_bytes);
       for (int q = 0; q < nchunks; ++q) {
         const uint4 *src = p.a + ((int64_t)b * nchunks + q) * p.Lp + row0;
-        bulk_g2s(a_s + q * a_bytes_chunk, src, a_bytes_chunk, bar_a);
+        bulk_g2s(a_s + q * a_pitch, src, a_bytes_chunk, bar_a);
       }
     }
     for (int blk = npre; blk < nblocks; ++blk) load_w(blk);
@@ -295,13 +298,15 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
     const bool swap = p.debug & 1;
     if (real_tile) mbar_wait(bar_a, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t sbo16 = 128u >> 4, a_lbo16 = a_bytes_chunk >> 4, b_lbo16 = p.n_tile;  // 16-byte units
+    const uint32_t sbo16 = 128u >> 4, a_lbo16 = p.Rs, b_lbo16 = p.NB;  // 16-byte units
     // SmemDescriptor hi word: SBO>>4 [0,14), version=1 at bit 14; lo word: addr>>4 [0,14), LBO>>4 [16,30)
     const uint32_t a_hi = (swap ? a_lbo16 : sbo16) | (1u << 14);
     const uint32_t b_hi = (swap ? b_lbo16 : sbo16) | (1u << 14);
-    const uint32_t a_lo0 = ((swap ? sbo16 : a_lbo16) << 16) | (a_s >> 4);   // + row + kc*2R
-    const uint32_t b_lo0 = ((swap ? sbo16 : b_lbo16) << 16) | (w_s >> 4);   // + stage*blk + g*kstep
-    const uint32_t a_kstep16 = 2u * (uint32_t)p.R, b_kstep16 = kstep_bytes >> 4, wblk16 = wblk_bytes >> 4;
+    // (inside a cluster the shared-window address carries the CTA rank in its upper bits: keep the
+    //  18-bit CTA-local offset only)
+    const uint32_t a_lo0 = ((swap ? sbo16 : a_lbo16) << 16) | ((a_s & 0x3FFFFu) >> 4);   // + row + kc*2R
+    const uint32_t b_lo0 = ((swap ? sbo16 : b_lbo16) << 16) | ((w_s & 0x3FFFFu) >> 4);   // + stage*blk + g*kstep
+    const uint32_t a_kstep16 = 2u * (uint32_t)p.Rs, b_kstep16 = kstep_bytes >> 4, wblk16 = wblk_bytes >> 4;
     const int G = p.G;
     const bool whole_taps = KC <= G;            // block = m whole taps, else a tap = bpt blocks
     const int m = whole_taps ? G / KC : 1;
@@ -407,22 +412,22 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
 // out[ph][nt][s][c2][n][e] = W(co = nt*n_tile + n, ci = 16*kc + 8*c2 + e, tap wj[ph][i]),  s = i*(Cin/16) + kc
 // element strides (s_co, s_ci) select Conv1d [Cout,Cin,k] or ConvTranspose1d [Cin,Cout,k] weights
 __global__ void pack_weight_kernel(const float *__restrict__ w, __half *__restrict__ out, int Cout, int Cin,
-                                   int k, int n_tile, int64_t s_co, int64_t s_ci, const TapTable tt) {
+                                   int k, int n_tile, int NB, int64_t s_co, int64_t s_ci, const TapTable tt) {
   const int KC = Cin >> 4;
   const int nco = Cout / n_tile;
   int64_t ph_base = 0;
   for (int ph = 0; ph < tt.nphase; ++ph) {
-    const int64_t cnt = (int64_t)tt.ntaps[ph] * KC * nco * 2 * n_tile * 8;
+    const int64_t cnt = (int64_t)tt.ntaps[ph] * KC * nco * 2 * NB * 8;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < cnt; i += (int64_t)gridDim.x * blockDim.x) {
       int64_t r = i;
       const int e = r % 8; r /= 8;
-      const int n = r % n_tile; r /= n_tile;
+      const int n = r % NB; r /= NB;
       const int c2 = r % 2; r /= 2;
       const int s = r % (tt.ntaps[ph] * KC); r /= (tt.ntaps[ph] * KC);
       const int nt = (int)r;
       const int ti = s / KC, kc = s % KC;
       const int co = nt * n_tile + n, ci = 16 * kc + 8 * c2 + e;
-      out[ph_base + i] = __float2half_rn(w[co * s_co + ci * s_ci + tt.wj[ph][ti]]);
+      out[ph_base + i] = n < n_tile ? __float2half_rn(w[co * s_co + ci * s_ci + tt.wj[ph][ti]]) : __float2half_rn(0.f);
     }
     ph_base += cnt;
   }
@@ -470,6 +475,7 @@ TapTable convT_taps(int k, int u) {
 
 int g_host_debug = 0;
 int g_cluster_override = 0;  // bring-up aid: force the cluster size (0 = automatic)
+int g_apad = 0, g_bpad = 0;  // experiment: extra rows between the K-chunks of the A tile / packed weights
 
 template <int NMAX, int MINB>
 int launch_variant(const Params &p, dim3 grid, int cluster, size_t smem, cudaStream_t st, const char *what) {
@@ -529,13 +535,15 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
   p.n_tile = n_tile; p.nco_tiles = Cout / n_tile;
   p.ntiles = (int)((L + TILE_M - 1) / TILE_M);
   p.R = TILE_M + tt.h_lo + tt.h_hi;
+  p.Rs = p.R + g_apad;
+  p.NB = n_tile + g_bpad;
   p.tt = tt;
   int max_ksteps = 0;
   for (int q = 0; q < tt.nphase; ++q) max_ksteps = tt.ntaps[q] * (Cin / 16) > max_ksteps ? tt.ntaps[q] * (Cin / 16) : max_ksteps;
-  const int kstep_bytes = 32 * n_tile;
-  // weight block = G K-steps (<= 32 KB), tap-aligned: whole taps if one tap fits, else a divisor of a tap
+  const int kstep_bytes = 32 * p.NB;
+  // weight block = G K-steps (<= 16 KB), tap-aligned: whole taps if one tap fits, else a divisor of a tap
   const int KC = Cin / 16;
-  int gmax = 32768 / kstep_bytes;
+  int gmax = 16384 / kstep_bytes;
   if (gmax < 1) gmax = 1;
   int G;
   if (KC <= gmax) {
@@ -557,9 +565,16 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
   p.tmem_cols = cols;
   p.debug = g_host_debug;
 
-  const size_t a_bytes = ((size_t)p.R * 16 * (Cin / 8) + 127) & ~(size_t)127;
+  const size_t a_bytes = ((size_t)p.Rs * 16 * (Cin / 8) + 127) & ~(size_t)127;
+  // shared-memory budget: leave room for as many co-resident CTAs per SM as the grid can use (they hide
+  // each other's prologue / epilogue latency), down to a 2-stage weight ring
+  const int64_t total_ctas = (int64_t)p.ntiles * p.nco_tiles * tt.nphase * B;
+  const int minb = n_tile <= 32 ? 8 : (n_tile <= 64 ? 4 : 2);
+  int want = (int)((total_ctas + 147) / 148);
+  want = want < 1 ? 1 : (want > minb ? minb : want);
+  const size_t budget = (size_t)(226 * 1024) / want - 1024;
   size_t smem = a_bytes + (size_t)p.stages * G * kstep_bytes;
-  while (smem > 200 * 1024 && p.stages > 2) {  // shrink the weight ring if the A tile is large
+  while (smem > budget && p.stages > 2) {
     p.stages--;
     smem = a_bytes + (size_t)p.stages * G * kstep_bytes;
   }
@@ -568,8 +583,10 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
   // (n_tile >= 64 -> K-step >= 2 KB) and there are at least two tiles to share them
   int cluster = 1;
   if (g_cluster_override > 0) cluster = g_cluster_override;
-  else if (n_tile >= 64) cluster = p.ntiles >= 8 ? 8 : (p.ntiles >= 4 ? 4 : (p.ntiles >= 2 ? 2 : 1));
+  // (measured on B200: clusters cost more in launch/co-scheduling than the multicast saves at these
+  //  sizes, so the automatic choice is 1; the path stays available through the bring-up override)
   if (n_tile < 64) cluster = 1;
+  while (cluster > 1 && (32 * p.NB) % (16 * cluster) != 0) cluster >>= 1;
   const int gx = ((p.ntiles + cluster - 1) / cluster) * cluster;
   dim3 grid((unsigned)gx, (unsigned)(p.nco_tiles * tt.nphase), (unsigned)B);
   int rc;
@@ -591,8 +608,8 @@ int pack(const float *w, void *packed, int Cout, int Cin, int k, int n_tile, int
          const TapTable &tt, cudaStream_t st, const char *what) {
   const int64_t total = (int64_t)Cout * Cin * k;
   const int blocks = (int)((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
-  pack_weight_kernel<<<blocks, 256, 0, st>>>(w, reinterpret_cast<__half *>(packed), Cout, Cin, k, n_tile, s_co,
-                                             s_ci, tt);
+  pack_weight_kernel<<<blocks, 256, 0, st>>>(w, reinterpret_cast<__half *>(packed), Cout, Cin, k, n_tile,
+                                             n_tile + g_bpad, s_co, s_ci, tt);
   return hsv::check_launch(what);
 }
 
@@ -602,6 +619,8 @@ int pack(const float *w, void *packed, int Cout, int Cin, int k, int n_tile, int
 extern "C" int hsv_set_umma_debug(int flags) {
   g_host_debug = flags & 0xff;
   g_cluster_override = (flags >> 8) & 0xff;  // bits 8..15: forced cluster size
+  g_apad = (flags >> 16) & 0xf;              // bits 16..19: A chunk padding rows
+  g_bpad = (flags >> 20) & 0xf;              // bits 20..23: weight chunk padding rows
   return HSV_OK;
 }
 

@@ -122,6 +122,12 @@ def weight_norm_fold(v: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
     return w
 
 
+def _wpad() -> int:
+    """Experimental weight-chunk padding rows (bring-up knob HSV_UMMA_DEBUG bits 20..23); 0 in production."""
+    import os
+    return (int(os.environ.get("HSV_UMMA_DEBUG", "0")) >> 20) & 0xF
+
+
 def pick_n_tile(cout: int) -> int:
     if cout <= 128:
         return cout
@@ -136,7 +142,7 @@ def pick_n_tile(cout: int) -> int:
 def pack_conv_weight(w: torch.Tensor, n_tile: int) -> torch.Tensor:
     _req(w, "w", ndim=3)
     cout, cin, k = w.shape
-    out = torch.empty(cout * cin * k, dtype=torch.float16, device=w.device)
+    out = torch.empty(cout * cin * k * (n_tile + _wpad()) // n_tile, dtype=torch.float16, device=w.device)
     lib = _lib.load()
     _lib.check(lib.hsv_pack_conv_weight(_p(w), _p(out), cout, cin, k, n_tile, _stream()), "hsv_pack_conv_weight")
     return out
@@ -151,7 +157,7 @@ def conv1d_umma(a_blk: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torc
     B = a_blk.shape[0]
     if tuple(a_blk.shape) != (B, cin // 8, blk16_rows(L), 8):
         raise ValueError(f"a_blk16 shape {tuple(a_blk.shape)} does not match Cin={cin}, L={L}")
-    if w_packed.numel() != cout * cin * k:
+    if w_packed.numel() < cout * cin * k:
         raise ValueError("w_packed size mismatch")
     for t, n in ((bias, "bias"), (residual, "residual"), (out, "out"), (acc, "acc")):
         if t is not None:
@@ -174,7 +180,7 @@ def pack_convT_weight(w: torch.Tensor, u: int, n_tile: int) -> torch.Tensor:
     """w: folded ConvTranspose1d weight [Cin, Cout, k] -> packed fp16 phase/tap stream."""
     _req(w, "w", ndim=3)
     cin, cout, k = w.shape
-    out = torch.empty(cout * cin * k, dtype=torch.float16, device=w.device)
+    out = torch.empty(cout * cin * k * (n_tile + _wpad()) // n_tile, dtype=torch.float16, device=w.device)
     lib = _lib.load()
     _lib.check(lib.hsv_pack_convT_weight(_p(w), _p(out), cin, cout, k, u, n_tile, _stream()), "hsv_pack_convT_weight")
     return out
@@ -187,7 +193,7 @@ def conv_transpose1d_umma(a_blk: torch.Tensor, w_packed: torch.Tensor, bias: Opt
     B = a_blk.shape[0]
     if tuple(a_blk.shape) != (B, cin // 8, blk16_rows(Lin), 8):
         raise ValueError(f"a_blk16 shape {tuple(a_blk.shape)} does not match Cin={cin}, L={Lin}")
-    if w_packed.numel() != cout * cin * k:
+    if w_packed.numel() < cout * cin * k:
         raise ValueError("w_packed size mismatch")
     out = torch.empty(B, cout, u * Lin, dtype=torch.float32, device=a_blk.device)
     if bias is not None:
