@@ -20,7 +20,7 @@
  *     reference's layout) unless stated otherwise;
  *   - "blk16" is the tensor-core operand layout produced by the activation
  *     kernel and consumed by hsv_conv1d_umma: fp16 [B][C/8][Lp][8] with
- *     Lp = HSV_BLK_PAD + roundup(L,128) + HSV_BLK_PAD rows per (b, 8-channel
+ *     Lp = HSV_BLK_PAD + roundup(L,HSV_BLK_ROUND) + HSV_BLK_PAD rows per (b, 8-channel
  *     chunk); rows outside [HSV_BLK_PAD, HSV_BLK_PAD+L) must be zero (they
  *     implement the conv's zero padding) and are never written.
  */
@@ -36,7 +36,8 @@ extern "C" {
 
 #define HSV_VERSION 100
 #define HSV_BLK_PAD 32          /* zero rows before/after each blk16 sequence */
-#define HSV_UMMA_TILE_M 128     /* output time rows per CTA of the tcgen05 conv */
+#define HSV_UMMA_TILE_M 128     /* rows of one tcgen05 accumulator tile */
+#define HSV_BLK_ROUND 512       /* blk16 sequences are padded to a multiple of this many rows (max CTA tile) */
 
 /* error codes */
 #define HSV_OK 0

@@ -57,7 +57,9 @@ struct Params {
   int Cin, Cout;
   int64_t L, Lp, Lout;
   int n_tile, nco_tiles;
-  int ntiles;   // real M-tiles (gridDim.x is rounded up to the cluster size; the extra CTAs only stream weights)
+  int ntiles;   // real CTA tiles (gridDim.x is rounded up to the cluster size; the extra CTAs only stream weights)
+  int msub;     // 128-row sub-tiles per CTA (1, 2 or 4): every weight K-step feeds msub MMAs, which divides the
+                // per-SM weight ingest (the B200 L2->SM port delivers ~42 B/clk, less than one N=128 MMA eats)
   int R;        // rows per chunk in the shared A tile = 128 + h_lo + h_hi
   int Rs;       // row spacing of the chunks in shared memory (>= R; LBO_A = Rs*16 B)
   int NB;       // rows per K-chunk of a packed weight K-step (>= n_tile; LBO_B = NB*16 B)
@@ -280,7 +282,7 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
     for (int blk = 0; blk < npre; ++blk) load_w(blk);
     hsv::pdl_wait();
     if (real_tile) {
-      const int64_t row0 = (int64_t)HSV_BLK_PAD + (int64_t)tile * TILE_M - p.tt.h_lo;
+      const int64_t row0 = (int64_t)HSV_BLK_PAD + (int64_t)tile * TILE_M * p.msub - p.tt.h_lo;
       mbar_expect_tx(bar_a, a_bytes);
       for (int q = 0; q < nchunks; ++q) {
         const uint4 *src = p.a + ((int64_t)b * nchunks + q) * p.Lp + row0;
@@ -307,7 +309,7 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
     const uint32_t a_lo0 = ((swap ? sbo16 : a_lbo16) << 16) | ((a_s & 0x3FFFFu) >> 4);   // + row + kc*2R
     const uint32_t b_lo0 = ((swap ? sbo16 : b_lbo16) << 16) | ((w_s & 0x3FFFFu) >> 4);   // + stage*blk + g*kstep
     const uint32_t a_kstep16 = 2u * (uint32_t)p.Rs, b_kstep16 = kstep_bytes >> 4, wblk16 = wblk_bytes >> 4;
-    const int G = p.G;
+    const int G = p.G, msub = p.msub;
     const bool whole_taps = KC <= G;            // block = m whole taps, else a tap = bpt blocks
     const int m = whole_taps ? G / KC : 1;
     const int bpt = whole_taps ? 1 : KC / G;
@@ -327,7 +329,9 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
           uint32_t a_lo = a_lo0 + (uint32_t)(p.tt.row_off[ph][j0 + tp] + p.tt.h_lo) + (uint32_t)kc0 * a_kstep16;
 #pragma unroll 4
           for (int kc = 0; kc < nkc; ++kc) {
-            umma_f16_lohi(tmem, a_lo, a_hi, b_lo, b_hi, idesc, acc_flag);
+            for (int sub = 0; sub < msub; ++sub)  // the same weight K-step feeds every 128-row sub-tile
+              umma_f16_lohi(tmem + (uint32_t)(sub * p.n_tile), a_lo + (uint32_t)(sub * TILE_M), a_hi, b_lo, b_hi, idesc,
+                            acc_flag);
             acc_flag = 1u;
             a_lo += a_kstep16;
             b_lo += b_kstep16;
@@ -347,35 +351,44 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
   // ---------------- epilogue: all 4 warps ----------------
   hsv::pdl_wait();  // residual / out / acc belong to predecessor kernels
   __syncwarp();
-  const int64_t t = (int64_t)tile * TILE_M + warp * 32 + lane;  // GEMM row = input time step
-  const bool valid = real_tile && t < p.L;
-  const int64_t o = (int64_t)p.tt.out_stride * t + p.tt.out_off[ph];
   const int co0 = nt * p.n_tile;
-  const int64_t base = ((int64_t)b * p.Cout + co0) * p.Lout + o;
-  const float *resp = p.residual ? p.residual + base : nullptr;
-  float *outp = p.out ? p.out + base : nullptr;
-  float *accp = p.acc ? p.acc + base : nullptr;
   const int64_t cs = p.Lout;  // channel stride
-  // the residual does not depend on the accumulator: fetch ALL of it (NMAX registers) while the MMAs run,
-  // so the epilogue exposes one memory latency instead of one per 16-column chunk
+  const int64_t chan_base = ((int64_t)b * p.Cout + co0) * p.Lout;
+  auto row_of = [&](int sub) { return ((int64_t)tile * p.msub + sub) * TILE_M + warp * 32 + lane; };  // GEMM row
+  auto off_of = [&](int64_t t) { return chan_base + (int64_t)p.tt.out_stride * t + p.tt.out_off[ph]; };
+  // The residual does not depend on the accumulator: fetch ALL of sub-tile 0's (NMAX registers) while the
+  // MMAs run; the registers are refilled with the next sub-tile's residual as they are consumed, so the
+  // epilogue exposes one memory latency instead of one per 16-column chunk.
   float res[NMAX];
 #pragma unroll
   for (int c = 0; c < NMAX; ++c) res[c] = 0.f;
-  if (valid && resp) {
+  {
+    const int64_t t = row_of(0);
+    if (real_tile && t < p.L && p.residual) {
+      const float *resp = p.residual + off_of(t);
 #pragma unroll
-    for (int c = 0; c < NMAX; ++c)
-      if (c < p.n_tile) res[c] = resp[c * cs];
+      for (int c = 0; c < NMAX; ++c)
+        if (c < p.n_tile) res[c] = resp[c * cs];
+    }
   }
   mbar_wait(bar_acc, 0);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   __syncwarp();
-  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+  for (int sub = 0; sub < p.msub; ++sub) {
+    const int64_t t = row_of(sub);
+    const bool valid = real_tile && t < p.L;
+    const int64_t base = off_of(t);
+    float *outp = p.out ? p.out + base : nullptr;
+    float *accp = p.acc ? p.acc + base : nullptr;
+    const int64_t tn = row_of(sub + 1);
+    const bool pre_next = real_tile && sub + 1 < p.msub && tn < p.L && p.residual;
+    const float *resn = p.residual + off_of(tn);
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(sub * p.n_tile);
 #pragma unroll
-  for (int c0 = 0; c0 < NMAX; c0 += 16) {
-    if (c0 < p.n_tile) {  // uniform
-      uint32_t r[16];
-      tmem_ld16(trow + c0, r);
-      if (valid) {
+    for (int c0 = 0; c0 < NMAX; c0 += 16) {
+      if (c0 < p.n_tile) {  // uniform
+        uint32_t r[16];
+        tmem_ld16(trow + c0, r);
         float v[16];
 #pragma unroll
         for (int c = 0; c < 16; ++c) v[c] = __uint_as_float(r[c]);
@@ -385,17 +398,22 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
         }
 #pragma unroll
         for (int c = 0; c < 16; ++c) v[c] += res[c0 + c];  // (conv + bias) + residual: the reference's order
-        if (p.acc_mode == 1) {
+        // refill with the next sub-tile's residual before this chunk's stores (out may alias residual)
 #pragma unroll
-          for (int c = 0; c < 16; ++c) accp[(int64_t)(c0 + c) * cs] = v[c];
-        } else if (p.acc_mode == 2) {
-          // red.global.add: no read, one add per element per kernel -> deterministic given stream order
+        for (int c = 0; c < 16; ++c) res[c0 + c] = pre_next ? resn[(int64_t)(c0 + c) * cs] : 0.f;
+        if (valid) {
+          if (p.acc_mode == 1) {
 #pragma unroll
-          for (int c = 0; c < 16; ++c) atomicAdd(accp + (int64_t)(c0 + c) * cs, v[c]);
-        }
-        if (outp) {
+            for (int c = 0; c < 16; ++c) accp[(int64_t)(c0 + c) * cs] = v[c];
+          } else if (p.acc_mode == 2) {
+            // red.global.add: no read, one add per element per kernel -> deterministic given stream order
 #pragma unroll
-          for (int c = 0; c < 16; ++c) outp[(int64_t)(c0 + c) * cs] = v[c];
+            for (int c = 0; c < 16; ++c) atomicAdd(accp + (int64_t)(c0 + c) * cs, v[c]);
+          }
+          if (outp) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) outp[(int64_t)(c0 + c) * cs] = v[c];
+          }
         }
       }
     }
@@ -475,6 +493,7 @@ TapTable convT_taps(int k, int u) {
 
 int g_host_debug = 0;
 int g_cluster_override = 0;  // bring-up aid: force the cluster size (0 = automatic)
+int g_msub_override = 0;     // bring-up aid: force the sub-tiles per CTA (0 = automatic)
 int g_apad = 0, g_bpad = 0;  // experiment: extra rows between the K-chunks of the A tile / packed weights
 
 template <int NMAX, int MINB>
@@ -533,8 +552,13 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
   p.acc_mode = acc_mode; p.acc_div = acc_div;
   p.Cin = Cin; p.Cout = Cout; p.L = L; p.Lp = hsv::blk16_rows(L); p.Lout = Lout;
   p.n_tile = n_tile; p.nco_tiles = Cout / n_tile;
-  p.ntiles = (int)((L + TILE_M - 1) / TILE_M);
-  p.R = TILE_M + tt.h_lo + tt.h_hi;
+  const int ntiles128 = (int)((L + TILE_M - 1) / TILE_M);
+  int msub = ntiles128 >= 2 ? 2 : 1;
+  if (g_msub_override > 0) msub = g_msub_override;
+  while (msub > 1 && (msub * n_tile > 512 || msub > ntiles128)) msub >>= 1;
+  p.msub = msub;
+  p.ntiles = (ntiles128 + msub - 1) / msub;
+  p.R = TILE_M * msub + tt.h_lo + tt.h_hi;
   p.Rs = p.R + g_apad;
   p.NB = n_tile + g_bpad;
   p.tt = tt;
@@ -543,7 +567,8 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
   const int kstep_bytes = 32 * p.NB;
   // weight block = G K-steps (<= 16 KB), tap-aligned: whole taps if one tap fits, else a divisor of a tap
   const int KC = Cin / 16;
-  int gmax = 16384 / kstep_bytes;
+  const int64_t total_ctas = (int64_t)p.ntiles * p.nco_tiles * tt.nphase * B;
+  int gmax = (total_ctas <= 148 ? 32768 : 16384) / kstep_bytes;
   if (gmax < 1) gmax = 1;
   int G;
   if (KC <= gmax) {
@@ -561,15 +586,14 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
   const int nblocks = (max_ksteps + G - 1) / G;
   p.stages = nblocks < MAX_STAGES ? nblocks : MAX_STAGES;
   uint32_t cols = 32;
-  while ((int)cols < n_tile) cols <<= 1;
+  while ((int)cols < n_tile * msub) cols <<= 1;
   p.tmem_cols = cols;
   p.debug = g_host_debug;
 
   const size_t a_bytes = ((size_t)p.Rs * 16 * (Cin / 8) + 127) & ~(size_t)127;
   // shared-memory budget: leave room for as many co-resident CTAs per SM as the grid can use (they hide
   // each other's prologue / epilogue latency), down to a 2-stage weight ring
-  const int64_t total_ctas = (int64_t)p.ntiles * p.nco_tiles * tt.nphase * B;
-  const int minb = n_tile <= 32 ? 8 : (n_tile <= 64 ? 4 : 2);
+  const int minb = n_tile <= 32 ? 6 : (n_tile <= 64 ? 4 : 2);
   int want = (int)((total_ctas + 147) / 148);
   want = want < 1 ? 1 : (want > minb ? minb : want);
   const size_t budget = (size_t)(226 * 1024) / want - 1024;
@@ -590,7 +614,7 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
   const int gx = ((p.ntiles + cluster - 1) / cluster) * cluster;
   dim3 grid((unsigned)gx, (unsigned)(p.nco_tiles * tt.nphase), (unsigned)B);
   int rc;
-  if (n_tile <= 32) rc = launch_variant<32, 8>(p, grid, cluster, smem, st, what);
+  if (n_tile <= 32) rc = launch_variant<32, 6>(p, grid, cluster, smem, st, what);
   else if (n_tile <= 64) rc = launch_variant<64, 4>(p, grid, cluster, smem, st, what);
   else rc = launch_variant<128, 2>(p, grid, cluster, smem, st, what);
   return rc;
@@ -621,6 +645,7 @@ extern "C" int hsv_set_umma_debug(int flags) {
   g_cluster_override = (flags >> 8) & 0xff;  // bits 8..15: forced cluster size
   g_apad = (flags >> 16) & 0xf;              // bits 16..19: A chunk padding rows
   g_bpad = (flags >> 20) & 0xf;              // bits 20..23: weight chunk padding rows
+  g_msub_override = (flags >> 24) & 0x7;     // bits 24..26: forced sub-tiles per CTA
   return HSV_OK;
 }
 

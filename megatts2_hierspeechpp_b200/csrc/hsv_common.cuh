@@ -43,7 +43,7 @@ inline int check_launch(const char *what) {
 #define HSV_F5 0.4432097971f
 
 __host__ __device__ inline int64_t blk16_rows(int64_t L) {
-  return 2 * (int64_t)HSV_BLK_PAD + ((L + HSV_UMMA_TILE_M - 1) / HSV_UMMA_TILE_M) * HSV_UMMA_TILE_M;
+  return 2 * (int64_t)HSV_BLK_PAD + ((L + HSV_BLK_ROUND - 1) / HSV_BLK_ROUND) * HSV_BLK_ROUND;
 }
 
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }

@@ -15,6 +15,7 @@ from . import _lib
 
 BLK_PAD = 32
 TILE_M = 128
+BLK_ROUND = 512
 
 CONV_LRELU_IN = 1
 CONV_TANH = 2
@@ -45,7 +46,7 @@ def _req(t: torch.Tensor, name: str, dtype=torch.float32, ndim: Optional[int] = 
 
 
 def blk16_rows(L: int) -> int:
-    return 2 * BLK_PAD + ((L + TILE_M - 1) // TILE_M) * TILE_M
+    return 2 * BLK_PAD + ((L + BLK_ROUND - 1) // BLK_ROUND) * BLK_ROUND
 
 
 _blk_pool: Dict[Tuple, torch.Tensor] = {}

@@ -33,9 +33,9 @@ def test_header_symbols_exported(lib):
 
 def test_version_and_helpers(lib):
     assert lib.hsv_version() == 100
-    assert lib.hsv_blk16_rows(1) == 64 + 128
-    assert lib.hsv_blk16_rows(128) == 64 + 128
-    assert lib.hsv_blk16_rows(129) == 64 + 256
+    assert lib.hsv_blk16_rows(1) == 64 + 512
+    assert lib.hsv_blk16_rows(512) == 64 + 512
+    assert lib.hsv_blk16_rows(513) == 64 + 1024
     from megatts2_hierspeechpp_b200 import ops
     for L in (1, 127, 128, 129, 2000, 160000):
         assert ops.blk16_rows(L) == lib.hsv_blk16_rows(L)
