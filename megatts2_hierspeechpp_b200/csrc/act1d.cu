@@ -390,7 +390,7 @@ extern "C" int hsv_act1d_snakebeta(const float *x, void *out, const float *alpha
   // run length per thread: 33 outputs (10 halo steps per 33: 1.15x redundant 2x-rate work) when the tensor is
   // large enough to still fill the GPU with the bigger tiles, else 17 (1.29x) for more CTAs
   const int64_t groups = ((int64_t)B * C + ROWS - 1) / ROWS;
-  const bool big = g_act_run ? g_act_run == 33 : (groups * ((L + 33 * RUNS - 1) / (33 * RUNS)) >= 4 * 148);
+  const bool big = g_act_run ? g_act_run == 33 : (groups * ((L + 33 * RUNS - 1) / (33 * RUNS)) >= 16 * 148);
   if (out_mode == 0)
     return big ? launch<33, 0>(x, out, alpha, beta, B, C, L, in_scale, st)
                : launch<17, 0>(x, out, alpha, beta, B, C, L, in_scale, st);

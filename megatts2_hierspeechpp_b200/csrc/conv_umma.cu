@@ -200,7 +200,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-template <int NMAX, int MINB>
+template <int MSUB, int MINB>
 __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bars[2 + 2 * MAX_STAGES];  // a_full, acc_full, w_full[S], w_empty[S]
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
     for (int blk = 0; blk < npre; ++blk) load_w(blk);
     hsv::pdl_wait();
     if (real_tile) {
-      const int64_t row0 = (int64_t)HSV_BLK_PAD + (int64_t)tile * TILE_M * p.msub - p.tt.h_lo;
+      const int64_t row0 = (int64_t)HSV_BLK_PAD + (int64_t)tile * TILE_M * MSUB - p.tt.h_lo;
       mbar_expect_tx(bar_a, a_bytes);
       for (int q = 0; q < nchunks; ++q) {
         const uint4 *src = p.a + ((int64_t)b * nchunks + q) * p.Lp + row0;
@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
     const uint32_t a_lo0 = ((swap ? sbo16 : a_lbo16) << 16) | ((a_s & 0x3FFFFu) >> 4);   // + row + kc*2R
     const uint32_t b_lo0 = ((swap ? sbo16 : b_lbo16) << 16) | ((w_s & 0x3FFFFu) >> 4);   // + stage*blk + g*kstep
     const uint32_t a_kstep16 = 2u * (uint32_t)p.Rs, b_kstep16 = kstep_bytes >> 4, wblk16 = wblk_bytes >> 4;
-    const int G = p.G, msub = p.msub;
+    const int G = p.G;
     const bool whole_taps = KC <= G;            // block = m whole taps, else a tap = bpt blocks
     const int m = whole_taps ? G / KC : 1;
     const int bpt = whole_taps ? 1 : KC / G;
@@ -329,7 +329,8 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
           uint32_t a_lo = a_lo0 + (uint32_t)(p.tt.row_off[ph][j0 + tp] + p.tt.h_lo) + (uint32_t)kc0 * a_kstep16;
 #pragma unroll 4
           for (int kc = 0; kc < nkc; ++kc) {
-            for (int sub = 0; sub < msub; ++sub)  // the same weight K-step feeds every 128-row sub-tile
+#pragma unroll
+            for (int sub = 0; sub < MSUB; ++sub)  // the same weight K-step feeds every 128-row sub-tile
               umma_f16_lohi(tmem + (uint32_t)(sub * p.n_tile), a_lo + (uint32_t)(sub * TILE_M), a_hi, b_lo, b_hi, idesc,
                             acc_flag);
             acc_flag = 1u;
@@ -349,72 +350,78 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
   }
 
   // ---------------- epilogue: all 4 warps ----------------
+  // A compact ROLLED loop over (sub-tile, 16-column chunk) units: the CTA has only four warps, so a fully
+  // unrolled epilogue is fetch-bound straight-line code (measured: +7 us per launch at 64 KB of SASS).
+  // Residual loads run two units ahead of their use (the first two are issued before the accumulator wait,
+  // so they overlap the MMAs); out may alias residual, hence the explicit ordering.
   hsv::pdl_wait();  // residual / out / acc belong to predecessor kernels
   __syncwarp();
   const int co0 = nt * p.n_tile;
   const int64_t cs = p.Lout;  // channel stride
-  const int64_t chan_base = ((int64_t)b * p.Cout + co0) * p.Lout;
-  auto row_of = [&](int sub) { return ((int64_t)tile * p.msub + sub) * TILE_M + warp * 32 + lane; };  // GEMM row
-  auto off_of = [&](int64_t t) { return chan_base + (int64_t)p.tt.out_stride * t + p.tt.out_off[ph]; };
-  // The residual does not depend on the accumulator: fetch ALL of sub-tile 0's (NMAX registers) while the
-  // MMAs run; the registers are refilled with the next sub-tile's residual as they are consumed, so the
-  // epilogue exposes one memory latency instead of one per 16-column chunk.
-  float res[NMAX];
-#pragma unroll
-  for (int c = 0; c < NMAX; ++c) res[c] = 0.f;
+  const int64_t chan_base = ((int64_t)b * p.Cout + co0) * p.Lout + p.tt.out_off[ph];
+  const int64_t row_base = (int64_t)tile * MSUB * TILE_M + warp * 32 + lane;  // GEMM row of sub-tile 0
+  const int nchk = p.n_tile >> 4;
+  const int nunits = MSUB * nchk;
+  const bool has_res = p.residual != nullptr;
+  auto unit_ptr = [&](int u, int64_t &off, bool &ok) {
+    const int sub = u / nchk, c0 = (u - sub * nchk) << 4;
+    const int64_t t = row_base + (int64_t)sub * TILE_M;
+    ok = real_tile && t < p.L;
+    off = chan_base + (int64_t)p.tt.out_stride * t + (int64_t)c0 * cs;
+  };
+  float ra[16], rb[16];  // residual ring: ra = unit u, rb = unit u+1
   {
-    const int64_t t = row_of(0);
-    if (real_tile && t < p.L && p.residual) {
-      const float *resp = p.residual + off_of(t);
+    int64_t off; bool ok;
+    unit_ptr(0, off, ok);
 #pragma unroll
-      for (int c = 0; c < NMAX; ++c)
-        if (c < p.n_tile) res[c] = resp[c * cs];
-    }
+    for (int c = 0; c < 16; ++c) ra[c] = (ok && has_res) ? p.residual[off + c * cs] : 0.f;
+    unit_ptr(nunits > 1 ? 1 : 0, off, ok);
+    ok = ok && nunits > 1;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) rb[c] = (ok && has_res) ? p.residual[off + c * cs] : 0.f;
   }
   mbar_wait(bar_acc, 0);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   __syncwarp();
-  for (int sub = 0; sub < p.msub; ++sub) {
-    const int64_t t = row_of(sub);
-    const bool valid = real_tile && t < p.L;
-    const int64_t base = off_of(t);
-    float *outp = p.out ? p.out + base : nullptr;
-    float *accp = p.acc ? p.acc + base : nullptr;
-    const int64_t tn = row_of(sub + 1);
-    const bool pre_next = real_tile && sub + 1 < p.msub && tn < p.L && p.residual;
-    const float *resn = p.residual + off_of(tn);
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(sub * p.n_tile);
+  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+  for (int u = 0; u < nunits; ++u) {
+    const int sub = u / nchk, c0 = (u - sub * nchk) << 4;
+    int64_t off; bool valid;
+    unit_ptr(u, off, valid);
+    uint32_t r[16];
+    tmem_ld16(trow + (uint32_t)(sub * p.n_tile + c0), r);
+    float v[16];
 #pragma unroll
-    for (int c0 = 0; c0 < NMAX; c0 += 16) {
-      if (c0 < p.n_tile) {  // uniform
-        uint32_t r[16];
-        tmem_ld16(trow + c0, r);
-        float v[16];
+    for (int c = 0; c < 16; ++c) v[c] = __uint_as_float(r[c]);
+    if (p.bias) {
 #pragma unroll
-        for (int c = 0; c < 16; ++c) v[c] = __uint_as_float(r[c]);
-        if (p.bias) {
+      for (int c = 0; c < 16; ++c) v[c] += __ldg(p.bias + co0 + c0 + c);
+    }
 #pragma unroll
-          for (int c = 0; c < 16; ++c) v[c] += __ldg(p.bias + co0 + c0 + c);
-        }
+    for (int c = 0; c < 16; ++c) v[c] += ra[c];  // (conv + bias) + residual: the reference's order
+    // rotate the ring and fetch unit u+2 before this unit's stores
 #pragma unroll
-        for (int c = 0; c < 16; ++c) v[c] += res[c0 + c];  // (conv + bias) + residual: the reference's order
-        // refill with the next sub-tile's residual before this chunk's stores (out may alias residual)
+    for (int c = 0; c < 16; ++c) ra[c] = rb[c];
+    {
+      int64_t offn; bool okn;
+      unit_ptr(u + 2 < nunits ? u + 2 : u, offn, okn);
+      okn = okn && has_res && u + 2 < nunits;
 #pragma unroll
-        for (int c = 0; c < 16; ++c) res[c0 + c] = pre_next ? resn[(int64_t)(c0 + c) * cs] : 0.f;
-        if (valid) {
-          if (p.acc_mode == 1) {
+      for (int c = 0; c < 16; ++c) rb[c] = okn ? p.residual[offn + c * cs] : 0.f;
+    }
+    if (valid) {
+      if (p.acc_mode == 1) {
 #pragma unroll
-            for (int c = 0; c < 16; ++c) accp[(int64_t)(c0 + c) * cs] = v[c];
-          } else if (p.acc_mode == 2) {
-            // red.global.add: no read, one add per element per kernel -> deterministic given stream order
+        for (int c = 0; c < 16; ++c) p.acc[off + c * cs] = v[c];
+      } else if (p.acc_mode == 2) {
+        // red.global.add: no read, one add per element per kernel -> deterministic given stream order
 #pragma unroll
-            for (int c = 0; c < 16; ++c) atomicAdd(accp + (int64_t)(c0 + c) * cs, v[c]);
-          }
-          if (outp) {
+        for (int c = 0; c < 16; ++c) atomicAdd(p.acc + off + c * cs, v[c]);
+      }
+      if (p.out) {
 #pragma unroll
-            for (int c = 0; c < 16; ++c) outp[(int64_t)(c0 + c) * cs] = v[c];
-          }
-        }
+        for (int c = 0; c < 16; ++c) p.out[off + c * cs] = v[c];
       }
     }
   }
@@ -496,7 +503,7 @@ int g_cluster_override = 0;  // bring-up aid: force the cluster size (0 = automa
 int g_msub_override = 0;     // bring-up aid: force the sub-tiles per CTA (0 = automatic)
 int g_apad = 0, g_bpad = 0;  // experiment: extra rows between the K-chunks of the A tile / packed weights
 
-template <int NMAX, int MINB>
+template <int MSUB, int MINB>
 int launch_variant(const Params &p, dim3 grid, int cluster, size_t smem, cudaStream_t st, const char *what) {
   // opt-in dynamic shared memory: 227 KB per block minus the kernel's static shared memory
   static int max_dyn[64] = {0};
@@ -505,11 +512,11 @@ int launch_variant(const Params &p, dim3 grid, int cluster, size_t smem, cudaStr
   if (dev < 0 || dev >= 64) dev = 0;
   if (max_dyn[dev] == 0) {
     cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, conv_umma_kernel<NMAX, MINB>);
+    cudaError_t e = cudaFuncGetAttributes(&fa, conv_umma_kernel<MSUB, MINB>);
     int want = 227 * 1024 - (e == cudaSuccess ? (int)fa.sharedSizeBytes : 1024);
     want &= ~1023;
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_umma_kernel<NMAX, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+      e = cudaFuncSetAttribute(conv_umma_kernel<MSUB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
     if (e != cudaSuccess) {
       cudaGetLastError();  // clear
       hsv::set_error("%s: cudaFuncSetAttribute(%d): %s", what, want, cudaGetErrorString(e));
@@ -533,7 +540,7 @@ int launch_variant(const Params &p, dim3 grid, int cluster, size_t smem, cudaStr
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = hsv::g_pdl ? 2 : 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<NMAX, MINB>, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<MSUB, MINB>, p);
   if (e != cudaSuccess) {
     cudaGetLastError();
     hsv::set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
@@ -555,7 +562,11 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
   const int ntiles128 = (int)((L + TILE_M - 1) / TILE_M);
   int msub = ntiles128 >= 2 ? 2 : 1;
   if (g_msub_override > 0) msub = g_msub_override;
-  while (msub > 1 && (msub * n_tile > 512 || msub > ntiles128)) msub >>= 1;
+  if (msub == 3) msub = 2;
+  // must fit: TMEM columns, tiles available, and the A tile (+ a 2-stage weight ring) in shared memory
+  while (msub > 1 && (msub * n_tile > 512 || msub > ntiles128 ||
+                      (size_t)(TILE_M * msub + tt.h_lo + tt.h_hi + g_apad) * 16 * (Cin / 8) + 2 * 16384 > 200 * 1024))
+    msub >>= 1;
   p.msub = msub;
   p.ntiles = (ntiles128 + msub - 1) / msub;
   p.R = TILE_M * msub + tt.h_lo + tt.h_hi;
@@ -593,7 +604,7 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
   const size_t a_bytes = ((size_t)p.Rs * 16 * (Cin / 8) + 127) & ~(size_t)127;
   // shared-memory budget: leave room for as many co-resident CTAs per SM as the grid can use (they hide
   // each other's prologue / epilogue latency), down to a 2-stage weight ring
-  const int minb = n_tile <= 32 ? 6 : (n_tile <= 64 ? 4 : 2);
+  const int minb = 4;
   int want = (int)((total_ctas + 147) / 148);
   want = want < 1 ? 1 : (want > minb ? minb : want);
   const size_t budget = (size_t)(226 * 1024) / want - 1024;
@@ -613,11 +624,9 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
   while (cluster > 1 && (32 * p.NB) % (16 * cluster) != 0) cluster >>= 1;
   const int gx = ((p.ntiles + cluster - 1) / cluster) * cluster;
   dim3 grid((unsigned)gx, (unsigned)(p.nco_tiles * tt.nphase), (unsigned)B);
-  int rc;
-  if (n_tile <= 32) rc = launch_variant<32, 6>(p, grid, cluster, smem, st, what);
-  else if (n_tile <= 64) rc = launch_variant<64, 4>(p, grid, cluster, smem, st, what);
-  else rc = launch_variant<128, 2>(p, grid, cluster, smem, st, what);
-  return rc;
+  if (p.msub == 1) return launch_variant<1, 4>(p, grid, cluster, smem, st, what);
+  if (p.msub == 2) return launch_variant<2, 4>(p, grid, cluster, smem, st, what);
+  return launch_variant<4, 4>(p, grid, cluster, smem, st, what);
 }
 
 int check_common(const char *what, const void *a, const void *w, int Cin, int Cout, int n_tile) {
