@@ -279,6 +279,48 @@ def kernel_roofline(model, dev_inputs, hbm_peak, tensor_peak, peak_kind, flush):
     return roof, extra, shares
 
 
+def saturated_rooflines(dev, hbm_peak, tensor_peak):
+    """The two hot kernels timed alone at a size that fills the GPU and exceeds L2 (config #3's per-layer
+    shape, batch 16: [16,32,480000]): what the kernels sustain when the workload is not latency-bound."""
+    import megatts2_hierspeechpp_b200 as hsv
+
+    B, C, L, k, d = 16, 32, 480000, 7, 3
+    x = torch.randn(B, C, L, device=dev)
+    a = torch.zeros(C, device=dev)
+    buf = hsv.ops.blk16_buffer(B, C, L, dev, slot=5)
+
+    def timeit(fn, n=5):
+        fn(); fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    ms_act = timeit(lambda: hsv.ops.act1d_blk16(x, a, a, buf))
+    w = torch.randn(C, C, k, device=dev) * 0.05
+    wp = hsv.ops.pack_conv_weight(w, C)
+    out = torch.empty_like(x)
+    ms_conv = timeit(lambda: hsv.ops.conv1d_umma(buf, wp, a, L, C, C, k, d, C, residual=x, out=out))
+    n = B * C * L
+    act_gbs = 6.0 * n / (ms_act * 1e-3) / 1e9
+    conv_gbs = 10.0 * n / (ms_conv * 1e-3) / 1e9
+    conv_tf = 2.0 * B * C * C * k * L / (ms_conv * 1e-3) / 1e12
+    del x, out
+    return {
+        "shape": "[16,32,480000] (SpeechSR48 layer, batch 16; inputs > L2)",
+        "act1d_kernel": {"bound": "hbm", "achieved": act_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": act_gbs / hbm_peak,
+                         "ms": ms_act, "bytes": "4 B read + 2 B written per element"},
+        "conv_umma_kernel": {"bound": "hbm", "achieved": conv_gbs, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": conv_gbs / hbm_peak, "ms": ms_conv, "tflops": conv_tf,
+                             "bytes": "2 B operand + 4 B residual read + 4 B written per element (C=32, k=7: "
+                                      "HBM-bound, SURVEY.md §7.3)"},
+    }
+
+
 def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -373,7 +415,7 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms, e2e_ms = float(t[0]), float(t[1])
 
-        roof = extra = shares = cpu = None
+        roof = extra = shares = cpu = sat = None
         if rank == 0:
             par = [m for m in model.modules() if getattr(m, "parallel_blocks", False)]
             for m in par:
@@ -381,6 +423,10 @@ def run_b200(args):
             roof, extra, shares = kernel_roofline(model, dev_in, hbm_peak, tensor_peak, peak_kind, flush)
             for m in par:
                 m.parallel_blocks = True
+            try:
+                sat = saturated_rooflines(dev, hbm_peak, tensor_peak)
+            except Exception as e:  # e.g. not enough free memory next to a large workload
+                sat = {"error": str(e)[:200]}
             if world == 1 and not args.no_cpu_baseline:
                 cores = os.cpu_count() or 1
                 torch.set_num_threads(cores)
@@ -413,7 +459,8 @@ def run_b200(args):
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches_per_step * args.steps,
         "launches_per_step": launches_per_step,
-        "clocks": clocks, "roofline": roof, "roofline_other": extra, "kernel_shares": shares, "cpu_baseline": cpu,
+        "clocks": clocks, "roofline": roof, "roofline_other": extra, "roofline_saturated": sat, "kernel_shares": shares,
+        "cpu_baseline": cpu,
         "step_ms_min_med_max": [min(step_ms), statistics.median(step_ms), max(step_ms)],
     }
     print(json.dumps(line), flush=True)

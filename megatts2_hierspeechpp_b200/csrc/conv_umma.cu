@@ -560,7 +560,11 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
   p.Cin = Cin; p.Cout = Cout; p.L = L; p.Lp = hsv::blk16_rows(L); p.Lout = Lout;
   p.n_tile = n_tile; p.nco_tiles = Cout / n_tile;
   const int ntiles128 = (int)((L + TILE_M - 1) / TILE_M);
-  int msub = ntiles128 >= 2 ? 2 : 1;
+  // Measured on B200: with the SWIZZLE_NONE operand layout one 128x128x16 MMA occupies the tensor pipe for
+  // ~150 cycles (vs 64 at peak), so the kernel is MMA-bound, not weight-ingest-bound, and extra sub-tiles
+  // per CTA only lengthen the serial MMA chain of each CTA.  Default 1; 2/4 stay available (override) for
+  // the throughput regime once the operands move to a swizzled layout.
+  int msub = 1;
   if (g_msub_override > 0) msub = g_msub_override;
   if (msub == 3) msub = 2;
   // must fit: TMEM columns, tiles available, and the A tile (+ a 2-stage weight ring) in shared memory
@@ -604,7 +608,7 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
   const size_t a_bytes = ((size_t)p.Rs * 16 * (Cin / 8) + 127) & ~(size_t)127;
   // shared-memory budget: leave room for as many co-resident CTAs per SM as the grid can use (they hide
   // each other's prologue / epilogue latency), down to a 2-stage weight ring
-  const int minb = 4;
+  const int minb = n_tile <= 32 ? 6 : (n_tile <= 64 ? 4 : 2);
   int want = (int)((total_ctas + 147) / 148);
   want = want < 1 ? 1 : (want > minb ? minb : want);
   const size_t budget = (size_t)(226 * 1024) / want - 1024;
@@ -624,9 +628,15 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
   while (cluster > 1 && (32 * p.NB) % (16 * cluster) != 0) cluster >>= 1;
   const int gx = ((p.ntiles + cluster - 1) / cluster) * cluster;
   dim3 grid((unsigned)gx, (unsigned)(p.nco_tiles * tt.nphase), (unsigned)B);
-  if (p.msub == 1) return launch_variant<1, 4>(p, grid, cluster, smem, st, what);
-  if (p.msub == 2) return launch_variant<2, 4>(p, grid, cluster, smem, st, what);
-  return launch_variant<4, 4>(p, grid, cluster, smem, st, what);
+  // small n_tile = HBM/latency-bound streaming layers: they want many co-resident CTAs (register cap 80);
+  // large n_tile = few fat CTAs per SM anyway
+  if (p.msub == 1) {
+    if (n_tile <= 32) return launch_variant<1, 6>(p, grid, cluster, smem, st, what);
+    if (n_tile <= 64) return launch_variant<1, 4>(p, grid, cluster, smem, st, what);
+    return launch_variant<1, 2>(p, grid, cluster, smem, st, what);
+  }
+  if (p.msub == 2) return launch_variant<2, 3>(p, grid, cluster, smem, st, what);
+  return launch_variant<4, 2>(p, grid, cluster, smem, st, what);
 }
 
 int check_common(const char *what, const void *a, const void *w, int Cin, int Cout, int n_tile) {
