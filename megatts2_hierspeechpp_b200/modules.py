@@ -235,23 +235,32 @@ class _Folded:
             self.key = key
         return self.w
 
-    def packed_weight(self):
+    def packed_weight(self, row_tiles: int = 1 << 30):
+        """(packed fp16 operand stream, n_tile) for a launch with ``row_tiles`` 128-row tiles (x batch)."""
         w = self.weight()
         if self.packed is None:
-            self.n_tile = ops.pick_n_tile(w.shape[0])
-            self.packed = ops.pack_conv_weight(w, self.n_tile)
-        return self.packed, self.n_tile
+            self.packed = {}
+        nt = ops.pick_n_tile(w.shape[0], row_tiles)
+        if nt not in self.packed:
+            self.packed[nt] = ops.pack_conv_weight(w, nt)
+        return self.packed[nt], nt
 
-    def packedT_weight(self, u: int):
+    def packedT_weight(self, u: int, row_tiles: int = 1 << 30):
         w = self.weight()
         if self.packed is None:
-            self.n_tile = ops.pick_n_tile(w.shape[1])
-            self.packed = ops.pack_convT_weight(w, u, self.n_tile)
-        return self.packed, self.n_tile
+            self.packed = {}
+        nt = ops.pick_n_tile(w.shape[1], row_tiles * u)
+        if nt not in self.packed:
+            self.packed[nt] = ops.pack_convT_weight(w, u, nt)
+        return self.packed[nt], nt
 
     def bias(self):
         b = getattr(self.conv, "bias", None)
         return None if b is None else b.detach()
+
+
+def _row_tiles(B: int, L: int) -> int:
+    return B * ((L + ops.TILE_M - 1) // ops.TILE_M)
 
 
 _MAIN_SLOT = 3   # blk16 workspace slot of the main stream (slots 0..2 belong to the per-resblock streams)
@@ -267,7 +276,7 @@ def _dense_conv(x: torch.Tensor, f: _Folded, k: int, d: int = 1, lrelu: bool = F
     if C % 16 == 0 and cout % 16 == 0 and ((k - 1) // 2) * d <= ops.BLK_PAD:
         buf = ops.blk16_buffer(B, C, L, x.device, _MAIN_SLOT)
         ops.pack_blk16(x, buf, lrelu)
-        wp, nt = f.packed_weight()
+        wp, nt = f.packed_weight(_row_tiles(B, L))
         return ops.conv1d_umma(buf, wp, f.bias(), L, C, cout, k, d, nt, residual=residual)
     pad = ((k - 1) // 2) * d
     if residual is not None:
@@ -285,7 +294,7 @@ def _dense_convT(x: torch.Tensor, f: _Folded, k: int, u: int, add: Optional[torc
     if C % 16 == 0 and cout % 16 == 0:
         buf = ops.blk16_buffer(B, C, L, x.device, _MAIN_SLOT)
         ops.pack_blk16(x, buf, scale=scale)
-        wp, nt = f.packedT_weight(u)
+        wp, nt = f.packedT_weight(u, _row_tiles(B, L))
         return ops.conv_transpose1d_umma(buf, wp, f.bias(), L, C, cout, k, u, nt, add=add)
     if scale != 1.0:
         raise NotImplementedError("channel counts that are not multiples of 16 are not supported on this path")
@@ -332,8 +341,8 @@ class AMPBlock1(nn.Module):
         for i, d in enumerate(self.dilation):
             a1, a2 = self.activations[2 * i], self.activations[2 * i + 1]
             a1.check_filters(); a2.check_filters()
-            w1, nt1 = self._f1[i].packed_weight()
-            w2, nt2 = self._f2[i].packed_weight()
+            w1, nt1 = self._f1[i].packed_weight(_row_tiles(B, L))
+            w2, nt2 = self._f2[i].packed_weight(_row_tiles(B, L))
             ops.act1d_blk16(cur, *a1.params(), buf)
             ops.conv1d_umma(buf, w1, self._f1[i].bias(), L, C, C, k, d, nt1, out=xt)
             ops.act1d_blk16(xt, *a2.params(), buf)

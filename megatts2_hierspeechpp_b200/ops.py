@@ -129,15 +129,23 @@ def _wpad() -> int:
     return (int(os.environ.get("HSV_UMMA_DEBUG", "0")) >> 20) & 0xF
 
 
-def pick_n_tile(cout: int) -> int:
-    if cout <= 128:
-        return cout
-    if cout % 128 == 0:
-        return 128
-    for n in range(128, 15, -16):
-        if cout % n == 0:
+def pick_n_tile(cout: int, row_tiles: int = 1 << 30) -> int:
+    """Output-channel tile of the tcgen05 conv.  ``row_tiles`` = number of 128-row tiles x batch x phases of the
+    launch: with few row tiles (batch-1 latency regime) a narrower n_tile puts more CTAs to work on the same
+    layer (shorter serial MMA chain and weight stream per CTA); with many, the widest tile (<= 128) has the
+    best tensor/shared-memory efficiency."""
+    cands = [n for n in (128, 64, 32, 16) if cout % n == 0]
+    if not cands:
+        for n in range(128, 15, -16):
+            if cout % n == 0:
+                cands = [n]
+                break
+    if not cands:
+        raise ValueError(f"Cout={cout} not a multiple of 16")
+    for n in cands:
+        if n <= 32 or row_tiles * (cout // n) >= 120:
             return n
-    raise ValueError(f"Cout={cout} not a multiple of 16")
+    return cands[-1]
 
 
 def pack_conv_weight(w: torch.Tensor, n_tile: int) -> torch.Tensor:
