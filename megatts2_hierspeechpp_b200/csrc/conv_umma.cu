@@ -200,7 +200,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-template <int MSUB, int MINB>
+template <int MSUB, int MINB, bool SMALLN>
 __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bars[2 + 2 * MAX_STAGES];  // a_full, acc_full, w_full[S], w_empty[S]
@@ -369,6 +369,48 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
     ok = real_tile && t < p.L;
     off = chan_base + (int64_t)p.tt.out_stride * t + (int64_t)c0 * cs;
   };
+  if constexpr (SMALLN) {
+    // n_tile <= 32 (one or two units, MSUB == 1): the streaming layers.  Everything is preloaded before the
+    // accumulator wait and the code is short enough to unroll; fits 64 registers -> 8 CTAs per SM.
+    int64_t off; bool valid;
+    unit_ptr(0, off, valid);
+    float res[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) res[c] = (valid && has_res && c < p.n_tile) ? p.residual[off + c * cs] : 0.f;
+    mbar_wait(bar_acc, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    __syncwarp();
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+    for (int c0 = 0; c0 < 32; c0 += 16) {
+      if (c0 < p.n_tile) {
+        uint32_t r[16];
+        tmem_ld16(trow + c0, r);
+        if (valid) {
+          float v[16];
+#pragma unroll
+          for (int c = 0; c < 16; ++c) v[c] = __uint_as_float(r[c]);
+          if (p.bias) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) v[c] += __ldg(p.bias + co0 + c0 + c);
+          }
+#pragma unroll
+          for (int c = 0; c < 16; ++c) v[c] += res[c0 + c];
+          if (p.acc_mode == 1) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) p.acc[off + (c0 + c) * cs] = v[c];
+          } else if (p.acc_mode == 2) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) atomicAdd(p.acc + off + (c0 + c) * cs, v[c]);
+          }
+          if (p.out) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) p.out[off + (c0 + c) * cs] = v[c];
+          }
+        }
+      }
+    }
+  } else {
   float ra[16], rb[16];  // residual ring: ra = unit u, rb = unit u+1
   {
     int64_t off; bool ok;
@@ -424,6 +466,7 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
         for (int c = 0; c < 16; ++c) p.out[off + c * cs] = v[c];
       }
     }
+  }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -503,7 +546,7 @@ int g_cluster_override = 0;  // bring-up aid: force the cluster size (0 = automa
 int g_msub_override = 0;     // bring-up aid: force the sub-tiles per CTA (0 = automatic)
 int g_apad = 0, g_bpad = 0;  // experiment: extra rows between the K-chunks of the A tile / packed weights
 
-template <int MSUB, int MINB>
+template <int MSUB, int MINB, bool SMALLN>
 int launch_variant(const Params &p, dim3 grid, int cluster, size_t smem, cudaStream_t st, const char *what) {
   // opt-in dynamic shared memory: 227 KB per block minus the kernel's static shared memory
   static int max_dyn[64] = {0};
@@ -512,11 +555,11 @@ int launch_variant(const Params &p, dim3 grid, int cluster, size_t smem, cudaStr
   if (dev < 0 || dev >= 64) dev = 0;
   if (max_dyn[dev] == 0) {
     cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, conv_umma_kernel<MSUB, MINB>);
+    cudaError_t e = cudaFuncGetAttributes(&fa, conv_umma_kernel<MSUB, MINB, SMALLN>);
     int want = 227 * 1024 - (e == cudaSuccess ? (int)fa.sharedSizeBytes : 1024);
     want &= ~1023;
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_umma_kernel<MSUB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+      e = cudaFuncSetAttribute(conv_umma_kernel<MSUB, MINB, SMALLN>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
     if (e != cudaSuccess) {
       cudaGetLastError();  // clear
       hsv::set_error("%s: cudaFuncSetAttribute(%d): %s", what, want, cudaGetErrorString(e));
@@ -540,7 +583,7 @@ int launch_variant(const Params &p, dim3 grid, int cluster, size_t smem, cudaStr
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = hsv::g_pdl ? 2 : 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<MSUB, MINB>, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<MSUB, MINB, SMALLN>, p);
   if (e != cudaSuccess) {
     cudaGetLastError();
     hsv::set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
@@ -608,7 +651,7 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
   const size_t a_bytes = ((size_t)p.Rs * 16 * (Cin / 8) + 127) & ~(size_t)127;
   // shared-memory budget: leave room for as many co-resident CTAs per SM as the grid can use (they hide
   // each other's prologue / epilogue latency), down to a 2-stage weight ring
-  const int minb = n_tile <= 32 ? 6 : (n_tile <= 64 ? 4 : 2);
+  const int minb = n_tile <= 32 ? 8 : (n_tile <= 64 ? 4 : 2);
   int want = (int)((total_ctas + 147) / 148);
   want = want < 1 ? 1 : (want > minb ? minb : want);
   const size_t budget = (size_t)(226 * 1024) / want - 1024;
@@ -631,12 +674,12 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
   // small n_tile = HBM/latency-bound streaming layers: they want many co-resident CTAs (register cap 80);
   // large n_tile = few fat CTAs per SM anyway
   if (p.msub == 1) {
-    if (n_tile <= 32) return launch_variant<1, 6>(p, grid, cluster, smem, st, what);
-    if (n_tile <= 64) return launch_variant<1, 4>(p, grid, cluster, smem, st, what);
-    return launch_variant<1, 2>(p, grid, cluster, smem, st, what);
+    if (n_tile <= 32) return launch_variant<1, 8, true>(p, grid, cluster, smem, st, what);
+    if (n_tile <= 64) return launch_variant<1, 4, false>(p, grid, cluster, smem, st, what);
+    return launch_variant<1, 2, false>(p, grid, cluster, smem, st, what);
   }
-  if (p.msub == 2) return launch_variant<2, 3>(p, grid, cluster, smem, st, what);
-  return launch_variant<4, 2>(p, grid, cluster, smem, st, what);
+  if (p.msub == 2) return launch_variant<2, 3, false>(p, grid, cluster, smem, st, what);
+  return launch_variant<4, 2, false>(p, grid, cluster, smem, st, what);
 }
 
 int check_common(const char *what, const void *a, const void *w, int Cin, int Cout, int n_tile) {
