@@ -165,3 +165,18 @@ def test_weight_cache_invalidation(hsv):
     ref = OF.speechsr(sd2, x.cpu(), 24)
     _check("SpeechSR24 after reload", y2, ref)
     assert not torch.equal(y1, y2)
+
+
+def test_two_gpu_sharding_matches_single(hsv):
+    """N>1 path on real GPUs: torchrun x2 (NCCL barrier + final gather only), sharded == single-process."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541",
+                        os.path.join(root, "tools", "multi_gpu_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "MULTI_GPU_OK world=2" in r.stdout
