@@ -180,3 +180,45 @@ def test_two_gpu_sharding_matches_single(hsv):
                         os.path.join(root, "tools", "multi_gpu_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "MULTI_GPU_OK world=2" in r.stdout
+
+
+@pytest.mark.parametrize("T", [1, 2, 3, 7])
+def test_vocoder_tiny_lengths(vocoder, T):
+    """Sequences shorter than every tile / halo in the path (T=1 frame -> 320 samples)."""
+    z, gg = synth.vocoder_inputs(2, T, seed=40 + T)
+    ref = OF.vocoder(synth.vocoder_sd(1234), z, gg)
+    wav = vocoder(z.to(DEV), gg.to(DEV))
+    assert wav.shape == (2, 1, 320 * T)
+    _check(f"vocoder T={T}", wav, ref)
+
+
+def test_empty_batch_and_ragged_buckets(hsv, vocoder):
+    z, gg = synth.vocoder_inputs(1, 8)
+    out = vocoder(z[:0].to(DEV), gg[:0].to(DEV))
+    assert out.shape == (0, 1, 2560)
+    # ragged utterances: equal-length buckets, results identical to running each alone
+    from megatts2_hierspeechpp_b200.runtime import bucket_by_length
+    lengths = [9, 5, 9, 7, 5]
+    ins = [synth.vocoder_inputs(1, lengths[i], seed=60 + i) for i in range(5)]
+    got = {}
+    for mb in bucket_by_length(range(5), lengths, max_batch=2):
+        w = vocoder(torch.cat([ins[i][0] for i in mb]).to(DEV), torch.cat([ins[i][1] for i in mb]).to(DEV))
+        for j, i in enumerate(mb):
+            got[i] = w[j:j + 1].clone()
+    for i in range(5):
+        assert torch.equal(got[i], vocoder(ins[i][0].to(DEV), ins[i][1].to(DEV)))
+
+
+def test_config4_vocoder_then_speechsr24(hsv, vocoder):
+    """Config #4's timed stage: vocoder output (tanh range) fed straight into SpeechSR24 (inference_plm.py:176-179)."""
+    sd_sr = golden_sd("speechsr24_state.npz")
+    sr = hsv.SpeechSR24(100, 40, **hsv.SR_CFG)
+    sr.load_state_dict(sd_sr, strict=True)
+    sr.to(DEV).eval()
+    z, gg = synth.vocoder_inputs(1, 50, seed=77)
+    wav16 = vocoder(z.to(DEV), gg.to(DEV))
+    wav24 = sr(wav16)
+    assert wav24.shape == (1, 1, 24000)
+    ref16 = OF.vocoder(synth.vocoder_sd(1234), z, gg)
+    ref24 = OF.speechsr(sd_sr, ref16, 24)
+    _check("vocoder -> SpeechSR24 chain", wav24, ref24)
