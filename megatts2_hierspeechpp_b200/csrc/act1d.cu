@@ -382,6 +382,7 @@ extern "C" int hsv_set_act_variant(int v) {
 
 extern "C" int hsv_act1d_snakebeta(const float *x, void *out, const float *alpha, const float *beta, int B,
                                    int C, int64_t L, int out_mode, float in_scale, void *stream) {
+  if (B == 0 || L == 0) return HSV_OK;  // empty batch / sequence
   HSV_REQUIRE(x && out && alpha && beta, "act1d: null pointer");
   HSV_REQUIRE(B >= 0 && C > 0 && L >= 0, "act1d: bad shape B=%d C=%d L=%lld", B, C, (long long)L);
   HSV_REQUIRE(out_mode == 0 || out_mode == 1, "act1d: out_mode must be 0 (fp32 NCL) or 1 (fp16 blk16)");

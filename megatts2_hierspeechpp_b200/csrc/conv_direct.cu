@@ -429,6 +429,7 @@ inline int grid_for(int64_t n, int threads) {
 extern "C" int hsv_conv1d_direct(const float *x, const float *w, const float *bias, float *out, int B, int Cin,
                                  int Cout, int64_t Lin, int64_t Lout, int k, int d, int pad, int flags,
                                  void *stream) {
+  if (B == 0 || Lout <= 0) return HSV_OK;  // empty batch / sequence
   HSV_REQUIRE(x && w && out, "conv1d_direct: null pointer");
   HSV_REQUIRE(Cin > 0 && Cout > 0 && k >= 1 && k <= KMAX && d >= 1, "conv1d_direct: bad shape");
   HSV_REQUIRE((k - 1) * d <= HALO_MAX, "conv1d_direct: (k-1)*d=%d exceeds %d", (k - 1) * d, HALO_MAX);
@@ -459,6 +460,7 @@ extern "C" int hsv_conv1d_direct(const float *x, const float *w, const float *bi
 extern "C" int hsv_conv_transpose1d_direct(const float *x, const float *w, const float *bias, const float *add,
                                            float *out, int B, int Cin, int Cout, int64_t Lin, int k, int u,
                                            void *stream) {
+  if (B == 0 || Lin == 0) return HSV_OK;
   HSV_REQUIRE(x && w && out, "conv_transpose1d: null pointer");
   HSV_REQUIRE(Cin > 0 && Cout > 0 && u >= 1 && k >= u && k <= KMAX, "conv_transpose1d: bad shape k=%d u=%d", k, u);
   HSV_REQUIRE((k + u - 1) / u <= 4, "conv_transpose1d: more than 4 taps per phase");
@@ -476,6 +478,7 @@ extern "C" int hsv_conv_transpose1d_direct(const float *x, const float *w, const
 
 extern "C" int hsv_sr_pre_interp(const float *x, const float *w, const float *bias, float *out, int B, int C,
                                  int64_t Lin, int64_t Lout, void *stream) {
+  if (B == 0) return HSV_OK;
   HSV_REQUIRE(x && w && out, "sr_pre_interp: null pointer");
   HSV_REQUIRE(C > 0 && Lin > 0 && Lout > 0, "sr_pre_interp: bad shape");
   if (B == 0) return HSV_OK;
@@ -494,6 +497,7 @@ extern "C" int hsv_interp_linear_table(int64_t Lin, int64_t Lout, int32_t *i0, i
 }
 
 extern "C" int hsv_nearest_gather(const float *x, float *out, int rows, int64_t Lin, int64_t Lout, void *stream) {
+  if (rows == 0) return HSV_OK;
   HSV_REQUIRE(x && out && rows >= 0 && Lin > 0 && Lout > 0, "nearest_gather: bad argument");
   if (rows == 0) return HSV_OK;
   const float scale = (float)Lin / (float)Lout;  // ATen compute_scales_value
@@ -504,6 +508,7 @@ extern "C" int hsv_nearest_gather(const float *x, float *out, int rows, int64_t 
 
 extern "C" int hsv_add3_bcast(const float *a, const float *b, const float *bc, float *out, int rows, int64_t L,
                               void *stream) {
+  if (rows == 0 || L == 0) return HSV_OK;
   HSV_REQUIRE(a && out && rows >= 0 && L >= 0, "add3_bcast: bad argument");
   if (rows == 0 || L == 0) return HSV_OK;
   add3_bcast_kernel<<<grid_for((int64_t)rows * L, 256), 256, 0, hsv::as_stream(stream)>>>(a, b, bc, out, rows, L);
@@ -518,7 +523,9 @@ extern "C" int hsv_weight_norm_fold(const float *v, const float *g, float *w, in
 
 extern "C" int hsv_pack_blk16(const float *x, void *out, int B, int C, int64_t L, int lrelu, float in_scale,
                               void *stream) {
-  HSV_REQUIRE(x && out && C > 0 && C % 8 == 0, "pack_blk16: C %% 8 != 0 (C=%d)", C);
+  if (B == 0 || L == 0) return HSV_OK;
+  HSV_REQUIRE(x && out, "pack_blk16: null pointer");
+  HSV_REQUIRE(C > 0 && C % 8 == 0, "pack_blk16: C %% 8 != 0 (C=%d)", C);
   if (B == 0 || L == 0) return HSV_OK;
   pack_blk16_kernel<<<grid_for((int64_t)B * (C / 8) * L, 256), 256, 0, hsv::as_stream(stream)>>>(
       x, reinterpret_cast<uint4 *>(out), B, C, L, hsv::blk16_rows(L), lrelu, in_scale);

@@ -731,6 +731,7 @@ extern "C" int hsv_pack_convT_weight(const float *w, void *packed, int Cin, int 
 extern "C" int hsv_conv1d_umma(const void *a_blk16, const void *w_packed, const float *bias,
                                const float *residual, float *out, float *acc, int acc_mode, float acc_div,
                                int B, int Cin, int Cout, int64_t L, int k, int d, int n_tile, void *stream) {
+  if (B == 0 || L == 0) return HSV_OK;  // empty batch / sequence
   if (int rc = check_common("conv1d_umma", a_blk16, w_packed, Cin, Cout, n_tile)) return rc;
   HSV_REQUIRE(k >= 1 && k <= MAX_TAPS && (k & 1) && d >= 1, "conv1d_umma: k must be odd and <= %d (k=%d d=%d)",
               MAX_TAPS, k, d);
@@ -746,6 +747,7 @@ extern "C" int hsv_conv1d_umma(const void *a_blk16, const void *w_packed, const 
 extern "C" int hsv_conv_transpose1d_umma(const void *a_blk16, const void *w_packed, const float *bias,
                                          const float *add, float *out, int B, int Cin, int Cout, int64_t Lin,
                                          int k, int u, int n_tile, void *stream) {
+  if (B == 0 || Lin == 0) return HSV_OK;
   if (int rc = check_common("conv_transpose1d_umma", a_blk16, w_packed, Cin, Cout, n_tile)) return rc;
   HSV_REQUIRE(u >= 1 && u <= MAX_PHASES && k >= u && k <= MAX_TAPS && k - 2 * ((k - u) / 2) == u,
               "conv_transpose1d_umma: unsupported (k,u)=(%d,%d)", k, u);
