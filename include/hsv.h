@@ -19,10 +19,16 @@
  *   - activations are fp32, layout [B, C, L] contiguous ("NCL", the
  *     reference's layout) unless stated otherwise;
  *   - "blk16" is the tensor-core operand layout produced by the activation
- *     kernel and consumed by hsv_conv1d_umma: fp16 [B][C/8][Lp][8] with
- *     Lp = HSV_BLK_PAD + roundup(L,HSV_BLK_ROUND) + HSV_BLK_PAD rows per (b, 8-channel
- *     chunk); rows outside [HSV_BLK_PAD, HSV_BLK_PAD+L) must be zero (they
- *     implement the conv's zero padding) and are never written.
+ *     kernel and consumed by hsv_conv1d_umma: fp16 [B][C/CW][Lp][CW], CW = 64
+ *     (C % 64 == 0), else 32 (C % 32 == 0), else 16 channels per row, with
+ *     Lp = HSV_BLK_PAD + roundup(L,HSV_BLK_ROUND) + HSV_BLK_PAD rows per (b, chunk);
+ *     within the buffer of one (b, chunk) the 16-byte unit at linear byte offset
+ *     o is stored at o ^ (((o >> 7) & (CW/8 - 1)) << 4)  -- tcgen05's K-major
+ *     SWIZZLE_128B/64B/32B pattern, so a linear (1-D bulk TMA) copy of a row span
+ *     into 1024-byte aligned shared memory is a ready MMA operand tile.  Rows
+ *     outside [HSV_BLK_PAD, HSV_BLK_PAD+L) must be zero (they implement the
+ *     conv's zero padding) and are never written.  Treat the buffer as opaque:
+ *     hsv_pack_blk16 / hsv_unpack_blk16 convert from / to fp32 [B,C,L].
  */
 #ifndef HSV_H_
 #define HSV_H_
@@ -59,7 +65,7 @@ int64_t hsv_blk16_rows(int64_t L);
  *   x      [B,C,L] fp32
  *   alpha, beta [C] fp32 (log scale, as stored in the state_dict)
  *   out_mode 0: out = fp32 [B,C,L]
- *   out_mode 1: out = fp16 blk16 (C % 8 == 0), rows per chunk = hsv_blk16_rows(L)
+ *   out_mode 1: out = fp16 blk16 (C % 16 == 0), rows per chunk = hsv_blk16_rows(L)
  *   in_scale    x is multiplied by this first (1/num_kernels: the "xs / self.num_kernels" of
  *               hierspeechpp_speechsynthesizer.py:446 when x is the un-normalised sum over resblocks)
  */
@@ -74,8 +80,9 @@ int hsv_act1d_snakebeta(const float *x, void *out, const float *alpha, const flo
 int hsv_weight_norm_fold(const float *v, const float *g, float *w, int n0, int inner, void *stream);
 
 /* ---- pack a folded Conv1d weight [Cout,Cin,k] fp32 into the tcgen05 B-operand
- * stream: fp16 [Cout/n_tile][k*Cin/16][2][n_tile][8] (K-major core matrices).
- * Cin % 16 == 0, Cout % n_tile == 0, n_tile % 16 == 0, n_tile <= 128.
+ * stream: fp16 [Cout/n_tile][Cin/CW][k] blocks of n_tile rows x CW channels
+ * (K-major, swizzled like blk16).  Cin % 16 == 0, Cout % n_tile == 0,
+ * n_tile % 16 == 0, n_tile <= 256.  Size: Cout*Cin*k halves.
  */
 int hsv_pack_conv_weight(const float *w, void *packed, int Cout, int Cin, int k, int n_tile, void *stream);
 
@@ -83,7 +90,7 @@ int hsv_pack_conv_weight(const float *w, void *packed, int Cout, int Cin, int k,
  * the AMPBlock convs (hierspeechpp_speechsynthesizer.py:349-364,380-384;
  * speechsr24k/speechsr.py:21-36,52-56): F.conv1d(x, w, b, dilation=d,
  * padding=(k*d-d)/2), fp16 operands, fp32 accumulation, fused epilogue.
- *   a_blk16   fp16 blk16 activations [B][Cin/8][Lp][8]
+ *   a_blk16   fp16 blk16 activations (B*Cin*Lp halves)
  *   w_packed  from hsv_pack_conv_weight (same n_tile)
  *   bias      [Cout] fp32 or NULL
  *   residual  [B,Cout,L] fp32 or NULL     (v = acc + bias + residual)
@@ -99,8 +106,8 @@ int hsv_conv1d_umma(const void *a_blk16, const void *w_packed, const float *bias
 /* ---- ConvTranspose1d (ups[i], hierspeechpp_speechsynthesizer.py:404-408,434) on the same
  * tcgen05 kernel: the u output phases are u stride-1 convolutions over the input rows
  * (SURVEY.md §A.3), each an N-tile group of one launch.
- *   hsv_pack_convT_weight: w [Cin,Cout,k] fp32 (folded) -> fp16 [phase][Cout/n_tile][taps*Cin/16][2][n_tile][8]
- *   hsv_conv_transpose1d_umma: a_blk16 [B][Cin/8][Lp(Lin)][8] -> out [B,Cout,u*Lin] fp32,
+ *   hsv_pack_convT_weight: w [Cin,Cout,k] fp32 (folded) -> fp16 [phase][Cout/n_tile][Cin/CW][taps] blocks
+ *   hsv_conv_transpose1d_umma: a_blk16 (rows per chunk = hsv_blk16_rows(Lin)) -> out [B,Cout,u*Lin] fp32,
  *   out = convT + bias (+ add, same shape as out: proj(pitch) at stage 0, :436-438).
  *   stride u <= 8, padding (k-u)/2, k - 2*((k-u)/2) == u (true for every (k,u) on the path).
  */
@@ -157,8 +164,10 @@ int hsv_nearest_gather(const float *x, float *out, int rows, int64_t Lin, int64_
 int hsv_add3_bcast(const float *a, const float *b, const float *bc, float *out,
                    int rows, int64_t L, void *stream);
 
-/* fp32 [B,C,L] * in_scale -> fp16 blk16 (optional leaky_relu(0.1) first); C % 8 == 0. */
+/* fp32 [B,C,L] * in_scale -> fp16 blk16 (optional leaky_relu(0.1) first); C % 16 == 0. */
 int hsv_pack_blk16(const float *x, void *out, int B, int C, int64_t L, int lrelu, float in_scale, void *stream);
+/* inverse (tests / debugging): fp16 blk16 -> fp32 [B,C,L]. */
+int hsv_unpack_blk16(const void *in, float *x, int B, int C, int64_t L, void *stream);
 
 #ifdef __cplusplus
 }

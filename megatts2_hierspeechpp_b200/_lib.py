@@ -38,6 +38,7 @@ SIGNATURES = {
     "hsv_nearest_gather": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p]),
     "hsv_add3_bcast": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p]),
     "hsv_pack_blk16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_float, c_void_p]),
+    "hsv_unpack_blk16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p]),
 }
 
 # bring-up aids exported by the library but not part of the drop-in contract
@@ -45,6 +46,8 @@ _EXTRA = {
     "hsv_set_umma_debug": (c_int, [c_int]),
     "hsv_set_act_variant": (c_int, [c_int]),
     "hsv_set_pdl": (c_int, [c_int]),
+    "hsv_set_layout": (c_int, [c_int]),
+    "hsv_get_layout": (c_int, []),
 }
 
 _lib = None
@@ -71,6 +74,8 @@ def load() -> ctypes.CDLL:
         fn.argtypes = args
     if lib.hsv_version() != 100:
         raise HsvError(f"libhsv.so version {lib.hsv_version()} does not match the Python binding (100)")
+    if os.environ.get("HSV_LAYOUT"):
+        lib.hsv_set_layout(int(os.environ["HSV_LAYOUT"]))
     if os.environ.get("HSV_UMMA_DEBUG"):
         lib.hsv_set_umma_debug(int(os.environ["HSV_UMMA_DEBUG"]))
     if os.environ.get("HSV_PDL"):

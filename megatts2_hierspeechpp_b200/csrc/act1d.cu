@@ -192,7 +192,7 @@ template <int R, int OUT_MODE, bool PACKED>
 __global__ void __launch_bounds__(NT) act1d_kernel(const float *__restrict__ x, void *__restrict__ outp,
                                                    const float *__restrict__ alpha,
                                                    const float *__restrict__ beta, int C, int64_t L,
-                                                   int64_t nrows, int ntiles, int64_t Lp, float sc) {
+                                                   int64_t nrows, int ntiles, int64_t Lp, float sc, int cw) {
   using K = Cfg<R>;
   // x_s[c][p] holds x[row0+c][t0 - XOFF + p]; XOFF = 8 keeps the tile start 16-byte aligned for TMA
   __shared__ __align__(16) float x_s[ROWS * K::PITCH];
@@ -200,8 +200,20 @@ __global__ void __launch_bounds__(NT) act1d_kernel(const float *__restrict__ x, 
   __shared__ __align__(8) uint64_t bar;
 
   const int tid = threadIdx.x;
-  const int tile = blockIdx.x % ntiles;
-  const int64_t rowgrp = blockIdx.x / ntiles;
+  int tile;
+  int64_t rowgrp;
+  if (OUT_MODE == 1 && cw > 0) {
+    // swizzled operand output: the cw/8 CTAs that fill the 16-byte units of the same operand rows are adjacent
+    // in launch order, so their partial-sector writes meet in L2
+    const int upc = cw >> 3;
+    const int u = blockIdx.x % upc;
+    const int64_t rest = blockIdx.x / upc;
+    tile = (int)(rest % ntiles);
+    rowgrp = (rest / ntiles) * upc + u;
+  } else {
+    tile = blockIdx.x % ntiles;
+    rowgrp = blockIdx.x / ntiles;
+  }
   const int64_t row0 = rowgrp * ROWS;
   const int64_t t0 = (int64_t)tile * K::TILE;
   const int c = tid % ROWS, run = tid / ROWS;
@@ -325,12 +337,22 @@ __global__ void __launch_bounds__(NT) act1d_kernel(const float *__restrict__ x, 
       for (int j = 0; j < R; ++j) o_h[(run * R + j) * 8 + c] = __float2half_rn(outv[j]);
     }
     __syncthreads();
-    // rows row0..row0+7 are one 8-channel chunk of one batch item (C % 8 == 0)
-    const int64_t chunk = row0 / 8;  // == b*(C/8) + q
-    uint4 *dst = reinterpret_cast<uint4 *>(outp) + chunk * Lp + HSV_BLK_PAD + t0;
+    // rows row0..row0+7 are one 8-channel unit of one batch item (C % 8 == 0)
     const uint4 *src = reinterpret_cast<const uint4 *>(o_s);
-    for (int p = tid; p < K::TILE; p += NT) {
-      if (t0 + p < L) dst[p] = src[p];
+    if (cw > 0) {
+      const int64_t bb = row0 / C;
+      const int c0 = (int)(row0 - bb * C);
+      uint8_t *base = reinterpret_cast<uint8_t *>(outp);
+      for (int p = tid; p < K::TILE; p += NT) {
+        if (t0 + p < L)
+          *reinterpret_cast<uint4 *>(base + hsv::blk_unit_offset(cw, Lp, C, bb, c0, HSV_BLK_PAD + t0 + p)) = src[p];
+      }
+    } else {
+      const int64_t chunk = row0 / 8;  // == b*(C/8) + q
+      uint4 *dst = reinterpret_cast<uint4 *>(outp) + chunk * Lp + HSV_BLK_PAD + t0;
+      for (int p = tid; p < K::TILE; p += NT) {
+        if (t0 + p < L) dst[p] = src[p];
+      }
     }
   }
 }
@@ -358,11 +380,12 @@ int launch(const float *x, void *out, const float *alpha, const float *beta, int
   cfg.numAttrs = hsv::g_pdl ? 1 : 0;
   const int nt_i = (int)ntiles;
   const int64_t Lp = hsv::blk16_rows(L);
+  const int cw = (OUT_MODE == 1 && hsv::g_layout == 1) ? hsv::blk_cw(C) : 0;
   cudaError_t e;
   if (g_act_variant)
-    e = cudaLaunchKernelEx(&cfg, act1d_kernel<R, OUT_MODE, true>, x, out, alpha, beta, C, L, nrows, nt_i, Lp, sc);
+    e = cudaLaunchKernelEx(&cfg, act1d_kernel<R, OUT_MODE, true>, x, out, alpha, beta, C, L, nrows, nt_i, Lp, sc, cw);
   else
-    e = cudaLaunchKernelEx(&cfg, act1d_kernel<R, OUT_MODE, false>, x, out, alpha, beta, C, L, nrows, nt_i, Lp, sc);
+    e = cudaLaunchKernelEx(&cfg, act1d_kernel<R, OUT_MODE, false>, x, out, alpha, beta, C, L, nrows, nt_i, Lp, sc, cw);
   if (e != cudaSuccess) {
     cudaGetLastError();
     hsv::set_error("act1d_snakebeta: launch failed: %s", cudaGetErrorString(e));
@@ -395,7 +418,8 @@ extern "C" int hsv_act1d_snakebeta(const float *x, void *out, const float *alpha
   if (out_mode == 0)
     return big ? launch<33, 0>(x, out, alpha, beta, B, C, L, in_scale, st)
                : launch<17, 0>(x, out, alpha, beta, B, C, L, in_scale, st);
-  HSV_REQUIRE(C % 8 == 0, "act1d: blk16 output needs C %% 8 == 0 (C=%d)", C);
+  HSV_REQUIRE(C % (hsv::g_layout == 1 ? 16 : 8) == 0, "act1d: blk16 output needs C %% %d == 0 (C=%d)",
+              hsv::g_layout == 1 ? 16 : 8, C);
   return big ? launch<33, 1>(x, out, alpha, beta, B, C, L, in_scale, st)
              : launch<17, 1>(x, out, alpha, beta, B, C, L, in_scale, st);
 }

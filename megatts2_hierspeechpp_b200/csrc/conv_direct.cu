@@ -398,7 +398,7 @@ __global__ void weight_norm_fold_kernel(const float *__restrict__ v, const float
 
 // fp32 [B,C,L] -> fp16 blk16; one thread per (b, chunk, t)
 __global__ void pack_blk16_kernel(const float *__restrict__ x, uint4 *__restrict__ out, int B, int C, int64_t L,
-                                  int64_t Lp, int lrelu, float sc) {
+                                  int64_t Lp, int lrelu, float sc, int cw) {
   const int nch = C >> 3;
   const int64_t n = (int64_t)B * nch * L;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -414,7 +414,37 @@ __global__ void pack_blk16_kernel(const float *__restrict__ x, uint4 *__restrict
       }
       h[e] = __floats2half2_rn(v0, v1);
     }
-    out[bq * Lp + HSV_BLK_PAD + t] = *reinterpret_cast<uint4 *>(h);
+    if (cw > 0) {
+      const int64_t bb = bq / nch;
+      const int c0 = (int)(bq - bb * nch) * 8;
+      *reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(out) +
+                                 hsv::blk_unit_offset(cw, Lp, C, bb, c0, HSV_BLK_PAD + t)) = *reinterpret_cast<uint4 *>(h);
+    } else {
+      out[bq * Lp + HSV_BLK_PAD + t] = *reinterpret_cast<uint4 *>(h);
+    }
+  }
+}
+
+// inverse of pack_blk16 (test / debugging aid): blk16 -> fp32 [B,C,L]
+__global__ void unpack_blk16_kernel(const uint4 *__restrict__ in, float *__restrict__ x, int B, int C, int64_t L,
+                                    int64_t Lp, int cw) {
+  const int nch = C >> 3;
+  const int64_t n = (int64_t)B * nch * L;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t bq = i / L, t = i - bq * L;
+    uint4 v;
+    if (cw > 0) {
+      const int64_t bb = bq / nch;
+      const int c0 = (int)(bq - bb * nch) * 8;
+      v = *reinterpret_cast<const uint4 *>(reinterpret_cast<const uint8_t *>(in) +
+                                           hsv::blk_unit_offset(cw, Lp, C, bb, c0, HSV_BLK_PAD + t));
+    } else {
+      v = in[bq * Lp + HSV_BLK_PAD + t];
+    }
+    const __half *h = reinterpret_cast<const __half *>(&v);
+    float *xr = x + bq * 8 * L + t;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) xr[e * L] = __half2float(h[e]);
   }
 }
 
@@ -525,9 +555,20 @@ extern "C" int hsv_pack_blk16(const float *x, void *out, int B, int C, int64_t L
                               void *stream) {
   if (B == 0 || L == 0) return HSV_OK;
   HSV_REQUIRE(x && out, "pack_blk16: null pointer");
-  HSV_REQUIRE(C > 0 && C % 8 == 0, "pack_blk16: C %% 8 != 0 (C=%d)", C);
-  if (B == 0 || L == 0) return HSV_OK;
+  const int gran = hsv::g_layout == 1 ? 16 : 8;
+  HSV_REQUIRE(C > 0 && C % gran == 0, "pack_blk16: C %% %d != 0 (C=%d)", gran, C);
   pack_blk16_kernel<<<grid_for((int64_t)B * (C / 8) * L, 256), 256, 0, hsv::as_stream(stream)>>>(
-      x, reinterpret_cast<uint4 *>(out), B, C, L, hsv::blk16_rows(L), lrelu, in_scale);
+      x, reinterpret_cast<uint4 *>(out), B, C, L, hsv::blk16_rows(L), lrelu, in_scale,
+      hsv::g_layout == 1 ? hsv::blk_cw(C) : 0);
   return hsv::check_launch("pack_blk16");
+}
+
+extern "C" int hsv_unpack_blk16(const void *in, float *x, int B, int C, int64_t L, void *stream) {
+  if (B == 0 || L == 0) return HSV_OK;
+  HSV_REQUIRE(in && x, "unpack_blk16: null pointer");
+  const int gran = hsv::g_layout == 1 ? 16 : 8;
+  HSV_REQUIRE(C > 0 && C % gran == 0, "unpack_blk16: C %% %d != 0 (C=%d)", gran, C);
+  unpack_blk16_kernel<<<grid_for((int64_t)B * (C / 8) * L, 256), 256, 0, hsv::as_stream(stream)>>>(
+      reinterpret_cast<const uint4 *>(in), x, B, C, L, hsv::blk16_rows(L), hsv::g_layout == 1 ? hsv::blk_cw(C) : 0);
+  return hsv::check_launch("unpack_blk16");
 }

@@ -1,4 +1,4 @@
-// Dense Conv1d / ConvTranspose1d as a tcgen05 / TMEM implicit GEMM (sm_100a).
+// Dense Conv1d / ConvTranspose1d as a tcgen05 / TMEM implicit GEMM (sm_100a), swizzled operands.
 //
 // Replaces the weight-normed convolutions of the reference's waveform path
 //   * AMPBlock convs    hierspeechpp_speechsynthesizer.py:349-364,380-384; speechsr24k/speechsr.py:21-36,52-56
@@ -8,24 +8,23 @@
 //   conv1d      out[t]       = b + sum_j  W[:, :, j]        a[t + (j-(k-1)/2) d]
 //   convT phase out[u q + r] = b + sum_i  W[:, :, r' + i u] a[q + c - i]      (r' = (r+p) mod u, c = (r+p) div u)
 // GEMM view per CTA:  D[M = 128 rows, N = n_tile out channels] += A_tap[128 x 16] * W_tap[16 x n_tile]
-// over all taps and 16-channel K-steps; fp16 operands, fp32 accumulation in TMEM.
+// over all channel chunks, taps and 16-channel K-steps; fp16 operands, fp32 accumulation in TMEM.
 //
-// Operand staging.  Activations arrive in the "blk16" layout written by the fused activation kernel
-// (or hsv_pack_blk16): fp16 [B][Cin/8][Lp][8] -- per 8-channel chunk the time rows are consecutive
-// 16-byte records with zero rows around every sequence.  A time tile (+halo) of one chunk is ONE
-// contiguous span, fetched with a 1-D bulk TMA copy into shared memory as [chunk][row][8 halves].
-// That is tcgen05's K-major SWIZZLE_NONE canonical layout with SBO = 128 B (8 rows x 16 B) and
-// LBO = rows*16 B, in which rows of one K-chunk are uniformly 16 B apart -- so the operand of a tap is
-// the SAME shared tile with the descriptor start address advanced by the tap's row offset.  The halo is
-// loaded once and reused by all taps; zero padding comes from the zero rows of the blk16 layout.
-// Weights are pre-packed as [phase][n-tile][K-step][2][n_tile][8] fp16 so a group of K-steps is one
-// contiguous span, streamed through a ring of shared stages by bulk TMA copies (mbarrier full/empty).
+// Operand staging.  Activations arrive in the swizzled "blk16" layout written by the fused activation kernel
+// (or hsv_pack_blk16): fp16 [B][Cin/CW][Lp][CW], CW = 64/32/16 channels per row, zero rows around every
+// sequence, 16-byte units XOR-swizzled with the row index (hsv_common.cuh).  A time tile (+halo, start rounded
+// down to a multiple of 8 rows) of one chunk is ONE contiguous span, fetched with a 1-D bulk TMA copy to a
+// 1024-byte aligned shared address: that IS tcgen05's K-major SWIZZLE_128B/64B/32B canonical layout (row pitch
+// = swizzle width, SBO = 8 rows).  Because the swizzle is a function of the shared-memory address bits, the
+// operand of a tap is the SAME tile with the descriptor start address advanced by the tap's row offset: the
+// halo is loaded once and reused by all taps; zero padding comes from the zero rows of the layout.
+// Weights are pre-packed per (phase, n-tile) as a stream of [chunk][tap] blocks of n_tile rows x CW channels in
+// the same swizzled K-major form, streamed through a ring of shared stages by bulk TMA copies.
 //
 // Roles (128 threads): warp0/lane0 TMA producer, warp1/lane0 MMA issuer, warp2 TMEM alloc/free, then all
 // four warps run the epilogue: tcgen05.ld (lane = row), + bias, + residual, store fp32 [B,C,L] (for
 // stride-1 outputs a warp stores 32 consecutive time steps of one channel = 128 B coalesced) and
-// optionally accumulate the mean over resblocks.  Residual loads are batched per 16-column chunk and
-// prefetched one chunk ahead (out may alias residual, so the compiler cannot do this itself).
+// optionally accumulate the sum over resblocks.
 #include "hsv_common.cuh"
 
 namespace {
@@ -34,6 +33,7 @@ constexpr int TILE_M = HSV_UMMA_TILE_M;  // 128
 constexpr int MAX_STAGES = 4;
 constexpr int MAX_PHASES = 8;
 constexpr int MAX_TAPS = 16;
+constexpr int MAX_CHUNKS = 16;
 
 struct TapTable {
   int nphase;
@@ -46,24 +46,24 @@ struct TapTable {
 };
 
 struct Params {
-  const uint4 *a;   // blk16 activations, 16-byte records
-  const uint4 *w;   // packed weights
+  const uint8_t *a;   // swizzled blk16 activations
+  const uint8_t *w;   // packed weights
   const float *bias;
   const float *residual;
   float *out;
   float *acc;
   int acc_mode;
-  float acc_div;
   int Cin, Cout;
   int64_t L, Lp, Lout;
   int n_tile, nco_tiles;
-  int ntiles;   // real CTA tiles (gridDim.x is rounded up to the cluster size; the extra CTAs only stream weights)
-  int msub;     // 128-row sub-tiles per CTA (1, 2 or 4): every weight K-step feeds msub MMAs, which divides the
-                // per-SM weight ingest (the B200 L2->SM port delivers ~42 B/clk, less than one N=128 MMA eats)
-  int R;        // rows per chunk in the shared A tile = 128 + h_lo + h_hi
-  int Rs;       // row spacing of the chunks in shared memory (>= R; LBO_A = Rs*16 B)
-  int NB;       // rows per K-chunk of a packed weight K-step (>= n_tile; LBO_B = NB*16 B)
-  int G;        // K-steps per weight block
+  int ntiles;
+  int msub;          // 128-row sub-tiles per CTA (1, 2 or 4): every weight K-step feeds msub MMAs
+  int cw;            // channels per operand row (64 / 32 / 16)
+  int nchunks;       // Cin / cw
+  int R;             // rows per chunk of the shared A tile = 128*msub + hlo8 + h_hi
+  int hlo8;          // halo rows before the tile, rounded up to a multiple of 8 (swizzle phase alignment)
+  uint32_t a_pitch;  // bytes between chunks of the shared A tile (multiple of 1024)
+  int G;             // weight blocks ([chunk][tap] units) per ring stage
   int stages;
   uint32_t tmem_cols;
   int debug;
@@ -109,69 +109,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
       "l"(src), "r"(bytes), "r"(bar)
       : "memory");
 }
-__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar,
-                                            uint16_t cta_mask) {
-  // multicast: the bytes land at the same shared offset of every CTA in cta_mask and complete_tx is
-  // signalled on the mbarrier at the same offset of each of them
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
-      "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-      "h"(cta_mask)
-      : "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-  // one lane of the (converged) warp; lets the surrounding address arithmetic stay warp-uniform so the
-  // compiler keeps descriptors in uniform registers instead of moving them per MMA (R2UR)
-  uint32_t pred;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}"
-      : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ uint32_t cluster_nctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  // cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
-  // base_offset 0, layout SWIZZLE_NONE (0) [61,64)
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  return d;
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                         uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 __device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
                                               uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -200,46 +137,40 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// bars: [0] acc_full, [1 .. 1+MAX_CHUNKS) a_full[chunk], then w_full[S], w_empty[S]
+constexpr int BAR_A = 1, BAR_WF = 1 + MAX_CHUNKS, BAR_WE = BAR_WF + MAX_STAGES, NBARS = BAR_WE + MAX_STAGES;
+
 template <int MSUB, int MINB, bool SMALLN>
 __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_constant__ Params p) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bars[2 + 2 * MAX_STAGES];  // a_full, acc_full, w_full[S], w_empty[S]
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[NBARS];
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x, b = blockIdx.z;
   const int ph = blockIdx.y / p.nco_tiles, nt = blockIdx.y - ph * p.nco_tiles;
-  const int nchunks = p.Cin >> 3;
-  const int KC = p.Cin >> 4;
   const int ntaps = p.tt.ntaps[ph];
-  const int ksteps = ntaps * KC;
-  const int nblocks = (ksteps + p.G - 1) / p.G;
-  const uint32_t a_bytes_chunk = (uint32_t)p.R * 16u;     // bytes copied per chunk
-  const uint32_t a_pitch = (uint32_t)p.Rs * 16u;          // chunk spacing in shared memory
-  const uint32_t a_bytes = a_bytes_chunk * nchunks;
-  const uint32_t kstep_bytes = 32u * p.NB;
-  const uint32_t wblk_bytes = kstep_bytes * p.G;
+  const int nblocks = p.nchunks * ntaps;          // [chunk][tap] weight blocks of this (phase, n-tile)
+  const int nrounds = (nblocks + p.G - 1) / p.G;  // ring rounds
+  const uint32_t rowbytes = (uint32_t)p.cw * 2u;
+  const uint32_t a_chunk_bytes = (uint32_t)p.R * rowbytes;
+  const uint32_t blk_bytes = (uint32_t)p.n_tile * rowbytes;
+  const uint32_t stage_bytes = blk_bytes * (uint32_t)p.G;
 
-  const uint32_t a_s = smem_u32(smem);
-  const uint32_t w_s = a_s + ((a_pitch * nchunks + 127u) & ~127u);
-  const uint32_t bar_a = smem_u32(&bars[0]), bar_acc = smem_u32(&bars[1]);
-  const uint32_t bar_wf = smem_u32(&bars[2]), bar_we = smem_u32(&bars[2 + MAX_STAGES]);
+  // swizzled tiles want 1024-byte aligned shared addresses: align by hand (1 KB slack is budgeted by the host)
+  const uint32_t a_s = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t w_s = a_s + p.a_pitch * (uint32_t)p.nchunks;
+  const uint32_t bar0 = smem_u32(&bars[0]);
+  const uint32_t bar_acc = bar0, bar_a = bar0 + 8 * BAR_A, bar_wf = bar0 + 8 * BAR_WF, bar_we = bar0 + 8 * BAR_WE;
 
-  // Cluster of CL CTAs = CL consecutive M-tiles of the same (phase, n-tile, batch): they need the same
-  // weights, so every CTA fetches 1/CL of each weight block and multicasts it to the whole cluster
-  // (L2 -> SM weight traffic per SM drops by CL).  A stage is free again when all CL consumers released it.
   hsv::pdl_launch_dependents();  // PDL: the next kernel may begin its prologue
-  const uint32_t CL = cluster_nctarank();
-  const uint32_t crank = cluster_ctarank();
-  const uint16_t cmask = (uint16_t)((1u << CL) - 1u);
-  const bool real_tile = tile < p.ntiles;
 
   if (threadIdx.x == 0) {
-    mbar_init(bar_a, 1);
     mbar_init(bar_acc, 1);
+    for (int c = 0; c < p.nchunks; ++c) mbar_init(bar_a + 8 * c, 1);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(bar_wf + 8 * s, 1);
-      mbar_init(bar_we + 8 * s, CL);
+      mbar_init(bar_we + 8 * s, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -252,95 +183,83 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (CL > 1) cluster_sync_all();  // every CTA's barriers are initialised before any remote arrive / multicast
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_base_s;
 
   if (warp == 0 && lane == 0) {
     // ---------------- TMA producer ----------------
-    // K-step offset of (phase, n-tile) in the packed weight stream
-    int64_t ks0 = 0;
-    for (int q = 0; q < ph; ++q) ks0 += (int64_t)p.tt.ntaps[q] * KC * p.nco_tiles;
-    ks0 += (int64_t)nt * ksteps;
-    const uint4 *wsrc = p.w + ks0 * (kstep_bytes >> 4);
-    auto load_w = [&](int blk) {
-      const int s = blk % p.stages;
-      if (blk >= p.stages) mbar_wait(bar_we + 8 * s, ((blk / p.stages) - 1) & 1);
-      const int nk = min(p.G, ksteps - blk * p.G);
-      const uint32_t bytes = kstep_bytes * nk;
-      mbar_expect_tx(bar_wf + 8 * s, bytes);  // the whole block lands here: own slice + the peers' multicasts
-      if (CL == 1) {
-        bulk_g2s(w_s + s * wblk_bytes, wsrc + (int64_t)blk * (wblk_bytes >> 4), bytes, bar_wf + 8 * s);
-      } else {
-        const uint32_t slice = bytes / CL;  // multiple of 16: kstep_bytes >= 2048 whenever CL > 1
-        bulk_g2s_mc(w_s + s * wblk_bytes + crank * slice,
-                    wsrc + (int64_t)blk * (wblk_bytes >> 4) + ((crank * slice) >> 4), slice, bar_wf + 8 * s, cmask);
-      }
+    int64_t blk0 = 0;  // first weight block of (phase, n-tile) in the packed stream
+    for (int q = 0; q < ph; ++q) blk0 += (int64_t)p.tt.ntaps[q] * p.nchunks * p.nco_tiles;
+    blk0 += (int64_t)nt * nblocks;
+    const uint8_t *wsrc = p.w + blk0 * blk_bytes;
+    auto load_w = [&](int rnd) {
+      const int s = rnd % p.stages;
+      if (rnd >= p.stages) mbar_wait(bar_we + 8 * s, ((rnd / p.stages) - 1) & 1);
+      const int nb = min(p.G, nblocks - rnd * p.G);
+      const uint32_t bytes = blk_bytes * (uint32_t)nb;
+      mbar_expect_tx(bar_wf + 8 * s, bytes);
+      bulk_g2s(w_s + s * stage_bytes, wsrc + (int64_t)rnd * stage_bytes, bytes, bar_wf + 8 * s);
     };
     // weights are static: fill the ring before waiting for the kernel that produces the activations
-    const int npre = nblocks < p.stages ? nblocks : p.stages;
-    for (int blk = 0; blk < npre; ++blk) load_w(blk);
+    const int npre = nrounds < p.stages ? nrounds : p.stages;
+    for (int rnd = 0; rnd < npre; ++rnd) load_w(rnd);
     hsv::pdl_wait();
-    if (real_tile) {
-      const int64_t row0 = (int64_t)HSV_BLK_PAD + (int64_t)tile * TILE_M * MSUB - p.tt.h_lo;
-      mbar_expect_tx(bar_a, a_bytes);
-      for (int q = 0; q < nchunks; ++q) {
-        const uint4 *src = p.a + ((int64_t)b * nchunks + q) * p.Lp + row0;
-        bulk_g2s(a_s + q * a_pitch, src, a_bytes_chunk, bar_a);
-      }
+    const int64_t row0 = (int64_t)HSV_BLK_PAD + (int64_t)tile * TILE_M * MSUB - p.hlo8;  // multiple of 8
+    for (int c = 0; c < p.nchunks; ++c) {
+      const uint8_t *src = p.a + (((int64_t)b * p.nchunks + c) * p.Lp + row0) * rowbytes;
+      mbar_expect_tx(bar_a + 8 * c, a_chunk_bytes);
+      bulk_g2s(a_s + c * p.a_pitch, src, a_chunk_bytes, bar_a + 8 * c);
     }
-    for (int blk = npre; blk < nblocks; ++blk) load_w(blk);
+    for (int rnd = npre; rnd < nrounds; ++rnd) load_w(rnd);
   } else if (warp == 1 && lane == 0) {
     // ---------------- MMA issuer ----------------
     // This loop runs on ONE thread, so every dependent scalar instruction per MMA is exposed latency.
-    // Weight blocks are tap-aligned (host picks G = whole taps, or a divisor of the K-steps of one tap),
-    // so the inner loop only bumps the two 14-bit address fields of the descriptors.
     // InstrDescriptor: D=F32 (1<<4), A=B=F16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
     const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
-    const bool swap = p.debug & 1;
-    if (real_tile) mbar_wait(bar_a, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t sbo16 = 128u >> 4, a_lbo16 = p.Rs, b_lbo16 = p.NB;  // 16-byte units
-    // SmemDescriptor hi word: SBO>>4 [0,14), version=1 at bit 14; lo word: addr>>4 [0,14), LBO>>4 [16,30)
-    const uint32_t a_hi = (swap ? a_lbo16 : sbo16) | (1u << 14);
-    const uint32_t b_hi = (swap ? b_lbo16 : sbo16) | (1u << 14);
-    // (inside a cluster the shared-window address carries the CTA rank in its upper bits: keep the
-    //  18-bit CTA-local offset only)
-    const uint32_t a_lo0 = ((swap ? sbo16 : a_lbo16) << 16) | ((a_s & 0x3FFFFu) >> 4);   // + row + kc*2R
-    const uint32_t b_lo0 = ((swap ? sbo16 : b_lbo16) << 16) | ((w_s & 0x3FFFFu) >> 4);   // + stage*blk + g*kstep
-    const uint32_t a_kstep16 = 2u * (uint32_t)p.Rs, b_kstep16 = kstep_bytes >> 4, wblk16 = wblk_bytes >> 4;
-    const int G = p.G;
-    const bool whole_taps = KC <= G;            // block = m whole taps, else a tap = bpt blocks
-    const int m = whole_taps ? G / KC : 1;
-    const int bpt = whole_taps ? 1 : KC / G;
+    // SmemDescriptor (cute::UMMA::SmemDescriptor): lo = start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled
+    // K-major); hi = SBO>>4 [0,14) (8 rows) | version=1 [14,16) | base_offset [17,20) | layout [29,32)
+    const uint32_t layout = p.cw == 64 ? 2u : (p.cw == 32 ? 4u : 6u);  // SWIZZLE_128B / 64B / 32B
+    const uint32_t hi0 = ((8u * rowbytes) >> 4) | (1u << 14) | (layout << 29);
+    const uint32_t swz_mask = (uint32_t)(p.cw >> 3) - 1u;
+    const int bo_mode = p.debug & 3;  // bring-up: 0 = base_offset 0 (swizzle is a function of the absolute address)
+    const uint32_t row16 = rowbytes >> 4;
+    const uint32_t a0 = (a_s & 0x3FFFFu) >> 4, w0 = (w_s & 0x3FFFFu) >> 4;
+    const uint32_t a_pitch16 = p.a_pitch >> 4, stage16 = stage_bytes >> 4, blk16 = blk_bytes >> 4;
+    const int KS = p.cw >> 4;  // K-steps (16 channels = 32 bytes) per block
     uint32_t acc_flag = 0;
-    int stage = 0;
+    int stage = 0, c = 0, j = 0;
     uint32_t parity = 0;
-    for (int blk = 0; blk < nblocks; ++blk) {
+    for (int rnd = 0; rnd < nrounds; ++rnd) {
       mbar_wait(bar_wf + 8 * stage, parity);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (real_tile) {
-        uint32_t b_lo = b_lo0 + (uint32_t)stage * wblk16;
-        const int j0 = whole_taps ? blk * m : blk / bpt;
-        const int nt_blk = whole_taps ? min(m, ntaps - j0) : 1;
-        const int kc0 = whole_taps ? 0 : (blk - j0 * bpt) * G;
-        const int nkc = whole_taps ? KC : G;
-        for (int tp = 0; tp < nt_blk; ++tp) {
-          uint32_t a_lo = a_lo0 + (uint32_t)(p.tt.row_off[ph][j0 + tp] + p.tt.h_lo) + (uint32_t)kc0 * a_kstep16;
+      const int nb = min(p.G, nblocks - rnd * p.G);
+      uint32_t b_start = w0 + (uint32_t)stage * stage16;
+      for (int g = 0; g < nb; ++g) {
+        if (j == 0) {
+          mbar_wait(bar_a + 8 * c, 0);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        const uint32_t a_start = a0 + (uint32_t)c * a_pitch16 + (uint32_t)(p.hlo8 + p.tt.row_off[ph][j]) * row16;
 #pragma unroll 4
-          for (int kc = 0; kc < nkc; ++kc) {
+        for (int ks = 0; ks < KS; ++ks) {
 #pragma unroll
-            for (int sub = 0; sub < MSUB; ++sub)  // the same weight K-step feeds every 128-row sub-tile
-              umma_f16_lohi(tmem + (uint32_t)(sub * p.n_tile), a_lo + (uint32_t)(sub * TILE_M), a_hi, b_lo, b_hi, idesc,
-                            acc_flag);
-            acc_flag = 1u;
-            a_lo += a_kstep16;
-            b_lo += b_kstep16;
+          for (int sub = 0; sub < MSUB; ++sub) {  // the same weight K-step feeds every 128-row sub-tile
+            const uint32_t as = a_start + (uint32_t)(sub * TILE_M) * row16 + 2u * ks;
+            uint32_t a_hi = hi0;
+            if (bo_mode == 1) a_hi |= ((as >> 3) & swz_mask) << 17;
+            else if (bo_mode == 2) a_hi |= ((as >> 3) & 7u) << 17;
+            umma_f16_lohi(tmem + (uint32_t)(sub * p.n_tile), (1u << 16) | (as & 0x3FFFu), a_hi,
+                          (1u << 16) | ((b_start + 2u * ks) & 0x3FFFu), hi0, idesc, acc_flag);
           }
+          acc_flag = 1u;
+        }
+        b_start += blk16;
+        if (++j == ntaps) {
+          j = 0;
+          ++c;
         }
       }
-      if (CL == 1) umma_commit(bar_we + 8 * stage);
-      else umma_commit_mc(bar_we + 8 * stage, cmask);  // release this stage in every CTA of the cluster
+      umma_commit(bar_we + 8 * stage);  // the stage is free once these MMAs have read it
       if (++stage == p.stages) {
         stage = 0;
         parity ^= 1u;
@@ -356,6 +275,7 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
   // so they overlap the MMAs); out may alias residual, hence the explicit ordering.
   hsv::pdl_wait();  // residual / out / acc belong to predecessor kernels
   __syncwarp();
+  const bool real_tile = true;
   const int co0 = nt * p.n_tile;
   const int64_t cs = p.Lout;  // channel stride
   const int64_t chan_base = ((int64_t)b * p.Cout + co0) * p.Lout + p.tt.out_off[ph];
@@ -411,62 +331,62 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
       }
     }
   } else {
-  float ra[16], rb[16];  // residual ring: ra = unit u, rb = unit u+1
-  {
-    int64_t off; bool ok;
-    unit_ptr(0, off, ok);
-#pragma unroll
-    for (int c = 0; c < 16; ++c) ra[c] = (ok && has_res) ? p.residual[off + c * cs] : 0.f;
-    unit_ptr(nunits > 1 ? 1 : 0, off, ok);
-    ok = ok && nunits > 1;
-#pragma unroll
-    for (int c = 0; c < 16; ++c) rb[c] = (ok && has_res) ? p.residual[off + c * cs] : 0.f;
-  }
-  mbar_wait(bar_acc, 0);
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  __syncwarp();
-  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-#pragma unroll 1
-  for (int u = 0; u < nunits; ++u) {
-    const int sub = u / nchk, c0 = (u - sub * nchk) << 4;
-    int64_t off; bool valid;
-    unit_ptr(u, off, valid);
-    uint32_t r[16];
-    tmem_ld16(trow + (uint32_t)(sub * p.n_tile + c0), r);
-    float v[16];
-#pragma unroll
-    for (int c = 0; c < 16; ++c) v[c] = __uint_as_float(r[c]);
-    if (p.bias) {
-#pragma unroll
-      for (int c = 0; c < 16; ++c) v[c] += __ldg(p.bias + co0 + c0 + c);
-    }
-#pragma unroll
-    for (int c = 0; c < 16; ++c) v[c] += ra[c];  // (conv + bias) + residual: the reference's order
-    // rotate the ring and fetch unit u+2 before this unit's stores
-#pragma unroll
-    for (int c = 0; c < 16; ++c) ra[c] = rb[c];
+    float ra[16], rb[16];  // residual ring: ra = unit u, rb = unit u+1
     {
-      int64_t offn; bool okn;
-      unit_ptr(u + 2 < nunits ? u + 2 : u, offn, okn);
-      okn = okn && has_res && u + 2 < nunits;
+      int64_t off; bool ok;
+      unit_ptr(0, off, ok);
 #pragma unroll
-      for (int c = 0; c < 16; ++c) rb[c] = okn ? p.residual[offn + c * cs] : 0.f;
+      for (int c = 0; c < 16; ++c) ra[c] = (ok && has_res) ? p.residual[off + c * cs] : 0.f;
+      unit_ptr(nunits > 1 ? 1 : 0, off, ok);
+      ok = ok && nunits > 1;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) rb[c] = (ok && has_res) ? p.residual[off + c * cs] : 0.f;
     }
-    if (valid) {
-      if (p.acc_mode == 1) {
+    mbar_wait(bar_acc, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    __syncwarp();
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int u = 0; u < nunits; ++u) {
+      const int sub = u / nchk, c0 = (u - sub * nchk) << 4;
+      int64_t off; bool valid;
+      unit_ptr(u, off, valid);
+      uint32_t r[16];
+      tmem_ld16(trow + (uint32_t)(sub * p.n_tile + c0), r);
+      float v[16];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) p.acc[off + c * cs] = v[c];
-      } else if (p.acc_mode == 2) {
-        // red.global.add: no read, one add per element per kernel -> deterministic given stream order
+      for (int c = 0; c < 16; ++c) v[c] = __uint_as_float(r[c]);
+      if (p.bias) {
 #pragma unroll
-        for (int c = 0; c < 16; ++c) atomicAdd(p.acc + off + c * cs, v[c]);
+        for (int c = 0; c < 16; ++c) v[c] += __ldg(p.bias + co0 + c0 + c);
       }
-      if (p.out) {
 #pragma unroll
-        for (int c = 0; c < 16; ++c) p.out[off + c * cs] = v[c];
+      for (int c = 0; c < 16; ++c) v[c] += ra[c];  // (conv + bias) + residual: the reference's order
+      // rotate the ring and fetch unit u+2 before this unit's stores
+#pragma unroll
+      for (int c = 0; c < 16; ++c) ra[c] = rb[c];
+      {
+        int64_t offn; bool okn;
+        unit_ptr(u + 2 < nunits ? u + 2 : u, offn, okn);
+        okn = okn && has_res && u + 2 < nunits;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) rb[c] = okn ? p.residual[offn + c * cs] : 0.f;
+      }
+      if (valid) {
+        if (p.acc_mode == 1) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) p.acc[off + c * cs] = v[c];
+        } else if (p.acc_mode == 2) {
+          // red.global.add: no read, one add per element per kernel -> deterministic given stream order
+#pragma unroll
+          for (int c = 0; c < 16; ++c) atomicAdd(p.acc + off + c * cs, v[c]);
+        }
+        if (p.out) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) p.out[off + c * cs] = v[c];
+        }
       }
     }
-  }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -474,30 +394,36 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(p.tmem_cols)
                  : "memory");
   }
-  if (CL > 1) cluster_sync_all();  // no CTA exits while peers may still multicast into it / arrive on its barriers
 }
 
-// out[ph][nt][s][c2][n][e] = W(co = nt*n_tile + n, ci = 16*kc + 8*c2 + e, tap wj[ph][i]),  s = i*(Cin/16) + kc
-// element strides (s_co, s_ci) select Conv1d [Cout,Cin,k] or ConvTranspose1d [Cin,Cout,k] weights
+// Packed weight stream: [phase][n-tile][chunk][tap] blocks of n_tile rows x cw channels (fp16, K-major, swizzled
+// relative to the block start):  W(co = nt*n_tile + n, ci = chunk*cw + 8*u + e, tap wj[ph][ti]) at byte
+// swz(n*rowbytes + 16*u) + 2*e of its block.  Element strides (s_co, s_ci) select Conv1d [Cout,Cin,k] or
+// ConvTranspose1d [Cin,Cout,k] weights.
 __global__ void pack_weight_kernel(const float *__restrict__ w, __half *__restrict__ out, int Cout, int Cin,
-                                   int k, int n_tile, int NB, int64_t s_co, int64_t s_ci, const TapTable tt) {
-  const int KC = Cin >> 4;
+                                   int n_tile, int cw, int64_t s_co, int64_t s_ci, const TapTable tt) {
+  const int nchunks = Cin / cw;
   const int nco = Cout / n_tile;
-  int64_t ph_base = 0;
+  const int blk_elems = n_tile * cw;
+  const uint32_t rowbytes = (uint32_t)cw * 2u, mask = (uint32_t)(cw >> 3) - 1u;
+  int64_t ph_base = 0;  // in blocks
   for (int ph = 0; ph < tt.nphase; ++ph) {
-    const int64_t cnt = (int64_t)tt.ntaps[ph] * KC * nco * 2 * NB * 8;
+    const int nt_ph = tt.ntaps[ph];
+    const int64_t cnt = (int64_t)nco * nchunks * nt_ph * blk_elems;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < cnt; i += (int64_t)gridDim.x * blockDim.x) {
       int64_t r = i;
-      const int e = r % 8; r /= 8;
-      const int n = r % NB; r /= NB;
-      const int c2 = r % 2; r /= 2;
-      const int s = r % (tt.ntaps[ph] * KC); r /= (tt.ntaps[ph] * KC);
+      const int cil = (int)(r % cw); r /= cw;       // channel within the chunk
+      const int n = (int)(r % n_tile); r /= n_tile;
+      const int ti = (int)(r % nt_ph); r /= nt_ph;
+      const int chunk = (int)(r % nchunks); r /= nchunks;
       const int nt = (int)r;
-      const int ti = s / KC, kc = s % KC;
-      const int co = nt * n_tile + n, ci = 16 * kc + 8 * c2 + e;
-      out[ph_base + i] = n < n_tile ? __float2half_rn(w[co * s_co + ci * s_ci + tt.wj[ph][ti]]) : __float2half_rn(0.f);
+      const int co = nt * n_tile + n, ci = chunk * cw + cil;
+      const uint32_t lin = (uint32_t)n * rowbytes + (uint32_t)(cil >> 3) * 16u;
+      const uint32_t phys = (lin ^ (((lin >> 7) & mask) << 4)) + 2u * (uint32_t)(cil & 7);
+      const int64_t blk = ph_base + ((int64_t)nt * nchunks + chunk) * nt_ph + ti;
+      out[blk * blk_elems + (phys >> 1)] = __float2half_rn(w[co * s_co + ci * s_ci + tt.wj[ph][ti]]);
     }
-    ph_base += cnt;
+    ph_base += (int64_t)nco * nchunks * nt_ph;
   }
 }
 
@@ -542,12 +468,10 @@ TapTable convT_taps(int k, int u) {
 }
 
 int g_host_debug = 0;
-int g_cluster_override = 0;  // bring-up aid: force the cluster size (0 = automatic)
-int g_msub_override = 0;     // bring-up aid: force the sub-tiles per CTA (0 = automatic)
-int g_apad = 0, g_bpad = 0;  // experiment: extra rows between the K-chunks of the A tile / packed weights
+int g_msub_override = 0;  // bring-up aid: force the sub-tiles per CTA (0 = automatic)
 
 template <int MSUB, int MINB, bool SMALLN>
-int launch_variant(const Params &p, dim3 grid, int cluster, size_t smem, cudaStream_t st, const char *what) {
+int launch_variant(const Params &p, dim3 grid, size_t smem, cudaStream_t st, const char *what) {
   // opt-in dynamic shared memory: 227 KB per block minus the kernel's static shared memory
   static int max_dyn[64] = {0};
   int dev = 0;
@@ -574,15 +498,11 @@ int launch_variant(const Params &p, dim3 grid, int cluster, size_t smem, cudaStr
   cfg.blockDim = dim3(128);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cluster;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = hsv::g_pdl ? 2 : 1;
+  cfg.numAttrs = hsv::g_pdl ? 1 : 0;
   cudaError_t e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<MSUB, MINB, SMALLN>, p);
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -593,99 +513,89 @@ int launch_variant(const Params &p, dim3 grid, int cluster, size_t smem, cudaStr
 }
 
 int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const float *bias,
-           const float *residual, float *out, float *acc, int acc_mode, float acc_div, int B, int Cin, int Cout,
-           int64_t L, int64_t Lout, int n_tile, cudaStream_t st, const char *what) {
+           const float *residual, float *out, float *acc, int acc_mode, int B, int Cin, int Cout, int64_t L,
+           int64_t Lout, int n_tile, cudaStream_t st, const char *what) {
   Params p;
-  p.a = reinterpret_cast<const uint4 *>(a_blk16);
-  p.w = reinterpret_cast<const uint4 *>(w_packed);
+  p.a = reinterpret_cast<const uint8_t *>(a_blk16);
+  p.w = reinterpret_cast<const uint8_t *>(w_packed);
   p.bias = bias; p.residual = residual; p.out = out; p.acc = acc;
-  p.acc_mode = acc_mode; p.acc_div = acc_div;
+  p.acc_mode = acc_mode;
   p.Cin = Cin; p.Cout = Cout; p.L = L; p.Lp = hsv::blk16_rows(L); p.Lout = Lout;
   p.n_tile = n_tile; p.nco_tiles = Cout / n_tile;
+  p.cw = hsv::blk_cw(Cin);
+  p.nchunks = Cin / p.cw;
+  HSV_REQUIRE(p.nchunks <= MAX_CHUNKS, "%s: Cin=%d needs %d operand chunks (max %d)", what, Cin, p.nchunks, MAX_CHUNKS);
+  const int rowbytes = p.cw * 2;
+  p.hlo8 = (tt.h_lo + 7) & ~7;
+  HSV_REQUIRE(p.hlo8 <= HSV_BLK_PAD && tt.h_hi <= HSV_BLK_PAD, "%s: halo (%d,%d) exceeds blk16 padding %d", what,
+              tt.h_lo, tt.h_hi, HSV_BLK_PAD);
   const int ntiles128 = (int)((L + TILE_M - 1) / TILE_M);
-  // Measured on B200: with the SWIZZLE_NONE operand layout one 128x128x16 MMA occupies the tensor pipe for
-  // ~150 cycles (vs 64 at peak), so the kernel is MMA-bound, not weight-ingest-bound, and extra sub-tiles
-  // per CTA only lengthen the serial MMA chain of each CTA.  Default 1; 2/4 stay available (override) for
-  // the throughput regime once the operands move to a swizzled layout.
+  const int blk_bytes = n_tile * rowbytes;
+  // sub-tiles per CTA: with msub = 2 every weight K-step read from shared memory feeds two MMAs, which keeps
+  // an N = 128 tile under the 128 B/clk shared-memory read limit (A 4 KB + B 4 KB per 64-cycle MMA otherwise).
+  // Worth it only when there are enough tiles to fill the GPU anyway.
   int msub = 1;
+  const int64_t ctas1 = (int64_t)ntiles128 * p.nco_tiles * tt.nphase * B;
+  if (n_tile >= 64 && ctas1 >= 2 * 148 * 2) msub = 2;
   if (g_msub_override > 0) msub = g_msub_override;
   if (msub == 3) msub = 2;
-  // must fit: TMEM columns, tiles available, and the A tile (+ a 2-stage weight ring) in shared memory
-  while (msub > 1 && (msub * n_tile > 512 || msub > ntiles128 ||
-                      (size_t)(TILE_M * msub + tt.h_lo + tt.h_hi + g_apad) * 16 * (Cin / 8) + 2 * 16384 > 200 * 1024))
+  auto a_bytes_for = [&](int ms) {
+    const size_t per = (((size_t)(TILE_M * ms + p.hlo8 + tt.h_hi) * rowbytes) + 1023) & ~(size_t)1023;
+    return per * p.nchunks;
+  };
+  while (msub > 1 && (msub * n_tile > 512 || msub > ntiles128 || a_bytes_for(msub) + 2 * (size_t)blk_bytes > 200 * 1024))
     msub >>= 1;
   p.msub = msub;
   p.ntiles = (ntiles128 + msub - 1) / msub;
-  p.R = TILE_M * msub + tt.h_lo + tt.h_hi;
-  p.Rs = p.R + g_apad;
-  p.NB = n_tile + g_bpad;
+  p.R = TILE_M * msub + p.hlo8 + tt.h_hi;
+  p.a_pitch = (uint32_t)((((size_t)p.R * rowbytes) + 1023) & ~(size_t)1023);
   p.tt = tt;
-  int max_ksteps = 0;
-  for (int q = 0; q < tt.nphase; ++q) max_ksteps = tt.ntaps[q] * (Cin / 16) > max_ksteps ? tt.ntaps[q] * (Cin / 16) : max_ksteps;
-  const int kstep_bytes = 32 * p.NB;
-  // weight block = G K-steps (<= 16 KB), tap-aligned: whole taps if one tap fits, else a divisor of a tap
-  const int KC = Cin / 16;
+  int max_blocks = 0;
+  for (int q = 0; q < tt.nphase; ++q) max_blocks = tt.ntaps[q] * p.nchunks > max_blocks ? tt.ntaps[q] * p.nchunks : max_blocks;
+  // ring stage = G blocks, about 16 KB (32 KB when the grid is small and each CTA is alone on its SM; 8 KB for
+  // the narrow streaming layers, which want 8 co-resident CTAs per SM)
   const int64_t total_ctas = (int64_t)p.ntiles * p.nco_tiles * tt.nphase * B;
-  int gmax = (total_ctas <= 148 ? 32768 : 16384) / kstep_bytes;
-  if (gmax < 1) gmax = 1;
-  int G;
-  if (KC <= gmax) {
-    G = KC * (gmax / KC);
-    if (G > max_ksteps) G = max_ksteps;  // max_ksteps is a multiple of KC
-  } else {
-    G = 1;
-    for (int q = gmax; q >= 1; --q)
-      if (KC % q == 0) {
-        G = q;
-        break;
-      }
-  }
+  int G = (n_tile <= 32 ? 8192 : (total_ctas <= 148 ? 32768 : 16384)) / blk_bytes;
+  if (G < 1) G = 1;
+  if (G > max_blocks) G = max_blocks;
   p.G = G;
-  const int nblocks = (max_ksteps + G - 1) / G;
-  p.stages = nblocks < MAX_STAGES ? nblocks : MAX_STAGES;
+  const int nrounds = (max_blocks + G - 1) / G;
+  p.stages = nrounds < MAX_STAGES ? nrounds : MAX_STAGES;
   uint32_t cols = 32;
   while ((int)cols < n_tile * msub) cols <<= 1;
   p.tmem_cols = cols;
   p.debug = g_host_debug;
 
-  const size_t a_bytes = ((size_t)p.Rs * 16 * (Cin / 8) + 127) & ~(size_t)127;
+  const size_t a_bytes = (size_t)p.a_pitch * p.nchunks;
   // shared-memory budget: leave room for as many co-resident CTAs per SM as the grid can use (they hide
   // each other's prologue / epilogue latency), down to a 2-stage weight ring
   const int minb = n_tile <= 32 ? 8 : (n_tile <= 64 ? 4 : 2);
   int want = (int)((total_ctas + 147) / 148);
   want = want < 1 ? 1 : (want > minb ? minb : want);
   const size_t budget = (size_t)(226 * 1024) / want - 1024;
-  size_t smem = a_bytes + (size_t)p.stages * G * kstep_bytes;
+  const size_t stage_bytes = (size_t)G * blk_bytes;
+  size_t smem = 1024 + a_bytes + (size_t)p.stages * stage_bytes;
   while (smem > budget && p.stages > 2) {
     p.stages--;
-    smem = a_bytes + (size_t)p.stages * G * kstep_bytes;
+    smem = 1024 + a_bytes + (size_t)p.stages * stage_bytes;
   }
   HSV_REQUIRE(B <= 65535 && (int64_t)p.nco_tiles * tt.nphase <= 65535, "%s: grid too large", what);
-  // weight multicast across a cluster of consecutive M-tiles pays when the weights are large
-  // (n_tile >= 64 -> K-step >= 2 KB) and there are at least two tiles to share them
-  int cluster = 1;
-  if (g_cluster_override > 0) cluster = g_cluster_override;
-  // (measured on B200: clusters cost more in launch/co-scheduling than the multicast saves at these
-  //  sizes, so the automatic choice is 1; the path stays available through the bring-up override)
-  if (n_tile < 64) cluster = 1;
-  while (cluster > 1 && (32 * p.NB) % (16 * cluster) != 0) cluster >>= 1;
-  const int gx = ((p.ntiles + cluster - 1) / cluster) * cluster;
-  dim3 grid((unsigned)gx, (unsigned)(p.nco_tiles * tt.nphase), (unsigned)B);
-  // small n_tile = HBM/latency-bound streaming layers: they want many co-resident CTAs (register cap 80);
+  dim3 grid((unsigned)p.ntiles, (unsigned)(p.nco_tiles * tt.nphase), (unsigned)B);
+  // small n_tile = HBM/latency-bound streaming layers: they want many co-resident CTAs (register cap 64);
   // large n_tile = few fat CTAs per SM anyway
   if (p.msub == 1) {
-    if (n_tile <= 32) return launch_variant<1, 8, true>(p, grid, cluster, smem, st, what);
-    if (n_tile <= 64) return launch_variant<1, 4, false>(p, grid, cluster, smem, st, what);
-    return launch_variant<1, 2, false>(p, grid, cluster, smem, st, what);
+    if (n_tile <= 32) return launch_variant<1, 8, true>(p, grid, smem, st, what);
+    if (n_tile <= 64) return launch_variant<1, 4, false>(p, grid, smem, st, what);
+    return launch_variant<1, 2, false>(p, grid, smem, st, what);
   }
-  if (p.msub == 2) return launch_variant<2, 3, false>(p, grid, cluster, smem, st, what);
-  return launch_variant<4, 2, false>(p, grid, cluster, smem, st, what);
+  if (p.msub == 2) return launch_variant<2, 2, false>(p, grid, smem, st, what);
+  return launch_variant<4, 1, false>(p, grid, smem, st, what);
 }
 
 int check_common(const char *what, const void *a, const void *w, int Cin, int Cout, int n_tile) {
   HSV_REQUIRE(a && w, "%s: null operand", what);
   HSV_REQUIRE(Cin > 0 && Cin % 16 == 0, "%s: Cin %% 16 != 0 (Cin=%d)", what, Cin);
-  HSV_REQUIRE(n_tile >= 16 && n_tile <= 128 && n_tile % 16 == 0 && Cout % n_tile == 0,
+  HSV_REQUIRE(n_tile >= 16 && n_tile <= 256 && n_tile % 16 == 0 && Cout % n_tile == 0,
               "%s: bad n_tile=%d for Cout=%d", what, n_tile, Cout);
   return HSV_OK;
 }
@@ -694,25 +604,26 @@ int pack(const float *w, void *packed, int Cout, int Cin, int k, int n_tile, int
          const TapTable &tt, cudaStream_t st, const char *what) {
   const int64_t total = (int64_t)Cout * Cin * k;
   const int blocks = (int)((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
-  pack_weight_kernel<<<blocks, 256, 0, st>>>(w, reinterpret_cast<__half *>(packed), Cout, Cin, k, n_tile,
-                                             n_tile + g_bpad, s_co, s_ci, tt);
+  pack_weight_kernel<<<blocks, 256, 0, st>>>(w, reinterpret_cast<__half *>(packed), Cout, Cin, n_tile,
+                                             hsv::blk_cw(Cin), s_co, s_ci, tt);
   return hsv::check_launch(what);
 }
 
 }  // namespace
 
-// bring-up aid only (bit0: swap LBO/SBO roles in the smem descriptors); not part of the drop-in contract
+// bring-up aid only; not part of the drop-in contract.
+//   bits 0..1: base_offset mode of the shifted A descriptors (0: none, 1: (addr>>7)&swizzle mask, 2: (addr>>7)&7)
+//   bits 24..26: forced sub-tiles per CTA.   (legacy layout: see conv_umma_v1.cu)
 extern "C" int hsv_set_umma_debug(int flags) {
+  if (hsv::g_layout == 0) return hsv_v1::set_umma_debug(flags);
   g_host_debug = flags & 0xff;
-  g_cluster_override = (flags >> 8) & 0xff;  // bits 8..15: forced cluster size
-  g_apad = (flags >> 16) & 0xf;              // bits 16..19: A chunk padding rows
-  g_bpad = (flags >> 20) & 0xf;              // bits 20..23: weight chunk padding rows
-  g_msub_override = (flags >> 24) & 0x7;     // bits 24..26: forced sub-tiles per CTA
+  g_msub_override = (flags >> 24) & 0x7;
   return HSV_OK;
 }
 
 extern "C" int hsv_pack_conv_weight(const float *w, void *packed, int Cout, int Cin, int k, int n_tile,
                                     void *stream) {
+  if (hsv::g_layout == 0) return hsv_v1::pack_conv_weight(w, packed, Cout, Cin, k, n_tile, stream);
   if (int rc = check_common("pack_conv_weight", w, packed, Cin, Cout, n_tile)) return rc;
   HSV_REQUIRE(k >= 1 && k <= MAX_TAPS && (k & 1), "pack_conv_weight: k=%d (odd, <= %d)", k, MAX_TAPS);
   return pack(w, packed, Cout, Cin, k, n_tile, (int64_t)Cin * k, k, conv_taps(k, 1), hsv::as_stream(stream),
@@ -721,6 +632,7 @@ extern "C" int hsv_pack_conv_weight(const float *w, void *packed, int Cout, int 
 
 extern "C" int hsv_pack_convT_weight(const float *w, void *packed, int Cin, int Cout, int k, int u, int n_tile,
                                      void *stream) {
+  if (hsv::g_layout == 0) return hsv_v1::pack_convT_weight(w, packed, Cin, Cout, k, u, n_tile, stream);
   if (int rc = check_common("pack_convT_weight", w, packed, Cin, Cout, n_tile)) return rc;
   HSV_REQUIRE(u >= 1 && u <= MAX_PHASES && k >= u && k <= MAX_TAPS && k - 2 * ((k - u) / 2) == u,
               "pack_convT_weight: unsupported (k,u)=(%d,%d)", k, u);
@@ -731,6 +643,9 @@ extern "C" int hsv_pack_convT_weight(const float *w, void *packed, int Cin, int 
 extern "C" int hsv_conv1d_umma(const void *a_blk16, const void *w_packed, const float *bias,
                                const float *residual, float *out, float *acc, int acc_mode, float acc_div,
                                int B, int Cin, int Cout, int64_t L, int k, int d, int n_tile, void *stream) {
+  if (hsv::g_layout == 0)
+    return hsv_v1::conv1d_umma(a_blk16, w_packed, bias, residual, out, acc, acc_mode, acc_div, B, Cin, Cout, L, k, d,
+                               n_tile, stream);
   if (B == 0 || L == 0) return HSV_OK;  // empty batch / sequence
   if (int rc = check_common("conv1d_umma", a_blk16, w_packed, Cin, Cout, n_tile)) return rc;
   HSV_REQUIRE(k >= 1 && k <= MAX_TAPS && (k & 1) && d >= 1, "conv1d_umma: k must be odd and <= %d (k=%d d=%d)",
@@ -739,20 +654,20 @@ extern "C" int hsv_conv1d_umma(const void *a_blk16, const void *w_packed, const 
               ((k - 1) / 2) * d, HSV_BLK_PAD);
   HSV_REQUIRE(acc_mode >= 0 && acc_mode <= 2 && (acc_mode == 0 || acc), "conv1d_umma: bad acc_mode/acc");
   HSV_REQUIRE(out || acc_mode, "conv1d_umma: no output");
-  if (B == 0 || L == 0) return HSV_OK;
-  return launch(conv_taps(k, d), a_blk16, w_packed, bias, residual, out, acc, acc_mode, acc_div, B, Cin, Cout, L,
-                L, n_tile, hsv::as_stream(stream), "conv1d_umma");
+  return launch(conv_taps(k, d), a_blk16, w_packed, bias, residual, out, acc, acc_mode, B, Cin, Cout, L, L, n_tile,
+                hsv::as_stream(stream), "conv1d_umma");
 }
 
 extern "C" int hsv_conv_transpose1d_umma(const void *a_blk16, const void *w_packed, const float *bias,
                                          const float *add, float *out, int B, int Cin, int Cout, int64_t Lin,
                                          int k, int u, int n_tile, void *stream) {
+  if (hsv::g_layout == 0)
+    return hsv_v1::conv_transpose1d_umma(a_blk16, w_packed, bias, add, out, B, Cin, Cout, Lin, k, u, n_tile, stream);
   if (B == 0 || Lin == 0) return HSV_OK;
   if (int rc = check_common("conv_transpose1d_umma", a_blk16, w_packed, Cin, Cout, n_tile)) return rc;
   HSV_REQUIRE(u >= 1 && u <= MAX_PHASES && k >= u && k <= MAX_TAPS && k - 2 * ((k - u) / 2) == u,
               "conv_transpose1d_umma: unsupported (k,u)=(%d,%d)", k, u);
   HSV_REQUIRE(out, "conv_transpose1d_umma: no output");
-  if (B == 0 || Lin == 0) return HSV_OK;
-  return launch(convT_taps(k, u), a_blk16, w_packed, bias, add, out, nullptr, 0, 1.f, B, Cin, Cout, Lin,
+  return launch(convT_taps(k, u), a_blk16, w_packed, bias, add, out, nullptr, 0, B, Cin, Cout, Lin,
                 (int64_t)u * Lin, n_tile, hsv::as_stream(stream), "conv_transpose1d_umma");
 }

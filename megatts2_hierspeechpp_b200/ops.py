@@ -49,21 +49,40 @@ def blk16_rows(L: int) -> int:
     return 2 * BLK_PAD + ((L + BLK_ROUND - 1) // BLK_ROUND) * BLK_ROUND
 
 
+def layout() -> int:
+    """Operand layout of the library: 1 = swizzled (default), 0 = legacy bring-up reference."""
+    return _lib.load().hsv_get_layout()
+
+
+def blk_cw(C: int) -> int:
+    """Channels per operand row of the swizzled blk16 layout (include/hsv.h)."""
+    return 64 if C % 64 == 0 else (32 if C % 32 == 0 else 16)
+
+
+def blk16_shape(B: int, C: int, L: int) -> Tuple[int, int, int, int]:
+    if layout() == 0:
+        if C % 8:
+            raise ValueError(f"blk16 needs C % 8 == 0 (C={C})")
+        return (B, C // 8, blk16_rows(L), 8)
+    if C % 16:
+        raise ValueError(f"blk16 needs C % 16 == 0 (C={C})")
+    cw = blk_cw(C)
+    return (B, C // cw, blk16_rows(L), cw)
+
+
 _blk_pool: Dict[Tuple, torch.Tensor] = {}
 
 
 def blk16_buffer(B: int, C: int, L: int, device, slot: int = 0) -> torch.Tensor:
-    """Zero-initialised fp16 [B, C/8, Lp, 8] operand buffer, cached per shape.
+    """Zero-initialised fp16 [B, C/CW, Lp, CW] operand buffer (opaque, swizzled), cached per shape.
 
     Producers only ever write rows [BLK_PAD, BLK_PAD+L), so the zero rows that
     implement the conv's zero padding survive reuse."""
     dev = torch.device(device)
-    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device(), B, C, L, slot)
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device(), B, C, L, slot, layout())
     buf = _blk_pool.get(key)
     if buf is None:
-        if C % 8:
-            raise ValueError(f"blk16 needs C % 8 == 0 (C={C})")
-        buf = torch.zeros(B, C // 8, blk16_rows(L), 8, dtype=torch.float16, device=dev)
+        buf = torch.zeros(*blk16_shape(B, C, L), dtype=torch.float16, device=dev)
         _blk_pool[key] = buf
     return buf
 
@@ -93,7 +112,7 @@ def act1d_blk16(x: torch.Tensor, alpha: torch.Tensor, beta: torch.Tensor, buf: t
     """Fused Activation1d(SnakeBeta) of ``x * scale``: fp32 [B,C,L] -> fp16 blk16 operand (into ``buf``)."""
     _req(x, "x", ndim=3); _req(alpha, "alpha"); _req(beta, "beta"); _req(buf, "buf", torch.float16, 4)
     B, C, L = x.shape
-    if tuple(buf.shape) != (B, C // 8, blk16_rows(L), 8):
+    if tuple(buf.shape) != blk16_shape(B, C, L):
         raise ValueError(f"blk16 buffer shape {tuple(buf.shape)} does not match x {tuple(x.shape)}")
     lib = _lib.load()
     _lib.check(lib.hsv_act1d_snakebeta(_p(x), _p(buf), _p(alpha), _p(beta), B, C, L, 1, float(scale), _stream()),
@@ -104,11 +123,23 @@ def act1d_blk16(x: torch.Tensor, alpha: torch.Tensor, beta: torch.Tensor, buf: t
 def pack_blk16(x: torch.Tensor, buf: torch.Tensor, lrelu: bool = False, scale: float = 1.0):
     _req(x, "x", ndim=3); _req(buf, "buf", torch.float16, 4)
     B, C, L = x.shape
-    if tuple(buf.shape) != (B, C // 8, blk16_rows(L), 8):
+    if tuple(buf.shape) != blk16_shape(B, C, L):
         raise ValueError("blk16 buffer shape mismatch")
     lib = _lib.load()
     _lib.check(lib.hsv_pack_blk16(_p(x), _p(buf), B, C, L, int(lrelu), float(scale), _stream()), "hsv_pack_blk16")
     return buf
+
+
+def unpack_blk16(buf: torch.Tensor, C: int, L: int) -> torch.Tensor:
+    """fp16 blk16 operand buffer -> fp32 [B,C,L] (tests / debugging)."""
+    _req(buf, "buf", torch.float16, 4)
+    B = buf.shape[0]
+    if tuple(buf.shape) != blk16_shape(B, C, L):
+        raise ValueError("blk16 buffer shape mismatch")
+    out = torch.empty(B, C, L, dtype=torch.float32, device=buf.device)
+    lib = _lib.load()
+    _lib.check(lib.hsv_unpack_blk16(_p(buf), _p(out), B, C, L, _stream()), "hsv_unpack_blk16")
+    return out
 
 
 def weight_norm_fold(v: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
@@ -126,6 +157,8 @@ def weight_norm_fold(v: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
 def _wpad() -> int:
     """Experimental weight-chunk padding rows (bring-up knob HSV_UMMA_DEBUG bits 20..23); 0 in production."""
     import os
+    if layout() != 0:
+        return 0
     return (int(os.environ.get("HSV_UMMA_DEBUG", "0")) >> 20) & 0xF
 
 
@@ -134,16 +167,17 @@ def pick_n_tile(cout: int, row_tiles: int = 1 << 30) -> int:
     launch: with few row tiles (batch-1 latency regime) a narrower n_tile puts more CTAs to work on the same
     layer (shorter serial MMA chain and weight stream per CTA); with many, the widest tile (<= 128) has the
     best tensor/shared-memory efficiency."""
-    cands = [n for n in (128, 64, 32, 16) if cout % n == 0]
+    widest = (128, 64, 32, 16) if layout() == 0 else (256, 128, 64, 32, 16)
+    cands = [n for n in widest if cout % n == 0]
     if not cands:
-        for n in range(128, 15, -16):
+        for n in range(widest[0], 15, -16):
             if cout % n == 0:
                 cands = [n]
                 break
     if not cands:
         raise ValueError(f"Cout={cout} not a multiple of 16")
     for n in cands:
-        if n <= 32 or row_tiles * (cout // n) >= 120:
+        if n <= 32 or row_tiles * (cout // n) >= (296 if n == 256 else 120):
             return n
     return cands[-1]
 
@@ -164,7 +198,7 @@ def conv1d_umma(a_blk: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torc
     """tcgen05 implicit-GEMM Conv1d.  Returns ``out`` (fp32 [B,Cout,L]) or None if want_out=False."""
     _req(a_blk, "a_blk16", torch.float16, 4); _req(w_packed, "w_packed", torch.float16)
     B = a_blk.shape[0]
-    if tuple(a_blk.shape) != (B, cin // 8, blk16_rows(L), 8):
+    if tuple(a_blk.shape) != blk16_shape(B, cin, L):
         raise ValueError(f"a_blk16 shape {tuple(a_blk.shape)} does not match Cin={cin}, L={L}")
     if w_packed.numel() < cout * cin * k:
         raise ValueError("w_packed size mismatch")
@@ -200,7 +234,7 @@ def conv_transpose1d_umma(a_blk: torch.Tensor, w_packed: torch.Tensor, bias: Opt
     """tcgen05 ConvTranspose1d (polyphase).  Returns fp32 [B, Cout, u*Lin]."""
     _req(a_blk, "a_blk16", torch.float16, 4); _req(w_packed, "w_packed", torch.float16)
     B = a_blk.shape[0]
-    if tuple(a_blk.shape) != (B, cin // 8, blk16_rows(Lin), 8):
+    if tuple(a_blk.shape) != blk16_shape(B, cin, Lin):
         raise ValueError(f"a_blk16 shape {tuple(a_blk.shape)} does not match Cin={cin}, L={Lin}")
     if w_packed.numel() < cout * cin * k:
         raise ValueError("w_packed size mismatch")

@@ -47,7 +47,7 @@ def test_argument_errors_are_reported(lib):
     assert rc == -1 and b"null" in lib.hsv_last_error()
     one = ctypes.c_void_p(16)
     rc = lib.hsv_act1d_snakebeta(one, one, one, one, 1, 12, 16, 1, 1.0, None)
-    assert rc == -1 and b"C % 8" in lib.hsv_last_error()
+    assert rc == -1 and b"C % 16" in lib.hsv_last_error()
     rc = lib.hsv_conv1d_umma(one, one, None, None, one, None, 0, 1.0, 1, 24, 32, 100, 3, 1, 32, None)
     assert rc == -1 and b"Cin" in lib.hsv_last_error()
     rc = lib.hsv_conv1d_umma(one, one, None, None, one, None, 0, 1.0, 1, 32, 32, 100, 11, 7, 32, None)

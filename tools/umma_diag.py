@@ -49,7 +49,12 @@ def probe(name, C, k, d, L, mode):
 
 
 CASES = [("gemm16_id", 16, 1, 1, 128, "identity"), ("gemm16_chan", 16, 1, 1, 128, "chan"),
-         ("gemm16_rand", 16, 1, 1, 256, "rand"), ("k3_tap0", 16, 3, 1, 256, "tap0"),
+         ("gemm16_rand", 16, 1, 1, 256, "rand"), ("gemm32_chan", 32, 1, 1, 128, "chan"),
+         ("gemm64_chan", 64, 1, 1, 128, "chan"), ("gemm64_rand", 64, 1, 1, 256, "rand"),
+         ("gemm128_rand", 128, 1, 1, 256, "rand"),
+         ("c64_k3_d8", 64, 3, 8, 256, "rand"),       # row shifts that are multiples of 8 (same swizzle phase)
+         ("c64_k3_tap0", 64, 3, 1, 256, "tap0"),     # shift by one row
+         ("c32_k3_tap0", 32, 3, 1, 256, "tap0"), ("c16_k3_tap0", 16, 3, 1, 256, "tap0"),
          ("k3_d3_tap0", 16, 3, 3, 256, "tap0"), ("c32_rand", 32, 7, 3, 300, "rand"),
          ("c64_rand", 64, 11, 5, 300, "rand"), ("c128_rand", 128, 7, 1, 300, "rand"),
          ("c256_rand", 256, 11, 5, 300, "rand")]
@@ -59,7 +64,7 @@ if __name__ == "__main__":
         name, C, k, d, L, mode = sys.argv[1], *map(int, sys.argv[2:6]), sys.argv[6]
         probe(name, C, k, d, L, mode)
         sys.exit(0)
-    for dbg in ("0", "1"):
+    for dbg in (os.environ.get("HSV_DIAG_MODES", "0,1,2").split(",")):
         print(f"==== HSV_UMMA_DEBUG={dbg}", flush=True)
         n_ok = 0
         for c in CASES:
