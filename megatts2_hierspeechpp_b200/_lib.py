@@ -47,6 +47,7 @@ _EXTRA = {
     "hsv_set_act_variant": (c_int, [c_int]),
     "hsv_set_pdl": (c_int, [c_int]),
     "hsv_set_layout": (c_int, [c_int]),
+    "hsv_set_umma_trace": (c_int, [c_void_p]),
     "hsv_get_layout": (c_int, []),
 }
 

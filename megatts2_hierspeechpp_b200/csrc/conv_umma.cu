@@ -66,9 +66,16 @@ struct Params {
   int G;             // weight blocks ([chunk][tap] units) per ring stage
   int stages;
   uint32_t tmem_cols;
+  int vec_epi;       // 1: float4 epilogue (stride-1 output, Lout % 4 == 0, 16-byte aligned tensors)
+  int tap_step;      // row offset between consecutive taps of a phase (taps are an arithmetic progression)
   int debug;
+  long long *trace;  // bring-up: clock64 stamps of CTA (0,0,0) (hsv_set_umma_trace), else nullptr
   TapTable tt;
 };
+
+__device__ __forceinline__ void stamp(const Params &p, int slot) {
+  if (p.trace != nullptr && (blockIdx.x | blockIdx.y | blockIdx.z) == 0) p.trace[slot] = clock64();
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -96,11 +103,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   // try_wait suspends in hardware for a bounded time; the iteration bound turns a protocol bug into a
   // trap instead of a hang
   for (uint32_t it = 0; !mbar_try(bar, parity); ++it) {
-    if (it > (1u << 26)) {
-      printf("hsv conv_umma: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y,
-             blockIdx.z, threadIdx.x);
-      __trap();
-    }
+    if (it > (1u << 26)) __trap();
   }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
@@ -137,6 +140,144 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+  // every lane polls; the vote makes the loop exit warp-uniform, which lets ptxas keep everything that follows
+  // (descriptors, loop counters) in UNIFORM registers: no R2UR / per-thread serialisation around the UTCHMMAs
+  uint32_t it = 0;
+  while (!__all_sync(0xffffffffu, mbar_try(bar, parity))) {
+    if (++it > (1u << 26)) __trap();  // a protocol bug becomes a trap instead of a hang (no printf: a call in
+                                      // this loop would force the loop state out of the uniform registers)
+  }
+}
+
+// The KS K-steps (16 channels = 32 bytes each) of one [chunk][tap] weight block on one 128-row sub-tile, issued by
+// the elected lane of a converged warp.  lo words: start>>4 | LBO; +2 per K-step (32 bytes); hi word shared.
+template <int KS>
+__device__ __forceinline__ void issue_ksteps(uint32_t tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                             uint32_t not_first) {
+  if constexpr (KS == 4) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pe, pa, pt;\n\t"
+        ".reg .b64 da, db;\n\t"
+        ".reg .b32 al, bl;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "setp.ne.b32 pa, %5, 0;\n\t"
+        "setp.eq.b32 pt, 0, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pa;\n\t"
+        "add.u32 al, %1, 2;\n\t"
+        "add.u32 bl, %2, 2;\n\t"
+        "mov.b64 da, {al, %3};\n\t"
+        "mov.b64 db, {bl, %3};\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pt;\n\t"
+        "add.u32 al, %1, 4;\n\t"
+        "add.u32 bl, %2, 4;\n\t"
+        "mov.b64 da, {al, %3};\n\t"
+        "mov.b64 db, {bl, %3};\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pt;\n\t"
+        "add.u32 al, %1, 6;\n\t"
+        "add.u32 bl, %2, 6;\n\t"
+        "mov.b64 da, {al, %3};\n\t"
+        "mov.b64 db, {bl, %3};\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pt;\n\t"
+        "}" ::"r"(tmem),
+        "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(not_first)
+        : "memory");
+  } else if constexpr (KS == 2) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pe, pa, pt;\n\t"
+        ".reg .b64 da, db;\n\t"
+        ".reg .b32 al, bl;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "setp.ne.b32 pa, %5, 0;\n\t"
+        "setp.eq.b32 pt, 0, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pa;\n\t"
+        "add.u32 al, %1, 2;\n\t"
+        "add.u32 bl, %2, 2;\n\t"
+        "mov.b64 da, {al, %3};\n\t"
+        "mov.b64 db, {bl, %3};\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pt;\n\t"
+        "}" ::"r"(tmem),
+        "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(not_first)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pe, pa;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "setp.ne.b32 pa, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pa;\n\t"
+        "}" ::"r"(tmem),
+        "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(not_first)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}" ::"r"(bar)
+      : "memory");
+}
+
+struct MmaCtx {
+  uint32_t tmem, hi, idesc, n_tile, sub16;
+  uint32_t a_first;     // lo word of the first tap's A descriptor in chunk 0
+  uint32_t a_step16;    // row offset between consecutive taps (16-byte units, may be "negative")
+  uint32_t a_pitch16, w_lo0, stage16, blk16;
+  uint32_t bar_wf, bar_we, bar_a, bar_acc;
+  int nrounds, nblocks, G, stages, ntaps;
+};
+
+// The MMA issue loop of one CTA: every value is warp-uniform and the whole warp walks it.
+template <int KS, int MSUB>
+__device__ __forceinline__ void mma_loop(const MmaCtx &m) {
+  int stage = 0, c = 0, j = 0;
+  uint32_t parity = 0, not_first = 0;
+  uint32_t a_chunk = m.a_first, a_lo = m.a_first;
+  for (int rnd = 0; rnd < m.nrounds; ++rnd) {
+    mbar_wait_warp(m.bar_wf + 8 * stage, parity);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int nb = min(m.G, m.nblocks - rnd * m.G);
+    uint32_t b_lo = m.w_lo0 + (uint32_t)stage * m.stage16;
+    for (int g = 0; g < nb; ++g) {
+      if (j == 0) {
+        mbar_wait_warp(m.bar_a + 8 * c, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
+#pragma unroll
+      for (int sub = 0; sub < MSUB; ++sub)  // the same weight block feeds every 128-row sub-tile
+        issue_ksteps<KS>(m.tmem + (uint32_t)sub * m.n_tile, a_lo + (uint32_t)sub * m.sub16, b_lo, m.hi, m.idesc,
+                         not_first);
+      not_first = 1u;
+      b_lo += m.blk16;
+      a_lo += m.a_step16;
+      if (++j == m.ntaps) {
+        j = 0;
+        ++c;
+        a_chunk += m.a_pitch16;
+        a_lo = a_chunk;
+      }
+    }
+    umma_commit_elect(m.bar_we + 8 * stage);  // the stage is free once these MMAs have read it
+    if (++stage == m.stages) {
+      stage = 0;
+      parity ^= 1u;
+    }
+  }
+  umma_commit_elect(m.bar_acc);
+}
+
 // bars: [0] acc_full, [1 .. 1+MAX_CHUNKS) a_full[chunk], then w_full[S], w_empty[S]
 constexpr int BAR_A = 1, BAR_WF = 1 + MAX_CHUNKS, BAR_WE = BAR_WF + MAX_STAGES, NBARS = BAR_WE + MAX_STAGES;
 
@@ -145,8 +286,10 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[NBARS];
   __shared__ uint32_t tmem_base_s;
+  __shared__ float bias_s[256];
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // canonical (shuffled) warp index: tells ptxas the role branches are warp-uniform
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int tile = blockIdx.x, b = blockIdx.z;
   const int ph = blockIdx.y / p.nco_tiles, nt = blockIdx.y - ph * p.nco_tiles;
   const int ntaps = p.tt.ntaps[ph];
@@ -164,6 +307,20 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
   const uint32_t bar_acc = bar0, bar_a = bar0 + 8 * BAR_A, bar_wf = bar0 + 8 * BAR_WF, bar_we = bar0 + 8 * BAR_WE;
 
   hsv::pdl_launch_dependents();  // PDL: the next kernel may begin its prologue
+  if (threadIdx.x == 0) stamp(p, 0);
+
+  // weight stream of this (phase, n-tile)
+  int64_t blk0 = 0;  // first weight block in the packed stream
+  for (int q = 0; q < ph; ++q) blk0 += (int64_t)p.tt.ntaps[q] * p.nchunks * p.nco_tiles;
+  blk0 += (int64_t)nt * nblocks;
+  const uint8_t *wsrc = p.w + blk0 * blk_bytes;
+  auto load_w = [&](int rnd, int s) {
+    const int nb = min(p.G, nblocks - rnd * p.G);
+    const uint32_t bytes = blk_bytes * (uint32_t)nb;
+    mbar_expect_tx(bar_wf + 8 * s, bytes);
+    bulk_g2s(w_s + s * stage_bytes, wsrc + (int64_t)rnd * stage_bytes, bytes, bar_wf + 8 * s);
+  };
+  const int npre = nrounds < p.stages ? nrounds : p.stages;
 
   if (threadIdx.x == 0) {
     mbar_init(bar_acc, 1);
@@ -181,215 +338,261 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // bias of this n-tile -> shared (static data; the epilogue reads it as broadcast LDS instead of 16 dependent
+  // global loads per 16-column unit)
+  for (int i = threadIdx.x; i < p.n_tile; i += 128) bias_s[i] = p.bias ? __ldg(p.bias + nt * p.n_tile + i) : 0.f;
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_base_s;
+  if (threadIdx.x == 0) stamp(p, 1);
 
   if (warp == 0 && lane == 0) {
     // ---------------- TMA producer ----------------
-    int64_t blk0 = 0;  // first weight block of (phase, n-tile) in the packed stream
-    for (int q = 0; q < ph; ++q) blk0 += (int64_t)p.tt.ntaps[q] * p.nchunks * p.nco_tiles;
-    blk0 += (int64_t)nt * nblocks;
-    const uint8_t *wsrc = p.w + blk0 * blk_bytes;
-    auto load_w = [&](int rnd) {
-      const int s = rnd % p.stages;
-      if (rnd >= p.stages) mbar_wait(bar_we + 8 * s, ((rnd / p.stages) - 1) & 1);
-      const int nb = min(p.G, nblocks - rnd * p.G);
-      const uint32_t bytes = blk_bytes * (uint32_t)nb;
-      mbar_expect_tx(bar_wf + 8 * s, bytes);
-      bulk_g2s(w_s + s * stage_bytes, wsrc + (int64_t)rnd * stage_bytes, bytes, bar_wf + 8 * s);
-    };
-    // weights are static: fill the ring before waiting for the kernel that produces the activations
-    const int npre = nrounds < p.stages ? nrounds : p.stages;
-    for (int rnd = 0; rnd < npre; ++rnd) load_w(rnd);
+    // weights are static data: fill the ring before waiting for the kernel that produces the activations
+    // (issuing a bulk copy costs the thread a few hundred cycles: measured ~900 cycles for 4 stages)
+    for (int rnd = 0; rnd < npre; ++rnd) load_w(rnd, rnd);
+    stamp(p, 10);
     hsv::pdl_wait();
+    stamp(p, 2);
     const int64_t row0 = (int64_t)HSV_BLK_PAD + (int64_t)tile * TILE_M * MSUB - p.hlo8;  // multiple of 8
     for (int c = 0; c < p.nchunks; ++c) {
       const uint8_t *src = p.a + (((int64_t)b * p.nchunks + c) * p.Lp + row0) * rowbytes;
       mbar_expect_tx(bar_a + 8 * c, a_chunk_bytes);
       bulk_g2s(a_s + c * p.a_pitch, src, a_chunk_bytes, bar_a + 8 * c);
     }
-    for (int rnd = npre; rnd < nrounds; ++rnd) load_w(rnd);
-  } else if (warp == 1 && lane == 0) {
-    // ---------------- MMA issuer ----------------
-    // This loop runs on ONE thread, so every dependent scalar instruction per MMA is exposed latency.
-    // InstrDescriptor: D=F32 (1<<4), A=B=F16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
-    const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
-    // SmemDescriptor (cute::UMMA::SmemDescriptor): lo = start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled
-    // K-major); hi = SBO>>4 [0,14) (8 rows) | version=1 [14,16) | base_offset [17,20) | layout [29,32)
-    const uint32_t layout = p.cw == 64 ? 2u : (p.cw == 32 ? 4u : 6u);  // SWIZZLE_128B / 64B / 32B
-    const uint32_t hi0 = ((8u * rowbytes) >> 4) | (1u << 14) | (layout << 29);
-    const uint32_t swz_mask = (uint32_t)(p.cw >> 3) - 1u;
-    const int bo_mode = p.debug & 3;  // bring-up: 0 = base_offset 0 (swizzle is a function of the absolute address)
-    const uint32_t row16 = rowbytes >> 4;
-    const uint32_t a0 = (a_s & 0x3FFFFu) >> 4, w0 = (w_s & 0x3FFFFu) >> 4;
-    const uint32_t a_pitch16 = p.a_pitch >> 4, stage16 = stage_bytes >> 4, blk16 = blk_bytes >> 4;
-    const int KS = p.cw >> 4;  // K-steps (16 channels = 32 bytes) per block
-    uint32_t acc_flag = 0;
-    int stage = 0, c = 0, j = 0;
-    uint32_t parity = 0;
-    for (int rnd = 0; rnd < nrounds; ++rnd) {
-      mbar_wait(bar_wf + 8 * stage, parity);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int nb = min(p.G, nblocks - rnd * p.G);
-      uint32_t b_start = w0 + (uint32_t)stage * stage16;
-      for (int g = 0; g < nb; ++g) {
-        if (j == 0) {
-          mbar_wait(bar_a + 8 * c, 0);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        }
-        const uint32_t a_start = a0 + (uint32_t)c * a_pitch16 + (uint32_t)(p.hlo8 + p.tt.row_off[ph][j]) * row16;
-#pragma unroll 4
-        for (int ks = 0; ks < KS; ++ks) {
-#pragma unroll
-          for (int sub = 0; sub < MSUB; ++sub) {  // the same weight K-step feeds every 128-row sub-tile
-            const uint32_t as = a_start + (uint32_t)(sub * TILE_M) * row16 + 2u * ks;
-            uint32_t a_hi = hi0;
-            if (bo_mode == 1) a_hi |= ((as >> 3) & swz_mask) << 17;
-            else if (bo_mode == 2) a_hi |= ((as >> 3) & 7u) << 17;
-            umma_f16_lohi(tmem + (uint32_t)(sub * p.n_tile), (1u << 16) | (as & 0x3FFFu), a_hi,
-                          (1u << 16) | ((b_start + 2u * ks) & 0x3FFFu), hi0, idesc, acc_flag);
-          }
-          acc_flag = 1u;
-        }
-        b_start += blk16;
-        if (++j == ntaps) {
-          j = 0;
-          ++c;
-        }
-      }
-      umma_commit(bar_we + 8 * stage);  // the stage is free once these MMAs have read it
-      if (++stage == p.stages) {
-        stage = 0;
-        parity ^= 1u;
+    int s = 0;
+    uint32_t par = 0;
+    for (int rnd = npre; rnd < nrounds; ++rnd) {  // ring slot s was last used by round rnd - stages
+      mbar_wait(bar_we + 8 * s, par);
+      load_w(rnd, s);
+      if (++s == p.stages) {
+        s = 0;
+        par ^= 1u;
       }
     }
-    umma_commit(bar_acc);
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    // The whole warp walks the loop with warp-uniform values; only the elected lane issues.  The tensor pipe
+    // retires a 128 x N x 16 MMA every N/2 cycles, so every dependent scalar instruction in this chain is
+    // directly visible (measured: 28 SASS instructions per MMA = 236 cycles per MMA, 4x the pipe time).
+    MmaCtx m;
+    m.tmem = tmem;
+    // InstrDescriptor: D=F32 (1<<4), A=B=F16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
+    m.idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+    // SmemDescriptor (cute::UMMA::SmemDescriptor): lo = start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled
+    // K-major); hi = SBO>>4 [0,14) (8 rows) | version=1 [14,16) | base_offset [17,20) = 0 | layout [29,32).
+    // base_offset stays 0 for row-shifted starts: the swizzle is a function of the absolute shared address
+    // (verified on B200: tools/umma_diag.py).
+    const uint32_t layout = p.cw == 64 ? 2u : (p.cw == 32 ? 4u : 6u);  // SWIZZLE_128B / 64B / 32B
+    m.hi = ((8u * rowbytes) >> 4) | (1u << 14) | (layout << 29);
+    const uint32_t row16 = rowbytes >> 4;
+    m.n_tile = (uint32_t)p.n_tile;
+    m.sub16 = (uint32_t)TILE_M * row16;
+    // 16-byte-unit addresses stay below 2^14 (228 KB of shared memory), so adding offsets never carries out
+    // of the 14-bit start-address field.  Taps are an arithmetic progression of row offsets (host-checked).
+    m.a_first = ((1u << 16) | ((a_s & 0x3FFFFu) >> 4)) + (uint32_t)((p.hlo8 + p.tt.row_off[ph][0]) * (int)row16);
+    m.a_step16 = (uint32_t)(p.tap_step * (int)row16);
+    m.a_pitch16 = p.a_pitch >> 4;
+    m.w_lo0 = (1u << 16) | ((w_s & 0x3FFFFu) >> 4);
+    m.stage16 = stage_bytes >> 4;
+    m.blk16 = blk_bytes >> 4;
+    m.bar_wf = bar_wf; m.bar_we = bar_we; m.bar_a = bar_a; m.bar_acc = bar_acc;
+    m.nrounds = nrounds; m.nblocks = nblocks; m.G = p.G; m.stages = p.stages; m.ntaps = ntaps;
+    // broadcast from lane 0: marks every loop input as warp-uniform for ptxas (uniform registers, no R2UR per MMA)
+    {
+      uint32_t *f = reinterpret_cast<uint32_t *>(&m);
+#pragma unroll
+      for (int q = 0; q < (int)(sizeof(MmaCtx) / 4); ++q) f[q] = __shfl_sync(0xffffffffu, f[q], 0);
+    }
+    if (p.cw == 64) mma_loop<4, MSUB>(m);
+    else if (p.cw == 32) mma_loop<2, MSUB>(m);
+    else mma_loop<1, MSUB>(m);
+    if (lane == 0) stamp(p, 5);
+    __syncwarp();
   }
 
   // ---------------- epilogue: all 4 warps ----------------
-  // A compact ROLLED loop over (sub-tile, 16-column chunk) units: the CTA has only four warps, so a fully
-  // unrolled epilogue is fetch-bound straight-line code (measured: +7 us per launch at 64 KB of SASS).
-  // Residual loads run two units ahead of their use (the first two are issued before the accumulator wait,
-  // so they overlap the MMAs); out may alias residual, hence the explicit ordering.
+  // Units of (sub-tile, 16 columns).  tcgen05.ld gives every lane ONE time row x 16 channels; stored straight to
+  // [B,C,L] that is 16 scalar accesses per lane per tensor with 64-bit address math each -- measured ~1000 cycles
+  // per unit of pure issue time for a lone warp per scheduler, as long as the whole MMA phase.  So each warp
+  // transposes the unit through a private 2 KB shared buffer ([16 ch][32 rows]) and then moves float4s: lane =
+  // (channel c = lane/8 + 4*pass, rows 4*(lane%8)..+3): one LDS.128 + one LDG.128 (residual, prefetched PF units
+  // ahead in registers, first PF before the accumulator wait) + one STG.128 per 4 elements.
+  // out may alias residual (same offsets): loads of a unit always precede its stores.
   hsv::pdl_wait();  // residual / out / acc belong to predecessor kernels
   __syncwarp();
-  const bool real_tile = true;
+  if (threadIdx.x == 0) stamp(p, 6);
   const int co0 = nt * p.n_tile;
   const int64_t cs = p.Lout;  // channel stride
   const int64_t chan_base = ((int64_t)b * p.Cout + co0) * p.Lout + p.tt.out_off[ph];
-  const int64_t row_base = (int64_t)tile * MSUB * TILE_M + warp * 32 + lane;  // GEMM row of sub-tile 0
   const int nchk = p.n_tile >> 4;
   const int nunits = MSUB * nchk;
   const bool has_res = p.residual != nullptr;
-  auto unit_ptr = [&](int u, int64_t &off, bool &ok) {
-    const int sub = u / nchk, c0 = (u - sub * nchk) << 4;
-    const int64_t t = row_base + (int64_t)sub * TILE_M;
-    ok = real_tile && t < p.L;
-    off = chan_base + (int64_t)p.tt.out_stride * t + (int64_t)c0 * cs;
-  };
-  if constexpr (SMALLN) {
-    // n_tile <= 32 (one or two units, MSUB == 1): the streaming layers.  Everything is preloaded before the
-    // accumulator wait and the code is short enough to unroll; fits 64 registers -> 8 CTAs per SM.
-    int64_t off; bool valid;
-    unit_ptr(0, off, valid);
-    float res[32];
+  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+  constexpr int PF = 2;
+  if (p.vec_epi) {
+    const int cq = lane >> 3, i4 = (lane & 7) << 2;
+    const int64_t t_warp = (int64_t)tile * MSUB * TILE_M + warp * 32 + i4;  // first row of this lane's float4 (sub 0)
+    const int64_t lane_off = chan_base + (int64_t)cq * cs + t_warp;
+    const int64_t cs4b = 16 * cs;                                   // 4 channels, in bytes
+    const int64_t unit_b = 64 * cs;                                 // 16 channels, in bytes
+    const int64_t wrap_b = 4 * ((int64_t)TILE_M - (int64_t)p.n_tile * cs);  // next sub-tile, first unit (bytes)
+    // the A tile / weight ring are idle once the accumulator is complete: reuse 2 KB per warp as staging
+    const uint32_t stg = a_s + (uint32_t)warp * 2048u;
+    const uint32_t stg_w = stg + (uint32_t)lane * 4u;                       // [c][lane]
+    const uint32_t stg_r = stg + (uint32_t)(cq * 32 + i4) * 4u;             // [cq + 4*pass][i4 .. i4+3]
+    // destinations as per-lane byte pointers of the current unit; all launch-uniform choices hoisted
+    const char *res_b = has_res ? reinterpret_cast<const char *>(p.residual + lane_off) : nullptr;  // unit u + PF
+    // exactly one destination on this path (host-checked): out, or acc written (mode 1) / accumulated (mode 2)
+    char *dst_b = reinterpret_cast<char *>((p.out ? p.out : p.acc) + lane_off);
+    const bool is_red = !p.out && p.acc_mode == 2;
+    int64_t cur_b = 0;  // byte offset of the current unit relative to the per-lane bases
+    // (sub, chunk) walkers: the unit being written and the unit being prefetched
+    int cur_sub = 0, cur_ch = 0, nxt_sub = 0, nxt_ch = 0, nxt_u = 0;
+    int64_t nxt_b = 0;
+    bool cur_ok = t_warp < p.L, nxt_ok = cur_ok;  // L % 4 == 0: a float4 is all-valid or all-invalid
+    float4 res[PF][4];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) res[c] = (valid && has_res && c < p.n_tile) ? p.residual[off + c * cs] : 0.f;
+    for (int q = 0; q < PF; ++q) {
+      const bool ok = nxt_ok && has_res && nxt_u < nunits;
+#pragma unroll
+      for (int ps = 0; ps < 4; ++ps)
+        res[q][ps] = ok ? *reinterpret_cast<const float4 *>(res_b + nxt_b + ps * cs4b) : make_float4(0.f, 0.f, 0.f, 0.f);
+      ++nxt_u;
+      nxt_b += unit_b;
+      if (++nxt_ch == nchk) {
+        nxt_ch = 0;
+        ++nxt_sub;
+        nxt_b += wrap_b;
+        nxt_ok = t_warp + (int64_t)nxt_sub * TILE_M < p.L;
+      }
+    }
     mbar_wait(bar_acc, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     __syncwarp();
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    if (threadIdx.x == 0) stamp(p, 7);
+#pragma unroll 1
+    for (int u0 = 0; u0 < nunits; u0 += PF) {
 #pragma unroll
-    for (int c0 = 0; c0 < 32; c0 += 16) {
-      if (c0 < p.n_tile) {
-        uint32_t r[16];
-        tmem_ld16(trow + c0, r);
-        if (valid) {
-          float v[16];
+      for (int q = 0; q < PF; ++q) {
+        if (u0 + q < nunits) {
+          uint32_t r[16];
+          tmem_ld16(trow + (uint32_t)(cur_sub * p.n_tile + (cur_ch << 4)), r);
 #pragma unroll
-          for (int c = 0; c < 16; ++c) v[c] = __uint_as_float(r[c]);
-          if (p.bias) {
+          for (int c = 0; c < 16; ++c)
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(stg_w + (uint32_t)c * 128u), "r"(r[c]) : "memory");
+          __syncwarp();
+          const bool okn = nxt_ok && has_res && nxt_u < nunits;
+          const float *bias_u = bias_s + (cur_ch << 4) + cq;
 #pragma unroll
-            for (int c = 0; c < 16; ++c) v[c] += __ldg(p.bias + co0 + c0 + c);
+          for (int ps = 0; ps < 4; ++ps) {
+            float4 a;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w)
+                         : "r"(stg_r + (uint32_t)ps * 512u)
+                         : "memory");
+            const float bch = bias_u[ps * 4];
+            const float4 rr = res[q][ps];
+            a.x = (a.x + bch) + rr.x;  // (conv + bias) + residual: the reference's order
+            a.y = (a.y + bch) + rr.y;
+            a.z = (a.z + bch) + rr.z;
+            a.w = (a.w + bch) + rr.w;
+            // refill this ring slot (unit u + PF) before this unit's stores
+            res[q][ps] = okn ? *reinterpret_cast<const float4 *>(res_b + nxt_b + ps * cs4b) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (cur_ok) {
+              char *o = dst_b + cur_b + ps * cs4b;
+              // red.global.add: no read, one add per element per kernel -> deterministic given stream order
+              if (is_red)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w)
+                             : "memory");
+              else
+                *reinterpret_cast<float4 *>(o) = a;
+            }
           }
-#pragma unroll
-          for (int c = 0; c < 16; ++c) v[c] += res[c0 + c];
-          if (p.acc_mode == 1) {
-#pragma unroll
-            for (int c = 0; c < 16; ++c) p.acc[off + (c0 + c) * cs] = v[c];
-          } else if (p.acc_mode == 2) {
-#pragma unroll
-            for (int c = 0; c < 16; ++c) atomicAdd(p.acc + off + (c0 + c) * cs, v[c]);
+          __syncwarp();  // the staging buffer is rewritten by the next unit
+          cur_b += unit_b;
+          if (++cur_ch == nchk) {
+            cur_ch = 0;
+            ++cur_sub;
+            cur_b += wrap_b;
+            cur_ok = t_warp + (int64_t)cur_sub * TILE_M < p.L;
           }
-          if (p.out) {
-#pragma unroll
-            for (int c = 0; c < 16; ++c) p.out[off + (c0 + c) * cs] = v[c];
+          ++nxt_u;
+          nxt_b += unit_b;
+          if (++nxt_ch == nchk) {
+            nxt_ch = 0;
+            ++nxt_sub;
+            nxt_b += wrap_b;
+            nxt_ok = t_warp + (int64_t)nxt_sub * TILE_M < p.L;
           }
         }
       }
     }
   } else {
-    float ra[16], rb[16];  // residual ring: ra = unit u, rb = unit u+1
-    {
+    // generic path (strided ConvTranspose1d phases, L % 4 != 0, unaligned tensors): lane = row, scalar accesses
+    const int64_t row_base = (int64_t)tile * MSUB * TILE_M + warp * 32 + lane;  // GEMM row of sub-tile 0
+    auto unit_ptr = [&](int u, int64_t &off, bool &ok) {
+      const int sub = u / nchk, c0 = (u - sub * nchk) << 4;
+      const int64_t t = row_base + (int64_t)sub * TILE_M;
+      ok = t < p.L;
+      off = chan_base + (int64_t)p.tt.out_stride * t + (int64_t)c0 * cs;
+    };
+    float res[PF][16];
+#pragma unroll
+    for (int q = 0; q < PF; ++q) {
       int64_t off; bool ok;
-      unit_ptr(0, off, ok);
+      unit_ptr(q < nunits ? q : 0, off, ok);
+      ok = ok && has_res && q < nunits;
 #pragma unroll
-      for (int c = 0; c < 16; ++c) ra[c] = (ok && has_res) ? p.residual[off + c * cs] : 0.f;
-      unit_ptr(nunits > 1 ? 1 : 0, off, ok);
-      ok = ok && nunits > 1;
-#pragma unroll
-      for (int c = 0; c < 16; ++c) rb[c] = (ok && has_res) ? p.residual[off + c * cs] : 0.f;
+      for (int c = 0; c < 16; ++c) res[q][c] = ok ? p.residual[off + c * cs] : 0.f;
     }
     mbar_wait(bar_acc, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     __syncwarp();
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    if (threadIdx.x == 0) stamp(p, 7);
 #pragma unroll 1
-    for (int u = 0; u < nunits; ++u) {
-      const int sub = u / nchk, c0 = (u - sub * nchk) << 4;
-      int64_t off; bool valid;
-      unit_ptr(u, off, valid);
-      uint32_t r[16];
-      tmem_ld16(trow + (uint32_t)(sub * p.n_tile + c0), r);
-      float v[16];
+    for (int u0 = 0; u0 < nunits; u0 += PF) {
 #pragma unroll
-      for (int c = 0; c < 16; ++c) v[c] = __uint_as_float(r[c]);
-      if (p.bias) {
+      for (int q = 0; q < PF; ++q) {
+        const int u = u0 + q;
+        if (u < nunits) {
+          const int sub = u / nchk, c0 = (u - sub * nchk) << 4;
+          int64_t off; bool valid;
+          unit_ptr(u, off, valid);
+          uint32_t r[16];
+          tmem_ld16(trow + (uint32_t)(sub * p.n_tile + c0), r);
+          float v[16];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) v[c] += __ldg(p.bias + co0 + c0 + c);
-      }
+          for (int c = 0; c < 16; ++c) v[c] = (__uint_as_float(r[c]) + bias_s[c0 + c]) + res[q][c];  // reference order
+          {
+            int64_t offn; bool okn;
+            unit_ptr(u + PF < nunits ? u + PF : u, offn, okn);
+            okn = okn && has_res && u + PF < nunits;
 #pragma unroll
-      for (int c = 0; c < 16; ++c) v[c] += ra[c];  // (conv + bias) + residual: the reference's order
-      // rotate the ring and fetch unit u+2 before this unit's stores
+            for (int c = 0; c < 16; ++c) res[q][c] = okn ? p.residual[offn + c * cs] : 0.f;
+          }
+          if (valid) {
+            if (p.acc_mode == 1) {
 #pragma unroll
-      for (int c = 0; c < 16; ++c) ra[c] = rb[c];
-      {
-        int64_t offn; bool okn;
-        unit_ptr(u + 2 < nunits ? u + 2 : u, offn, okn);
-        okn = okn && has_res && u + 2 < nunits;
+              for (int c = 0; c < 16; ++c) p.acc[off + c * cs] = v[c];
+            } else if (p.acc_mode == 2) {
 #pragma unroll
-        for (int c = 0; c < 16; ++c) rb[c] = okn ? p.residual[offn + c * cs] : 0.f;
-      }
-      if (valid) {
-        if (p.acc_mode == 1) {
+              for (int c = 0; c < 16; ++c) atomicAdd(p.acc + off + c * cs, v[c]);
+            }
+            if (p.out) {
 #pragma unroll
-          for (int c = 0; c < 16; ++c) p.acc[off + c * cs] = v[c];
-        } else if (p.acc_mode == 2) {
-          // red.global.add: no read, one add per element per kernel -> deterministic given stream order
-#pragma unroll
-          for (int c = 0; c < 16; ++c) atomicAdd(p.acc + off + c * cs, v[c]);
-        }
-        if (p.out) {
-#pragma unroll
-          for (int c = 0; c < 16; ++c) p.out[off + c * cs] = v[c];
+              for (int c = 0; c < 16; ++c) p.out[off + c * cs] = v[c];
+            }
+          }
         }
       }
     }
   }
+  if (threadIdx.x == 0) stamp(p, 8);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (threadIdx.x == 0) stamp(p, 9);
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(p.tmem_cols)
                  : "memory");
@@ -468,6 +671,7 @@ TapTable convT_taps(int k, int u) {
 }
 
 int g_host_debug = 0;
+long long *g_trace = nullptr;
 int g_msub_override = 0;  // bring-up aid: force the sub-tiles per CTA (0 = automatic)
 
 template <int MSUB, int MINB, bool SMALLN>
@@ -550,6 +754,13 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
   p.R = TILE_M * msub + p.hlo8 + tt.h_hi;
   p.a_pitch = (uint32_t)((((size_t)p.R * rowbytes) + 1023) & ~(size_t)1023);
   p.tt = tt;
+  p.tap_step = 0;
+  for (int q = 0; q < tt.nphase; ++q)
+    for (int j = 1; j < tt.ntaps[q]; ++j) {
+      const int st = tt.row_off[q][j] - tt.row_off[q][j - 1];
+      HSV_REQUIRE(p.tap_step == 0 || st == p.tap_step, "%s: taps are not an arithmetic progression", what);
+      p.tap_step = st;
+    }
   int max_blocks = 0;
   for (int q = 0; q < tt.nphase; ++q) max_blocks = tt.ntaps[q] * p.nchunks > max_blocks ? tt.ntaps[q] * p.nchunks : max_blocks;
   // ring stage = G blocks, about 16 KB (32 KB when the grid is small and each CTA is alone on its SM; 8 KB for
@@ -565,11 +776,15 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
   while ((int)cols < n_tile * msub) cols <<= 1;
   p.tmem_cols = cols;
   p.debug = g_host_debug;
+  p.trace = g_trace;
+  auto al16 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  p.vec_epi = tt.out_stride == 1 && (Lout % 4) == 0 && al16(residual) && al16(out) && al16(acc) &&
+              ((out != nullptr) != (acc_mode != 0)) && !(g_host_debug & 16);
 
   const size_t a_bytes = (size_t)p.a_pitch * p.nchunks;
   // shared-memory budget: leave room for as many co-resident CTAs per SM as the grid can use (they hide
   // each other's prologue / epilogue latency), down to a 2-stage weight ring
-  const int minb = n_tile <= 32 ? 8 : (n_tile <= 64 ? 4 : 2);
+  const int minb = n_tile <= 32 ? 6 : (n_tile <= 64 ? 4 : 2);
   int want = (int)((total_ctas + 147) / 148);
   want = want < 1 ? 1 : (want > minb ? minb : want);
   const size_t budget = (size_t)(226 * 1024) / want - 1024;
@@ -579,12 +794,13 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
     p.stages--;
     smem = 1024 + a_bytes + (size_t)p.stages * stage_bytes;
   }
+  if (smem < 1024 + 8192) smem = 1024 + 8192;  // the epilogue stages 4 x 2 KB in the (then idle) operand area
   HSV_REQUIRE(B <= 65535 && (int64_t)p.nco_tiles * tt.nphase <= 65535, "%s: grid too large", what);
   dim3 grid((unsigned)p.ntiles, (unsigned)(p.nco_tiles * tt.nphase), (unsigned)B);
-  // small n_tile = HBM/latency-bound streaming layers: they want many co-resident CTAs (register cap 64);
+  // small n_tile = HBM/latency-bound streaming layers: they want many co-resident CTAs (register cap 80);
   // large n_tile = few fat CTAs per SM anyway
   if (p.msub == 1) {
-    if (n_tile <= 32) return launch_variant<1, 8, true>(p, grid, smem, st, what);
+    if (n_tile <= 32) return launch_variant<1, 6, true>(p, grid, smem, st, what);
     if (n_tile <= 64) return launch_variant<1, 4, false>(p, grid, smem, st, what);
     return launch_variant<1, 2, false>(p, grid, smem, st, what);
   }
@@ -612,12 +828,18 @@ int pack(const float *w, void *packed, int Cout, int Cin, int k, int n_tile, int
 }  // namespace
 
 // bring-up aid only; not part of the drop-in contract.
-//   bits 0..1: base_offset mode of the shifted A descriptors (0: none, 1: (addr>>7)&swizzle mask, 2: (addr>>7)&7)
 //   bits 24..26: forced sub-tiles per CTA.   (legacy layout: see conv_umma_v1.cu)
 extern "C" int hsv_set_umma_debug(int flags) {
   if (hsv::g_layout == 0) return hsv_v1::set_umma_debug(flags);
   g_host_debug = flags & 0xff;
   g_msub_override = (flags >> 24) & 0x7;
+  return HSV_OK;
+}
+
+// bring-up aid: device buffer of >= 16 int64 that CTA (0,0,0) of every conv launch stamps with clock64() at its
+// phase boundaries (nullptr = off)
+extern "C" int hsv_set_umma_trace(void *dev_buf) {
+  g_trace = reinterpret_cast<long long *>(dev_buf);
   return HSV_OK;
 }
 

@@ -28,12 +28,13 @@ def graph_time(fn, n=20, reps=5):
 
 
 def conv_case(B, C, L, k, d, residual=True):
+    hsv.ops.clear_workspace()
     x = torch.randn(B, C, L, device=dev)
     w = torch.randn(C, C, k, device=dev) * 0.05
     bias = torch.zeros(C, device=dev)
     buf = hsv.ops.blk16_buffer(B, C, L, dev, slot=1)
     hsv.ops.pack_blk16(x, buf)
-    nt = hsv.ops.pick_n_tile(C)
+    nt = hsv.ops.pick_n_tile(C, B * ((L + 127) // 128)) if L > 128 else hsv.ops.pick_n_tile(C)
     wp = hsv.ops.pack_conv_weight(w, nt)
     out = torch.empty_like(x)
     us = graph_time(lambda: hsv.ops.conv1d_umma(buf, wp, bias, L, C, C, k, d, nt, residual=x if residual else None, out=out))
@@ -54,6 +55,10 @@ print("== B=1 stage shapes")
 for (C, L) in ((256, 2000), (128, 10000), (64, 40000), (32, 80000), (16, 160000)):
     for (k, d) in ((3, 1), (11, 5)):
         conv_case(1, C, L, k, d)
+print("== B=16 stage shapes (throughput regime)")
+for (C, L) in ((256, 2000), (128, 10000), (64, 40000), (32, 80000)):
+    for (k, d) in ((3, 1), (7, 3), (11, 5)):
+        conv_case(16, C, L, k, d)
 print("== act kernel (blk16 out), graph-timed")
 for (C, L) in ((128, 1000), (256, 2000), (128, 10000), (64, 40000), (32, 80000), (16, 160000)):
     x = torch.randn(1, C, L, device=dev)

@@ -59,7 +59,7 @@ elif what == "umma":
     bias = torch.zeros(C, device=dev)
     buf = hsv.ops.blk16_buffer(B, C, L, dev)
     hsv.ops.pack_blk16(x, buf)
-    nt = hsv.ops.pick_n_tile(C)
+    nt = hsv.ops.pick_n_tile(C, B * ((L + 127) // 128))
     wp = hsv.ops.pack_conv_weight(w, nt)
     out = torch.empty_like(x)
     for _ in range(5):
