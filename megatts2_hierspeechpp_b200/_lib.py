@@ -46,9 +46,7 @@ _EXTRA = {
     "hsv_set_umma_debug": (c_int, [c_int]),
     "hsv_set_act_variant": (c_int, [c_int]),
     "hsv_set_pdl": (c_int, [c_int]),
-    "hsv_set_layout": (c_int, [c_int]),
     "hsv_set_umma_trace": (c_int, [c_void_p]),
-    "hsv_get_layout": (c_int, []),
 }
 
 _lib = None
@@ -75,8 +73,6 @@ def load() -> ctypes.CDLL:
         fn.argtypes = args
     if lib.hsv_version() != 100:
         raise HsvError(f"libhsv.so version {lib.hsv_version()} does not match the Python binding (100)")
-    if os.environ.get("HSV_LAYOUT"):
-        lib.hsv_set_layout(int(os.environ["HSV_LAYOUT"]))
     if os.environ.get("HSV_UMMA_DEBUG"):
         lib.hsv_set_umma_debug(int(os.environ["HSV_UMMA_DEBUG"]))
     if os.environ.get("HSV_PDL"):

@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(NT) act1d_kernel(const float *__restrict__ x, 
   const int tid = threadIdx.x;
   int tile;
   int64_t rowgrp;
-  if (OUT_MODE == 1 && cw > 0) {
+  if (OUT_MODE == 1) {
     // swizzled operand output: the cw/8 CTAs that fill the 16-byte units of the same operand rows are adjacent
     // in launch order, so their partial-sector writes meet in L2
     const int upc = cw >> 3;
@@ -339,19 +339,19 @@ __global__ void __launch_bounds__(NT) act1d_kernel(const float *__restrict__ x, 
     __syncthreads();
     // rows row0..row0+7 are one 8-channel unit of one batch item (C % 8 == 0)
     const uint4 *src = reinterpret_cast<const uint4 *>(o_s);
-    if (cw > 0) {
-      const int64_t bb = row0 / C;
-      const int c0 = (int)(row0 - bb * C);
-      uint8_t *base = reinterpret_cast<uint8_t *>(outp);
-      for (int p = tid; p < K::TILE; p += NT) {
-        if (t0 + p < L)
-          *reinterpret_cast<uint4 *>(base + hsv::blk_unit_offset(cw, Lp, C, bb, c0, HSV_BLK_PAD + t0 + p)) = src[p];
-      }
-    } else {
-      const int64_t chunk = row0 / 8;  // == b*(C/8) + q
-      uint4 *dst = reinterpret_cast<uint4 *>(outp) + chunk * Lp + HSV_BLK_PAD + t0;
-      for (int p = tid; p < K::TILE; p += NT) {
-        if (t0 + p < L) dst[p] = src[p];
+    // one division per CTA; inside the loop the swizzled offset is shifts and xors (cw is a power of two)
+    const int64_t bb = row0 / C;
+    const int c0 = (int)(row0 - bb * C);
+    const int lg = cw == 64 ? 7 : (cw == 32 ? 6 : 5);              // log2(row bytes)
+    const uint32_t mask = (uint32_t)(cw >> 3) - 1u;
+    const int chunk = c0 >> (lg - 1);
+    const uint32_t ub = (uint32_t)((c0 & (cw - 1)) >> 3) << 4;     // byte offset of this CTA's unit in a row
+    uint8_t *base = reinterpret_cast<uint8_t *>(outp) + ((bb * (C >> (lg - 1)) + chunk) * Lp << lg);
+    const uint64_t r0 = (uint64_t)(HSV_BLK_PAD + t0);
+    for (int p = tid; p < K::TILE; p += NT) {
+      if (t0 + p < L) {
+        const uint64_t lin = ((r0 + (uint64_t)p) << lg) + ub;
+        *reinterpret_cast<uint4 *>(base + (lin ^ (((lin >> 7) & mask) << 4))) = src[p];
       }
     }
   }
@@ -380,7 +380,7 @@ int launch(const float *x, void *out, const float *alpha, const float *beta, int
   cfg.numAttrs = hsv::g_pdl ? 1 : 0;
   const int nt_i = (int)ntiles;
   const int64_t Lp = hsv::blk16_rows(L);
-  const int cw = (OUT_MODE == 1 && hsv::g_layout == 1) ? hsv::blk_cw(C) : 0;
+  const int cw = OUT_MODE == 1 ? hsv::blk_cw(C) : 0;
   cudaError_t e;
   if (g_act_variant)
     e = cudaLaunchKernelEx(&cfg, act1d_kernel<R, OUT_MODE, true>, x, out, alpha, beta, C, L, nrows, nt_i, Lp, sc, cw);
@@ -418,8 +418,7 @@ extern "C" int hsv_act1d_snakebeta(const float *x, void *out, const float *alpha
   if (out_mode == 0)
     return big ? launch<33, 0>(x, out, alpha, beta, B, C, L, in_scale, st)
                : launch<17, 0>(x, out, alpha, beta, B, C, L, in_scale, st);
-  HSV_REQUIRE(C % (hsv::g_layout == 1 ? 16 : 8) == 0, "act1d: blk16 output needs C %% %d == 0 (C=%d)",
-              hsv::g_layout == 1 ? 16 : 8, C);
+  HSV_REQUIRE(C % 16 == 0, "act1d: blk16 output needs C %% 16 == 0 (C=%d)", C);
   return big ? launch<33, 1>(x, out, alpha, beta, B, C, L, in_scale, st)
              : launch<17, 1>(x, out, alpha, beta, B, C, L, in_scale, st);
 }

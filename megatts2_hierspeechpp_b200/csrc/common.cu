@@ -5,7 +5,6 @@
 
 namespace hsv {
 int g_pdl = 1;
-int g_layout = 1;
 static thread_local char g_err[512] = "";
 
 void set_error(const char *fmt, ...) {
@@ -23,14 +22,6 @@ extern "C" int hsv_set_pdl(int on) {
   hsv::g_pdl = on ? 1 : 0;
   return HSV_OK;
 }
-
-// bring-up switch (not part of the drop-in contract): operand layout 1 = swizzled (default), 0 = legacy.
-// Buffers and packed weights written under one layout must be consumed under the same one.
-extern "C" int hsv_set_layout(int layout) {
-  hsv::g_layout = layout ? 1 : 0;
-  return HSV_OK;
-}
-extern "C" int hsv_get_layout(void) { return hsv::g_layout; }
 
 extern "C" const char *hsv_last_error(void) { return hsv::g_err; }
 

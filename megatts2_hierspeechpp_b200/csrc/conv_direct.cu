@@ -414,14 +414,10 @@ __global__ void pack_blk16_kernel(const float *__restrict__ x, uint4 *__restrict
       }
       h[e] = __floats2half2_rn(v0, v1);
     }
-    if (cw > 0) {
-      const int64_t bb = bq / nch;
-      const int c0 = (int)(bq - bb * nch) * 8;
-      *reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(out) +
-                                 hsv::blk_unit_offset(cw, Lp, C, bb, c0, HSV_BLK_PAD + t)) = *reinterpret_cast<uint4 *>(h);
-    } else {
-      out[bq * Lp + HSV_BLK_PAD + t] = *reinterpret_cast<uint4 *>(h);
-    }
+    const int64_t bb = bq / nch;
+    const int c0 = (int)(bq - bb * nch) * 8;
+    *reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(out) +
+                               hsv::blk_unit_offset(cw, Lp, C, bb, c0, HSV_BLK_PAD + t)) = *reinterpret_cast<uint4 *>(h);
   }
 }
 
@@ -432,15 +428,10 @@ __global__ void unpack_blk16_kernel(const uint4 *__restrict__ in, float *__restr
   const int64_t n = (int64_t)B * nch * L;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t bq = i / L, t = i - bq * L;
-    uint4 v;
-    if (cw > 0) {
-      const int64_t bb = bq / nch;
-      const int c0 = (int)(bq - bb * nch) * 8;
-      v = *reinterpret_cast<const uint4 *>(reinterpret_cast<const uint8_t *>(in) +
-                                           hsv::blk_unit_offset(cw, Lp, C, bb, c0, HSV_BLK_PAD + t));
-    } else {
-      v = in[bq * Lp + HSV_BLK_PAD + t];
-    }
+    const int64_t bb = bq / nch;
+    const int c0 = (int)(bq - bb * nch) * 8;
+    const uint4 v = *reinterpret_cast<const uint4 *>(reinterpret_cast<const uint8_t *>(in) +
+                                                     hsv::blk_unit_offset(cw, Lp, C, bb, c0, HSV_BLK_PAD + t));
     const __half *h = reinterpret_cast<const __half *>(&v);
     float *xr = x + bq * 8 * L + t;
 #pragma unroll
@@ -555,20 +546,17 @@ extern "C" int hsv_pack_blk16(const float *x, void *out, int B, int C, int64_t L
                               void *stream) {
   if (B == 0 || L == 0) return HSV_OK;
   HSV_REQUIRE(x && out, "pack_blk16: null pointer");
-  const int gran = hsv::g_layout == 1 ? 16 : 8;
-  HSV_REQUIRE(C > 0 && C % gran == 0, "pack_blk16: C %% %d != 0 (C=%d)", gran, C);
+  HSV_REQUIRE(C > 0 && C % 16 == 0, "pack_blk16: C %% 16 != 0 (C=%d)", C);
   pack_blk16_kernel<<<grid_for((int64_t)B * (C / 8) * L, 256), 256, 0, hsv::as_stream(stream)>>>(
-      x, reinterpret_cast<uint4 *>(out), B, C, L, hsv::blk16_rows(L), lrelu, in_scale,
-      hsv::g_layout == 1 ? hsv::blk_cw(C) : 0);
+      x, reinterpret_cast<uint4 *>(out), B, C, L, hsv::blk16_rows(L), lrelu, in_scale, hsv::blk_cw(C));
   return hsv::check_launch("pack_blk16");
 }
 
 extern "C" int hsv_unpack_blk16(const void *in, float *x, int B, int C, int64_t L, void *stream) {
   if (B == 0 || L == 0) return HSV_OK;
   HSV_REQUIRE(in && x, "unpack_blk16: null pointer");
-  const int gran = hsv::g_layout == 1 ? 16 : 8;
-  HSV_REQUIRE(C > 0 && C % gran == 0, "unpack_blk16: C %% %d != 0 (C=%d)", gran, C);
+  HSV_REQUIRE(C > 0 && C % 16 == 0, "unpack_blk16: C %% 16 != 0 (C=%d)", C);
   unpack_blk16_kernel<<<grid_for((int64_t)B * (C / 8) * L, 256), 256, 0, hsv::as_stream(stream)>>>(
-      reinterpret_cast<const uint4 *>(in), x, B, C, L, hsv::blk16_rows(L), hsv::g_layout == 1 ? hsv::blk_cw(C) : 0);
+      reinterpret_cast<const uint4 *>(in), x, B, C, L, hsv::blk16_rows(L), hsv::blk_cw(C));
   return hsv::check_launch("unpack_blk16");
 }

@@ -338,9 +338,15 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // bias of this n-tile -> shared (static data; the epilogue reads it as broadcast LDS instead of 16 dependent
-  // global loads per 16-column unit)
-  for (int i = threadIdx.x; i < p.n_tile; i += 128) bias_s[i] = p.bias ? __ldg(p.bias + nt * p.n_tile + i) : 0.f;
+  // bias of this n-tile (static data): loaded to registers now, parked in shared memory at the start of the
+  // epilogue (its global latency must not sit in front of the set-up barrier), read there as broadcast LDS
+  // instead of 16 dependent global loads per 16-column unit
+  float bias_r[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int i = threadIdx.x + 128 * q;
+    bias_r[q] = (p.bias && i < p.n_tile) ? __ldg(p.bias + nt * p.n_tile + i) : 0.f;
+  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -422,6 +428,8 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
   // out may alias residual (same offsets): loads of a unit always precede its stores.
   hsv::pdl_wait();  // residual / out / acc belong to predecessor kernels
   __syncwarp();
+  bias_s[threadIdx.x] = bias_r[0];
+  bias_s[threadIdx.x + 128] = bias_r[1];
   if (threadIdx.x == 0) stamp(p, 6);
   const int co0 = nt * p.n_tile;
   const int64_t cs = p.Lout;  // channel stride
@@ -468,6 +476,7 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
         nxt_ok = t_warp + (int64_t)nxt_sub * TILE_M < p.L;
       }
     }
+    __syncthreads();  // bias_s complete (every warp is past its role loop here; the MMAs are in flight)
     mbar_wait(bar_acc, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     __syncwarp();
@@ -547,6 +556,7 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
 #pragma unroll
       for (int c = 0; c < 16; ++c) res[q][c] = ok ? p.residual[off + c * cs] : 0.f;
     }
+    __syncthreads();  // bias_s complete (every warp is past its role loop here; the MMAs are in flight)
     mbar_wait(bar_acc, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     __syncwarp();
@@ -828,9 +838,9 @@ int pack(const float *w, void *packed, int Cout, int Cin, int k, int n_tile, int
 }  // namespace
 
 // bring-up aid only; not part of the drop-in contract.
-//   bits 24..26: forced sub-tiles per CTA.   (legacy layout: see conv_umma_v1.cu)
+//   bit 2: skip the epilogue's global stores, bit 3: skip its TMEM loads, bit 4: force the scalar epilogue;
+//   bits 24..26: forced sub-tiles per CTA.
 extern "C" int hsv_set_umma_debug(int flags) {
-  if (hsv::g_layout == 0) return hsv_v1::set_umma_debug(flags);
   g_host_debug = flags & 0xff;
   g_msub_override = (flags >> 24) & 0x7;
   return HSV_OK;
@@ -845,7 +855,6 @@ extern "C" int hsv_set_umma_trace(void *dev_buf) {
 
 extern "C" int hsv_pack_conv_weight(const float *w, void *packed, int Cout, int Cin, int k, int n_tile,
                                     void *stream) {
-  if (hsv::g_layout == 0) return hsv_v1::pack_conv_weight(w, packed, Cout, Cin, k, n_tile, stream);
   if (int rc = check_common("pack_conv_weight", w, packed, Cin, Cout, n_tile)) return rc;
   HSV_REQUIRE(k >= 1 && k <= MAX_TAPS && (k & 1), "pack_conv_weight: k=%d (odd, <= %d)", k, MAX_TAPS);
   return pack(w, packed, Cout, Cin, k, n_tile, (int64_t)Cin * k, k, conv_taps(k, 1), hsv::as_stream(stream),
@@ -854,7 +863,6 @@ extern "C" int hsv_pack_conv_weight(const float *w, void *packed, int Cout, int 
 
 extern "C" int hsv_pack_convT_weight(const float *w, void *packed, int Cin, int Cout, int k, int u, int n_tile,
                                      void *stream) {
-  if (hsv::g_layout == 0) return hsv_v1::pack_convT_weight(w, packed, Cin, Cout, k, u, n_tile, stream);
   if (int rc = check_common("pack_convT_weight", w, packed, Cin, Cout, n_tile)) return rc;
   HSV_REQUIRE(u >= 1 && u <= MAX_PHASES && k >= u && k <= MAX_TAPS && k - 2 * ((k - u) / 2) == u,
               "pack_convT_weight: unsupported (k,u)=(%d,%d)", k, u);
@@ -865,9 +873,6 @@ extern "C" int hsv_pack_convT_weight(const float *w, void *packed, int Cin, int 
 extern "C" int hsv_conv1d_umma(const void *a_blk16, const void *w_packed, const float *bias,
                                const float *residual, float *out, float *acc, int acc_mode, float acc_div,
                                int B, int Cin, int Cout, int64_t L, int k, int d, int n_tile, void *stream) {
-  if (hsv::g_layout == 0)
-    return hsv_v1::conv1d_umma(a_blk16, w_packed, bias, residual, out, acc, acc_mode, acc_div, B, Cin, Cout, L, k, d,
-                               n_tile, stream);
   if (B == 0 || L == 0) return HSV_OK;  // empty batch / sequence
   if (int rc = check_common("conv1d_umma", a_blk16, w_packed, Cin, Cout, n_tile)) return rc;
   HSV_REQUIRE(k >= 1 && k <= MAX_TAPS && (k & 1) && d >= 1, "conv1d_umma: k must be odd and <= %d (k=%d d=%d)",
@@ -883,8 +888,6 @@ extern "C" int hsv_conv1d_umma(const void *a_blk16, const void *w_packed, const 
 extern "C" int hsv_conv_transpose1d_umma(const void *a_blk16, const void *w_packed, const float *bias,
                                          const float *add, float *out, int B, int Cin, int Cout, int64_t Lin,
                                          int k, int u, int n_tile, void *stream) {
-  if (hsv::g_layout == 0)
-    return hsv_v1::conv_transpose1d_umma(a_blk16, w_packed, bias, add, out, B, Cin, Cout, Lin, k, u, n_tile, stream);
   if (B == 0 || Lin == 0) return HSV_OK;
   if (int rc = check_common("conv_transpose1d_umma", a_blk16, w_packed, Cin, Cout, n_tile)) return rc;
   HSV_REQUIRE(u >= 1 && u <= MAX_PHASES && k >= u && k <= MAX_TAPS && k - 2 * ((k - u) / 2) == u,

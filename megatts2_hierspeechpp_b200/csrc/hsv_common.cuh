@@ -47,12 +47,11 @@ __host__ __device__ inline int64_t blk16_rows(int64_t L) {
 }
 
 // ---- tensor-core operand layout ("blk16" buffers) ----
-// layout 1 (default): fp16 [B][C/CW][Lp][CW], CW = 64 / 32 / 16 channels per row (128 / 64 / 32-byte rows); the
-// 16-byte units of a row are XOR-swizzled with the row index exactly as tcgen05's K-major SWIZZLE_128B / 64B /
-// 32B shared-memory layouts expect (byte-offset bits [4,7) ^= bits [7,10) & mask), so that a span of rows that
-// starts at a multiple of 8 rows, copied linearly (1-D bulk TMA) to a 1024-byte aligned shared address, IS the
-// canonical swizzled operand tile.  layout 0 (legacy bring-up reference): [B][C/8][Lp][8], SWIZZLE_NONE.
-extern int g_layout;
+// fp16 [B][C/CW][Lp][CW], CW = 64 / 32 / 16 channels per row (128 / 64 / 32-byte rows); the 16-byte units of a
+// row are XOR-swizzled with the row index exactly as tcgen05's K-major SWIZZLE_128B / 64B / 32B shared-memory
+// layouts expect (byte-offset bits [4,7) ^= bits [7,10) & mask), so that a span of rows that starts at a
+// multiple of 8 rows, copied linearly (1-D bulk TMA) to a 1024-byte aligned shared address, IS the canonical
+// swizzled operand tile.
 __host__ __device__ inline int blk_cw(int C) { return (C % 64 == 0) ? 64 : ((C % 32 == 0) ? 32 : 16); }
 // byte offset (within the whole tensor) of the 16-byte unit holding channels [c0, c0+8) of padded row r
 __host__ __device__ inline int64_t blk_unit_offset(int cw, int64_t Lp, int C, int64_t b, int c0, int64_t r) {
@@ -75,15 +74,3 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 }  // namespace hsv
-
-// legacy SWIZZLE_NONE conv (conv_umma_v1.cu), reachable only through hsv_set_layout(0)
-namespace hsv_v1 {
-int set_umma_debug(int flags);
-int pack_conv_weight(const float *w, void *packed, int Cout, int Cin, int k, int n_tile, void *stream);
-int pack_convT_weight(const float *w, void *packed, int Cin, int Cout, int k, int u, int n_tile, void *stream);
-int conv1d_umma(const void *a_blk16, const void *w_packed, const float *bias, const float *residual, float *out,
-                float *acc, int acc_mode, float acc_div, int B, int Cin, int Cout, int64_t L, int k, int d,
-                int n_tile, void *stream);
-int conv_transpose1d_umma(const void *a_blk16, const void *w_packed, const float *bias, const float *add, float *out,
-                          int B, int Cin, int Cout, int64_t Lin, int k, int u, int n_tile, void *stream);
-}  // namespace hsv_v1

@@ -49,21 +49,12 @@ def blk16_rows(L: int) -> int:
     return 2 * BLK_PAD + ((L + BLK_ROUND - 1) // BLK_ROUND) * BLK_ROUND
 
 
-def layout() -> int:
-    """Operand layout of the library: 1 = swizzled (default), 0 = legacy bring-up reference."""
-    return _lib.load().hsv_get_layout()
-
-
 def blk_cw(C: int) -> int:
     """Channels per operand row of the swizzled blk16 layout (include/hsv.h)."""
     return 64 if C % 64 == 0 else (32 if C % 32 == 0 else 16)
 
 
 def blk16_shape(B: int, C: int, L: int) -> Tuple[int, int, int, int]:
-    if layout() == 0:
-        if C % 8:
-            raise ValueError(f"blk16 needs C % 8 == 0 (C={C})")
-        return (B, C // 8, blk16_rows(L), 8)
     if C % 16:
         raise ValueError(f"blk16 needs C % 16 == 0 (C={C})")
     cw = blk_cw(C)
@@ -79,7 +70,7 @@ def blk16_buffer(B: int, C: int, L: int, device, slot: int = 0) -> torch.Tensor:
     Producers only ever write rows [BLK_PAD, BLK_PAD+L), so the zero rows that
     implement the conv's zero padding survive reuse."""
     dev = torch.device(device)
-    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device(), B, C, L, slot, layout())
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device(), B, C, L, slot)
     buf = _blk_pool.get(key)
     if buf is None:
         buf = torch.zeros(*blk16_shape(B, C, L), dtype=torch.float16, device=dev)
@@ -154,20 +145,12 @@ def weight_norm_fold(v: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
     return w
 
 
-def _wpad() -> int:
-    """Experimental weight-chunk padding rows (bring-up knob HSV_UMMA_DEBUG bits 20..23); 0 in production."""
-    import os
-    if layout() != 0:
-        return 0
-    return (int(os.environ.get("HSV_UMMA_DEBUG", "0")) >> 20) & 0xF
-
-
 def pick_n_tile(cout: int, row_tiles: int = 1 << 30) -> int:
     """Output-channel tile of the tcgen05 conv.  ``row_tiles`` = number of 128-row tiles x batch x phases of the
     launch: with few row tiles (batch-1 latency regime) a narrower n_tile puts more CTAs to work on the same
     layer (shorter serial MMA chain and weight stream per CTA); with many, the widest tile (<= 128) has the
     best tensor/shared-memory efficiency."""
-    widest = (128, 64, 32, 16) if layout() == 0 else (256, 128, 64, 32, 16)
+    widest = (256, 128, 64, 32, 16)
     cands = [n for n in widest if cout % n == 0]
     if not cands:
         for n in range(widest[0], 15, -16):
@@ -185,7 +168,7 @@ def pick_n_tile(cout: int, row_tiles: int = 1 << 30) -> int:
 def pack_conv_weight(w: torch.Tensor, n_tile: int) -> torch.Tensor:
     _req(w, "w", ndim=3)
     cout, cin, k = w.shape
-    out = torch.empty(cout * cin * k * (n_tile + _wpad()) // n_tile, dtype=torch.float16, device=w.device)
+    out = torch.empty(cout * cin * k, dtype=torch.float16, device=w.device)
     lib = _lib.load()
     _lib.check(lib.hsv_pack_conv_weight(_p(w), _p(out), cout, cin, k, n_tile, _stream()), "hsv_pack_conv_weight")
     return out
@@ -223,7 +206,7 @@ def pack_convT_weight(w: torch.Tensor, u: int, n_tile: int) -> torch.Tensor:
     """w: folded ConvTranspose1d weight [Cin, Cout, k] -> packed fp16 phase/tap stream."""
     _req(w, "w", ndim=3)
     cin, cout, k = w.shape
-    out = torch.empty(cout * cin * k * (n_tile + _wpad()) // n_tile, dtype=torch.float16, device=w.device)
+    out = torch.empty(cout * cin * k, dtype=torch.float16, device=w.device)
     lib = _lib.load()
     _lib.check(lib.hsv_pack_convT_weight(_p(w), _p(out), cin, cout, k, u, n_tile, _stream()), "hsv_pack_convT_weight")
     return out
