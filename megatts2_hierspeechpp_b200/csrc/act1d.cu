@@ -200,31 +200,32 @@ __global__ void __launch_bounds__(NT) act1d_kernel(const float *__restrict__ x, 
   __shared__ __align__(8) uint64_t bar;
 
   const int tid = threadIdx.x;
-  int tile;
-  int64_t rowgrp;
+  int tile, ch;        // time tile; channel of this thread's row
+  int64_t row0;        // first of the CTA's 8 (b, channel) rows
+  const int c = tid % ROWS, run = tid / ROWS;
   if (OUT_MODE == 1) {
-    // swizzled operand output: the cw/8 CTAs that fill the 16-byte units of the same operand rows are adjacent
-    // in launch order, so their partial-sector writes meet in L2
-    const int upc = cw >> 3;
-    const int u = blockIdx.x % upc;
-    const int64_t rest = blockIdx.x / upc;
-    tile = (int)(rest % ntiles);
-    rowgrp = (rest / ntiles) * upc + u;
+    // swizzled operand output: grid = (tiles x units-per-chunk, chunks, batch), no divisions.  The cw/8 CTAs that
+    // fill the 16-byte units of the same operand rows are adjacent in launch order, so their partial-sector
+    // writes meet in L2.
+    const int lgu = cw == 64 ? 3 : (cw == 32 ? 2 : 1);  // log2(units per chunk)
+    tile = (int)(blockIdx.x >> lgu);
+    const int c0 = (int)blockIdx.y * cw + (int)(blockIdx.x & ((1u << lgu) - 1u)) * 8;
+    row0 = (int64_t)blockIdx.z * C + c0;
+    ch = c0 + c;
   } else {
     tile = blockIdx.x % ntiles;
-    rowgrp = blockIdx.x / ntiles;
+    row0 = (int64_t)(blockIdx.x / ntiles) * ROWS;
+    ch = (int)((row0 + c) % C);
   }
-  const int64_t row0 = rowgrp * ROWS;
   const int64_t t0 = (int64_t)tile * K::TILE;
-  const int c = tid % ROWS, run = tid / ROWS;
   const int64_t row = row0 + c;
   // PDL: let the next kernel start its prologue now; parameters are static, so load them before waiting
   // for the producer of x
   hsv::pdl_launch_dependents();
   float al = 0.f, be = 0.f;
   if (row < nrows) {
-    al = __ldg(alpha + (int)(row % C));
-    be = __ldg(beta + (int)(row % C));
+    al = __ldg(alpha + ch);
+    be = __ldg(beta + ch);
   }
   hsv::pdl_wait();
 
@@ -339,14 +340,11 @@ __global__ void __launch_bounds__(NT) act1d_kernel(const float *__restrict__ x, 
     __syncthreads();
     // rows row0..row0+7 are one 8-channel unit of one batch item (C % 8 == 0)
     const uint4 *src = reinterpret_cast<const uint4 *>(o_s);
-    // one division per CTA; inside the loop the swizzled offset is shifts and xors (cw is a power of two)
-    const int64_t bb = row0 / C;
-    const int c0 = (int)(row0 - bb * C);
+    // the swizzled offset is shifts and xors (cw is a power of two)
     const int lg = cw == 64 ? 7 : (cw == 32 ? 6 : 5);              // log2(row bytes)
     const uint32_t mask = (uint32_t)(cw >> 3) - 1u;
-    const int chunk = c0 >> (lg - 1);
-    const uint32_t ub = (uint32_t)((c0 & (cw - 1)) >> 3) << 4;     // byte offset of this CTA's unit in a row
-    uint8_t *base = reinterpret_cast<uint8_t *>(outp) + ((bb * (C >> (lg - 1)) + chunk) * Lp << lg);
+    const uint32_t ub = (blockIdx.x & mask) << 4;                  // byte offset of this CTA's unit in a row
+    uint8_t *base = reinterpret_cast<uint8_t *>(outp) + (((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * Lp << lg);
     const uint64_t r0 = (uint64_t)(HSV_BLK_PAD + t0);
     for (int p = tid; p < K::TILE; p += NT) {
       if (t0 + p < L) {
@@ -370,7 +368,13 @@ int launch(const float *x, void *out, const float *alpha, const float *beta, int
   const int64_t nblk = ntiles * ngrp;
   HSV_REQUIRE(nblk < (1ll << 31) && ntiles < (1ll << 31), "act1d: grid too large");
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)nblk);
+  if (OUT_MODE == 1) {
+    const int cwl = hsv::blk_cw(C);
+    HSV_REQUIRE(ntiles * (cwl / 8) < (1ll << 31) && C / cwl <= 65535 && B <= 65535, "act1d: grid too large");
+    cfg.gridDim = dim3((unsigned)(ntiles * (cwl / 8)), (unsigned)(C / cwl), (unsigned)B);
+  } else {
+    cfg.gridDim = dim3((unsigned)nblk);
+  }
   cfg.blockDim = dim3(NT);
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
