@@ -103,6 +103,20 @@ int hsv_conv1d_umma(const void *a_blk16, const void *w_packed, const float *bias
                     const float *residual, float *out, float *acc, int acc_mode, float acc_div,
                     int B, int Cin, int Cout, int64_t L, int k, int d, int n_tile, void *stream);
 
+/* ---- whole AMP half-layer: Activation1d(SnakeBeta) followed by the dilated Conv1d,
+ *   xt = conv(Activation1d(x * in_scale))            (hierspeechpp_speechsynthesizer.py:380-384)
+ * in ONE kernel: the CTA evaluates the fused activation on the fp32 input and writes the fp16 operand
+ * straight into the shared-memory MMA tile, so the operand never exists in HBM.  Same arithmetic as
+ * hsv_act1d_snakebeta(out_mode 1) + hsv_conv1d_umma (bit-identical results).
+ *   x [B,Cin,L] fp32, Cin in {16, 32, 64}; w_packed from hsv_pack_conv_weight with n_tile = Cout (<= 256);
+ *   bias / residual / out / acc / acc_mode as hsv_conv1d_umma; out and acc must not alias x
+ *   (other CTAs still read x's halo); residual may alias out.
+ */
+int hsv_act_conv1d_umma(const float *x, const float *alpha, const float *beta, float in_scale,
+                        const void *w_packed, const float *bias, const float *residual, float *out,
+                        float *acc, int acc_mode, int B, int Cin, int Cout, int64_t L, int k, int d,
+                        void *stream);
+
 /* ---- ConvTranspose1d (ups[i], hierspeechpp_speechsynthesizer.py:404-408,434) on the same
  * tcgen05 kernel: the u output phases are u stride-1 convolutions over the input rows
  * (SURVEY.md §A.3), each an N-tile group of one launch.
@@ -168,6 +182,18 @@ int hsv_add3_bcast(const float *a, const float *b, const float *bc, float *out,
 int hsv_pack_blk16(const float *x, void *out, int B, int C, int64_t L, int lrelu, float in_scale, void *stream);
 /* inverse (tests / debugging): fp16 blk16 -> fp32 [B,C,L]. */
 int hsv_unpack_blk16(const void *in, float *x, int B, int C, int64_t L, void *stream);
+
+/* ---- the step after the path: peak-normalise + int16 quantise on the device.
+ * Replaces inference_plm.py:183-188 (audio / abs(audio).max() * 32767.0 * s) and
+ * inference_speechsr.py:39-41 (audio / abs(audio).max() * 0.999 * 32767.0), each followed by
+ * .cpu().numpy().astype('int16'):  out = trunc(((x / peak) * s1) * s2), fp32, operations rounded
+ * separately in that order (bit-exact with the reference), saturated to int16.
+ *   x [rows, L] fp32, out [rows, L] int16, peak_ws [rows] fp32 workspace (receives the peaks)
+ *   per_row 0: peak = max |x| over the whole tensor (the reference's semantics, one utterance);
+ *           1: one peak per row (batched utterances are normalised independently).
+ */
+int hsv_peak_norm_pcm16(const float *x, int16_t *out, float *peak_ws, int rows, int64_t L, float s1, float s2,
+                        int per_row, void *stream);
 
 #ifdef __cplusplus
 }

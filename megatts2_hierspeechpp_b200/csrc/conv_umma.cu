@@ -25,7 +25,7 @@
 // four warps run the epilogue: tcgen05.ld (lane = row), + bias, + residual, store fp32 [B,C,L] (for
 // stride-1 outputs a warp stores 32 consecutive time steps of one channel = 128 B coalesced) and
 // optionally accumulate the sum over resblocks.
-#include "hsv_common.cuh"
+#include "act_core.cuh"
 
 namespace {
 
@@ -68,6 +68,12 @@ struct Params {
   uint32_t tmem_cols;
   int vec_epi;       // 1: float4 epilogue (stride-1 output, Lout % 4 == 0, 16-byte aligned tensors)
   int tap_step;      // row offset between consecutive taps of a phase (taps are an arithmetic progression)
+  // activation-producing variant (RR > 0): the A tile is computed in the CTA from the fp32 tensor fx
+  const float *fx;     // [B, Cin, L] fp32 input of Activation1d
+  const float *alpha;  // [Cin] log-scale SnakeBeta parameters
+  const float *beta;
+  float in_scale;
+  uint32_t x_off;      // byte offset (from the aligned shared base) of the two fp32 staging buffers
   int debug;
   long long *trace;  // bring-up: clock64 stamps of CTA (0,0,0) (hsv_set_umma_trace), else nullptr
   TapTable tt;
@@ -281,10 +287,15 @@ __device__ __forceinline__ void mma_loop(const MmaCtx &m) {
 // bars: [0] acc_full, [1 .. 1+MAX_CHUNKS) a_full[chunk], then w_full[S], w_empty[S]
 constexpr int BAR_A = 1, BAR_WF = 1 + MAX_CHUNKS, BAR_WE = BAR_WF + MAX_STAGES, NBARS = BAR_WE + MAX_STAGES;
 
-template <int MSUB, int MINB, bool SMALLN>
+// RR == 0: A tile = bulk copies of the pre-activated fp16 operand tensor (p.a).
+// RR  > 0: activation-producing variant (whole-layer fusion): the CTA evaluates the fused
+//          Activation1d (act_core.cuh; 8 channels x 16 runs of RR rows per pass, the mapping of act1d.cu) on the
+//          fp32 input and writes the fp16 results straight into the swizzled shared A tile -- the operand never
+//          exists in HBM.  Single-chunk inputs only (Cin = cw <= 64), n_tile = Cout (no recomputation).
+template <int MSUB, int MINB, bool SMALLN, int RR>
 __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[NBARS];
+  __shared__ __align__(8) uint64_t bars[NBARS + 2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float bias_s[256];
 
@@ -329,6 +340,10 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
       mbar_init(bar_wf + 8 * s, 1);
       mbar_init(bar_we + 8 * s, 1);
     }
+    if (RR > 0) {
+      mbar_init(bar0 + 8 * NBARS, 1);
+      mbar_init(bar0 + 8 * (NBARS + 1), 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -353,19 +368,117 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
   const uint32_t tmem = tmem_base_s;
   if (threadIdx.x == 0) stamp(p, 1);
 
+  if constexpr (RR > 0) {
+    // ---------------- activation producer: all 128 threads ----------------
+    using K = hsv_act::Cfg<RR>;
+    if (threadIdx.x == 0) {
+      for (int rnd = 0; rnd < npre; ++rnd) load_w(rnd, rnd);  // static data, before the dependency wait
+      stamp(p, 10);
+    }
+    hsv::pdl_wait();  // fx belongs to the predecessor kernel
+    if (threadIdx.x == 0) stamp(p, 2);
+    const uint32_t bar_x = bar0 + 8 * NBARS;                      // two staging barriers
+    uint8_t *smem_al = smem_raw + (a_s - smem_u32(smem_raw));     // generic pointer to the aligned base
+    float *xs = reinterpret_cast<float *>(smem_al + p.x_off);     // [2][8][PITCH]
+    const int tid = threadIdx.x;
+    const int c = tid % hsv_act::ROWS, run = tid / hsv_act::ROWS;
+    const int64_t t_first = (int64_t)tile * TILE_M * MSUB - p.hlo8;   // time of A-tile row 0 (multiple of 8)
+    const int ngroups = p.Cin >> 3;
+    const bool fast = ((p.L & 3) == 0) && t_first >= K::XOFF && t_first + K::TILE + K::XOFF <= p.L &&
+                      ((reinterpret_cast<uintptr_t>(p.fx) & 15) == 0);
+    constexpr uint32_t ROW_BYTES = (uint32_t)K::XW * 4u;
+    auto issue = [&](int g) {   // TMA staging of group g (fast tiles): one bulk copy per channel row
+      const uint32_t bar = bar_x + 8 * (g & 1);
+      if (tid == 0) mbar_expect_tx(bar, ROW_BYTES * hsv_act::ROWS);
+      if (tid < hsv_act::ROWS) {
+        const float *src = p.fx + ((int64_t)b * p.Cin + g * 8 + tid) * p.L + (t_first - K::XOFF);
+        bulk_g2s(smem_u32(xs + (g & 1) * (hsv_act::ROWS * K::PITCH) + tid * K::PITCH), src, ROW_BYTES, bar);
+      }
+    };
+    if (fast) issue(0);
+    const int64_t ta = t_first + (int64_t)run * RR;
+    const bool need = run * RR < p.R && ta < p.L && ta + RR > 0;     // this run holds rows of the A tile inside [0, L)
+    float al = __ldg(p.alpha + c), be = __ldg(p.beta + c);
+    for (int g = 0; g < ngroups; ++g) {
+      float *xb = xs + (g & 1) * (hsv_act::ROWS * K::PITCH);
+      const float al_g = al, be_g = be;
+      if (g + 1 < ngroups) {
+        al = __ldg(p.alpha + (g + 1) * 8 + c);
+        be = __ldg(p.beta + (g + 1) * 8 + c);
+      }
+      if (fast) {
+        if (g + 1 < ngroups) issue(g + 1);   // its buffer was released by the barrier that ended pass g - 1
+        mbar_wait(bar_x + 8 * (g & 1), (uint32_t)(g >> 1) & 1u);
+      } else {
+        // tiles touching either end of the sequence (or unaligned tensors): clamped loads, all issued before
+        // the first store
+        constexpr int NLD = (hsv_act::ROWS * K::XW + 127) / 128;
+        const int Lm1 = (int)(p.L - 1);
+        float v[NLD];
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) {
+          const int idx = tid + 128 * i;
+          const int cc = idx / K::XW, pp = idx - cc * K::XW;
+          const int64_t t = t_first - K::XOFF + pp;
+          const int tc = t < 0 ? 0 : (t > Lm1 ? Lm1 : (int)t);
+          v[i] = idx < hsv_act::ROWS * K::XW ? __ldg(p.fx + ((int64_t)b * p.Cin + g * 8 + cc) * p.L + tc) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) {
+          const int idx = tid + 128 * i;
+          const int cc = idx / K::XW, pp = idx - cc * K::XW;
+          if (idx < hsv_act::ROWS * K::XW) xb[cc * K::PITCH + pp] = v[i];
+        }
+        __syncthreads();
+      }
+      if (run * RR < p.R) {
+        float outv[RR];
+        if (need) {
+          const float *xw = xb + c * K::PITCH + run * RR + (K::XOFF - 5);
+          hsv_act::act_run<RR, true>(xw, outv, al_g, be_g, ta, p.L, p.fx + ((int64_t)b * p.Cin + g * 8 + c) * p.L,
+                                     p.in_scale);
+        }
+        // fp16 into the swizzled A tile: row = run*RR + j, 16-byte unit g, half c; rows outside [0, L) are the
+        // conv's zero padding
+        const uint32_t swz_mask = (uint32_t)(p.cw >> 3) - 1u;
+#pragma unroll
+        for (int j = 0; j < RR; ++j) {
+          const int rowt = run * RR + j;
+          const int64_t t = ta + j;
+          const float val = (need && t >= 0 && t < p.L) ? outv[j] : 0.f;
+          if (rowt < p.R) {
+            const uint32_t lin = (uint32_t)rowt * rowbytes + (uint32_t)g * 16u;
+            const uint32_t addr = a_s + (lin ^ (((lin >> 7) & swz_mask) << 4)) + (uint32_t)c * 2u;
+            const unsigned short hbits = __half_as_ushort(__float2half_rn(val));
+            asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(hbits) : "memory");
+          }
+        }
+      }
+      // generic-proxy writes of the A tile must be visible to the tensor core (async proxy)
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();  // staging buffer reusable; after the last pass: the A tile is complete
+    }
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_a) : "memory");  // A chunk 0 "landed"
+      stamp(p, 4);
+    }
+  }
+
   if (warp == 0 && lane == 0) {
     // ---------------- TMA producer ----------------
-    // weights are static data: fill the ring before waiting for the kernel that produces the activations
-    // (issuing a bulk copy costs the thread a few hundred cycles: measured ~900 cycles for 4 stages)
-    for (int rnd = 0; rnd < npre; ++rnd) load_w(rnd, rnd);
-    stamp(p, 10);
-    hsv::pdl_wait();
-    stamp(p, 2);
-    const int64_t row0 = (int64_t)HSV_BLK_PAD + (int64_t)tile * TILE_M * MSUB - p.hlo8;  // multiple of 8
-    for (int c = 0; c < p.nchunks; ++c) {
-      const uint8_t *src = p.a + (((int64_t)b * p.nchunks + c) * p.Lp + row0) * rowbytes;
-      mbar_expect_tx(bar_a + 8 * c, a_chunk_bytes);
-      bulk_g2s(a_s + c * p.a_pitch, src, a_chunk_bytes, bar_a + 8 * c);
+    if constexpr (RR == 0) {
+      // weights are static data: fill the ring before waiting for the kernel that produces the activations
+      // (issuing a bulk copy costs the thread a few hundred cycles: measured ~900 cycles for 4 stages)
+      for (int rnd = 0; rnd < npre; ++rnd) load_w(rnd, rnd);
+      stamp(p, 10);
+      hsv::pdl_wait();
+      stamp(p, 2);
+      const int64_t row0 = (int64_t)HSV_BLK_PAD + (int64_t)tile * TILE_M * MSUB - p.hlo8;  // multiple of 8
+      for (int c = 0; c < p.nchunks; ++c) {
+        const uint8_t *src = p.a + (((int64_t)b * p.nchunks + c) * p.Lp + row0) * rowbytes;
+        mbar_expect_tx(bar_a + 8 * c, a_chunk_bytes);
+        bulk_g2s(a_s + c * p.a_pitch, src, a_chunk_bytes, bar_a + 8 * c);
+      }
     }
     int s = 0;
     uint32_t par = 0;
@@ -684,7 +797,7 @@ int g_host_debug = 0;
 long long *g_trace = nullptr;
 int g_msub_override = 0;  // bring-up aid: force the sub-tiles per CTA (0 = automatic)
 
-template <int MSUB, int MINB, bool SMALLN>
+template <int MSUB, int MINB, bool SMALLN, int RR = 0>
 int launch_variant(const Params &p, dim3 grid, size_t smem, cudaStream_t st, const char *what) {
   // opt-in dynamic shared memory: 227 KB per block minus the kernel's static shared memory
   static int max_dyn[64] = {0};
@@ -693,11 +806,11 @@ int launch_variant(const Params &p, dim3 grid, size_t smem, cudaStream_t st, con
   if (dev < 0 || dev >= 64) dev = 0;
   if (max_dyn[dev] == 0) {
     cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, conv_umma_kernel<MSUB, MINB, SMALLN>);
+    cudaError_t e = cudaFuncGetAttributes(&fa, conv_umma_kernel<MSUB, MINB, SMALLN, RR>);
     int want = 227 * 1024 - (e == cudaSuccess ? (int)fa.sharedSizeBytes : 1024);
     want &= ~1023;
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_umma_kernel<MSUB, MINB, SMALLN>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+      e = cudaFuncSetAttribute(conv_umma_kernel<MSUB, MINB, SMALLN, RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
     if (e != cudaSuccess) {
       cudaGetLastError();  // clear
       hsv::set_error("%s: cudaFuncSetAttribute(%d): %s", what, want, cudaGetErrorString(e));
@@ -717,7 +830,7 @@ int launch_variant(const Params &p, dim3 grid, size_t smem, cudaStream_t st, con
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = hsv::g_pdl ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<MSUB, MINB, SMALLN>, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<MSUB, MINB, SMALLN, RR>, p);
   if (e != cudaSuccess) {
     cudaGetLastError();
     hsv::set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
@@ -726,10 +839,20 @@ int launch_variant(const Params &p, dim3 grid, size_t smem, cudaStream_t st, con
   return hsv::check_launch(what);
 }
 
+struct FusedAct {  // activation-producing variant: fp32 input of Activation1d instead of the fp16 operand tensor
+  const float *x, *alpha, *beta;
+  float in_scale;
+};
+
 int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const float *bias,
            const float *residual, float *out, float *acc, int acc_mode, int B, int Cin, int Cout, int64_t L,
-           int64_t Lout, int n_tile, cudaStream_t st, const char *what) {
+           int64_t Lout, int n_tile, cudaStream_t st, const char *what, const FusedAct *fa = nullptr) {
   Params p;
+  p.fx = fa ? fa->x : nullptr;
+  p.alpha = fa ? fa->alpha : nullptr;
+  p.beta = fa ? fa->beta : nullptr;
+  p.in_scale = fa ? fa->in_scale : 1.f;
+  p.x_off = 0;
   p.a = reinterpret_cast<const uint8_t *>(a_blk16);
   p.w = reinterpret_cast<const uint8_t *>(w_packed);
   p.bias = bias; p.residual = residual; p.out = out; p.acc = acc;
@@ -745,19 +868,29 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
               tt.h_lo, tt.h_hi, HSV_BLK_PAD);
   const int ntiles128 = (int)((L + TILE_M - 1) / TILE_M);
   const int blk_bytes = n_tile * rowbytes;
-  // sub-tiles per CTA: with msub = 2 every weight K-step read from shared memory feeds two MMAs, which keeps
-  // an N = 128 tile under the 128 B/clk shared-memory read limit (A 4 KB + B 4 KB per 64-cycle MMA otherwise).
-  // Worth it only when there are enough tiles to fill the GPU anyway.
+  // sub-tiles per CTA (measured policy, tools/microbench4.py on B200): msub = 2 shares every weight block between
+  // two 128-row MMAs and halves the per-row prologue/weight traffic, but doubles the A tile.  It pays for
+  // compute-heavy layers (Cin * taps >= 512) when the grid is large and either the tile is narrow (n_tile <= 64)
+  // or msub = 1 could not keep two CTAs per SM anyway (C = 256: 535 -> 746 TFLOP/s); where msub = 1 fits two
+  // CTAs with a 3-stage ring it is better (C = 128: 690 vs 466 TFLOP/s), and so it is for the HBM-bound k = 3 layers.
   int msub = 1;
   const int64_t ctas1 = (int64_t)ntiles128 * p.nco_tiles * tt.nphase * B;
-  if (n_tile >= 64 && ctas1 >= 2 * 148 * 2) msub = 2;
+  int max_taps = 0;
+  for (int q = 0; q < tt.nphase; ++q) max_taps = tt.ntaps[q] > max_taps ? tt.ntaps[q] : max_taps;
+  if (Cin * max_taps >= 512 && ctas1 >= 2 * 148 * 2) {
+    const size_t stage1 = (size_t)(16384 / blk_bytes > 0 ? 16384 / blk_bytes : 1) * blk_bytes;
+    const size_t a1 = ((((size_t)(TILE_M + p.hlo8 + tt.h_hi) * rowbytes) + 1023) & ~(size_t)1023) * p.nchunks;
+    if (n_tile <= 64 || 1024 + a1 + 3 * stage1 > 113 * 1024) msub = 2;
+  }
   if (g_msub_override > 0) msub = g_msub_override;
   if (msub == 3) msub = 2;
+  if (fa) msub = 2;  // 256-row tiles: the activation's 5-row run halo and the conv halo are amortised over more rows
   auto a_bytes_for = [&](int ms) {
     const size_t per = (((size_t)(TILE_M * ms + p.hlo8 + tt.h_hi) * rowbytes) + 1023) & ~(size_t)1023;
     return per * p.nchunks;
   };
-  while (msub > 1 && (msub * n_tile > 512 || msub > ntiles128 || a_bytes_for(msub) + 2 * (size_t)blk_bytes > 200 * 1024))
+  while (!fa && msub > 1 &&
+         (msub * n_tile > 512 || msub > ntiles128 || a_bytes_for(msub) + 2 * (size_t)blk_bytes > 200 * 1024))
     msub >>= 1;
   p.msub = msub;
   p.ntiles = (ntiles128 + msub - 1) / msub;
@@ -805,8 +938,24 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
     smem = 1024 + a_bytes + (size_t)p.stages * stage_bytes;
   }
   if (smem < 1024 + 8192) smem = 1024 + 8192;  // the epilogue stages 4 x 2 KB in the (then idle) operand area
+  int rr = 0;
+  if (fa) {
+    // run length of the in-CTA activation: 16 runs must cover the A tile (256 + halo rows)
+    rr = p.R <= 16 * 17 ? 17 : 20;
+    HSV_REQUIRE(p.R <= 16 * rr && p.nchunks == 1 && p.nco_tiles == 1 && tt.nphase == 1 && msub == 2 && n_tile <= 256,
+                "%s: shape not supported by the activation-producing variant (Cin=%d Cout=%d n_tile=%d rows=%d)", what,
+                Cin, Cout, n_tile, p.R);
+    const size_t pitch = rr == 17 ? hsv_act::Cfg<17>::PITCH : hsv_act::Cfg<20>::PITCH;
+    smem = (smem + 15) & ~(size_t)15;
+    p.x_off = (uint32_t)(smem - 1024);
+    smem += 2 * hsv_act::ROWS * pitch * sizeof(float);
+  }
   HSV_REQUIRE(B <= 65535 && (int64_t)p.nco_tiles * tt.nphase <= 65535, "%s: grid too large", what);
   dim3 grid((unsigned)p.ntiles, (unsigned)(p.nco_tiles * tt.nphase), (unsigned)B);
+  if (fa) {
+    if (rr == 17) return launch_variant<2, 3, false, 17>(p, grid, smem, st, what);
+    return launch_variant<2, 3, false, 20>(p, grid, smem, st, what);
+  }
   // small n_tile = HBM/latency-bound streaming layers: they want many co-resident CTAs (register cap 80);
   // large n_tile = few fat CTAs per SM anyway
   if (p.msub == 1) {
@@ -883,6 +1032,25 @@ extern "C" int hsv_conv1d_umma(const void *a_blk16, const void *w_packed, const 
   HSV_REQUIRE(out || acc_mode, "conv1d_umma: no output");
   return launch(conv_taps(k, d), a_blk16, w_packed, bias, residual, out, acc, acc_mode, B, Cin, Cout, L, L, n_tile,
                 hsv::as_stream(stream), "conv1d_umma");
+}
+
+extern "C" int hsv_act_conv1d_umma(const float *x, const float *alpha, const float *beta, float in_scale,
+                                   const void *w_packed, const float *bias, const float *residual, float *out,
+                                   float *acc, int acc_mode, int B, int Cin, int Cout, int64_t L, int k, int d,
+                                   void *stream) {
+  if (B == 0 || L == 0) return HSV_OK;  // empty batch / sequence
+  HSV_REQUIRE(x && alpha && beta, "act_conv1d_umma: null pointer");
+  HSV_REQUIRE(Cin == 16 || Cin == 32 || Cin == 64, "act_conv1d_umma: Cin must be 16, 32 or 64 (Cin=%d)", Cin);
+  if (int rc = check_common("act_conv1d_umma", x, w_packed, Cin, Cout, Cout)) return rc;
+  HSV_REQUIRE(k >= 1 && k <= MAX_TAPS && (k & 1) && d >= 1, "act_conv1d_umma: k must be odd and <= %d (k=%d d=%d)",
+              MAX_TAPS, k, d);
+  HSV_REQUIRE(((k - 1) / 2) * d <= HSV_BLK_PAD, "act_conv1d_umma: halo %d exceeds %d", ((k - 1) / 2) * d, HSV_BLK_PAD);
+  HSV_REQUIRE(acc_mode >= 0 && acc_mode <= 2 && (acc_mode == 0 || acc), "act_conv1d_umma: bad acc_mode/acc");
+  HSV_REQUIRE(out || acc_mode, "act_conv1d_umma: no output");
+  HSV_REQUIRE(out != x && acc != x, "act_conv1d_umma: the output must not alias the activation input");
+  const FusedAct fa = {x, alpha, beta, in_scale};
+  return launch(conv_taps(k, d), x, w_packed, bias, residual, out, acc, acc_mode, B, Cin, Cout, L, L, Cout,
+                hsv::as_stream(stream), "act_conv1d_umma", &fa);
 }
 
 extern "C" int hsv_conv_transpose1d_umma(const void *a_blk16, const void *w_packed, const float *bias,

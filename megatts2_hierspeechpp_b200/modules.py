@@ -235,12 +235,13 @@ class _Folded:
             self.key = key
         return self.w
 
-    def packed_weight(self, row_tiles: int = 1 << 30):
-        """(packed fp16 operand stream, n_tile) for a launch with ``row_tiles`` 128-row tiles (x batch)."""
+    def packed_weight(self, row_tiles: int = 1 << 30, n_tile: Optional[int] = None):
+        """(packed fp16 operand stream, n_tile) for a launch with ``row_tiles`` 128-row tiles (x batch), or for
+        the given ``n_tile``."""
         w = self.weight()
         if self.packed is None:
             self.packed = {}
-        nt = ops.pick_n_tile(w.shape[0], row_tiles)
+        nt = n_tile if n_tile is not None else ops.pick_n_tile(w.shape[0], row_tiles, w.shape[1] * w.shape[2])
         if nt not in self.packed:
             self.packed[nt] = ops.pack_conv_weight(w, nt)
         return self.packed[nt], nt
@@ -262,6 +263,13 @@ class _Folded:
 def _row_tiles(B: int, L: int) -> int:
     return B * ((L + ops.TILE_M - 1) // ops.TILE_M)
 
+
+# Whole-layer fusion: AMP half-layers whose channel count is at most this run as ONE kernel
+# (activation evaluated inside the conv CTA, bit-identical results).  Measured on B200 it is
+# SLOWER than the act kernel + conv kernel pair -- the activation is FP32-issue-bound and needs ~24 resident
+# warps per SM, the fused CTA (144 registers, 66 KB) allows 12 -- so the default is 0 (off); set
+# HSV_FUSE_MAX_C=32|64 or FUSE_MAX_CHANNELS[0] to use it.
+FUSE_MAX_CHANNELS = [int(__import__("os").environ.get("HSV_FUSE_MAX_C", "0"))]
 
 _MAIN_SLOT = 3   # blk16 workspace slot of the main stream (slots 0..2 belong to the per-resblock streams)
 
@@ -334,19 +342,35 @@ class AMPBlock1(nn.Module):
         if C != self.channels or C % 16:
             raise ValueError(f"AMP block expects {self.channels} channels (multiple of 16), got {C}")
         k = self.kernel_size
-        buf = ops.blk16_buffer(B, C, L, x.device, slot)
+        fused = C in ops.FUSED_CIN and C <= FUSE_MAX_CHANNELS[0]
+        buf = None if fused else ops.blk16_buffer(B, C, L, x.device, slot)
         xt = torch.empty_like(x)
         cur = x
         nl = len(self.dilation)
         for i, d in enumerate(self.dilation):
             a1, a2 = self.activations[2 * i], self.activations[2 * i + 1]
             a1.check_filters(); a2.check_filters()
+            last = i == nl - 1
+            if fused:
+                # act -> conv as one kernel per half-layer (the fp16 operand stays in shared memory)
+                w1, _ = self._f1[i].packed_weight(n_tile=C)
+                w2, _ = self._f2[i].packed_weight(n_tile=C)
+                ops.act_conv1d_umma(cur, *a1.params(), w1, self._f1[i].bias(), C, k, d, out=xt)
+                if last and before_final is not None:
+                    before_final()
+                if last and acc_mode != ops.ACC_NONE:
+                    ops.act_conv1d_umma(xt, *a2.params(), w2, self._f2[i].bias(), C, k, 1, residual=cur, acc=acc,
+                                        acc_mode=acc_mode, want_out=False)
+                    return None
+                out = torch.empty_like(x) if cur is x else cur
+                ops.act_conv1d_umma(xt, *a2.params(), w2, self._f2[i].bias(), C, k, 1, residual=cur, out=out)
+                cur = out
+                continue
             w1, nt1 = self._f1[i].packed_weight(_row_tiles(B, L))
             w2, nt2 = self._f2[i].packed_weight(_row_tiles(B, L))
             ops.act1d_blk16(cur, *a1.params(), buf)
             ops.conv1d_umma(buf, w1, self._f1[i].bias(), L, C, C, k, d, nt1, out=xt)
             ops.act1d_blk16(xt, *a2.params(), buf)
-            last = i == nl - 1
             if last and before_final is not None:
                 before_final()
             if last and acc_mode != ops.ACC_NONE:

@@ -145,12 +145,13 @@ def weight_norm_fold(v: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
     return w
 
 
-def pick_n_tile(cout: int, row_tiles: int = 1 << 30) -> int:
-    """Output-channel tile of the tcgen05 conv.  ``row_tiles`` = number of 128-row tiles x batch x phases of the
-    launch: with few row tiles (batch-1 latency regime) a narrower n_tile puts more CTAs to work on the same
-    layer (shorter serial MMA chain and weight stream per CTA); with many, the widest tile (<= 128) has the
-    best tensor/shared-memory efficiency."""
-    widest = (256, 128, 64, 32, 16)
+def pick_n_tile(cout: int, row_tiles: int = 1 << 30, cin_taps: int = 1 << 30) -> int:
+    """Output-channel tile of the tcgen05 conv (measured policy, tools/microbench4.py).  ``row_tiles`` = number of
+    128-row tiles x batch x phases of the launch: with few row tiles (batch-1 latency regime) a narrower n_tile
+    puts more CTAs to work on the same layer (shorter serial MMA chain and weight stream per CTA); with many, a
+    wide tile has the best tensor/shared-memory efficiency -- 128, not 256 (746 vs 725 TFLOP/s at C = 256), and
+    64 for the HBM-bound light layers (``cin_taps`` = Cin x taps < 512: 3.9 vs 3.4 TB/s at C = 128, k = 3)."""
+    widest = (128, 64, 32, 16) if cin_taps >= 512 else (64, 32, 16)
     cands = [n for n in widest if cout % n == 0]
     if not cands:
         for n in range(widest[0], 15, -16):
@@ -160,7 +161,7 @@ def pick_n_tile(cout: int, row_tiles: int = 1 << 30) -> int:
     if not cands:
         raise ValueError(f"Cout={cout} not a multiple of 16")
     for n in cands:
-        if n <= 32 or row_tiles * (cout // n) >= (296 if n == 256 else 120):
+        if n <= 32 or row_tiles * (cout // n) >= (120 if n >= 128 else 60):
             return n
     return cands[-1]
 
@@ -200,6 +201,46 @@ def conv1d_umma(a_blk: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torc
     _lib.check(lib.hsv_conv1d_umma(_p(a_blk), _p(w_packed), _p(bias), _p(residual), _p(out), _p(acc), acc_mode,
                                    float(acc_div), B, cin, cout, L, k, d, n_tile, _stream()), "hsv_conv1d_umma")
     return out
+
+
+def act_conv1d_umma(x: torch.Tensor, alpha: torch.Tensor, beta: torch.Tensor, w_packed: torch.Tensor,
+                    bias: Optional[torch.Tensor], cout: int, k: int, d: int, residual: Optional[torch.Tensor] = None,
+                    out: Optional[torch.Tensor] = None, acc: Optional[torch.Tensor] = None, acc_mode: int = ACC_NONE,
+                    scale: float = 1.0, want_out: bool = True):
+    """Whole AMP half-layer in one kernel: ``conv1d(Activation1d(x * scale))`` (+bias, +residual, accumulate).
+
+    x fp32 [B,Cin,L] with Cin in {16,32,64}; ``w_packed`` from ``pack_conv_weight(w, n_tile=cout)``.  Bit-identical to
+    ``act1d_blk16`` + ``conv1d_umma``; the fp16 operand never goes to HBM.  ``out``/``acc`` must not alias ``x``."""
+    _req(x, "x", ndim=3); _req(alpha, "alpha"); _req(beta, "beta"); _req(w_packed, "w_packed", torch.float16)
+    B, cin, L = x.shape
+    if cin not in FUSED_CIN:
+        raise ValueError(f"act_conv1d_umma: Cin must be one of {FUSED_CIN} (Cin={cin})")
+    if alpha.numel() != cin or beta.numel() != cin:
+        raise ValueError(f"alpha/beta must have {cin} elements")
+    if w_packed.numel() < cout * cin * k:
+        raise ValueError("w_packed size mismatch")
+    for t, n in ((bias, "bias"), (residual, "residual"), (out, "out"), (acc, "acc")):
+        if t is not None:
+            _req(t, n)
+    if residual is not None and tuple(residual.shape) != (B, cout, L):
+        raise ValueError("residual shape mismatch")
+    if out is None and want_out:
+        out = torch.empty(B, cout, L, dtype=torch.float32, device=x.device)
+    if out is not None and tuple(out.shape) != (B, cout, L):
+        raise ValueError("out shape mismatch")
+    if acc is not None and tuple(acc.shape) != (B, cout, L):
+        raise ValueError("acc shape mismatch")
+    for t in (out, acc):
+        if t is not None and x.numel() and t.data_ptr() == x.data_ptr():
+            raise ValueError("act_conv1d_umma: out/acc must not alias x")
+    lib = _lib.load()
+    _lib.check(lib.hsv_act_conv1d_umma(_p(x), _p(alpha), _p(beta), float(scale), _p(w_packed), _p(bias), _p(residual),
+                                       _p(out), _p(acc), acc_mode, B, cin, cout, L, k, d, _stream()),
+               "hsv_act_conv1d_umma")
+    return out
+
+
+FUSED_CIN = (16, 32, 64)   # channel counts the activation-producing conv variant takes (single operand chunk)
 
 
 def pack_convT_weight(w: torch.Tensor, u: int, n_tile: int) -> torch.Tensor:
@@ -327,6 +368,24 @@ def add3_bcast(a: torch.Tensor, b: Optional[torch.Tensor], bc: Optional[torch.Te
     lib = _lib.load()
     _lib.check(lib.hsv_add3_bcast(_p(a), _p(b), _p(bc), _p(out), B * C, L, _stream()), "hsv_add3_bcast")
     return out
+
+
+def peak_norm_pcm16(x: torch.Tensor, s1: float = 32767.0, s2: float = 0.999, per_row: bool = False):
+    """int16 PCM of ``x / max|x| * s1 * s2`` (fp32, reference operation order, truncation like numpy's astype).
+
+    x: fp32 [..., L]; leading dims are rows.  ``per_row=False`` uses one peak for the whole tensor
+    (inference_plm.py:183-188 / inference_speechsr.py:39-41), ``True`` one per row.  Returns (pcm int16, peaks fp32)."""
+    _req(x, "x")
+    if x.dim() < 1:
+        raise ValueError("x must have at least one dim")
+    L = x.shape[-1]
+    rows = x.numel() // L if L else 0
+    out = torch.empty(x.shape, dtype=torch.int16, device=x.device)
+    peaks = torch.zeros(max(rows, 1), dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    _lib.check(lib.hsv_peak_norm_pcm16(_p(x), _p(out), _p(peaks), rows, L, float(s1), float(s2), int(per_row), _stream()),
+               "hsv_peak_norm_pcm16")
+    return out, (peaks if per_row else peaks[:1])
 
 
 def set_umma_debug(flags: int):

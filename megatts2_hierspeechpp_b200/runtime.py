@@ -12,6 +12,24 @@ from typing import Callable, Dict, List, Sequence, Tuple
 import torch
 
 
+def to_pcm16(audio: torch.Tensor, scale_norm: str = "max", prompt_audio_max: float = 1.0, order: str = "plm",
+             per_utterance: bool = False) -> torch.Tensor:
+    """int16 PCM of a generated waveform, on the device (the step after the path).
+
+    ``order="plm"``: ``audio / |audio|.max() * 32767.0 * s`` with s = 0.999, or ``prompt_audio_max`` when
+    ``scale_norm == "prompt"`` (inference_plm.py:183-188); ``order="speechsr"``: ``... * 0.999 * 32767.0``
+    (inference_speechsr.py:39-41).  Bit-exact with the reference's fp32 arithmetic + ``astype('int16')``."""
+    from . import ops
+    if order == "plm":
+        s1, s2 = 32767.0, (float(prompt_audio_max) if scale_norm == "prompt" else 0.999)
+    elif order == "speechsr":
+        s1, s2 = 0.999, 32767.0
+    else:
+        raise ValueError("order must be 'plm' or 'speechsr'")
+    pcm, _ = ops.peak_norm_pcm16(audio.detach().contiguous(), s1, s2, per_row=per_utterance)
+    return pcm
+
+
 class CudaGraphRunner:
     """Capture ``fn(*tensors)`` once per input-shape signature and replay it.
 

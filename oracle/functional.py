@@ -183,3 +183,11 @@ def vocoder(sd: SD, z, g, sn_prefix="sn.", dec_prefix="dec."):
     """The sn -> dec pair of SynthesizerTrn.infer hierspeechpp_speechsynthesizer.py:648-649."""
     e, _ = source_network(sd, sn_prefix, z, g)
     return hier_generator(sd, dec_prefix, z, e, g)
+
+
+def peak_norm_pcm16(audio: torch.Tensor, s1: float = 32767.0, s2: float = 0.999) -> "np.ndarray":
+    """inference_plm.py:183-188 (s1=32767.0, s2=0.999 or the prompt peak) / inference_speechsr.py:39-41
+    (s1=0.999, s2=32767.0): ``audio / abs(audio).max() * s1 * s2`` in fp32, then numpy ``astype('int16')``."""
+    a = audio.squeeze()
+    a = a / (torch.abs(a).max()) * s1 * s2
+    return a.cpu().numpy().astype("int16")

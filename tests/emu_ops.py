@@ -82,6 +82,25 @@ def conv1d_umma(a_blk, wp, bias, L, cin, cout, k, d, n_tile, residual=None, out=
     return v if want_out else None
 
 
+def act_conv1d_umma(x, alpha, beta, wp, bias, cout, k, d, residual=None, out=None, acc=None, acc_mode=0, scale=1.0,
+                    want_out=True):
+    B, cin, L = x.shape
+    assert out is None or out.data_ptr() != x.data_ptr()
+    assert acc is None or acc.data_ptr() != x.data_ptr()
+    a = _act(x * scale, alpha, beta).half().float()          # the kernel's fp16 operand rounding
+    v = F.conv1d(a, wp.float().view(cout, cin, k), bias, padding=(k - 1) // 2 * d, dilation=d)
+    if residual is not None:
+        v = v + residual
+    if acc_mode == 1:
+        acc.copy_(v)
+    elif acc_mode == 2:
+        acc.add_(v)
+    if out is not None:
+        out.copy_(v)
+        return out
+    return v if want_out else None
+
+
 def pack_convT_weight(w, u, n_tile):
     return w.half().flatten().clone()
 
@@ -130,7 +149,7 @@ def add3_bcast(a, b, bc, out=None):
     return v
 
 
-NAMES = ["blk16_buffer", "act1d", "act1d_blk16", "pack_blk16", "weight_norm_fold", "pack_conv_weight", "conv1d_umma", "pack_convT_weight", "conv_transpose1d_umma",
+NAMES = ["blk16_buffer", "act1d", "act1d_blk16", "pack_blk16", "weight_norm_fold", "pack_conv_weight", "conv1d_umma", "act_conv1d_umma", "pack_convT_weight", "conv_transpose1d_umma",
          "conv1d_direct", "conv_transpose1d", "sr_pre_interp", "nearest_gather", "add3_bcast"]
 
 

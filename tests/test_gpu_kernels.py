@@ -279,6 +279,22 @@ def test_conv1d_umma_rectangular_and_acc_modes(hsv):
     assert (acc.cpu().double() - ref).abs().max().item() <= 2e-4
 
 
+@pytest.mark.parametrize("n_tile", [16, 64, 256])
+def test_conv1d_umma_explicit_n_tiles(hsv, n_tile):
+    """Every N-tile width the kernel accepts (16 .. 256) gives the same result; 256 = one CTA column per tile."""
+    gen = torch.Generator().manual_seed(n_tile)
+    B, C, L, k, d = 2, 256, 700, 7, 3
+    x = torch.randn(B, C, L, generator=gen)
+    w = torch.randn(C, C, k, generator=gen) / (C * k) ** 0.5
+    b = torch.randn(C, generator=gen) * 0.1
+    ref = F.conv1d(x.half().double(), w.half().double(), b.double(), padding=OF.get_padding(k, d), dilation=d)
+    buf = hsv.ops.blk16_buffer(B, C, L, DEV, slot=9)
+    hsv.ops.pack_blk16(x.to(DEV), buf)
+    wp = hsv.ops.pack_conv_weight(w.to(DEV), n_tile)
+    y = hsv.ops.conv1d_umma(buf, wp, b.to(DEV), L, C, C, k, d, n_tile).cpu().double()
+    assert (y - ref).abs().max().item() <= 2e-4 * max(1.0, ref.abs().max().item())
+
+
 def test_conv1d_umma_full_size_linearity(hsv):
     """Stage-4 size (C=16, L=160000): conv(a)+conv(b) == conv(a+b) with bias counted once (fp32 accumulate)."""
     gen = torch.Generator().manual_seed(4)
@@ -303,3 +319,84 @@ def test_conv1d_umma_full_size_linearity(hsv):
     got = outs[0][:, :, sl].cpu().double()
     off = 70000 - 69900 - (k - 1) // 2 * d
     assert (got - ref[:, :, off:off + 500]).abs().max().item() <= 2e-4
+
+
+# ----------------------------------------------------------------------------------------------
+# the step after the path: peak-normalise + int16 -- integer output, bit-exact
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("s1,s2", [(32767.0, 0.999), (0.999, 32767.0), (32767.0, 0.4173)])
+@pytest.mark.parametrize("shape", [(1, 1, 160000), (1, 1, 7), (1, 1, 72001)])
+def test_peak_norm_pcm16_bit_exact(hsv, s1, s2, shape):
+    gen = torch.Generator().manual_seed(int(s2 * 1000) + shape[-1])
+    x = torch.tanh(torch.randn(*shape, generator=gen) * 0.7)
+    ref = OF.peak_norm_pcm16(x, s1, s2)
+    pcm, peak = hsv.ops.peak_norm_pcm16(x.to(DEV), s1, s2)
+    assert pcm.dtype == torch.int16 and tuple(pcm.shape) == shape
+    assert peak.item() == x.abs().max().item()
+    assert np.array_equal(pcm.cpu().numpy().reshape(-1), ref.reshape(-1))
+
+
+def test_peak_norm_pcm16_rows_and_edges(hsv):
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(3, 1, 5000, generator=gen) * torch.tensor([0.1, 1.0, 3.0]).view(3, 1, 1)
+    pcm, peaks = hsv.ops.peak_norm_pcm16(x.to(DEV), 32767.0, 0.999, per_row=True)
+    for b in range(3):   # every utterance normalised on its own == the reference applied per utterance
+        assert np.array_equal(pcm[b].cpu().numpy().reshape(-1), OF.peak_norm_pcm16(x[b:b + 1]).reshape(-1))
+        assert peaks[b].item() == x[b].abs().max().item()
+    # whole-tensor peak (the reference's semantics when handed a batch)
+    pcm_g, peak = hsv.ops.peak_norm_pcm16(x.to(DEV), 32767.0, 0.999, per_row=False)
+    assert peak.item() == x.abs().max().item()
+    assert np.array_equal(pcm_g.cpu().numpy().reshape(-1), OF.peak_norm_pcm16(x.reshape(1, 1, -1)).reshape(-1))
+    # full scale hits +-32734 (32767 * 0.999 truncated), never overflows; empty input is a no-op
+    assert int(pcm_g.abs().max()) == int(np.float32(np.float32(32767.0) * np.float32(0.999)))
+    e, _ = hsv.ops.peak_norm_pcm16(torch.empty(0, 1, 0, device=DEV))
+    assert e.numel() == 0
+
+
+# ----------------------------------------------------------------------------------------------
+# whole-layer fusion: act -> conv in one kernel == act kernel + conv kernel, bit for bit
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,C,L,k,d", [(1, 32, 1000, 7, 3), (2, 16, 4096, 11, 5), (1, 64, 2048, 3, 1), (2, 32, 300, 11, 5),
+                                       (1, 16, 257, 3, 5), (1, 32, 7, 7, 1), (1, 64, 515, 11, 3), (1, 16, 5121, 7, 1),
+                                       (3, 32, 2304, 11, 1)])
+def test_act_conv_fused_equals_unfused(hsv, B, C, L, k, d):
+    gen = torch.Generator().manual_seed(B + C + L + k + d)
+    x = (torch.randn(B, C, L, generator=gen) * 1.5).to(DEV)
+    al = (torch.rand(C, generator=gen) * 1.5 - 0.5).to(DEV)
+    be = (torch.rand(C, generator=gen) * 1.3 - 0.5).to(DEV)
+    w = (torch.randn(C, C, k, generator=gen) / (C * k) ** 0.5).to(DEV)
+    bias = (torch.randn(C, generator=gen) * 0.1).to(DEV)
+    res = torch.randn(B, C, L, generator=gen).to(DEV)
+    wp = hsv.ops.pack_conv_weight(w, C)
+    buf = hsv.ops.blk16_buffer(B, C, L, DEV, slot=8)
+    hsv.ops.act1d_blk16(x, al, be, buf, scale=0.5)
+    ref = hsv.ops.conv1d_umma(buf, wp, bias, L, C, C, k, d, C, residual=res)
+    got = hsv.ops.act_conv1d_umma(x, al, be, wp, bias, C, k, d, residual=res, scale=0.5)
+    torch.cuda.synchronize()
+    assert torch.equal(got, ref), (got - ref).abs().max().item()
+    # and against the CPU oracle (fp16 operand rounding emulated)
+    a = _act_oracle(x.cpu() * 0.5, al.cpu(), be.cpu()).half().double()
+    o = F.conv1d(a, w.cpu().half().double(), bias.cpu().double(), padding=OF.get_padding(k, d), dilation=d) + res.cpu().double()
+    assert (got.cpu().double() - o).abs().max().item() <= 3e-3 * max(1.0, o.abs().max().item())
+
+
+def test_act_conv_fused_acc_modes_and_aliasing(hsv):
+    gen = torch.Generator().manual_seed(11)
+    B, C, L, k = 2, 32, 1500, 7
+    x = torch.randn(B, C, L, generator=gen).to(DEV)
+    al = (torch.rand(C, generator=gen) - 0.5).to(DEV)
+    be = (torch.rand(C, generator=gen) - 0.5).to(DEV)
+    w = (torch.randn(C, C, k, generator=gen) / (C * k) ** 0.5).to(DEV)
+    wp = hsv.ops.pack_conv_weight(w, C)
+    res = torch.randn(B, C, L, generator=gen).to(DEV)
+    base = hsv.ops.act_conv1d_umma(x, al, be, wp, None, C, k, 1, residual=res)
+    # out aliasing the residual (the AMP block's in-place residual update)
+    r2 = res.clone()
+    hsv.ops.act_conv1d_umma(x, al, be, wp, None, C, k, 1, residual=r2, out=r2)
+    assert torch.equal(r2, base)
+    acc = torch.empty_like(x)
+    hsv.ops.act_conv1d_umma(x, al, be, wp, None, C, k, 1, residual=res, acc=acc, acc_mode=hsv.ops.ACC_SET, want_out=False)
+    hsv.ops.act_conv1d_umma(x, al, be, wp, None, C, k, 1, residual=res, acc=acc, acc_mode=hsv.ops.ACC_ADD, want_out=False)
+    assert torch.equal(acc, base + base)
+    with pytest.raises(ValueError):
+        hsv.ops.act_conv1d_umma(x, al, be, wp, None, C, k, 1, out=x)

@@ -222,3 +222,20 @@ def test_config4_vocoder_then_speechsr24(hsv, vocoder):
     ref16 = OF.vocoder(synth.vocoder_sd(1234), z, gg)
     ref24 = OF.speechsr(sd_sr, ref16, 24)
     _check("vocoder -> SpeechSR24 chain", wav24, ref24)
+
+
+def test_fused_half_layers_are_bit_identical(hsv, vocoder):
+    """Whole-layer fusion (opt-in): act evaluated inside the conv CTA for C <= 64 gives the same
+    bits as the act kernel + conv kernel pair (same fp16 operand rounding, same MMA order)."""
+    import megatts2_hierspeechpp_b200.modules as M
+    z, gg = synth.vocoder_inputs(2, 30, seed=91)
+    z, gg = z.to(DEV), gg.to(DEV)
+    old = M.FUSE_MAX_CHANNELS[0]
+    try:
+        M.FUSE_MAX_CHANNELS[0] = 0
+        ref = vocoder(z, gg).clone()
+        M.FUSE_MAX_CHANNELS[0] = 64
+        got = vocoder(z, gg).clone()
+    finally:
+        M.FUSE_MAX_CHANNELS[0] = old
+    assert torch.equal(got, ref)

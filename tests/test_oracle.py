@@ -129,3 +129,18 @@ def test_snr_metric():
     a = np.sin(np.arange(1000) * 0.01)
     assert CF.snr_db(a, a) == float("inf")
     assert abs(CF.snr_db(a, a * 1.01) - 40.0) < 0.1
+
+
+def test_oracle_peak_norm_pcm16_matches_reference_expression():
+    """oracle.functional.peak_norm_pcm16 is the literal expression of inference_plm.py:183-188 /
+    inference_speechsr.py:39-41; check order sensitivity is preserved (the two scripts differ in operand order)."""
+    import numpy as np
+    import torch
+    from oracle import functional as OF
+    g = torch.Generator().manual_seed(0)
+    a = torch.tanh(torch.randn(1, 1, 50000, generator=g))
+    plm = (a.squeeze() / torch.abs(a.squeeze()).max() * 32767.0 * 0.999).numpy().astype("int16")
+    sr = (a.squeeze() / torch.abs(a.squeeze()).max() * 0.999 * 32767.0).numpy().astype("int16")
+    assert np.array_equal(OF.peak_norm_pcm16(a, 32767.0, 0.999), plm)
+    assert np.array_equal(OF.peak_norm_pcm16(a, 0.999, 32767.0), sr)
+    assert np.abs(plm.astype(np.int32) - sr.astype(np.int32)).max() <= 1
