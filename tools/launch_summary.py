@@ -35,13 +35,17 @@ def short(name):
 
 if __name__ == "__main__":
     rows = load(sys.argv[1])
-    # keep the launches of the LAST forward: everything after the last weight-fold / pack launch
-    last_setup = max((i for i, r in enumerate(rows) if "fold" in r[0] or "pack_weight" in r[0]), default=-1)
-    steady = rows[last_setup + 1:]
-    nfwd = int(sys.argv[2]) if len(sys.argv) > 2 else 1
-    # steady holds (n_total - 1) full forwards + the tail of the first; take the last len/nfwd
-    per = len(steady) // nfwd if nfwd > 1 else len(steady)
-    sel = steady[-per:]
+    if "--all" in sys.argv:
+        # whole command (e.g. bench.py: warm-up + timed steps + per-kernel roofline passes): every hsv launch
+        # except the one-time weight fold / pack kernels and torch's own fill/copy kernels
+        sel = [r for r in rows if "fold" not in r[0] and "pack_weight" not in r[0] and "at::" not in r[0]
+               and "Memcpy" not in r[0]]
+    else:
+        # every forward issues the same launches apart from the one-time weight fold / pack kernels: drop those
+        # and keep the last of the nfwd forwards
+        steady = [r for r in rows if "fold" not in r[0] and "pack_weight" not in r[0]]
+        nfwd = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 1
+        sel = steady[-(len(steady) // nfwd):]
     agg = defaultdict(lambda: [0, 0.0])
     for name, us, *_ in sel:
         a = agg[short(name)]
