@@ -46,13 +46,16 @@ def case(B, C, L, k, d, nt, msub):
     print(f"  B={B} C={C:3d} L={L:6d} k={k:2d} n_tile={nt:3d} msub={msub}: {us:8.2f} us  {tf:7.1f} TFLOP/s  {gb:7.1f} GB/s", flush=True)
 
 
+SHAPES = ((256, 2000, (256, 128, 64)), (128, 10000, (128, 64)), (64, 40000, (64,)), (32, 80000, (32,)))
+if len(sys.argv) > 1 and sys.argv[1] == "small":
+    SHAPES = ((16, 160000, (16,)), (32, 80000, (32,)))
 for B in (16, 1):
     print(f"== B={B}")
-    for (C, L, nts) in ((256, 2000, (256, 128, 64)), (128, 10000, (128, 64)), (64, 40000, (64,)), (32, 80000, (32,))):
-        for k, d in ((3, 1), (11, 5)):
+    for (C, L, nts) in SHAPES:
+        for k, d in ((3, 1), (7, 1), (11, 5)):
             for nt in nts:
                 for msub in (1, 2, 4):
-                    if B == 1 and msub == 4:
+                    if B == 1 and msub == 4 and C > 32:
                         continue
                     case(B, C, L, k, d, nt, msub)
 hsv.ops.set_umma_debug(0)
