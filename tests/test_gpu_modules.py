@@ -239,3 +239,20 @@ def test_fused_half_layers_are_bit_identical(hsv, vocoder):
     finally:
         M.FUSE_MAX_CHANNELS[0] = old
     assert torch.equal(got, ref)
+
+
+def test_long_form_config5_slice_properties(hsv, vocoder):
+    """Config #5's unit of work (30 s utterances, utterance-sharded): at full length the result of an utterance
+    does not depend on its batch neighbours, is deterministic, and its first seconds equal... the reference's
+    receptive field bounds the influence of the future: samples far from the cut are identical."""
+    z, gg = synth.vocoder_inputs(2, 1500, seed=123)             # 2 x 30 s
+    z, gg = z.to(DEV), gg.to(DEV)
+    w2 = vocoder(z, gg).clone()
+    assert w2.shape == (2, 1, 480000) and torch.isfinite(w2).all()
+    assert torch.equal(w2, vocoder(z, gg))                       # deterministic
+    w1 = vocoder(z[1:].contiguous(), gg[1:].contiguous())
+    assert torch.equal(w2[1:], w1)                               # independent of batch neighbours
+    # a 10 s prefix agrees with the 30 s run away from the cut (finite receptive field: < 0.5 s at 16 kHz)
+    wp = vocoder(z[:1, :, :500].contiguous(), gg[:1])
+    a, b = wp[0, 0, :160000 - 16000], w2[0, 0, :160000 - 16000]
+    assert (a - b).abs().max().item() <= 1e-4
