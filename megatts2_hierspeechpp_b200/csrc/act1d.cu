@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(NT) act1d_kernel(const float *__restrict__ x, 
 }
 
 int g_act_variant = 1;  // 1: packed f32x2 math (default), 0: scalar math
-int g_act_run = 0;      // bring-up aid: force the run length (17 or 33); 0 = automatic
+int g_act_run = 0;      // bring-up aid: force the run length (17 or 25); 0 = automatic
 
 template <int R, int OUT_MODE>
 int launch(const float *x, void *out, const float *alpha, const float *beta, int B, int C, int64_t L, float sc,
@@ -229,14 +229,15 @@ extern "C" int hsv_act1d_snakebeta(const float *x, void *out, const float *alpha
   HSV_REQUIRE(out_mode == 0 || out_mode == 1, "act1d: out_mode must be 0 (fp32 NCL) or 1 (fp16 blk16)");
   if (B == 0 || L == 0) return HSV_OK;
   cudaStream_t st = hsv::as_stream(stream);
-  // run length per thread: 33 outputs (10 halo steps per 33: 1.15x redundant 2x-rate work) when the tensor is
-  // large enough to still fill the GPU with the bigger tiles, else 17 (1.29x) for more CTAs
+  // run length per thread: 25 outputs (5 halo steps per 25: 1.2x redundant 2x-rate work, 66 registers -> 7 CTAs
+  // per SM; measured 3.97 TB/s vs 3.85 for 33 and 3.06 for 17 on [16,32,480000]) when the tensor is large enough
+  // to still fill the GPU with the bigger tiles, else 17 (1.29x) for more CTAs (batch-1 layers: 17 beats 9/25/33)
   const int64_t groups = ((int64_t)B * C + ROWS - 1) / ROWS;
-  const bool big = g_act_run ? g_act_run == 33 : (groups * ((L + 33 * RUNS - 1) / (33 * RUNS)) >= 16 * 148);
+  const bool big = g_act_run ? g_act_run == 25 : (groups * ((L + 25 * RUNS - 1) / (25 * RUNS)) >= 16 * 148);
   if (out_mode == 0)
-    return big ? launch<33, 0>(x, out, alpha, beta, B, C, L, in_scale, st)
+    return big ? launch<25, 0>(x, out, alpha, beta, B, C, L, in_scale, st)
                : launch<17, 0>(x, out, alpha, beta, B, C, L, in_scale, st);
   HSV_REQUIRE(C % 16 == 0, "act1d: blk16 output needs C %% 16 == 0 (C=%d)", C);
-  return big ? launch<33, 1>(x, out, alpha, beta, B, C, L, in_scale, st)
+  return big ? launch<25, 1>(x, out, alpha, beta, B, C, L, in_scale, st)
              : launch<17, 1>(x, out, alpha, beta, B, C, L, in_scale, st);
 }
