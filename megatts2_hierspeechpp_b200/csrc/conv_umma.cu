@@ -551,7 +551,10 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
   const int nunits = MSUB * nchk;
   const bool has_res = p.residual != nullptr;
   const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+  // residual prefetch depth (units).  4 in flight was measured too (136 registers): no gain at batch 16
+  // (C=128, k=11: 82.0 vs 83.6 us) and one CTA per SM less for the n_tile = 64 variant, so 2.
   constexpr int PF = 2;
+  constexpr int PFG = 2;  // the generic (scalar) path keeps 2
   if (p.vec_epi) {
     const int cq = lane >> 3, i4 = (lane & 7) << 2;
     const int64_t t_warp = (int64_t)tile * MSUB * TILE_M + warp * 32 + i4;  // first row of this lane's float4 (sub 0)
@@ -660,9 +663,9 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
       ok = t < p.L;
       off = chan_base + (int64_t)p.tt.out_stride * t + (int64_t)c0 * cs;
     };
-    float res[PF][16];
+    float res[PFG][16];
 #pragma unroll
-    for (int q = 0; q < PF; ++q) {
+    for (int q = 0; q < PFG; ++q) {
       int64_t off; bool ok;
       unit_ptr(q < nunits ? q : 0, off, ok);
       ok = ok && has_res && q < nunits;
@@ -675,9 +678,9 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
     __syncwarp();
     if (threadIdx.x == 0) stamp(p, 7);
 #pragma unroll 1
-    for (int u0 = 0; u0 < nunits; u0 += PF) {
+    for (int u0 = 0; u0 < nunits; u0 += PFG) {
 #pragma unroll
-      for (int q = 0; q < PF; ++q) {
+      for (int q = 0; q < PFG; ++q) {
         const int u = u0 + q;
         if (u < nunits) {
           const int sub = u / nchk, c0 = (u - sub * nchk) << 4;
@@ -690,8 +693,8 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
           for (int c = 0; c < 16; ++c) v[c] = (__uint_as_float(r[c]) + bias_s[c0 + c]) + res[q][c];  // reference order
           {
             int64_t offn; bool okn;
-            unit_ptr(u + PF < nunits ? u + PF : u, offn, okn);
-            okn = okn && has_res && u + PF < nunits;
+            unit_ptr(u + PFG < nunits ? u + PFG : u, offn, okn);
+            okn = okn && has_res && u + PFG < nunits;
 #pragma unroll
             for (int c = 0; c < 16; ++c) res[q][c] = okn ? p.residual[offn + c * cs] : 0.f;
           }

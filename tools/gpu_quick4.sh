@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -q -m gpu -x > gpurun_out/t_all.log 2>&1; tail -2 gpurun_out/t_all.log
+timeout 600 python tools/microbench2.py > gpurun_out/microbench2_sw.log 2>&1
+grep -A40 "B=1 stage shapes" gpurun_out/microbench2_sw.log | grep -v "d=3\|d=4" | head -40
+bash tools/gpu_quick3.sh 2>&1 | grep -v "passed\|^\.\.\." 
