@@ -366,17 +366,60 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_base_s;
-  if (threadIdx.x == 0) stamp(p, 1);
+  if (threadIdx.x == 0) {
+    stamp(p, 1);
+    // weights are static data: fill the ring before waiting for the kernel that produces the activations
+    // (issuing a bulk copy costs the thread a few hundred cycles: measured ~900 cycles for 4 stages)
+    for (int rnd = 0; rnd < npre; ++rnd) load_w(rnd, rnd);
+    stamp(p, 10);
+  }
+  hsv::pdl_wait();  // activations / residual / out / acc belong to predecessor kernels
+  if (threadIdx.x == 0) stamp(p, 2);
+
+  // ---- epilogue addressing + EARLY residual prefetch (float4 path) ----
+  // Every warp issues the residual loads of its first PF units NOW, before its role loop: warps 0 and 1 used to
+  // issue them only after producing / issuing (ncu: 23 % of the stall samples sat on the first use).
+  constexpr int PF = 2;   // residual prefetch depth (units).  4 was measured too (136 registers): no gain at batch
+                          // 16 (C=128, k=11: 82.0 vs 83.6 us) and one CTA per SM less for the n_tile = 64 variant
+  constexpr int PFG = 2;  // the generic (scalar) path
+  const int co0 = nt * p.n_tile;
+  const int64_t cs = p.Lout;  // channel stride
+  const int64_t chan_base = ((int64_t)b * p.Cout + co0) * p.Lout + p.tt.out_off[ph];
+  const int nchk = p.n_tile >> 4;
+  const int nunits = MSUB * nchk;
+  const bool has_res = p.residual != nullptr;
+  const int cq = lane >> 3, i4 = (lane & 7) << 2;
+  const int64_t t_warp = (int64_t)tile * MSUB * TILE_M + warp * 32 + i4;  // first row of this lane's float4 (sub 0)
+  const int64_t lane_off = chan_base + (int64_t)cq * cs + t_warp;
+  const int64_t cs4b = 16 * cs;                                   // 4 channels, in bytes
+  const int64_t unit_b = 64 * cs;                                 // 16 channels, in bytes
+  const int64_t wrap_b = 4 * ((int64_t)TILE_M - (int64_t)p.n_tile * cs);  // next sub-tile, first unit (bytes)
+  const char *res_b = has_res ? reinterpret_cast<const char *>(p.residual + lane_off) : nullptr;  // unit u + PF
+  int nxt_sub = 0, nxt_ch = 0, nxt_u = 0;   // (sub, chunk) walker of the unit being prefetched
+  int64_t nxt_b = 0;
+  bool nxt_ok = t_warp < p.L;               // L % 4 == 0: a float4 is all-valid or all-invalid
+  float4 res[PF][4];
+  if (p.vec_epi) {
+#pragma unroll
+    for (int q = 0; q < PF; ++q) {
+      const bool ok = nxt_ok && has_res && nxt_u < nunits;
+#pragma unroll
+      for (int ps = 0; ps < 4; ++ps)
+        res[q][ps] = ok ? *reinterpret_cast<const float4 *>(res_b + nxt_b + ps * cs4b) : make_float4(0.f, 0.f, 0.f, 0.f);
+      ++nxt_u;
+      nxt_b += unit_b;
+      if (++nxt_ch == nchk) {
+        nxt_ch = 0;
+        ++nxt_sub;
+        nxt_b += wrap_b;
+        nxt_ok = t_warp + (int64_t)nxt_sub * TILE_M < p.L;
+      }
+    }
+  }
 
   if constexpr (RR > 0) {
     // ---------------- activation producer: all 128 threads ----------------
     using K = hsv_act::Cfg<RR>;
-    if (threadIdx.x == 0) {
-      for (int rnd = 0; rnd < npre; ++rnd) load_w(rnd, rnd);  // static data, before the dependency wait
-      stamp(p, 10);
-    }
-    hsv::pdl_wait();  // fx belongs to the predecessor kernel
-    if (threadIdx.x == 0) stamp(p, 2);
     const uint32_t bar_x = bar0 + 8 * NBARS;                      // two staging barriers
     uint8_t *smem_al = smem_raw + (a_s - smem_u32(smem_raw));     // generic pointer to the aligned base
     float *xs = reinterpret_cast<float *>(smem_al + p.x_off);     // [2][8][PITCH]
@@ -467,12 +510,6 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
   if (warp == 0 && lane == 0) {
     // ---------------- TMA producer ----------------
     if constexpr (RR == 0) {
-      // weights are static data: fill the ring before waiting for the kernel that produces the activations
-      // (issuing a bulk copy costs the thread a few hundred cycles: measured ~900 cycles for 4 stages)
-      for (int rnd = 0; rnd < npre; ++rnd) load_w(rnd, rnd);
-      stamp(p, 10);
-      hsv::pdl_wait();
-      stamp(p, 2);
       const int64_t row0 = (int64_t)HSV_BLK_PAD + (int64_t)tile * TILE_M * MSUB - p.hlo8;  // multiple of 8
       for (int c = 0; c < p.nchunks; ++c) {
         const uint8_t *src = p.a + (((int64_t)b * p.nchunks + c) * p.Lp + row0) * rowbytes;
@@ -539,59 +576,22 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
   // (channel c = lane/8 + 4*pass, rows 4*(lane%8)..+3): one LDS.128 + one LDG.128 (residual, prefetched PF units
   // ahead in registers, first PF before the accumulator wait) + one STG.128 per 4 elements.
   // out may alias residual (same offsets): loads of a unit always precede its stores.
-  hsv::pdl_wait();  // residual / out / acc belong to predecessor kernels
   __syncwarp();
   bias_s[threadIdx.x] = bias_r[0];
   bias_s[threadIdx.x + 128] = bias_r[1];
   if (threadIdx.x == 0) stamp(p, 6);
-  const int co0 = nt * p.n_tile;
-  const int64_t cs = p.Lout;  // channel stride
-  const int64_t chan_base = ((int64_t)b * p.Cout + co0) * p.Lout + p.tt.out_off[ph];
-  const int nchk = p.n_tile >> 4;
-  const int nunits = MSUB * nchk;
-  const bool has_res = p.residual != nullptr;
   const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-  // residual prefetch depth (units).  4 in flight was measured too (136 registers): no gain at batch 16
-  // (C=128, k=11: 82.0 vs 83.6 us) and one CTA per SM less for the n_tile = 64 variant, so 2.
-  constexpr int PF = 2;
-  constexpr int PFG = 2;  // the generic (scalar) path keeps 2
   if (p.vec_epi) {
-    const int cq = lane >> 3, i4 = (lane & 7) << 2;
-    const int64_t t_warp = (int64_t)tile * MSUB * TILE_M + warp * 32 + i4;  // first row of this lane's float4 (sub 0)
-    const int64_t lane_off = chan_base + (int64_t)cq * cs + t_warp;
-    const int64_t cs4b = 16 * cs;                                   // 4 channels, in bytes
-    const int64_t unit_b = 64 * cs;                                 // 16 channels, in bytes
-    const int64_t wrap_b = 4 * ((int64_t)TILE_M - (int64_t)p.n_tile * cs);  // next sub-tile, first unit (bytes)
     // the A tile / weight ring are idle once the accumulator is complete: reuse 2 KB per warp as staging
     const uint32_t stg = a_s + (uint32_t)warp * 2048u;
     const uint32_t stg_w = stg + (uint32_t)lane * 4u;                       // [c][lane]
     const uint32_t stg_r = stg + (uint32_t)(cq * 32 + i4) * 4u;             // [cq + 4*pass][i4 .. i4+3]
-    // destinations as per-lane byte pointers of the current unit; all launch-uniform choices hoisted
-    const char *res_b = has_res ? reinterpret_cast<const char *>(p.residual + lane_off) : nullptr;  // unit u + PF
     // exactly one destination on this path (host-checked): out, or acc written (mode 1) / accumulated (mode 2)
     char *dst_b = reinterpret_cast<char *>((p.out ? p.out : p.acc) + lane_off);
     const bool is_red = !p.out && p.acc_mode == 2;
     int64_t cur_b = 0;  // byte offset of the current unit relative to the per-lane bases
-    // (sub, chunk) walkers: the unit being written and the unit being prefetched
-    int cur_sub = 0, cur_ch = 0, nxt_sub = 0, nxt_ch = 0, nxt_u = 0;
-    int64_t nxt_b = 0;
-    bool cur_ok = t_warp < p.L, nxt_ok = cur_ok;  // L % 4 == 0: a float4 is all-valid or all-invalid
-    float4 res[PF][4];
-#pragma unroll
-    for (int q = 0; q < PF; ++q) {
-      const bool ok = nxt_ok && has_res && nxt_u < nunits;
-#pragma unroll
-      for (int ps = 0; ps < 4; ++ps)
-        res[q][ps] = ok ? *reinterpret_cast<const float4 *>(res_b + nxt_b + ps * cs4b) : make_float4(0.f, 0.f, 0.f, 0.f);
-      ++nxt_u;
-      nxt_b += unit_b;
-      if (++nxt_ch == nchk) {
-        nxt_ch = 0;
-        ++nxt_sub;
-        nxt_b += wrap_b;
-        nxt_ok = t_warp + (int64_t)nxt_sub * TILE_M < p.L;
-      }
-    }
+    int cur_sub = 0, cur_ch = 0;
+    bool cur_ok = t_warp < p.L;
     __syncthreads();  // bias_s complete (every warp is past its role loop here; the MMAs are in flight)
     mbar_wait(bar_acc, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
