@@ -292,8 +292,11 @@ constexpr int BAR_A = 1, BAR_WF = 1 + MAX_CHUNKS, BAR_WE = BAR_WF + MAX_STAGES, 
 //          Activation1d (act_core.cuh; 8 channels x 16 runs of RR rows per pass, the mapping of act1d.cu) on the
 //          fp32 input and writes the fp16 results straight into the swizzled shared A tile -- the operand never
 //          exists in HBM.  Single-chunk inputs only (Cin = cw <= 64), n_tile = Cout (no recomputation).
-template <int MSUB, int MINB, bool SMALLN, int RR>
-__global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_constant__ Params p) {
+// NW = warps per CTA: 4, or 8 for the wide variants -- warps 4..7 only take part in the epilogue (two warps per
+// TMEM lane quarter, alternating 16-column units), which is a chain of ~180 dependent instructions per unit for
+// a lone warp per scheduler.
+template <int MSUB, int MINB, bool SMALLN, int RR, int NW>
+__global__ void __launch_bounds__(32 * NW, MINB) conv_umma_kernel(const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[NBARS + 2];
   __shared__ uint32_t tmem_base_s;
@@ -356,10 +359,11 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
   // bias of this n-tile (static data): loaded to registers now, parked in shared memory at the start of the
   // epilogue (its global latency must not sit in front of the set-up barrier), read there as broadcast LDS
   // instead of 16 dependent global loads per 16-column unit
-  float bias_r[2];
+  constexpr int NBR = 256 / (32 * NW);
+  float bias_r[NBR];
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const int i = threadIdx.x + 128 * q;
+  for (int q = 0; q < NBR; ++q) {
+    const int i = threadIdx.x + 32 * NW * q;
     bias_r[q] = (p.bias && i < p.n_tile) ? __ldg(p.bias + nt * p.n_tile + i) : 0.f;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -388,16 +392,30 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
   const int nchk = p.n_tile >> 4;
   const int nunits = MSUB * nchk;
   const bool has_res = p.residual != nullptr;
+  constexpr int NH = NW / 4;                 // warps per TMEM lane quarter
+  const int wq = warp & 3, half = warp >> 2;  // lane quarter (rows 32*wq..), and which of its NH unit streams
   const int cq = lane >> 3, i4 = (lane & 7) << 2;
-  const int64_t t_warp = (int64_t)tile * MSUB * TILE_M + warp * 32 + i4;  // first row of this lane's float4 (sub 0)
+  const int64_t t_warp = (int64_t)tile * MSUB * TILE_M + wq * 32 + i4;  // first row of this lane's float4 (sub 0)
   const int64_t lane_off = chan_base + (int64_t)cq * cs + t_warp;
   const int64_t cs4b = 16 * cs;                                   // 4 channels, in bytes
   const int64_t unit_b = 64 * cs;                                 // 16 channels, in bytes
   const int64_t wrap_b = 4 * ((int64_t)TILE_M - (int64_t)p.n_tile * cs);  // next sub-tile, first unit (bytes)
   const char *res_b = has_res ? reinterpret_cast<const char *>(p.residual + lane_off) : nullptr;  // unit u + PF
-  int nxt_sub = 0, nxt_ch = 0, nxt_u = 0;   // (sub, chunk) walker of the unit being prefetched
+  // (sub, chunk) walkers over this warp's unit stream (units half, half + NH, ...): advance by one unit
+  auto advance = [&](int &u, int &sub, int &ch, int64_t &off, bool &ok) {
+    ++u;
+    off += unit_b;
+    if (++ch == nchk) {
+      ch = 0;
+      ++sub;
+      off += wrap_b;
+      ok = t_warp + (int64_t)sub * TILE_M < p.L;
+    }
+  };
+  int nxt_sub = 0, nxt_ch = 0, nxt_u = 0;   // the unit being prefetched
   int64_t nxt_b = 0;
   bool nxt_ok = t_warp < p.L;               // L % 4 == 0: a float4 is all-valid or all-invalid
+  if (NH > 1 && half) advance(nxt_u, nxt_sub, nxt_ch, nxt_b, nxt_ok);
   float4 res[PF][4];
   if (p.vec_epi) {
 #pragma unroll
@@ -406,14 +424,8 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
 #pragma unroll
       for (int ps = 0; ps < 4; ++ps)
         res[q][ps] = ok ? *reinterpret_cast<const float4 *>(res_b + nxt_b + ps * cs4b) : make_float4(0.f, 0.f, 0.f, 0.f);
-      ++nxt_u;
-      nxt_b += unit_b;
-      if (++nxt_ch == nchk) {
-        nxt_ch = 0;
-        ++nxt_sub;
-        nxt_b += wrap_b;
-        nxt_ok = t_warp + (int64_t)nxt_sub * TILE_M < p.L;
-      }
+#pragma unroll
+      for (int h = 0; h < NH; ++h) advance(nxt_u, nxt_sub, nxt_ch, nxt_b, nxt_ok);
     }
   }
 
@@ -577,10 +589,10 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
   // ahead in registers, first PF before the accumulator wait) + one STG.128 per 4 elements.
   // out may alias residual (same offsets): loads of a unit always precede its stores.
   __syncwarp();
-  bias_s[threadIdx.x] = bias_r[0];
-  bias_s[threadIdx.x + 128] = bias_r[1];
+#pragma unroll
+  for (int q = 0; q < NBR; ++q) bias_s[threadIdx.x + 32 * NW * q] = bias_r[q];
   if (threadIdx.x == 0) stamp(p, 6);
-  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t trow = tmem + ((uint32_t)(wq * 32) << 16);
   if (p.vec_epi) {
     // the A tile / weight ring are idle once the accumulator is complete: reuse 2 KB per warp as staging
     const uint32_t stg = a_s + (uint32_t)warp * 2048u;
@@ -590,18 +602,19 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
     char *dst_b = reinterpret_cast<char *>((p.out ? p.out : p.acc) + lane_off);
     const bool is_red = !p.out && p.acc_mode == 2;
     int64_t cur_b = 0;  // byte offset of the current unit relative to the per-lane bases
-    int cur_sub = 0, cur_ch = 0;
+    int cur_sub = 0, cur_ch = 0, cur_u = 0;
     bool cur_ok = t_warp < p.L;
+    if (NH > 1 && half) advance(cur_u, cur_sub, cur_ch, cur_b, cur_ok);
     __syncthreads();  // bias_s complete (every warp is past its role loop here; the MMAs are in flight)
     mbar_wait(bar_acc, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     __syncwarp();
     if (threadIdx.x == 0) stamp(p, 7);
 #pragma unroll 1
-    for (int u0 = 0; u0 < nunits; u0 += PF) {
+    for (int u0 = half; u0 < nunits; u0 += PF * NH) {
 #pragma unroll
       for (int q = 0; q < PF; ++q) {
-        if (u0 + q < nunits) {
+        if (u0 + q * NH < nunits) {
           uint32_t r[16];
           tmem_ld16(trow + (uint32_t)(cur_sub * p.n_tile + (cur_ch << 4)), r);
 #pragma unroll
@@ -636,27 +649,17 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
             }
           }
           __syncwarp();  // the staging buffer is rewritten by the next unit
-          cur_b += unit_b;
-          if (++cur_ch == nchk) {
-            cur_ch = 0;
-            ++cur_sub;
-            cur_b += wrap_b;
-            cur_ok = t_warp + (int64_t)cur_sub * TILE_M < p.L;
-          }
-          ++nxt_u;
-          nxt_b += unit_b;
-          if (++nxt_ch == nchk) {
-            nxt_ch = 0;
-            ++nxt_sub;
-            nxt_b += wrap_b;
-            nxt_ok = t_warp + (int64_t)nxt_sub * TILE_M < p.L;
+#pragma unroll
+          for (int h = 0; h < NH; ++h) {
+            advance(cur_u, cur_sub, cur_ch, cur_b, cur_ok);
+            advance(nxt_u, nxt_sub, nxt_ch, nxt_b, nxt_ok);
           }
         }
       }
     }
   } else {
     // generic path (strided ConvTranspose1d phases, L % 4 != 0, unaligned tensors): lane = row, scalar accesses
-    const int64_t row_base = (int64_t)tile * MSUB * TILE_M + warp * 32 + lane;  // GEMM row of sub-tile 0
+    const int64_t row_base = (int64_t)tile * MSUB * TILE_M + wq * 32 + lane;  // GEMM row of sub-tile 0
     auto unit_ptr = [&](int u, int64_t &off, bool &ok) {
       const int sub = u / nchk, c0 = (u - sub * nchk) << 4;
       const int64_t t = row_base + (int64_t)sub * TILE_M;
@@ -668,7 +671,7 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
     for (int q = 0; q < PFG; ++q) {
       int64_t off; bool ok;
       unit_ptr(q < nunits ? q : 0, off, ok);
-      ok = ok && has_res && q < nunits;
+      ok = ok && has_res && q < nunits && half == 0;
 #pragma unroll
       for (int c = 0; c < 16; ++c) res[q][c] = ok ? p.residual[off + c * cs] : 0.f;
     }
@@ -678,7 +681,7 @@ __global__ void __launch_bounds__(128, MINB) conv_umma_kernel(const __grid_const
     __syncwarp();
     if (threadIdx.x == 0) stamp(p, 7);
 #pragma unroll 1
-    for (int u0 = 0; u0 < nunits; u0 += PFG) {
+    for (int u0 = half ? nunits : 0; u0 < nunits; u0 += PFG) {  // warps 4..7 (NW = 8) sit this path out
 #pragma unroll
       for (int q = 0; q < PFG; ++q) {
         const int u = u0 + q;
@@ -800,7 +803,7 @@ int g_host_debug = 0;
 long long *g_trace = nullptr;
 int g_msub_override = 0;  // bring-up aid: force the sub-tiles per CTA (0 = automatic)
 
-template <int MSUB, int MINB, bool SMALLN, int RR = 0>
+template <int MSUB, int MINB, bool SMALLN, int RR = 0, int NW = 4>
 int launch_variant(const Params &p, dim3 grid, size_t smem, cudaStream_t st, const char *what) {
   // opt-in dynamic shared memory: 227 KB per block minus the kernel's static shared memory
   static int max_dyn[64] = {0};
@@ -809,11 +812,11 @@ int launch_variant(const Params &p, dim3 grid, size_t smem, cudaStream_t st, con
   if (dev < 0 || dev >= 64) dev = 0;
   if (max_dyn[dev] == 0) {
     cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, conv_umma_kernel<MSUB, MINB, SMALLN, RR>);
+    cudaError_t e = cudaFuncGetAttributes(&fa, conv_umma_kernel<MSUB, MINB, SMALLN, RR, NW>);
     int want = 227 * 1024 - (e == cudaSuccess ? (int)fa.sharedSizeBytes : 1024);
     want &= ~1023;
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_umma_kernel<MSUB, MINB, SMALLN, RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+      e = cudaFuncSetAttribute(conv_umma_kernel<MSUB, MINB, SMALLN, RR, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
     if (e != cudaSuccess) {
       cudaGetLastError();  // clear
       hsv::set_error("%s: cudaFuncSetAttribute(%d): %s", what, want, cudaGetErrorString(e));
@@ -825,7 +828,7 @@ int launch_variant(const Params &p, dim3 grid, size_t smem, cudaStream_t st, con
               max_dyn[dev], p.Cin);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
-  cfg.blockDim = dim3(128);
+  cfg.blockDim = dim3(32 * NW);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -833,7 +836,7 @@ int launch_variant(const Params &p, dim3 grid, size_t smem, cudaStream_t st, con
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = hsv::g_pdl ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<MSUB, MINB, SMALLN, RR>, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<MSUB, MINB, SMALLN, RR, NW>, p);
   if (e != cudaSuccess) {
     cudaGetLastError();
     hsv::set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
@@ -933,7 +936,11 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
   const size_t a_bytes = (size_t)p.a_pitch * p.nchunks;
   // shared-memory budget: leave room for as many co-resident CTAs per SM as the grid can use (they hide
   // each other's prologue / epilogue latency), down to a 2-stage weight ring
-  const int minb = n_tile <= 32 ? 6 : (n_tile <= 64 ? 4 : 2);
+  // 8-warp CTAs (two epilogue warps per TMEM lane quarter) for n_tile >= 128 only: measured +7 % on the C=128/256
+  // layers at batch 16 (722 -> 770 TFLOP/s), but -20 % on n_tile = 64 (two CTAs per SM instead of four) and on
+  // the 512-row C=16 tiles
+  const bool w8 = !(g_host_debug & 32) && !fa && n_tile >= 128;
+  const int minb = n_tile <= 32 && msub == 1 ? 6 : (w8 ? 2 : (n_tile <= 64 ? 4 : 2));
   int want = (int)((total_ctas + 147) / 148);
   want = want < 1 ? 1 : (want > minb ? minb : want);
   const size_t budget = (size_t)(226 * 1024) / want - 1024;
@@ -943,7 +950,7 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
     p.stages--;
     smem = 1024 + a_bytes + (size_t)p.stages * stage_bytes;
   }
-  if (smem < 1024 + 8192) smem = 1024 + 8192;  // the epilogue stages 4 x 2 KB in the (then idle) operand area
+  if (smem < 1024 + 16384) smem = 1024 + 16384;  // the epilogue stages 2 KB per warp in the (then idle) operand area
   int rr = 0;
   if (fa) {
     // run length of the in-CTA activation: 16 runs must cover the A tile (256 + halo rows)
@@ -959,17 +966,22 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
   HSV_REQUIRE(B <= 65535 && (int64_t)p.nco_tiles * tt.nphase <= 65535, "%s: grid too large", what);
   dim3 grid((unsigned)p.ntiles, (unsigned)(p.nco_tiles * tt.nphase), (unsigned)B);
   if (fa) {
-    if (rr == 17) return launch_variant<2, 3, false, 17>(p, grid, smem, st, what);
-    return launch_variant<2, 3, false, 20>(p, grid, smem, st, what);
+    if (rr == 17) return launch_variant<2, 3, false, 17, 4>(p, grid, smem, st, what);
+    return launch_variant<2, 3, false, 20, 4>(p, grid, smem, st, what);
   }
   // small n_tile = HBM/latency-bound streaming layers: they want many co-resident CTAs (register cap 80);
   // large n_tile = few fat CTAs per SM anyway
+  // wide tiles (>= 4 units of 16 columns per CTA) run 8 warps: two epilogue warps per TMEM lane quarter
   if (p.msub == 1) {
     if (n_tile <= 32) return launch_variant<1, 6, true>(p, grid, smem, st, what);
+    if (w8) return launch_variant<1, 2, false, 0, 8>(p, grid, smem, st, what);
     if (n_tile <= 64) return launch_variant<1, 4, false>(p, grid, smem, st, what);
     return launch_variant<1, 2, false>(p, grid, smem, st, what);
   }
-  if (p.msub == 2) return launch_variant<2, 2, false>(p, grid, smem, st, what);
+  if (p.msub == 2) {
+    if (w8) return launch_variant<2, 2, false, 0, 8>(p, grid, smem, st, what);
+    return launch_variant<2, 2, false>(p, grid, smem, st, what);
+  }
   return launch_variant<4, 1, false>(p, grid, smem, st, what);
 }
 
@@ -993,7 +1005,8 @@ int pack(const float *w, void *packed, int Cout, int Cin, int k, int n_tile, int
 }  // namespace
 
 // bring-up aid only; not part of the drop-in contract.
-//   bit 2: skip the epilogue's global stores, bit 3: skip its TMEM loads, bit 4: force the scalar epilogue;
+//   bit 2: skip the epilogue's global stores, bit 3: skip its TMEM loads, bit 4: force the scalar epilogue,
+//   bit 5: 4-warp CTAs for the wide variants too;
 //   bits 24..26: forced sub-tiles per CTA.
 extern "C" int hsv_set_umma_debug(int flags) {
   g_host_debug = flags & 0xff;
