@@ -14,6 +14,8 @@ timeout 600 python bench.py > gpurun_out/bench.log 2>&1
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.log 2>&1
 timeout 300 python bench.py --steps 5 --warmup 3 --workload speechsr48 --batch 16 --no-cpu-baseline > gpurun_out/bench_sr48.log 2>&1
 timeout 300 python bench.py --steps 5 --warmup 3 --batch 16 --no-cpu-baseline > gpurun_out/bench_voc_b16.log 2>&1
+timeout 600 python bench.py --steps 3 --warmup 3 --workload speechsr48 --batch 64 --no-cpu-baseline > gpurun_out/bench_sr48_b64.log 2>&1
+timeout 600 python bench.py --steps 3 --warmup 3 --batch 32 --seconds 30 --no-cpu-baseline > gpurun_out/bench_voc_b32x30s.log 2>&1
 $NCU --metrics gpu__time_duration.sum --csv --log-file gpurun_out/launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/p_bench.log 2>&1
 $NCU --set full --import-source on -k regex:act1d -s 2 -c 1 -o gpurun_out/prof3_act_sat -f python tools/profile_kernels.py act 16 32 480000 1 > gpurun_out/p3_act.log 2>&1
 $NCU --set full --import-source on -k regex:conv_umma -s 2 -c 1 -o gpurun_out/prof3_umma_c32_b16 -f python tools/profile_kernels.py umma 16 32 480000 7 3 > gpurun_out/p3_umma1.log 2>&1

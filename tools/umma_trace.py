@@ -20,7 +20,7 @@ NAMES = ["entry", "setup done", "producer: pdl_wait done", "mma: w_full[0]", "mm
 
 def trace(B, C, L, k, d, residual=True, nt=None):
     lib = _lib.load()
-    buf_t = torch.zeros(16, dtype=torch.int64, device=dev)
+    buf_t = torch.zeros(32, dtype=torch.int64, device=dev)
     x = torch.randn(B, C, L, device=dev)
     w = torch.randn(C, C, k, device=dev) * 0.05
     bias = torch.zeros(C, device=dev)
@@ -41,15 +41,18 @@ def trace(B, C, L, k, d, residual=True, nt=None):
     t = buf_t.cpu().tolist()
     t0 = t[0]
     print(f"C={C} L={L} B={B} k={k} d={d} n_tile={nt} res={int(residual)}  (SM cycles since entry; ~1.9 cycles/ns)")
+    t1 = t[16]
     for i, n in enumerate(NAMES):
-        print(f"   {n:28s} {t[i] - t0:8d}")
+        print(f"   {n:28s} {t[i] - t0:8d}     mid-grid CTA: {t[16 + i] - t1 if t1 else 0:8d}")
 
 
 if __name__ == "__main__":
     if os.environ.get("TRACE_SHORT"):
-        trace(1, 256, 128, 11, 1)
         trace(1, 128, 10000, 11, 5)
         trace(16, 128, 10000, 11, 5)
+        trace(16, 256, 2000, 11, 5)
+        trace(16, 64, 40000, 11, 5)
+        trace(16, 32, 80000, 7, 3)
         sys.exit(0)
     trace(1, 256, 128, 1, 1)
     trace(1, 256, 128, 11, 1)
