@@ -57,6 +57,7 @@ struct Params {
   int64_t L, Lp, Lout;
   int n_tile, nco_tiles;
   int ntiles;
+  int B;             // batch (persistent variant: tiles are enumerated over (b, n-tile, row tile))
   int msub;          // 128-row sub-tiles per CTA (1, 2 or 4): every weight K-step feeds msub MMAs
   int cw;            // channels per operand row (64 / 32 / 16)
   int nchunks;       // Cin / cw
@@ -732,6 +733,303 @@ __global__ void __launch_bounds__(32 * NW, MINB) conv_umma_kernel(const __grid_c
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Persistent variant for the wide layers (n_tile >= 128) at batch scale.
+// One CTA per SM walks its share of the (batch, n-tile, 128-row tile) list; the three roles run concurrently on
+// DIFFERENT tiles: warp 0 streams the A tile of tile i+1 and the weights of tile i, warp 1 issues the MMAs of
+// tile i into TMEM buffer i & 1, warps 2..5 drain tile i-1 from the other TMEM buffer (float4 epilogue).  The
+// tensor pipe therefore never waits for a prologue or an epilogue (ncu on the one-tile-per-CTA kernel at C=128,
+// batch 16: two co-resident CTAs, tensor pipe 36-48 % busy, the rest is their load / drain phases).
+// Restrictions: stride-1 conv, MSUB = 1, float4 epilogue, A tile <= ~60 KB (double-buffered): C = 128 layers today
+// (C = 256 needs an A-chunk ring).  Measured at batch 16, C = 128: k=3 49.1 -> 38.7 us, k=7 60.2 -> 53.3 us,
+// k=11 74.3 -> 70.3 us (820 TFLOP/s = 60 % of the measured sustained bf16 peak).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int PB_ACC_F = 0, PB_ACC_E = 2, PB_A_F = 4, PB_A_E = 6, PB_WF = 8, PB_WE = PB_WF + MAX_STAGES,
+              PB_N = PB_WE + MAX_STAGES;
+
+// EPW = epilogue warps per TMEM lane quarter: the drain of a tile is a chain of global round trips, so it takes
+// many warps (each with its own units of 16 columns, residual prefetched before the accumulator is complete)
+// to keep up with the MMAs of the next tile (measured: 4 warps in all -> 2300 cycles per unit under load).
+template <int EPW>
+__global__ void __launch_bounds__(64 + 128 * EPW, 1) conv_umma_persist_kernel(const __grid_constant__ Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[PB_N];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int ntaps = p.tt.ntaps[0];
+  const int nblocks = p.nchunks * ntaps;
+  const int nrounds = (nblocks + p.G - 1) / p.G;
+  const uint32_t rowbytes = (uint32_t)p.cw * 2u;
+  const uint32_t a_chunk_bytes = (uint32_t)p.R * rowbytes;
+  const uint32_t a_tile_bytes = p.a_pitch * (uint32_t)p.nchunks;
+  const uint32_t blk_bytes = (uint32_t)p.n_tile * rowbytes;
+  const uint32_t stage_bytes = blk_bytes * (uint32_t)p.G;
+  const uint32_t a_s = (smem_u32(smem_raw) + 1023u) & ~1023u;       // two A tiles
+  const uint32_t w_s = a_s + 2u * a_tile_bytes;                      // weight ring
+  const uint32_t stg_s = w_s + (uint32_t)p.stages * stage_bytes;     // 2 KB of epilogue staging per warp
+  const uint32_t bar0 = smem_u32(&bars[0]);
+  const int total = p.ntiles * p.nco_tiles * p.B;                    // tiles of the launch
+  const int my_n = (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles of this CTA
+
+  hsv::pdl_launch_dependents();
+  if (threadIdx.x == 0) {
+    mbar_init(bar0 + 8 * (PB_ACC_F + 0), 1); mbar_init(bar0 + 8 * (PB_ACC_F + 1), 1);
+    mbar_init(bar0 + 8 * (PB_ACC_E + 0), 128 * EPW); mbar_init(bar0 + 8 * (PB_ACC_E + 1), 128 * EPW);
+    mbar_init(bar0 + 8 * (PB_A_F + 0), 1); mbar_init(bar0 + 8 * (PB_A_F + 1), 1);
+    mbar_init(bar0 + 8 * (PB_A_E + 0), 1); mbar_init(bar0 + 8 * (PB_A_E + 1), 1);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(bar0 + 8 * (PB_WF + s), 1);
+      mbar_init(bar0 + 8 * (PB_WE + s), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"(p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  hsv::pdl_wait();
+
+  auto tile_coords = [&](int i, int &b, int &nt, int &tile) {
+    const int lin = (int)blockIdx.x + i * (int)gridDim.x;
+    tile = lin % p.ntiles;
+    const int r = lin / p.ntiles;
+    nt = r % p.nco_tiles;
+    b = r / p.nco_tiles;
+  };
+
+  if (warp == 0) {
+    // ---------------- TMA producer (one lane) ----------------
+    if (lane == 0) {
+      auto load_a = [&](int i) {
+        int b, nt, tile;
+        tile_coords(i, b, nt, tile);
+        const int buf = i & 1;
+        if (i >= 2) mbar_wait(bar0 + 8 * (PB_A_E + buf), (uint32_t)((i >> 1) - 1) & 1u);
+        const int64_t row0 = (int64_t)HSV_BLK_PAD + (int64_t)tile * TILE_M - p.hlo8;
+        mbar_expect_tx(bar0 + 8 * (PB_A_F + buf), a_chunk_bytes * (uint32_t)p.nchunks);
+        for (int c = 0; c < p.nchunks; ++c) {
+          const uint8_t *src = p.a + (((int64_t)b * p.nchunks + c) * p.Lp + row0) * rowbytes;
+          bulk_g2s(a_s + buf * a_tile_bytes + c * p.a_pitch, src, a_chunk_bytes, bar0 + 8 * (PB_A_F + buf));
+        }
+      };
+      int it = 0, ws = 0;
+      uint32_t wpar = 0;
+      if (my_n > 0) load_a(0);
+      for (int i = 0; i < my_n; ++i) {
+        int b, nt, tile;
+        tile_coords(i, b, nt, tile);
+        const uint8_t *wsrc = p.w + (int64_t)nt * nblocks * blk_bytes;
+        if (i + 1 < my_n) load_a(i + 1);  // one tile ahead of the MMAs
+        for (int rnd = 0; rnd < nrounds; ++rnd, ++it) {
+          if (it >= p.stages) mbar_wait(bar0 + 8 * (PB_WE + ws), wpar ^ 1u);
+          const int nb = min(p.G, nblocks - rnd * p.G);
+          const uint32_t bytes = blk_bytes * (uint32_t)nb;
+          mbar_expect_tx(bar0 + 8 * (PB_WF + ws), bytes);
+          bulk_g2s(w_s + ws * stage_bytes, wsrc + (int64_t)rnd * stage_bytes, bytes, bar0 + 8 * (PB_WF + ws));
+          if (++ws == p.stages) {
+            ws = 0;
+            wpar ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer (whole warp walks, elected lane issues) ----------------
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+    const uint32_t layout = p.cw == 64 ? 2u : (p.cw == 32 ? 4u : 6u);
+    const uint32_t hi = ((8u * rowbytes) >> 4) | (1u << 14) | (layout << 29);
+    const uint32_t row16 = rowbytes >> 4;
+    const uint32_t a_lo00 = ((1u << 16) | ((a_s & 0x3FFFFu) >> 4)) + (uint32_t)((p.hlo8 + p.tt.row_off[0][0]) * (int)row16);
+    const uint32_t a_step16 = (uint32_t)(p.tap_step * (int)row16);
+    const uint32_t a_pitch16 = p.a_pitch >> 4, a_tile16 = a_tile_bytes >> 4;
+    const uint32_t w_lo0 = (1u << 16) | ((w_s & 0x3FFFFu) >> 4);
+    const uint32_t stage16 = stage_bytes >> 4, blk16 = blk_bytes >> 4;
+    int ws = 0;
+    uint32_t wpar = 0;
+    for (int i = 0; i < my_n; ++i) {
+      const int buf = i & 1;
+      if (i >= 2) mbar_wait_warp(bar0 + 8 * (PB_ACC_E + buf), (uint32_t)((i >> 1) - 1) & 1u);  // TMEM buffer drained
+      mbar_wait_warp(bar0 + 8 * (PB_A_F + buf), (uint32_t)(i >> 1) & 1u);                      // A tile landed
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tacc = tmem + (uint32_t)(buf * p.n_tile);
+      uint32_t a_chunk = a_lo00 + (uint32_t)buf * a_tile16, a_lo = a_chunk, not_first = 0;
+      int j = 0;
+      for (int rnd = 0; rnd < nrounds; ++rnd) {
+        mbar_wait_warp(bar0 + 8 * (PB_WF + ws), wpar);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int nb = min(p.G, nblocks - rnd * p.G);
+        uint32_t b_lo = w_lo0 + (uint32_t)ws * stage16;
+        for (int g = 0; g < nb; ++g) {
+          if (p.cw == 64) issue_ksteps<4>(tacc, a_lo, b_lo, hi, idesc, not_first);
+          else if (p.cw == 32) issue_ksteps<2>(tacc, a_lo, b_lo, hi, idesc, not_first);
+          else issue_ksteps<1>(tacc, a_lo, b_lo, hi, idesc, not_first);
+          not_first = 1u;
+          b_lo += blk16;
+          a_lo += a_step16;
+          if (++j == ntaps) {
+            j = 0;
+            a_chunk += a_pitch16;
+            a_lo = a_chunk;
+          }
+        }
+        umma_commit_elect(bar0 + 8 * (PB_WE + ws));
+        if (++ws == p.stages) {
+          ws = 0;
+          wpar ^= 1u;
+        }
+      }
+      umma_commit_elect(bar0 + 8 * (PB_A_E + buf));    // the A buffer may be refilled
+      umma_commit_elect(bar0 + 8 * (PB_ACC_F + buf));  // the accumulator is complete
+    }
+  } else {
+    // ---------------- epilogue: warps 2.. (TMEM lane quarter = warp & 3, unit stream = (warp - 2) / 4) ----------
+    const int wq = warp & 3, strm = (warp - 2) >> 2;
+    const int cq = lane >> 3, i4 = (lane & 7) << 2;
+    const int64_t cs = p.Lout;
+    const int64_t cs4b = 16 * cs, unit_b = 64 * cs;
+    const int nchk = p.n_tile >> 4;
+    const bool has_res = p.residual != nullptr;
+    const bool is_red = !p.out && p.acc_mode == 2;
+    const uint32_t stg = stg_s + (uint32_t)(warp - 2) * 2048u;
+    const uint32_t stg_w = stg + (uint32_t)lane * 4u;
+    const uint32_t stg_r = stg + (uint32_t)(cq * 32 + i4) * 4u;
+    constexpr int PF = 2;   // in units of this warp's stream (units strm, strm + EPW, ...)
+    for (int i = 0; i < my_n; ++i) {
+      int b, nt, tile;
+      tile_coords(i, b, nt, tile);
+      const int buf = i & 1;
+      const int co0 = nt * p.n_tile;
+      const int64_t t_warp = (int64_t)tile * TILE_M + wq * 32 + i4;
+      const bool ok_rows = t_warp < p.L;
+      const int64_t lane_off = ((int64_t)b * p.Cout + co0 + cq) * p.Lout + t_warp;
+      const char *res_b = has_res ? reinterpret_cast<const char *>(p.residual + lane_off) : nullptr;
+      char *dst_b = reinterpret_cast<char *>((p.out ? p.out : p.acc) + lane_off);
+      float4 res[PF][4];
+#pragma unroll
+      for (int q = 0; q < PF; ++q) {
+        const int u = strm + q * EPW;
+        const bool ok = ok_rows && has_res && u < nchk;
+#pragma unroll
+        for (int ps = 0; ps < 4; ++ps)
+          res[q][ps] = ok ? *reinterpret_cast<const float4 *>(res_b + (int64_t)u * unit_b + ps * cs4b)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      mbar_wait(bar0 + 8 * (PB_ACC_F + buf), (uint32_t)(i >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      __syncwarp();
+      const uint32_t trow = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * p.n_tile);
+#pragma unroll 1
+      for (int u0 = strm; u0 < nchk; u0 += PF * EPW) {
+#pragma unroll
+        for (int q = 0; q < PF; ++q) {
+          const int u = u0 + q * EPW;
+          if (u < nchk) {
+            uint32_t r[16];
+            tmem_ld16(trow + (uint32_t)(u << 4), r);
+#pragma unroll
+            for (int c = 0; c < 16; ++c)
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(stg_w + (uint32_t)c * 128u), "r"(r[c]) : "memory");
+            __syncwarp();
+            const bool okn = ok_rows && has_res && u + PF * EPW < nchk;
+#pragma unroll
+            for (int ps = 0; ps < 4; ++ps) {
+              float4 a;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w)
+                           : "r"(stg_r + (uint32_t)ps * 512u)
+                           : "memory");
+              const float bch = p.bias ? __ldg(p.bias + co0 + (u << 4) + ps * 4 + cq) : 0.f;
+              const float4 rr = res[q][ps];
+              a.x = (a.x + bch) + rr.x;  // (conv + bias) + residual: the reference's order
+              a.y = (a.y + bch) + rr.y;
+              a.z = (a.z + bch) + rr.z;
+              a.w = (a.w + bch) + rr.w;
+              res[q][ps] = okn ? *reinterpret_cast<const float4 *>(res_b + (int64_t)(u + PF * EPW) * unit_b + ps * cs4b)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+              if (ok_rows) {
+                char *o = dst_b + (int64_t)u * unit_b + ps * cs4b;
+                if (is_red)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w)
+                               : "memory");
+                else
+                  *reinterpret_cast<float4 *>(o) = a;
+              }
+            }
+            __syncwarp();
+          }
+        }
+      }
+      // this TMEM buffer may be overwritten by the MMAs of tile i + 2
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar0 + 8 * (PB_ACC_E + buf)) : "memory");
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+int g_persist = 1;  // persistent variant for eligible launches (hsv_set_umma_debug bit 6 turns it off)
+
+constexpr int PERSIST_EPW = 4;
+
+int launch_persist(Params p, int B, cudaStream_t st, const char *what) {
+  static int max_dyn[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (max_dyn[dev] == 0) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, conv_umma_persist_kernel<PERSIST_EPW>);
+    int want = 227 * 1024 - (e == cudaSuccess ? (int)fa.sharedSizeBytes : 1024);
+    want &= ~1023;
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma_persist_kernel<PERSIST_EPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      hsv::set_error("%s: cudaFuncSetAttribute(%d): %s", what, want, cudaGetErrorString(e));
+      return HSV_ERR_CUDA;
+    }
+    max_dyn[dev] = want;
+  }
+  p.B = B;
+  p.stages = MAX_STAGES;
+  const size_t stage_bytes = (size_t)p.G * p.n_tile * p.cw * 2;
+  size_t smem = 1024 + 2 * (size_t)p.a_pitch * p.nchunks + 4 * PERSIST_EPW * 2048;
+  while (p.stages > 2 && smem + p.stages * stage_bytes > (size_t)max_dyn[dev]) p.stages--;
+  smem += p.stages * stage_bytes;
+  if (smem > (size_t)max_dyn[dev]) return 1;  // not eligible: fall back to the one-tile-per-CTA kernel
+  uint32_t cols = 32;
+  while ((int)cols < 2 * p.n_tile) cols <<= 1;
+  p.tmem_cols = cols;
+  const int total = p.ntiles * p.nco_tiles * B;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(total < 148 ? total : 148));
+  cfg.blockDim = dim3(64 + 128 * PERSIST_EPW);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = hsv::g_pdl ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_umma_persist_kernel<PERSIST_EPW>, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    hsv::set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+    return HSV_ERR_CUDA;
+  }
+  return hsv::check_launch(what);
+}
+
 // Packed weight stream: [phase][n-tile][chunk][tap] blocks of n_tile rows x cw channels (fp16, K-major, swizzled
 // relative to the block start):  W(co = nt*n_tile + n, ci = chunk*cw + 8*u + e, tap wj[ph][ti]) at byte
 // swz(n*rowbytes + 16*u) + 2*e of its block.  Element strides (s_co, s_ci) select Conv1d [Cout,Cin,k] or
@@ -897,6 +1195,13 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
   if (n_tile <= 16 && ctas1 >= 2 * 148 * 2) msub = 4;
   if (g_msub_override > 0) msub = g_msub_override;
   if (msub == 3) msub = 2;
+  // persistent variant (opt-in): one 128-row tile at a time per CTA, roles overlapped across tiles
+  auto al16e = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const bool force_persist = (g_host_debug & 128) != 0;  // tests: any size / tile width
+  const bool want_persist = g_persist && !fa && tt.nphase == 1 && tt.out_stride == 1 &&
+                            (force_persist || (n_tile >= 128 && ctas1 >= 4 * 148)) && (Lout % 4) == 0 && al16e(residual) && al16e(out) && al16e(acc) &&
+                            ((out != nullptr) != (acc_mode != 0));
+  if (want_persist) msub = 1;
   if (fa) msub = 2;  // 256-row tiles: the activation's 5-row run halo and the conv halo are amortised over more rows
   auto a_bytes_for = [&](int ms) {
     const size_t per = (((size_t)(TILE_M * ms + p.hlo8 + tt.h_hi) * rowbytes) + 1023) & ~(size_t)1023;
@@ -937,6 +1242,10 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
   p.vec_epi = tt.out_stride == 1 && (Lout % 4) == 0 && al16(residual) && al16(out) && al16(acc) &&
               ((out != nullptr) != (acc_mode != 0)) && !(g_host_debug & 16);
 
+  if (want_persist && p.msub == 1 && p.vec_epi) {
+    const int rc = launch_persist(p, B, st, what);
+    if (rc != 1) return rc;  // 1 = does not fit (A tile too large to double-buffer): one-tile-per-CTA kernel below
+  }
   const size_t a_bytes = (size_t)p.a_pitch * p.nchunks;
   // shared-memory budget: leave room for as many co-resident CTAs per SM as the grid can use (they hide
   // each other's prologue / epilogue latency), down to a 2-stage weight ring
@@ -1010,10 +1319,13 @@ int pack(const float *w, void *packed, int Cout, int Cin, int k, int n_tile, int
 
 // bring-up aid only; not part of the drop-in contract.
 //   bit 2: skip the epilogue's global stores, bit 3: skip its TMEM loads, bit 4: force the scalar epilogue,
-//   bit 5: 4-warp CTAs for the wide variants too;
+//   bit 5: 4-warp CTAs for the wide variants too, bit 6: persistent variant off,
+//   bit 7: persistent variant for every launch it can run (tests);
 //   bits 24..26: forced sub-tiles per CTA.
 extern "C" int hsv_set_umma_debug(int flags) {
   g_host_debug = flags & 0xff;
+  g_persist = ((flags >> 6) & 1) ? 0 : 1;
+  if (flags & 128) g_persist = 1;
   g_msub_override = (flags >> 24) & 0x7;
   return HSV_OK;
 }

@@ -400,3 +400,30 @@ def test_act_conv_fused_acc_modes_and_aliasing(hsv):
     assert torch.equal(acc, base + base)
     with pytest.raises(ValueError):
         hsv.ops.act_conv1d_umma(x, al, be, wp, None, C, k, 1, out=x)
+
+
+def test_conv1d_umma_persistent_variant(hsv):
+    """The persistent CTA variant (TMEM double buffering; automatic for n_tile >= 128 at batch scale) gives the same
+    bits as the one-tile-per-CTA kernel: forced on (debug bit 7) vs off (bit 6) on shapes with several tiles per CTA."""
+    gen = torch.Generator().manual_seed(77)
+    try:
+        for (B, C, L, k, d, nt) in ((3, 128, 9000, 7, 3, 128), (2, 64, 30000, 11, 5, 64), (40, 32, 2500, 3, 1, 32)):
+            x = torch.randn(B, C, L, generator=gen).to(DEV)
+            w = (torch.randn(C, C, k, generator=gen) / (C * k) ** 0.5).to(DEV)
+            bias = (torch.randn(C, generator=gen) * 0.1).to(DEV)
+            res = torch.randn(B, C, L, generator=gen).to(DEV)
+            buf = hsv.ops.blk16_buffer(B, C, L, DEV, slot=9)
+            hsv.ops.pack_blk16(x, buf)
+            wp = hsv.ops.pack_conv_weight(w, nt)
+            hsv.ops.set_umma_debug(64)
+            ref = hsv.ops.conv1d_umma(buf, wp, bias, L, C, C, k, d, nt, residual=res)
+            hsv.ops.set_umma_debug(128)
+            got = hsv.ops.conv1d_umma(buf, wp, bias, L, C, C, k, d, nt, residual=res)
+            acc = torch.zeros_like(res)
+            hsv.ops.conv1d_umma(buf, wp, bias, L, C, C, k, d, nt, residual=res, acc=acc, acc_mode=hsv.ops.ACC_ADD,
+                                want_out=False)
+            torch.cuda.synchronize()
+            assert torch.equal(got, ref), (C, (got - ref).abs().max().item())
+            assert torch.equal(acc, ref)
+    finally:
+        hsv.ops.set_umma_debug(0)
