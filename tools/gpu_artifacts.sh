@@ -20,5 +20,6 @@ $NCU --metrics gpu__time_duration.sum --csv --log-file gpurun_out/launches_bench
 $NCU --set full --import-source on -k regex:act1d -s 2 -c 1 -o gpurun_out/prof3_act_sat -f python tools/profile_kernels.py act 16 32 480000 1 > gpurun_out/p3_act.log 2>&1
 $NCU --set full --import-source on -k regex:conv_umma -s 2 -c 1 -o gpurun_out/prof3_umma_c32_b16 -f python tools/profile_kernels.py umma 16 32 480000 7 3 > gpurun_out/p3_umma1.log 2>&1
 $NCU --set full --import-source on -k regex:conv_umma -s 2 -c 1 -o gpurun_out/prof3_umma_c128_b16 -f python tools/profile_kernels.py umma 16 128 10000 11 5 > gpurun_out/p3_umma2.log 2>&1
+$NCU --set full --import-source on -k regex:conv_umma -s 2 -c 1 -o gpurun_out/prof3_umma_c256_b16 -f python tools/profile_kernels.py umma 16 256 2000 11 5 > gpurun_out/p3_umma4.log 2>&1
 $NCU --set full --import-source on -k regex:conv_umma -s 2 -c 1 -o gpurun_out/prof3_umma_c128_b1 -f python tools/profile_kernels.py umma 1 128 10000 11 5 > gpurun_out/p3_umma3.log 2>&1
 tail -c 600 gpurun_out/bench.log; echo; tail -c 300 gpurun_out/bench_ref.log; cat gpurun_out/traffic.log | head -40

@@ -23,7 +23,7 @@ def load(path):
 
 
 def short(name):
-    for key in ("act1d_kernel", "conv_umma_kernel", "conv1d_tiled_kernel", "conv1d_thin_kernel",
+    for key in ("act1d_kernel", "conv_umma_persist_kernel", "conv_umma_kernel", "conv1d_tiled_kernel", "conv1d_thin_kernel",
                 "conv_transpose1d_kernel", "sr_pre_interp_kernel", "pack_weight_kernel", "weight_norm_fold_kernel",
                 "pack_blk16_kernel", "nearest_gather_kernel", "add3_bcast_kernel", "interp_table_kernel"):
         if key in name:

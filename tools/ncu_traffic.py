@@ -38,7 +38,7 @@ def main(workload, path, nfwd=1):
     per = len(steady) // nfwd
     sel = steady[-per:]
     fam = {"act1d": [r for r in sel if "act1d_kernel" in r["name"]],
-           "conv1d_umma": [r for r in sel if "conv_umma_kernel" in r["name"]]}
+           "conv1d_umma": [r for r in sel if "conv_umma" in r["name"]]}
     out = {}
     for k, rs in fam.items():
         if not rs:
