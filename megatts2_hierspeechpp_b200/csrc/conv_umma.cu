@@ -1185,10 +1185,11 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
   const int64_t ctas1 = (int64_t)ntiles128 * p.nco_tiles * tt.nphase * B;
   int max_taps = 0;
   for (int q = 0; q < tt.nphase; ++q) max_taps = tt.ntaps[q] > max_taps ? tt.ntaps[q] : max_taps;
-  if (Cin * max_taps >= 512 && ctas1 >= 2 * 148 * 2) {
+  if (Cin * max_taps >= 512 && ctas1 >= 2 * 148) {
     const size_t stage1 = (size_t)(16384 / blk_bytes > 0 ? 16384 / blk_bytes : 1) * blk_bytes;
     const size_t a1 = ((((size_t)(TILE_M + p.hlo8 + tt.h_hi) * rowbytes) + 1023) & ~(size_t)1023) * p.nchunks;
-    if (n_tile <= 64 || 1024 + a1 + 3 * stage1 > 113 * 1024) msub = 2;
+    if (1024 + a1 + 3 * stage1 > 113 * 1024) msub = 2;              // one CTA per SM either way (C = 256)
+    else if (n_tile <= 64 && ctas1 >= 2 * 148 * 2) msub = 2;
   }
   // C = 16 streaming layers: a 128-row tile moves only 20 KB, the per-CTA prologue dominates -> 512-row tiles
   // (3.5 -> 5.4 TB/s at batch 16, 8.7 -> 6.5 us at batch 1 on [16, 160000])
