@@ -519,7 +519,7 @@ def main():
         args.warmup = args.warmup if args.warmup is not None else 1
         run_reference(args)
     else:
-        args.steps = args.steps if args.steps is not None else 50
+        args.steps = args.steps if args.steps is not None else 200   # ~0.3 s per timed region: several clock samples
         args.warmup = max(3, args.warmup if args.warmup is not None else 5)
         run_b200(args)
 
