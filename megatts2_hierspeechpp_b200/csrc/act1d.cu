@@ -24,7 +24,7 @@ namespace {
 
 using namespace hsv_act;
 
-template <int R, int OUT_MODE, bool PACKED>
+template <int R, int OUT_MODE>
 __global__ void __launch_bounds__(NT) act1d_kernel(const float *__restrict__ x, void *__restrict__ outp,
                                                    const float *__restrict__ alpha,
                                                    const float *__restrict__ beta, int C, int64_t L,
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(NT) act1d_kernel(const float *__restrict__ x, 
   const bool active = row < nrows && ta < L;
   if (active) {
     const float *xw = x_s + c * K::PITCH + run * R + (K::XOFF - 5);
-    act_run<R, PACKED>(xw, outv, al, be, ta, L, x + row * L, sc);
+    act_run<R>(xw, outv, al, be, ta, L, x + row * L, sc);
   }
 
   // ---- stage results, write back coalesced ----
@@ -169,7 +169,6 @@ __global__ void __launch_bounds__(NT) act1d_kernel(const float *__restrict__ x, 
   }
 }
 
-int g_act_variant = 1;  // 1: packed f32x2 math (default), 0: scalar math
 int g_act_run = 0;      // bring-up aid: force the run length (17 or 25); 0 = automatic
 
 template <int R, int OUT_MODE>
@@ -199,11 +198,7 @@ int launch(const float *x, void *out, const float *alpha, const float *beta, int
   const int nt_i = (int)ntiles;
   const int64_t Lp = hsv::blk16_rows(L);
   const int cw = OUT_MODE == 1 ? hsv::blk_cw(C) : 0;
-  cudaError_t e;
-  if (g_act_variant)
-    e = cudaLaunchKernelEx(&cfg, act1d_kernel<R, OUT_MODE, true>, x, out, alpha, beta, C, L, nrows, nt_i, Lp, sc, cw);
-  else
-    e = cudaLaunchKernelEx(&cfg, act1d_kernel<R, OUT_MODE, false>, x, out, alpha, beta, C, L, nrows, nt_i, Lp, sc, cw);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, act1d_kernel<R, OUT_MODE>, x, out, alpha, beta, C, L, nrows, nt_i, Lp, sc, cw);
   if (e != cudaSuccess) {
     cudaGetLastError();
     hsv::set_error("act1d_snakebeta: launch failed: %s", cudaGetErrorString(e));
@@ -214,9 +209,8 @@ int launch(const float *x, void *out, const float *alpha, const float *beta, int
 
 }  // namespace
 
-// bring-up aid (A/B of the packed-math variant); not part of the drop-in contract
+// bring-up aid (forced run length, bits 8..15); not part of the drop-in contract
 extern "C" int hsv_set_act_variant(int v) {
-  g_act_variant = v & 1;
   g_act_run = v >> 8;  // bits 8..: forced run length
   return HSV_OK;
 }

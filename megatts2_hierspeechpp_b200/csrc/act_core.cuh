@@ -53,46 +53,7 @@ __device__ __forceinline__ ZPair up_snake(const float w0, const float w1, const 
   return z;
 }
 
-__device__ __forceinline__ float down6(const ZPair &p0, const ZPair &p1, const ZPair &p2, const ZPair &p3,
-                                       const ZPair &p4, const ZPair &p5) {
-  // out[t] = f0 zo(t-2) + f1 ze(t-2) + f2 zo(t-1) + f3 ze(t-1) + f4 zo(t) + f5 ze(t)
-  //        + f5 zo(t+1) + f4 ze(t+1) + f3 zo(t+2) + f2 ze(t+2) + f1 zo(t+3) + f0 ze(t+3)
-  float s0 = HSV_F0 * (p0.o + p5.e);
-  float s1 = HSV_F1 * (p0.e + p5.o);
-  s0 = fmaf(HSV_F2, p1.o + p4.e, s0);
-  s1 = fmaf(HSV_F3, p1.e + p4.o, s1);
-  s0 = fmaf(HSV_F4, p2.o + p3.e, s0);
-  s1 = fmaf(HSV_F5, p2.e + p3.o, s1);
-  return s0 + s1;
-}
-
-template <int R, bool EDGE>
-__device__ __forceinline__ void walk(const float *__restrict__ xw, float *__restrict__ outv, float a, float ib,
-                                     int64_t ta, int64_t L, float zL, float zR, float sc) {
-  // xw[0 .. R+9] = x[ta-5 .. ta+R+4] (already clamped);  outv[0..R-1] = out[ta .. ta+R-1]
-  ZPair ring[6];
-  float w0 = xw[0] * sc, w1 = xw[1] * sc, w2 = xw[2] * sc, w3 = xw[3] * sc, w4 = xw[4] * sc;
-  const int64_t n_last = 2 * L - 1;
-#pragma unroll
-  for (int s = 0; s < R + 5; ++s) {
-    const float w5 = xw[s + 5] * sc;
-    ZPair z = up_snake(w0, w1, w2, w3, w4, w5, a, ib);
-    if (EDGE) {
-      const int64_t m = ta - 2 + s;
-      const int64_t no = 2 * m - 1, ne = 2 * m;
-      z.o = no < 0 ? zL : (no > n_last ? zR : z.o);
-      z.e = ne < 0 ? zL : (ne > n_last ? zR : z.e);
-    }
-    ring[s % 6] = z;
-    if (s >= 5) {
-      outv[s - 5] = down6(ring[(s - 5) % 6], ring[(s - 4) % 6], ring[(s - 3) % 6], ring[(s - 2) % 6],
-                          ring[(s - 1) % 6], ring[s % 6]);
-    }
-    w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5;
-  }
-}
-
-// ---- packed-pair variant: Blackwell's FFMA2/FMUL2 (fma.rn.f32x2) process the (odd, even) 2x samples of
+// ---- packed pairs: Blackwell's FFMA2/FMUL2 (fma.rn.f32x2) process the (odd, even) 2x samples of
 // one step in one instruction; a scalar operand broadcasts for free, tap pairs live in uniform registers.
 typedef unsigned long long u64;
 __device__ __forceinline__ u64 pk(float lo, float hi) {
@@ -177,15 +138,14 @@ __device__ __forceinline__ void walk2(const float *__restrict__ xw, float *__res
 //   by runs that touch either end of the sequence); al, be = log-scale alpha / beta of the channel.
 // Edge semantics: the *activated* 2x signal is replicate-clamped on the 2x grid -- runs whose
 // window touches an end substitute z[0] / z[2L-1]; interior runs take the branch-free path.
-template <int R, bool PACKED>
+template <int R>
 __device__ __forceinline__ void act_run(const float *__restrict__ xw, float *__restrict__ outv, float al, float be,
                                         int64_t ta, int64_t L, const float *__restrict__ xr, float sc) {
   const float a = expf(al);
   const float ib = 1.0f / (expf(be) + 0.000000001f);
   const bool edge = (2 * ta - 5 < 0) || (2 * (ta + R - 1) + 6 > 2 * L - 1);
   if (!edge) {
-    if (PACKED) walk2<R, false>(xw, outv, a, ib, ta, L, 0.f, 0.f, sc);
-    else walk<R, false>(xw, outv, a, ib, ta, L, 0.f, 0.f, sc);
+    walk2<R, false>(xw, outv, a, ib, ta, L, 0.f, 0.f, sc);
   } else {
     // z[0] (m=0, even) and z[2L-1] (m=L, odd) from clamped global x
     float wl[6], wr[6];
@@ -199,8 +159,7 @@ __device__ __forceinline__ void act_run(const float *__restrict__ xw, float *__r
     }
     const float zL = up_snake(wl[0], wl[1], wl[2], wl[3], wl[4], wl[5], a, ib).e;
     const float zR = up_snake(wr[0], wr[1], wr[2], wr[3], wr[4], wr[5], a, ib).o;
-    if (PACKED) walk2<R, true>(xw, outv, a, ib, ta, L, zL, zR, sc);
-    else walk<R, true>(xw, outv, a, ib, ta, L, zL, zR, sc);
+    walk2<R, true>(xw, outv, a, ib, ta, L, zL, zR, sc);
   }
 }
 

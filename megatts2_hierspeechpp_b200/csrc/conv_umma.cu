@@ -495,7 +495,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) conv_umma_kernel(const __grid_c
         float outv[RR];
         if (need) {
           const float *xw = xb + c * K::PITCH + run * RR + (K::XOFF - 5);
-          hsv_act::act_run<RR, true>(xw, outv, al_g, be_g, ta, p.L, p.fx + ((int64_t)b * p.Cin + g * 8 + c) * p.L,
+          hsv_act::act_run<RR>(xw, outv, al_g, be_g, ta, p.L, p.fx + ((int64_t)b * p.Cin + g * 8 + c) * p.L,
                                      p.in_scale);
         }
         // fp16 into the swizzled A tile: row = run*RR + j, 16-byte unit g, half c; rows outside [0, L) are the
