@@ -47,7 +47,7 @@ def peaks():
 # ----------------------------------------------------------------------------------------------
 def make_workload(args, rank):
     """Returns dict(name, sd, host_inputs(list of CPU tensors), audio_seconds, which)."""
-    from oracle import synth
+    from megatts2_hierspeechpp_b200 import synthetic as synth
     import numpy as np
 
     if args.workload == "vocoder":

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import megatts2_hierspeechpp_b200 as hsv  # noqa: E402
 from megatts2_hierspeechpp_b200.runtime import bucket_by_length, gather_waveforms, shard_utterances  # noqa: E402
-from oracle import synth  # noqa: E402
+from megatts2_hierspeechpp_b200 import synthetic as synth  # noqa: E402
 
 
 def main():

@@ -13,7 +13,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import megatts2_hierspeechpp_b200 as hsv  # noqa: E402
-from oracle import synth  # noqa: E402
+from megatts2_hierspeechpp_b200 import synthetic as synth  # noqa: E402
 
 dev = "cuda:0"
 what = sys.argv[1]

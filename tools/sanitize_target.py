@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import megatts2_hierspeechpp_b200 as hsv  # noqa: E402
 import megatts2_hierspeechpp_b200.modules as M  # noqa: E402
-from oracle import synth  # noqa: E402
+from megatts2_hierspeechpp_b200 import synthetic as synth  # noqa: E402
 
 dev = "cuda:0"
 m = hsv.Vocoder()
