@@ -123,24 +123,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
       "l"(src), "r"(bytes), "r"(bar)
       : "memory");
 }
-__device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
-                                              uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      ".reg .b64 da, db;\n\t"
-      "mov.b64 da, {%1, %2};\n\t"
-      "mov.b64 db, {%3, %4};\n\t"
-      "setp.ne.b32 p, %6, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-               : "memory");
-}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -1356,7 +1338,7 @@ extern "C" int hsv_pack_convT_weight(const float *w, void *packed, int Cin, int 
 }
 
 extern "C" int hsv_conv1d_umma(const void *a_blk16, const void *w_packed, const float *bias,
-                               const float *residual, float *out, float *acc, int acc_mode, float acc_div,
+                               const float *residual, float *out, float *acc, int acc_mode, float /*acc_div: reserved*/,
                                int B, int Cin, int Cout, int64_t L, int k, int d, int n_tile, void *stream) {
   if (B == 0 || L == 0) return HSV_OK;  // empty batch / sequence
   if (int rc = check_common("conv1d_umma", a_blk16, w_packed, Cin, Cout, n_tile)) return rc;
