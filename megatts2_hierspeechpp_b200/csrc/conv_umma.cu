@@ -960,6 +960,7 @@ __global__ void __launch_bounds__(64 + 128 * EPW, 1) conv_umma_persist_kernel(co
   }
 }
 
+int g_host_debug = 0;
 int g_persist = 1;  // persistent variant for eligible launches (hsv_set_umma_debug bit 6 turns it off)
 
 constexpr int PERSIST_EPW = 4;
@@ -984,6 +985,19 @@ int launch_persist(Params p, int B, cudaStream_t st, const char *what) {
   }
   p.B = B;
   p.stages = MAX_STAGES;
+  // weight-ring stage: 32 KB when three of them fit next to the two A tiles (one elected thread issues every
+  // bulk copy of the CTA: fewer, larger copies), else the 16 KB of the one-tile kernel
+  {
+    const int blk_bytes = p.n_tile * p.cw * 2;
+    const int nblk = p.nchunks * p.tt.ntaps[0];
+    int g32 = 32768 / blk_bytes;
+    g32 = g32 < 1 ? 1 : (g32 > nblk ? nblk : g32);
+    const size_t fixed = 1024 + 2 * (size_t)p.a_pitch * p.nchunks + 4 * PERSIST_EPW * 2048;
+    // (measured at C=128, batch 16: k=11 70.8 -> 64.3 us = 897 TFLOP/s, k=7 53.9 -> 51.3 us; short K loops prefer
+    //  four small stages: k=3 38.0 vs 47.1 us)
+    if (!(g_host_debug & 1) && nblk >= 12 && g32 > p.G && fixed + 3 * (size_t)g32 * blk_bytes <= (size_t)max_dyn[dev])
+      p.G = g32;
+  }
   const size_t stage_bytes = (size_t)p.G * p.n_tile * p.cw * 2;
   size_t smem = 1024 + 2 * (size_t)p.a_pitch * p.nchunks + 4 * PERSIST_EPW * 2048;
   while (p.stages > 2 && smem + p.stages * stage_bytes > (size_t)max_dyn[dev]) p.stages--;
@@ -1083,7 +1097,6 @@ TapTable convT_taps(int k, int u) {
   return tt;
 }
 
-int g_host_debug = 0;
 long long *g_trace = nullptr;
 int g_msub_override = 0;  // bring-up aid: force the sub-tiles per CTA (0 = automatic)
 
@@ -1301,7 +1314,7 @@ int pack(const float *w, void *packed, int Cout, int Cin, int k, int n_tile, int
 }  // namespace
 
 // bring-up aid only; not part of the drop-in contract.
-//   bit 2: skip the epilogue's global stores, bit 3: skip its TMEM loads, bit 4: force the scalar epilogue,
+//   bit 0: persistent variant keeps 16 KB weight-ring stages, bit 2: skip the epilogue's global stores, bit 3: skip its TMEM loads, bit 4: force the scalar epilogue,
 //   bit 5: 4-warp CTAs for the wide variants too, bit 6: persistent variant off,
 //   bit 7: persistent variant for every launch it can run (tests);
 //   bits 24..26: forced sub-tiles per CTA.
