@@ -58,6 +58,7 @@ struct Params {
   int n_tile, nco_tiles;
   int ntiles;
   int B;             // batch (persistent variant: tiles are enumerated over (b, n-tile, row tile))
+  int nabuf;         // persistent variant: A-tile buffers (2 = double-buffered, 1 when two do not fit: C = 256)
   int msub;          // 128-row sub-tiles per CTA (1, 2 or 4): every weight K-step feeds msub MMAs
   int cw;            // channels per operand row (64 / 32 / 16)
   int nchunks;       // Cin / cw
@@ -722,9 +723,10 @@ __global__ void __launch_bounds__(32 * NW, MINB) conv_umma_kernel(const __grid_c
 // tile i into TMEM buffer i & 1, warps 2..5 drain tile i-1 from the other TMEM buffer (float4 epilogue).  The
 // tensor pipe therefore never waits for a prologue or an epilogue (ncu on the one-tile-per-CTA kernel at C=128,
 // batch 16: two co-resident CTAs, tensor pipe 36-48 % busy, the rest is their load / drain phases).
-// Restrictions: stride-1 conv, MSUB = 1, float4 epilogue, A tile <= ~60 KB (double-buffered): C = 128 layers today
-// (C = 256 needs an A-chunk ring).  Measured at batch 16, C = 128: k=3 49.1 -> 38.7 us, k=7 60.2 -> 53.3 us,
-// k=11 74.3 -> 70.3 us (820 TFLOP/s = 60 % of the measured sustained bf16 peak).
+// Restrictions: stride-1 conv, MSUB = 1, float4 epilogue.  The A tile is double-buffered when two fit (C = 128),
+// else single (C = 256: the next tile is staged after this tile's MMAs).  Measured at batch 16: C = 128 k=3 49.1
+// -> 38.0 us, k=7 60.2 -> 51.3, k=11 74.3 -> 64.3 us (897 TFLOP/s); C = 256 k=3 25.5 -> 23.1 us, k=7 38.1 -> 33.3,
+// k=11 50.5 -> 46.0 us (1003 TFLOP/s = 73 % of the measured sustained bf16 peak).
 // ------------------------------------------------------------------------------------------------------------
 constexpr int PB_ACC_F = 0, PB_ACC_E = 2, PB_A_F = 4, PB_A_E = 6, PB_WF = 8, PB_WE = PB_WF + MAX_STAGES,
               PB_N = PB_WE + MAX_STAGES;
@@ -747,8 +749,9 @@ __global__ void __launch_bounds__(64 + 128 * EPW, 1) conv_umma_persist_kernel(co
   const uint32_t a_tile_bytes = p.a_pitch * (uint32_t)p.nchunks;
   const uint32_t blk_bytes = (uint32_t)p.n_tile * rowbytes;
   const uint32_t stage_bytes = blk_bytes * (uint32_t)p.G;
-  const uint32_t a_s = (smem_u32(smem_raw) + 1023u) & ~1023u;       // two A tiles
-  const uint32_t w_s = a_s + 2u * a_tile_bytes;                      // weight ring
+  const uint32_t a_s = (smem_u32(smem_raw) + 1023u) & ~1023u;       // one or two A tiles
+  const uint32_t w_s = a_s + (uint32_t)p.nabuf * a_tile_bytes;       // weight ring
+  const bool a2 = p.nabuf == 2;
   const uint32_t stg_s = w_s + (uint32_t)p.stages * stage_bytes;     // 2 KB of epilogue staging per warp
   const uint32_t bar0 = smem_u32(&bars[0]);
   const int total = p.ntiles * p.nco_tiles * p.B;                    // tiles of the launch
@@ -792,8 +795,8 @@ __global__ void __launch_bounds__(64 + 128 * EPW, 1) conv_umma_persist_kernel(co
       auto load_a = [&](int i) {
         int b, nt, tile;
         tile_coords(i, b, nt, tile);
-        const int buf = i & 1;
-        if (i >= 2) mbar_wait(bar0 + 8 * (PB_A_E + buf), (uint32_t)((i >> 1) - 1) & 1u);
+        const int buf = a2 ? (i & 1) : 0, use = a2 ? (i >> 1) : i;   // use-th fill of this buffer
+        if (use >= 1) mbar_wait(bar0 + 8 * (PB_A_E + buf), (uint32_t)(use - 1) & 1u);
         const int64_t row0 = (int64_t)HSV_BLK_PAD + (int64_t)tile * TILE_M - p.hlo8;
         mbar_expect_tx(bar0 + 8 * (PB_A_F + buf), a_chunk_bytes * (uint32_t)p.nchunks);
         for (int c = 0; c < p.nchunks; ++c) {
@@ -808,7 +811,7 @@ __global__ void __launch_bounds__(64 + 128 * EPW, 1) conv_umma_persist_kernel(co
         int b, nt, tile;
         tile_coords(i, b, nt, tile);
         const uint8_t *wsrc = p.w + (int64_t)nt * nblocks * blk_bytes;
-        if (i + 1 < my_n) load_a(i + 1);  // one tile ahead of the MMAs
+        if (a2 && i + 1 < my_n) load_a(i + 1);  // one tile ahead of the MMAs
         for (int rnd = 0; rnd < nrounds; ++rnd, ++it) {
           if (it >= p.stages) mbar_wait(bar0 + 8 * (PB_WE + ws), wpar ^ 1u);
           const int nb = min(p.G, nblocks - rnd * p.G);
@@ -820,6 +823,9 @@ __global__ void __launch_bounds__(64 + 128 * EPW, 1) conv_umma_persist_kernel(co
             wpar ^= 1u;
           }
         }
+        // single A buffer: the next tile can only be staged once this tile's MMAs have read it (its weights are
+        // all issued by now, so the wait inside load_a cannot deadlock)
+        if (!a2 && i + 1 < my_n) load_a(i + 1);
       }
     }
   } else if (warp == 1) {
@@ -836,12 +842,13 @@ __global__ void __launch_bounds__(64 + 128 * EPW, 1) conv_umma_persist_kernel(co
     int ws = 0;
     uint32_t wpar = 0;
     for (int i = 0; i < my_n; ++i) {
-      const int buf = i & 1;
+      const int buf = i & 1;                                            // TMEM accumulator buffer
+      const int abuf = a2 ? buf : 0, ause = a2 ? (i >> 1) : i;          // A-tile buffer and its use count
       if (i >= 2) mbar_wait_warp(bar0 + 8 * (PB_ACC_E + buf), (uint32_t)((i >> 1) - 1) & 1u);  // TMEM buffer drained
-      mbar_wait_warp(bar0 + 8 * (PB_A_F + buf), (uint32_t)(i >> 1) & 1u);                      // A tile landed
+      mbar_wait_warp(bar0 + 8 * (PB_A_F + abuf), (uint32_t)ause & 1u);                         // A tile landed
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tacc = tmem + (uint32_t)(buf * p.n_tile);
-      uint32_t a_chunk = a_lo00 + (uint32_t)buf * a_tile16, a_lo = a_chunk, not_first = 0;
+      uint32_t a_chunk = a_lo00 + (uint32_t)abuf * a_tile16, a_lo = a_chunk, not_first = 0;
       int j = 0;
       for (int rnd = 0; rnd < nrounds; ++rnd) {
         mbar_wait_warp(bar0 + 8 * (PB_WF + ws), wpar);
@@ -867,7 +874,7 @@ __global__ void __launch_bounds__(64 + 128 * EPW, 1) conv_umma_persist_kernel(co
           wpar ^= 1u;
         }
       }
-      umma_commit_elect(bar0 + 8 * (PB_A_E + buf));    // the A buffer may be refilled
+      umma_commit_elect(bar0 + 8 * (PB_A_E + abuf));   // the A buffer may be refilled
       umma_commit_elect(bar0 + 8 * (PB_ACC_F + buf));  // the accumulator is complete
     }
   } else {
@@ -985,6 +992,8 @@ int launch_persist(Params p, int B, cudaStream_t st, const char *what) {
   }
   p.B = B;
   p.stages = MAX_STAGES;
+  // two A tiles when they leave room for a 3-stage ring of 16 KB, else one (C = 256: 92 KB per tile)
+  p.nabuf = 1024 + 2 * (size_t)p.a_pitch * p.nchunks + 4 * PERSIST_EPW * 2048 + 3 * 16384 <= (size_t)max_dyn[dev] ? 2 : 1;
   // weight-ring stage: 32 KB when three of them fit next to the two A tiles (one elected thread issues every
   // bulk copy of the CTA: fewer, larger copies), else the 16 KB of the one-tile kernel
   {
@@ -992,15 +1001,15 @@ int launch_persist(Params p, int B, cudaStream_t st, const char *what) {
     const int nblk = p.nchunks * p.tt.ntaps[0];
     int g32 = 32768 / blk_bytes;
     g32 = g32 < 1 ? 1 : (g32 > nblk ? nblk : g32);
-    const size_t fixed = 1024 + 2 * (size_t)p.a_pitch * p.nchunks + 4 * PERSIST_EPW * 2048;
+    const size_t fixed = 1024 + p.nabuf * (size_t)p.a_pitch * p.nchunks + 4 * PERSIST_EPW * 2048;
     // (measured at C=128, batch 16: k=11 70.8 -> 64.3 us = 897 TFLOP/s, k=7 53.9 -> 51.3 us; short K loops prefer
     //  four small stages: k=3 38.0 vs 47.1 us)
     if (!(g_host_debug & 1) && nblk >= 12 && g32 > p.G && fixed + 3 * (size_t)g32 * blk_bytes <= (size_t)max_dyn[dev])
       p.G = g32;
   }
   const size_t stage_bytes = (size_t)p.G * p.n_tile * p.cw * 2;
-  size_t smem = 1024 + 2 * (size_t)p.a_pitch * p.nchunks + 4 * PERSIST_EPW * 2048;
-  while (p.stages > 2 && smem + p.stages * stage_bytes > (size_t)max_dyn[dev]) p.stages--;
+  size_t smem = 1024 + p.nabuf * (size_t)p.a_pitch * p.nchunks + 4 * PERSIST_EPW * 2048;
+  while (p.stages > 3 && smem + p.stages * stage_bytes > (size_t)max_dyn[dev]) p.stages--;
   smem += p.stages * stage_bytes;
   if (smem > (size_t)max_dyn[dev]) return 1;  // not eligible: fall back to the one-tile-per-CTA kernel
   uint32_t cols = 32;
@@ -1195,7 +1204,7 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
   auto al16e = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   const bool force_persist = (g_host_debug & 128) != 0;  // tests: any size / tile width
   const bool want_persist = g_persist && !fa && tt.nphase == 1 && tt.out_stride == 1 &&
-                            (force_persist || (n_tile >= 128 && ctas1 >= 4 * 148)) && (Lout % 4) == 0 && al16e(residual) && al16e(out) && al16e(acc) &&
+                            (force_persist || (n_tile >= 128 && ctas1 >= 2 * 148)) && (Lout % 4) == 0 && al16e(residual) && al16e(out) && al16e(acc) &&
                             ((out != nullptr) != (acc_mode != 0));
   if (want_persist) msub = 1;
   if (fa) msub = 2;  // 256-row tiles: the activation's 5-row run halo and the conv halo are amortised over more rows

@@ -407,7 +407,8 @@ def test_conv1d_umma_persistent_variant(hsv):
     bits as the one-tile-per-CTA kernel: forced on (debug bit 7) vs off (bit 6) on shapes with several tiles per CTA."""
     gen = torch.Generator().manual_seed(77)
     try:
-        for (B, C, L, k, d, nt) in ((3, 128, 9000, 7, 3, 128), (2, 64, 30000, 11, 5, 64), (40, 32, 2500, 3, 1, 32)):
+        for (B, C, L, k, d, nt) in ((3, 128, 9000, 7, 3, 128), (2, 64, 30000, 11, 5, 64), (40, 32, 2500, 3, 1, 32),
+                                    (2, 256, 20000, 11, 5, 128)):   # the last one: single A buffer (C = 256)
             x = torch.randn(B, C, L, generator=gen).to(DEV)
             w = (torch.randn(C, C, k, generator=gen) / (C * k) ** 0.5).to(DEV)
             bias = (torch.randn(C, generator=gen) * 0.1).to(DEV)
