@@ -58,6 +58,7 @@ struct Params {
   int n_tile, nco_tiles;
   int ntiles;
   int B;             // batch (persistent variant: tiles are enumerated over (b, n-tile, row tile))
+  int resident;      // persistent variant: 1 = all weight blocks stay in shared memory (loaded once per CTA)
   int nabuf;         // persistent variant: A-tile buffers (2 = double-buffered, 1 when two do not fit: C = 256)
   int msub;          // 128-row sub-tiles per CTA (1, 2 or 4): every weight K-step feeds msub MMAs
   int cw;            // channels per operand row (64 / 32 / 16)
@@ -726,7 +727,8 @@ __global__ void __launch_bounds__(32 * NW, MINB) conv_umma_kernel(const __grid_c
 // Restrictions: stride-1 conv, MSUB = 1, float4 epilogue.  The A tile is double-buffered when two fit (C = 128),
 // else single (C = 256: the next tile is staged after this tile's MMAs).  Measured at batch 16: C = 128 k=3 49.1
 // -> 38.0 us, k=7 60.2 -> 51.3, k=11 74.3 -> 64.3 us (897 TFLOP/s); C = 256 k=3 25.5 -> 23.1 us, k=7 38.1 -> 33.3,
-// k=11 50.5 -> 46.0 us (1003 TFLOP/s = 73 % of the measured sustained bf16 peak).
+// k=11 50.5 -> 46.0 us (1003 TFLOP/s = 73 % of the measured sustained bf16 peak); C = 64 (weights resident in shared
+// memory) k=11 103.7 -> 79.0 us.  C <= 32 loses (two units per tile leave half the epilogue warps idle).
 // ------------------------------------------------------------------------------------------------------------
 constexpr int PB_ACC_F = 0, PB_ACC_E = 2, PB_A_F = 4, PB_A_E = 6, PB_WF = 8, PB_WE = PB_WF + MAX_STAGES,
               PB_N = PB_WE + MAX_STAGES;
@@ -812,7 +814,7 @@ __global__ void __launch_bounds__(64 + 128 * EPW, 1) conv_umma_persist_kernel(co
         tile_coords(i, b, nt, tile);
         const uint8_t *wsrc = p.w + (int64_t)nt * nblocks * blk_bytes;
         if (a2 && i + 1 < my_n) load_a(i + 1);  // one tile ahead of the MMAs
-        for (int rnd = 0; rnd < nrounds; ++rnd, ++it) {
+        for (int rnd = 0; rnd < nrounds && !(p.resident && i > 0); ++rnd, ++it) {  // resident: first tile only
           if (it >= p.stages) mbar_wait(bar0 + 8 * (PB_WE + ws), wpar ^ 1u);
           const int nb = min(p.G, nblocks - rnd * p.G);
           const uint32_t bytes = blk_bytes * (uint32_t)nb;
@@ -851,8 +853,10 @@ __global__ void __launch_bounds__(64 + 128 * EPW, 1) conv_umma_persist_kernel(co
       uint32_t a_chunk = a_lo00 + (uint32_t)abuf * a_tile16, a_lo = a_chunk, not_first = 0;
       int j = 0;
       for (int rnd = 0; rnd < nrounds; ++rnd) {
-        mbar_wait_warp(bar0 + 8 * (PB_WF + ws), wpar);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (!(p.resident && i > 0)) {  // resident weights: landed once, never recycled
+          mbar_wait_warp(bar0 + 8 * (PB_WF + ws), wpar);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
         const int nb = min(p.G, nblocks - rnd * p.G);
         uint32_t b_lo = w_lo0 + (uint32_t)ws * stage16;
         for (int g = 0; g < nb; ++g) {
@@ -868,10 +872,12 @@ __global__ void __launch_bounds__(64 + 128 * EPW, 1) conv_umma_persist_kernel(co
             a_lo = a_chunk;
           }
         }
-        umma_commit_elect(bar0 + 8 * (PB_WE + ws));
-        if (++ws == p.stages) {
-          ws = 0;
-          wpar ^= 1u;
+        if (!p.resident) {
+          umma_commit_elect(bar0 + 8 * (PB_WE + ws));
+          if (++ws == p.stages) {
+            ws = 0;
+            wpar ^= 1u;
+          }
         }
       }
       umma_commit_elect(bar0 + 8 * (PB_A_E + abuf));   // the A buffer may be refilled
@@ -994,6 +1000,19 @@ int launch_persist(Params p, int B, cudaStream_t st, const char *what) {
   p.stages = MAX_STAGES;
   // two A tiles when they leave room for a 3-stage ring of 16 KB, else one (C = 256: 92 KB per tile)
   p.nabuf = 1024 + 2 * (size_t)p.a_pitch * p.nchunks + 4 * PERSIST_EPW * 2048 + 3 * 16384 <= (size_t)max_dyn[dev] ? 2 : 1;
+  // weights resident in shared memory (one stage holding every block, loaded once per CTA) when the whole set of
+  // one n-tile fits next to the A tiles: the C <= 64 layers (<= 90 KB), whose weight stream per 128-row tile would
+  // otherwise need more L2->SM bandwidth than the MMAs leave time for
+  p.resident = 0;
+  {
+    const size_t wall = (size_t)p.nchunks * p.tt.ntaps[0] * p.n_tile * p.cw * 2;
+    const size_t fixed = 1024 + p.nabuf * (size_t)p.a_pitch * p.nchunks + 4 * PERSIST_EPW * 2048;
+    if (p.nco_tiles == 1 && wall < (1u << 20) && fixed + wall <= (size_t)max_dyn[dev] && !(g_host_debug & 2)) {
+      p.resident = 1;
+      p.G = p.nchunks * p.tt.ntaps[0];
+      p.stages = 1;
+    }
+  }
   // weight-ring stage: 32 KB when three of them fit next to the two A tiles (one elected thread issues every
   // bulk copy of the CTA: fewer, larger copies), else the 16 KB of the one-tile kernel
   {
@@ -1004,12 +1023,13 @@ int launch_persist(Params p, int B, cudaStream_t st, const char *what) {
     const size_t fixed = 1024 + p.nabuf * (size_t)p.a_pitch * p.nchunks + 4 * PERSIST_EPW * 2048;
     // (measured at C=128, batch 16: k=11 70.8 -> 64.3 us = 897 TFLOP/s, k=7 53.9 -> 51.3 us; short K loops prefer
     //  four small stages: k=3 38.0 vs 47.1 us)
-    if (!(g_host_debug & 1) && nblk >= 12 && g32 > p.G && fixed + 3 * (size_t)g32 * blk_bytes <= (size_t)max_dyn[dev])
+    if (!p.resident && !(g_host_debug & 1) && nblk >= 12 && g32 > p.G &&
+        fixed + 3 * (size_t)g32 * blk_bytes <= (size_t)max_dyn[dev])
       p.G = g32;
   }
   const size_t stage_bytes = (size_t)p.G * p.n_tile * p.cw * 2;
   size_t smem = 1024 + p.nabuf * (size_t)p.a_pitch * p.nchunks + 4 * PERSIST_EPW * 2048;
-  while (p.stages > 3 && smem + p.stages * stage_bytes > (size_t)max_dyn[dev]) p.stages--;
+  while (!p.resident && p.stages > 3 && smem + p.stages * stage_bytes > (size_t)max_dyn[dev]) p.stages--;
   smem += p.stages * stage_bytes;
   if (smem > (size_t)max_dyn[dev]) return 1;  // not eligible: fall back to the one-tile-per-CTA kernel
   uint32_t cols = 32;
@@ -1204,7 +1224,8 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
   auto al16e = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   const bool force_persist = (g_host_debug & 128) != 0;  // tests: any size / tile width
   const bool want_persist = g_persist && !fa && tt.nphase == 1 && tt.out_stride == 1 &&
-                            (force_persist || (n_tile >= 128 && ctas1 >= 2 * 148)) && (Lout % 4) == 0 && al16e(residual) && al16e(out) && al16e(acc) &&
+                            (force_persist || (n_tile >= 128 && ctas1 >= 2 * 148) || (n_tile == 64 && Cout == 64 && ctas1 >= 4 * 148)) &&
+                            (Lout % 4) == 0 && al16e(residual) && al16e(out) && al16e(acc) &&
                             ((out != nullptr) != (acc_mode != 0));
   if (want_persist) msub = 1;
   if (fa) msub = 2;  // 256-row tiles: the activation's 5-row run halo and the conv halo are amortised over more rows
@@ -1323,7 +1344,7 @@ int pack(const float *w, void *packed, int Cout, int Cin, int k, int n_tile, int
 }  // namespace
 
 // bring-up aid only; not part of the drop-in contract.
-//   bit 0: persistent variant keeps 16 KB weight-ring stages, bit 2: skip the epilogue's global stores, bit 3: skip its TMEM loads, bit 4: force the scalar epilogue,
+//   bit 0: persistent variant keeps 16 KB weight-ring stages, bit 1: ... never keeps the weights resident, bit 2: skip the epilogue's global stores, bit 3: skip its TMEM loads, bit 4: force the scalar epilogue,
 //   bit 5: 4-warp CTAs for the wide variants too, bit 6: persistent variant off,
 //   bit 7: persistent variant for every launch it can run (tests);
 //   bits 24..26: forced sub-tiles per CTA.
