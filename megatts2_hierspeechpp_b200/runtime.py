@@ -33,7 +33,7 @@ def to_pcm16(audio: torch.Tensor, scale_norm: str = "max", prompt_audio_max: flo
 class CudaGraphRunner:
     """Capture ``fn(*tensors)`` once per input-shape signature and replay it.
 
-    One forward of the vocoder is ~330 small kernels; replaying them as a CUDA graph removes the
+    One forward of the vocoder is 288 small kernels; replaying them as a CUDA graph removes the
     launch gaps that dominate batch-1 latency.  Inputs are copied into static buffers; the returned
     tensors are the graph's static outputs (valid until the next call with the same shapes)."""
 
