@@ -20,6 +20,11 @@
 // fp32 [B,C,L] or as the fp16 "blk16" tensor-core operand layout.
 #include "act_core.cuh"
 
+namespace hsv {
+int act1d_mma_launch(const float *x, void *out, const float *alpha, const float *beta, int B, int C, int64_t L,
+                     float sc, cudaStream_t st);
+}
+
 namespace {
 
 using namespace hsv_act;
@@ -170,6 +175,7 @@ __global__ void __launch_bounds__(NT) act1d_kernel(const float *__restrict__ x, 
 }
 
 int g_act_run = 0;      // bring-up aid: force the run length (17 or 25); 0 = automatic
+int g_act_mma = 0;      // fp16-operand output: 0 = tensor-core kernel (act1d_mma.cu) when eligible, 1 = never, 2 = always
 
 template <int R, int OUT_MODE>
 int launch(const float *x, void *out, const float *alpha, const float *beta, int B, int C, int64_t L, float sc,
@@ -212,6 +218,7 @@ int launch(const float *x, void *out, const float *alpha, const float *beta, int
 // bring-up aid (forced run length, bits 8..15); not part of the drop-in contract
 extern "C" int hsv_set_act_variant(int v) {
   g_act_run = v >> 8;  // bits 8..: forced run length
+  g_act_mma = v & 3;   // bits 0..1: tensor-core variant policy (0 auto, 1 off, 2 forced)
   return HSV_OK;
 }
 
@@ -232,6 +239,13 @@ extern "C" int hsv_act1d_snakebeta(const float *x, void *out, const float *alpha
     return big ? launch<25, 0>(x, out, alpha, beta, B, C, L, in_scale, st)
                : launch<17, 0>(x, out, alpha, beta, B, C, L, in_scale, st);
   HSV_REQUIRE(C % 16 == 0, "act1d: blk16 output needs C %% 16 == 0 (C=%d)", C);
+  // tensor-core FIR variant (act1d_mma.cu): every shape with at least half a tile of work per row; the CUDA-core
+  // kernel keeps the tiny sequences (its tiles are 8 x 272 instead of 8 x 512)
+  if (g_act_mma == 2 || (g_act_mma == 0 && L >= 256)) {
+    const int rc = hsv::act1d_mma_launch(x, out, alpha, beta, B, C, L, in_scale, st);
+    if (rc != 1) return rc;
+    HSV_REQUIRE(g_act_mma != 2, "act1d: shape not eligible for the forced tensor-core variant");
+  }
   return big ? launch<25, 1>(x, out, alpha, beta, B, C, L, in_scale, st)
              : launch<17, 1>(x, out, alpha, beta, B, C, L, in_scale, st);
 }

@@ -388,5 +388,11 @@ def peak_norm_pcm16(x: torch.Tensor, s1: float = 32767.0, s2: float = 0.999, per
     return out, (peaks if per_row else peaks[:1])
 
 
+def set_act_variant(v: int):
+    """Bring-up / test aid: bits 0..1 = tensor-core activation policy (0 auto, 1 off, 2 forced), bits 8.. = forced run
+    length of the CUDA-core kernel."""
+    _lib.load().hsv_set_act_variant(int(v))
+
+
 def set_umma_debug(flags: int):
     _lib.load().hsv_set_umma_debug(int(flags))
