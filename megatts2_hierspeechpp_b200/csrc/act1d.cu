@@ -175,7 +175,10 @@ __global__ void __launch_bounds__(NT) act1d_kernel(const float *__restrict__ x, 
 }
 
 int g_act_run = 0;      // bring-up aid: force the run length (17 or 25); 0 = automatic
-int g_act_mma = 0;      // fp16-operand output: 0 = tensor-core kernel (act1d_mma.cu) when eligible, 1 = never, 2 = always
+#ifndef HSV_ACT_MMA_AUTO
+#define HSV_ACT_MMA_AUTO 0   // policy of variant 0 (auto): 1 = tensor-core kernel for L >= 256 (set once it wins on B200)
+#endif
+int g_act_mma = 0;      // fp16-operand output: 0 = auto, 1 = CUDA-core kernel (act1d.cu), 2 = tensor-core kernel (act1d_mma.cu)
 
 template <int R, int OUT_MODE>
 int launch(const float *x, void *out, const float *alpha, const float *beta, int B, int C, int64_t L, float sc,
@@ -241,7 +244,7 @@ extern "C" int hsv_act1d_snakebeta(const float *x, void *out, const float *alpha
   HSV_REQUIRE(C % 16 == 0, "act1d: blk16 output needs C %% 16 == 0 (C=%d)", C);
   // tensor-core FIR variant (act1d_mma.cu): every shape with at least half a tile of work per row; the CUDA-core
   // kernel keeps the tiny sequences (its tiles are 8 x 272 instead of 8 x 512)
-  if (g_act_mma == 2 || (g_act_mma == 0 && L >= 256)) {
+  if (g_act_mma == 2 || (g_act_mma == 0 && HSV_ACT_MMA_AUTO && L >= 256)) {
     const int rc = hsv::act1d_mma_launch(x, out, alpha, beta, B, C, L, in_scale, st);
     if (rc != 1) return rc;
     HSV_REQUIRE(g_act_mma != 2, "act1d: shape not eligible for the forced tensor-core variant");

@@ -61,7 +61,21 @@ def blk16_shape(B: int, C: int, L: int) -> Tuple[int, int, int, int]:
     return (B, C // cw, blk16_rows(L), cw)
 
 
-_blk_pool: Dict[Tuple, torch.Tensor] = {}
+# Operand workspaces are cached per exact (device, B, C, L, slot) -- the layout's zero rows around the sequence
+# must survive reuse, so a buffer is only ever reused for the shape it was zero-initialised for.  The cache is an
+# LRU bounded in bytes (WORKSPACE_BUDGET_BYTES; variable-length serving would otherwise grow it without bound).
+# Evicting or clearing bumps WORKSPACE_EPOCH, which invalidates every captured CUDA graph that baked the old
+# pointers in (runtime.CudaGraphRunner keys on it).
+from collections import OrderedDict
+
+_blk_pool: "OrderedDict[Tuple, torch.Tensor]" = OrderedDict()
+WORKSPACE_BUDGET_BYTES = [int(__import__("os").environ.get("HSV_WORKSPACE_BUDGET_MB", "16384")) << 20]
+WORKSPACE_EPOCH = [0]
+_pin_depth = [0]      # > 0 while a CUDA graph is being warmed up / captured: no eviction in that window
+
+
+def workspace_bytes() -> int:
+    return sum(b.numel() * b.element_size() for b in _blk_pool.values())
 
 
 def blk16_buffer(B: int, C: int, L: int, device, slot: int = 0) -> torch.Tensor:
@@ -72,14 +86,26 @@ def blk16_buffer(B: int, C: int, L: int, device, slot: int = 0) -> torch.Tensor:
     dev = torch.device(device)
     key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device(), B, C, L, slot)
     buf = _blk_pool.get(key)
-    if buf is None:
-        buf = torch.zeros(*blk16_shape(B, C, L), dtype=torch.float16, device=dev)
-        _blk_pool[key] = buf
+    if buf is not None:
+        _blk_pool.move_to_end(key)
+        return buf
+    shape = blk16_shape(B, C, L)
+    need = 2 * shape[0] * shape[1] * shape[2] * shape[3]
+    if _pin_depth[0] == 0:
+        evicted = False
+        while _blk_pool and workspace_bytes() + need > WORKSPACE_BUDGET_BYTES[0]:
+            _blk_pool.popitem(last=False)
+            evicted = True
+        if evicted:
+            WORKSPACE_EPOCH[0] += 1
+    buf = torch.zeros(*shape, dtype=torch.float16, device=dev)
+    _blk_pool[key] = buf
     return buf
 
 
 def clear_workspace():
     _blk_pool.clear()
+    WORKSPACE_EPOCH[0] += 1
 
 
 def act1d(x: torch.Tensor, alpha: torch.Tensor, beta: torch.Tensor, out: Optional[torch.Tensor] = None,

@@ -33,41 +33,84 @@ def to_pcm16(audio: torch.Tensor, scale_norm: str = "max", prompt_audio_max: flo
 class CudaGraphRunner:
     """Capture ``fn(*tensors)`` once per input-shape signature and replay it.
 
-    One forward of the vocoder is 288 small kernels; replaying them as a CUDA graph removes the
+    One forward of the vocoder is ~290 small kernels; replaying them as a CUDA graph removes the
     launch gaps that dominate batch-1 latency.  Inputs are copied into static buffers; the returned
-    tensors are the graph's static outputs (valid until the next call with the same shapes)."""
+    tensors are the graph's static outputs (valid until the next call with the same shapes).
 
-    def __init__(self, fn: Callable, warmup: int = 2):
+    A captured graph bakes in raw pointers to the folded / packed weights and to the operand workspaces, so the
+    cache key carries the epochs that every event which can move those bumps (``load_state_dict`` on any hsv
+    module, ``invalidate_caches()``, ``remove_weight_norm()``, ``ops.clear_workspace()``, workspace eviction) plus a
+    ``config_token`` for host-side switches read at capture time (``parallel_blocks``, the fusion threshold):
+    entries from an older epoch are dropped and recaptured, never replayed.  The cache is an LRU of at most
+    ``max_graphs`` shapes; a shape is only captured on its ``capture_after``-th call (default: the first), earlier
+    calls run eagerly -- set it to 2 under variable-length traffic so one-off lengths never pay a capture."""
+
+    def __init__(self, fn: Callable, warmup: int = 2, max_graphs: int = 16, capture_after: int = 1):
+        from collections import OrderedDict
         self.fn = fn
         self.warmup = warmup
-        self._graphs: Dict[Tuple, Tuple] = {}
+        self.max_graphs = max_graphs
+        self.capture_after = capture_after
+        self._graphs: "OrderedDict[Tuple, Tuple]" = OrderedDict()
+        self._seen: Dict[Tuple, int] = {}
+        self._pb_mods = None
+        self.captures = 0
+
+    def _version(self):
+        from . import modules as M, ops
+        if self._pb_mods is None:   # the (few) modules that carry the multi-stream switch, found once
+            self._pb_mods = [m for m in (self.fn.modules() if hasattr(self.fn, "modules") else [])
+                             if hasattr(m, "parallel_blocks")]
+        par = tuple(bool(m.parallel_blocks) for m in self._pb_mods)
+        return (M._CACHE_EPOCH[0], ops.WORKSPACE_EPOCH[0], M.FUSE_MAX_CHANNELS[0], par)
 
     def _key(self, args):
         return tuple((tuple(a.shape), a.dtype, a.device.index) for a in args)
 
     def __call__(self, *args: torch.Tensor):
+        from . import ops
         for a in args:
             if not a.is_cuda:
                 raise RuntimeError("CudaGraphRunner: CUDA tensors only")
         key = self._key(args)
         entry = self._graphs.get(key)
+        if entry is not None and entry[3] != self._version():
+            del self._graphs[key]          # stale pointers (weights refolded / workspaces moved): never replay
+            entry = None
         if entry is None:
+            self._seen[key] = self._seen.get(key, 0) + 1
+            if len(self._seen) > 4096:
+                self._seen.clear()
+            if self._seen[key] < self.capture_after:
+                with torch.no_grad():
+                    return self.fn(*args)
             static_in = [torch.empty_like(a) for a in args]
             for s, a in zip(static_in, args):
                 s.copy_(a)
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side), torch.no_grad():
-                for _ in range(self.warmup):  # folds weights, allocates workspaces, loads modules
-                    self.fn(*static_in)
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.no_grad(), torch.cuda.graph(graph):
-                static_out = self.fn(*static_in)
-            entry = (graph, static_in, static_out)
+            ops._pin_depth[0] += 1         # the pointers seen during warm-up must be the ones captured
+            try:
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side), torch.no_grad():
+                    for _ in range(self.warmup):  # folds weights, allocates workspaces, loads modules
+                        self.fn(*static_in)
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                version = self._version()      # after warm-up: folding / packing may have happened in it
+                graph = torch.cuda.CUDAGraph()
+                with torch.no_grad(), torch.cuda.graph(graph):
+                    static_out = self.fn(*static_in)
+            finally:
+                ops._pin_depth[0] -= 1
+            if version != self._version():
+                raise RuntimeError("CudaGraphRunner: weights or workspaces changed during capture")
+            entry = (graph, static_in, static_out, version)
             self._graphs[key] = entry
-        graph, static_in, static_out = entry
+            self.captures += 1
+            while len(self._graphs) > self.max_graphs:
+                self._graphs.popitem(last=False)
+        self._graphs.move_to_end(key)
+        graph, static_in, static_out, _ = entry
         for s, a in zip(static_in, args):
             if s.data_ptr() != a.data_ptr():
                 s.copy_(a, non_blocking=True)
@@ -78,6 +121,10 @@ class CudaGraphRunner:
         """The static input buffers for this shape signature (capture first if needed)."""
         self(*args)
         return self._graphs[self._key(args)][1]
+
+    def clear(self):
+        self._graphs.clear()
+        self._seen.clear()
 
 
 def shard_utterances(lengths: Sequence[int], world_size: int, rank: int) -> List[int]:

@@ -70,8 +70,7 @@ def act_tile(xrow, alpha, beta, L, tw, sc=1.0):
         j = bi - 1
         a = zq[1 + shift:1 + shift + RUNS, 16 * ks:16 * ks + 16]
         even = (j % 2 == 0)
-        th, tl = (tabs["dn_even_hi"], tabs["dn_even_lo"]) if even else (tabs["dn_odd_hi"], tabs["dn_odd_lo"])
-        contrib = a @ th.T + a @ tl.T
+        contrib = a @ (tabs["dn_even"] if even else tabs["dn_odd"]).T
         w0 = (8 * j - 16) if even else (8 * j - 8)
         c0 = w0 + 16
         if n_done < 2:
@@ -82,7 +81,7 @@ def act_tile(xrow, alpha, beta, L, tw, sc=1.0):
 
 
 def _edge_z(xrow, alpha, beta, L, sc):
-    f = T.TAPS.astype(np.float32)
+    f = T.TAPS.astype(np.float32)   # the edge samples come from the fp32 scalar path of the kernel
 
     def up(m, q):   # y[2m-1] (q=0) / y[2m] (q=1)
         acc = np.float32(0)

@@ -23,20 +23,20 @@ def test_toeplitz_header_is_current():
 
 def test_toeplitz_tables_reproduce_the_taps():
     import gen_act_tables as T
-    tabs = dict(T.tables())
     f = CF.FILTER_TAPS_F32.astype(np.float64)
-    # hi + lo of every table entry reproduces the fp32 coefficient to 2^-22 relative
+    g = T.TAPS16.astype(np.float64)
+    # fp16 taps: symmetric, within 1.5 fp16 ulp of the fp32 taps, both polyphase sums exactly 0.5 (unit DC gain)
+    assert np.array_equal(g, g[::-1])
+    assert np.all(np.abs(g - f) <= 1.5 * np.spacing(np.abs(f).astype(np.float16)).astype(np.float64))
+    assert g[0::2].sum() == 0.5 and g[1::2].sum() == 0.5
+    tabs = dict(T.tables())
+    # up-FIR taps: hi + lo reproduces the fp32 coefficient to 2^-22; the lo part of x meets only the hi taps
     up = T.up_matrix().astype(np.float64)
     got = tabs["up_hi"].astype(np.float64) + tabs["up_lo"].astype(np.float64)
-    assert np.abs(got[:, 0::2] - up[:, 0::2]).max() <= 2.0 ** -22       # hi rows carry hi + lo
-    assert np.abs(tabs["up_lo"][:, 1::2]).max() == 0                    # lo part of x meets only the hi taps
-    for even in (False, True):
-        d = T.down_matrix(even).astype(np.float64)
-        n = "dn_even" if even else "dn_odd"
-        got = tabs[n + "_hi"].astype(np.float64) + tabs[n + "_lo"].astype(np.float64)
-        assert np.abs(got - d).max() <= 2.0 ** -22
-        # every output column of the middle of the window sees all 12 taps exactly once over the three K-blocks
-    assert abs(f.sum() - 1.0) < 1e-6
+    assert np.abs(got[:, 0::2] - up[:, 0::2]).max() <= 2.0 ** -22
+    assert np.abs(tabs["up_lo"][:, 1::2]).max() == 0
+    for name in ("dn_odd", "dn_even"):
+        assert set(np.unique(tabs[name].astype(np.float64))) <= set(np.concatenate([g, [0.0]]))
 
 
 @pytest.mark.parametrize("L", [1, 2, 5, 31, 32, 33, 447, 448, 449, 512, 896, 1000])
@@ -49,7 +49,8 @@ def test_model_vs_closed_form(L):
     ref = CF.activation1d(x, al, be)
     got = E.activation1d(x, al, be)
     # error budget: z rounded to fp16 (2^-11 relative per sample, 12 taps with sum f^2 = 0.43)
-    assert np.abs(got - ref).max() <= 6e-4 * max(1.0, np.abs(ref).max())
+    # (+ the fp16 taps of the low-pass FIR: <= 1.2 ulp, 2e-4 of the white-noise part of z)
+    assert np.abs(got - ref).max() <= 1e-3 * max(1.0, np.abs(ref).max())
 
 
 def test_model_in_scale():
