@@ -182,6 +182,11 @@ int hsv_add3_bcast(const float *a, const float *b, const float *bc, float *out,
 int hsv_pack_blk16(const float *x, void *out, int B, int C, int64_t L, int lrelu, float in_scale, void *stream);
 /* inverse (tests / debugging): fp16 blk16 -> fp32 [B,C,L]. */
 int hsv_unpack_blk16(const void *in, float *x, int B, int C, int64_t L, void *stream);
+/* operand health (debugging aid; the reference keeps fp32 everywhere, the tensor-core operands here are fp16):
+ * stats[0] (uint32) += number of non-finite values in the valid rows of a blk16 buffer (an activation beyond
+ * +-65504 saturates to inf when the operand is produced), stats[1] (float bits, non-negative) = max(stats[1],
+ * max |finite value|).  The caller zeroes stats[2] first. */
+int hsv_blk16_stats(const void *in, void *stats, int B, int C, int64_t L, void *stream);
 
 /* ---- the step after the path: peak-normalise + int16 quantise on the device.
  * Replaces inference_plm.py:183-188 (audio / abs(audio).max() * 32767.0 * s) and

@@ -439,6 +439,38 @@ __global__ void unpack_blk16_kernel(const uint4 *__restrict__ in, float *__restr
   }
 }
 
+// operand health of a blk16 buffer (debugging aid): stats[0] += number of non-finite fp16 values (an fp32 value
+// beyond +-65504 became inf when the operand was produced), stats[1] = max |value| as float bits (atomicMax on the
+// non-negative bit pattern)
+__global__ void blk16_stats_kernel(const uint4 *__restrict__ in, unsigned int *__restrict__ stats, int B, int C,
+                                   int64_t L, int64_t Lp, int cw) {
+  const int nch = C >> 3;
+  const int64_t n = (int64_t)B * nch * L;
+  unsigned int bad = 0, mx = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t bq = i / L, t = i - bq * L;
+    const int64_t bb = bq / nch;
+    const int c0 = (int)(bq - bb * nch) * 8;
+    const uint4 v = *reinterpret_cast<const uint4 *>(reinterpret_cast<const uint8_t *>(in) +
+                                                     hsv::blk_unit_offset(cw, Lp, C, bb, c0, HSV_BLK_PAD + t));
+    const unsigned short *h = reinterpret_cast<const unsigned short *>(&v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const unsigned int a = h[e] & 0x7fffu;
+      if (a >= 0x7c00u) ++bad;                                   // inf / nan
+      else mx = max(mx, __float_as_uint(__half2float(__ushort_as_half((unsigned short)a))));
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    bad += __shfl_xor_sync(0xffffffffu, bad, o);
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (bad) atomicAdd(stats, bad);
+    atomicMax(stats + 1, mx);
+  }
+}
+
 inline int grid_for(int64_t n, int threads) {
   int64_t b = (n + threads - 1) / threads;
   const int64_t cap = 148 * 32;
@@ -559,4 +591,14 @@ extern "C" int hsv_unpack_blk16(const void *in, float *x, int B, int C, int64_t 
   unpack_blk16_kernel<<<grid_for((int64_t)B * (C / 8) * L, 256), 256, 0, hsv::as_stream(stream)>>>(
       reinterpret_cast<const uint4 *>(in), x, B, C, L, hsv::blk16_rows(L), hsv::blk_cw(C));
   return hsv::check_launch("unpack_blk16");
+}
+
+extern "C" int hsv_blk16_stats(const void *in, void *stats, int B, int C, int64_t L, void *stream) {
+  if (B == 0 || L == 0) return HSV_OK;
+  HSV_REQUIRE(in && stats, "blk16_stats: null pointer");
+  HSV_REQUIRE(C > 0 && C % 16 == 0, "blk16_stats: C %% 16 != 0 (C=%d)", C);
+  blk16_stats_kernel<<<grid_for((int64_t)B * (C / 8) * L, 256), 256, 0, hsv::as_stream(stream)>>>(
+      reinterpret_cast<const uint4 *>(in), reinterpret_cast<unsigned int *>(stats), B, C, L, hsv::blk16_rows(L),
+      hsv::blk_cw(C));
+  return hsv::check_launch("blk16_stats");
 }

@@ -284,6 +284,7 @@ def _dense_conv(x: torch.Tensor, f: _Folded, k: int, d: int = 1, lrelu: bool = F
     if C % 16 == 0 and cout % 16 == 0 and ((k - 1) // 2) * d <= ops.BLK_PAD:
         buf = ops.blk16_buffer(B, C, L, x.device, _MAIN_SLOT)
         ops.pack_blk16(x, buf, lrelu)
+        ops.check_saturation(buf, C, L)
         wp, nt = f.packed_weight(_row_tiles(B, L))
         return ops.conv1d_umma(buf, wp, f.bias(), L, C, cout, k, d, nt, residual=residual)
     pad = ((k - 1) // 2) * d
@@ -302,6 +303,7 @@ def _dense_convT(x: torch.Tensor, f: _Folded, k: int, u: int, add: Optional[torc
     if C % 16 == 0 and cout % 16 == 0:
         buf = ops.blk16_buffer(B, C, L, x.device, _MAIN_SLOT)
         ops.pack_blk16(x, buf, scale=scale)
+        ops.check_saturation(buf, C, L)
         wp, nt = f.packedT_weight(u, _row_tiles(B, L))
         return ops.conv_transpose1d_umma(buf, wp, f.bias(), L, C, cout, k, u, nt, add=add)
     if scale != 1.0:
@@ -369,8 +371,10 @@ class AMPBlock1(nn.Module):
             w1, nt1 = self._f1[i].packed_weight(_row_tiles(B, L))
             w2, nt2 = self._f2[i].packed_weight(_row_tiles(B, L))
             ops.act1d_blk16(cur, *a1.params(), buf)
+            ops.check_saturation(buf, C, L)
             ops.conv1d_umma(buf, w1, self._f1[i].bias(), L, C, C, k, d, nt1, out=xt)
             ops.act1d_blk16(xt, *a2.params(), buf)
+            ops.check_saturation(buf, C, L)
             if last and before_final is not None:
                 before_final()
             if last and acc_mode != ops.ACC_NONE:

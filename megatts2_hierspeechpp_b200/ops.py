@@ -159,6 +159,46 @@ def unpack_blk16(buf: torch.Tensor, C: int, L: int) -> torch.Tensor:
     return out
 
 
+def blk16_stats(buf: torch.Tensor, C: int, L: int, stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Operand health of a blk16 buffer: int32 [2] = (count of non-finite fp16 values, float bits of max |value|),
+    accumulated into ``stats`` (zeroed by the caller) or a fresh tensor.  Debugging aid: the reference keeps fp32
+    activations, the tensor-core operands here are fp16 and saturate beyond +-65504."""
+    _req(buf, "buf", torch.float16, 4)
+    B = buf.shape[0]
+    if tuple(buf.shape) != blk16_shape(B, C, L):
+        raise ValueError("blk16 buffer shape mismatch")
+    if stats is None:
+        stats = torch.zeros(2, dtype=torch.int32, device=buf.device)
+    lib = _lib.load()
+    _lib.check(lib.hsv_blk16_stats(_p(buf), _p(stats), B, C, L, _stream()), "hsv_blk16_stats")
+    return stats
+
+
+SATURATION = {"enabled": bool(int(__import__("os").environ.get("HSV_CHECK_SATURATION", "0"))), "stats": None}
+
+
+def check_saturation(buf: torch.Tensor, C: int, L: int):
+    """Called by the module layer after every operand producer when HSV_CHECK_SATURATION=1 (or
+    ``ops.SATURATION["enabled"] = True``): accumulates into one device counter, no host sync;
+    ``saturation_report()`` reads it."""
+    if not SATURATION["enabled"]:
+        return
+    if SATURATION["stats"] is None or SATURATION["stats"].device != buf.device:
+        SATURATION["stats"] = torch.zeros(2, dtype=torch.int32, device=buf.device)
+    blk16_stats(buf, C, L, SATURATION["stats"])
+
+
+def saturation_report(reset: bool = True):
+    """(non-finite operand values seen, largest finite |operand|) since the last reset; raises nothing."""
+    st = SATURATION["stats"]
+    if st is None:
+        return 0, 0.0
+    n, mx = int(st[0].item()), float(st[1:2].view(torch.float32).item())
+    if reset:
+        st.zero_()
+    return n, mx
+
+
 def weight_norm_fold(v: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
     """w = v * g/||v|| (norm over all dims but 0) == torch._weight_norm(v, g, 0)."""
     _req(v, "weight_v"); _req(g, "weight_g")

@@ -157,21 +157,60 @@ def bucket_by_length(indices: Sequence[int], lengths: Sequence[int], max_batch: 
     return out
 
 
-def gather_waveforms(local: Dict[int, torch.Tensor], dst: int = 0):
-    """Final gather of {utterance index: waveform} onto rank ``dst`` (the only collective of the job)."""
+def gather_waveforms(local: Dict[int, torch.Tensor], dst: int = 0, sizes: Dict[int, int] = None):
+    """Final gather of {utterance index: waveform} onto rank ``dst`` -- the only collective of the job.
+
+    The payload moves as ONE flat tensor per rank through ``torch.distributed.gather`` (NCCL over NVLink for CUDA
+    tensors -- no host staging, no pickling of audio; gloo for the CPU tests): every rank concatenates its
+    waveforms (any common dtype: the int16 PCM of ``to_pcm16`` for the real job, fp32 for checks) into a buffer
+    padded to the largest per-rank total, rank ``dst`` receives ``world`` such buffers into one preallocated
+    tensor and returns views into it (original shapes).  Only the (index, shape) lists -- a few bytes per
+    utterance -- are exchanged as Python objects; ``sizes`` = {utterance index: samples}, if given, is checked
+    against them."""
     import torch.distributed as dist
 
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
         return dict(local)
-    payload = {k: v.cpu() for k, v in local.items()}
-    gathered = [None] * dist.get_world_size() if dist.get_rank() == dst else None
-    dist.gather_object(payload, gathered, dst=dst)
-    if dist.get_rank() != dst:
-        return None
-    merged = {}
-    for part in gathered:
-        merged.update(part)
-    return merged
+    world, rank = dist.get_world_size(), dist.get_rank()
+    mine = [(int(k), tuple(v.shape)) for k, v in sorted(local.items())]
+    layout = [None] * world
+    dist.all_gather_object(layout, mine)      # (index, shape) lists: a few bytes per utterance
+    if sizes is not None:
+        for part in layout:
+            for k, shp in part:
+                if int(sizes[k]) != int(torch.Size(shp).numel()):
+                    raise ValueError(f"utterance {k}: {torch.Size(shp).numel()} samples, expected {sizes[k]}")
+    layout = [[(k, shp, int(torch.Size(shp).numel())) for k, shp in part] for part in layout]
+    totals = [sum(n for _, _, n in part) for part in layout]
+    cap = max(totals) if totals else 0
+    any_t = next(iter(local.values())) if local else None
+    # dtype / device must agree across ranks: take them from rank-local data, fall back to fp32 CPU for empty shards
+    meta = [None] * world
+    dist.all_gather_object(meta, None if any_t is None else (str(any_t.dtype), any_t.device.type))
+    meta = [m for m in meta if m is not None]
+    if not meta or cap == 0:
+        return {} if rank == dst else None
+    dtype = getattr(torch, meta[0][0].split(".")[-1])
+    dev = any_t.device if any_t is not None else (torch.device("cuda", torch.cuda.current_device())
+                                                  if meta[0][1] == "cuda" else torch.device("cpu"))
+    flat = torch.zeros(cap, dtype=dtype, device=dev)
+    off = 0
+    for k, _shp in mine:
+        n = local[k].numel()
+        flat[off:off + n].copy_(local[k].reshape(-1))
+        off += n
+    if rank == dst:
+        recv = torch.empty(world, cap, dtype=dtype, device=dev)
+        dist.gather(flat, list(recv.unbind(0)), dst=dst)
+        merged = {}
+        for r, part in enumerate(layout):
+            off = 0
+            for k, shp, n in part:
+                merged[k] = recv[r, off:off + n].view(shp)
+                off += n
+        return merged
+    dist.gather(flat, None, dst=dst)
+    return None
 
 
 def patch_reference(modules=None) -> List[str]:

@@ -1,10 +1,15 @@
-"""Import shim for the REAL reference (``/root/reference``) — oracle pinning only.
+"""Import shim for the REAL reference — oracle pinning and the reference-vs-B200 tests only.
 
 The reference is a flat script collection whose hot-path modules import a few
 third-party packages that are absent here (``timm``, ``monotonic_align``).
-Neither is reached by the waveform-generation path, so placeholders are
-enough.  ``/root/reference`` does not exist on the GPU
-box; callers must check :func:`available` first.
+``monotonic_align`` is never reached at inference; ``timm``'s ``Attention`` is
+reached by the flows of the full ``SynthesizerTrn`` (modules.py:397), so it is
+restated functionally below (timm 0.6.13, the version requirements.txt:10 pins).
+
+Roots probed, in order: ``$HSV_REFERENCE_ROOT``, ``/root/reference`` (authoring
+container), ``<repo>/baseline/_ref`` (the copy ``baseline/install_ref.py``
+makes; git-ignored, it travels to the GPU box).  Callers must check
+:func:`available` first.
 """
 from __future__ import annotations
 
@@ -14,11 +19,51 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("HSV_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root() -> str:
+    cands = [os.environ.get("HSV_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "hierspeechpp_speechsynthesizer.py")):
+            return c
+    return cands[1]
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def available() -> bool:
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "hierspeechpp_speechsynthesizer.py"))
+
+
+def _timm_attention():
+    """timm 0.6.13 ``timm.models.vision_transformer.Attention`` (requirements.txt:10), restated: qkv Linear ->
+    softmax(q k^T / sqrt(head_dim)) v -> proj Linear.  Same parameter names (qkv, proj), so state_dicts match."""
+    import torch
+    from torch import nn
+
+    class Attention(nn.Module):
+        def __init__(self, dim, num_heads=8, qkv_bias=False, attn_drop=0., proj_drop=0.):
+            super().__init__()
+            assert dim % num_heads == 0
+            self.num_heads = num_heads
+            self.scale = (dim // num_heads) ** -0.5
+            self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+            self.attn_drop = nn.Dropout(attn_drop)
+            self.proj = nn.Linear(dim, dim)
+            self.proj_drop = nn.Dropout(proj_drop)
+
+        def forward(self, x):
+            B, N, C = x.shape
+            qkv = self.qkv(x).reshape(B, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)
+            q, k, v = qkv.unbind(0)
+            attn = (q @ k.transpose(-2, -1)) * self.scale
+            attn = self.attn_drop(attn.softmax(dim=-1))
+            x = (attn @ v).transpose(1, 2).reshape(B, N, C)
+            return self.proj_drop(self.proj(x))
+
+    return Attention
 
 
 def _stub(name: str, **attrs):
@@ -44,13 +89,9 @@ def load():
     sys.dont_write_bytecode = True  # the reference tree is read-only
     import transformers  # noqa: F401  (must precede the timm stub)
 
-    class _Attention:  # never called on the hot path
-        def __init__(self, *a, **k):
-            raise RuntimeError("timm Attention placeholder")
-
     _stub("timm")
     _stub("timm.models")
-    _stub("timm.models.vision_transformer", Attention=_Attention)
+    _stub("timm.models.vision_transformer", Attention=_timm_attention())
     _stub("monotonic_align", mask_from_lens=None)
     _stub("monotonic_align.core", maximum_path_c=None)
     if REFERENCE_ROOT not in sys.path:
@@ -67,6 +108,36 @@ def load():
     act = importlib.import_module("activations")
     _loaded.update(utils=utils, H=H, sr24=sr24, sr48=sr48, alias_free_torch=aft, activations=act)
     return types.SimpleNamespace(**_loaded)
+
+
+HIER_SYNTH_CFG = dict(spec_channels=513, segment_size=30, inter_channels=192, hidden_channels=192,
+                      filter_channels=768, n_heads=2, n_layers=6, kernel_size=3, p_dropout=0.1, resblock="1",
+                      resblock_kernel_sizes=[3, 7, 11], resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5], [1, 3, 5]],
+                      upsample_rates=[4, 5, 4, 2, 2], upsample_initial_channel=512,
+                      upsample_kernel_sizes=[8, 11, 8, 4, 4], gin_channels=256)
+
+
+def build_synthesizer(seed: int = 1234):
+    """The reference's own ``SynthesizerTrn`` (hierspeechpp_speechsynthesizer.py:562-633) with the libritts960
+    architecture of SURVEY.md §B.1, seeded random init (no checkpoint is shipped), SnakeBeta
+    parameters drawn as in ``synth.vocoder_sd`` so that the activation is exercised.  eval mode, CPU."""
+    import torch
+
+    ref = load()
+    torch.manual_seed(seed)
+    m = ref.H.SynthesizerTrn(**HIER_SYNTH_CFG)
+    gen = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for n, p_ in m.named_parameters():
+            if n.endswith("act.alpha"):
+                p_.copy_(torch.rand(p_.shape, generator=gen) * 1.5 - 0.5)
+            elif n.endswith("act.beta"):
+                p_.copy_(torch.rand(p_.shape, generator=gen) * 1.3 - 0.5)
+            elif n.endswith("post.weight") or n.endswith("adaLN_modulation.1.weight"):
+                # the reference zero-initialises these (flows = identity at init): give the flows something to do
+                p_.copy_(torch.randn(p_.shape, generator=gen) * 0.02)
+    m.eval()
+    return m
 
 
 def load_speechsr(which: int):

@@ -40,6 +40,13 @@ def main():
         np.savez_compressed(os.path.join(OUT, f"speechsr{which}_example.npz"),
                             x_int16=np.round(x.numpy().reshape(-1) * 32768.0).astype(np.int16), y=y.numpy())
         print("sr", which, tuple(x.shape), "->", tuple(y.shape), float(y.abs().max()), float(y.sum()))
+        if which == 48:
+            # the full 3 s example through the 48k twin (fp16 output: 2^-11 relative, far below the 2e-3 bar)
+            with torch.no_grad():
+                yf = m(wav)
+            np.savez_compressed(os.path.join(OUT, "speechsr48_example_full.npz"), y_f16=yf.numpy().astype(np.float16),
+                                absmax=np.float32(yf.abs().max()), std=np.float32(yf.std()))
+            print("sr 48 full", tuple(yf.shape), float(yf.abs().max()), float(yf.std()))
 
     # ---- Activation1d cases: odd / even / tiny lengths, checkpoint-like alpha/beta ranges ----
     g = torch.Generator().manual_seed(7)
