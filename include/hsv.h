@@ -200,6 +200,18 @@ int hsv_blk16_stats(const void *in, void *stats, int B, int C, int64_t L, void *
 int hsv_peak_norm_pcm16(const float *x, int16_t *out, float *peak_ws, int rows, int64_t L, float s1, float s2,
                         int per_row, void *stream);
 
+/* ---- f0-driven harmonic sine source (BASELINE.json north_star item 3; NSF / HiFTNet-style SineGen -- the
+ * reference repository has no counterpart on this path).  The phase accumulator is 64-bit fixed point
+ * (2^64 = one cycle): the cumulative sum is exact integer arithmetic, so a 30 s utterance does not drift.
+ *   f0        [B, T] fp32, Hz per frame (<= 0: unvoiced, the phase holds)
+ *   out       [B, harmonics, T*hop] fp32 = amp * voiced * sin(2 pi (h+1) phase[n]),  phase[n] = sum_{k<=n} f0[k/hop]/sr
+ *   uv        [B, T*hop] fp32 voiced mask (may be NULL)
+ *   workspace hsv_sinegen_workspace(B, T, hop) bytes
+ */
+int64_t hsv_sinegen_workspace(int B, int64_t T, int hop);
+int hsv_sinegen(const float *f0, float *out, float *uv, void *workspace, int B, int64_t T, int hop,
+                float sample_rate, int harmonics, float amp, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,6 +42,9 @@ SIGNATURES = {
     "hsv_pack_blk16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_float, c_void_p]),
     "hsv_unpack_blk16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p]),
     "hsv_blk16_stats": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p]),
+    "hsv_sinegen_workspace": (c_int64, [c_int, c_int64, c_int]),
+    "hsv_sinegen": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_float, c_int, c_float,
+                            c_void_p]),
     "hsv_peak_norm_pcm16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_float, c_float, c_int, c_void_p]),
 }
 

@@ -247,7 +247,6 @@ __global__ void __launch_bounds__(32 * NW, MINB) conv_umma_kernel(const __grid_c
   const uint32_t bar0 = smem_u32(&bars[0]);
   const uint32_t bar_acc = bar0, bar_a = bar0 + 8 * BAR_A, bar_wf = bar0 + 8 * BAR_WF, bar_we = bar0 + 8 * BAR_WE;
 
-  hsv::pdl_launch_dependents();  // PDL: the next kernel may begin its prologue
   if (threadIdx.x == 0) stamp(p, 0);
 
   // weight stream of this (phase, n-tile)
@@ -297,6 +296,10 @@ __global__ void __launch_bounds__(32 * NW, MINB) conv_umma_kernel(const __grid_c
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_base_s;
+  // PDL: the next kernel may begin its prologue.  Triggered only AFTER this CTA owns its TMEM columns: a dependent
+  // CTA that became resident earlier could take the columns and then park in griddepcontrol.wait -- which only
+  // returns when this grid has finished -- while this CTA blocks in tcgen05.alloc.
+  hsv::pdl_launch_dependents();
   if (threadIdx.x == 0) {
     stamp(p, 1);
     // weights are static data: fill the ring before waiting for the kernel that produces the activations
@@ -697,7 +700,6 @@ __global__ void __launch_bounds__(64 + 128 * EPW, 1) conv_umma_persist_kernel(co
   const int total = p.ntiles * p.nco_tiles * p.B;                    // tiles of the launch
   const int my_n = (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles of this CTA
 
-  hsv::pdl_launch_dependents();
   if (threadIdx.x == 0) {
     mbar_init(bar0 + 8 * (PB_ACC_F + 0), 1); mbar_init(bar0 + 8 * (PB_ACC_F + 1), 1);
     mbar_init(bar0 + 8 * (PB_ACC_E + 0), 128 * EPW); mbar_init(bar0 + 8 * (PB_ACC_E + 1), 128 * EPW);
@@ -719,6 +721,7 @@ __global__ void __launch_bounds__(64 + 128 * EPW, 1) conv_umma_persist_kernel(co
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_base_s;
+  hsv::pdl_launch_dependents();  // after the TMEM allocation (see conv_umma_kernel)
   hsv::pdl_wait();
 
   auto tile_coords = [&](int i, int &b, int &nt, int &tile) {

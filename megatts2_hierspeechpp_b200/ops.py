@@ -199,6 +199,18 @@ def saturation_report(reset: bool = True):
     return n, mx
 
 
+def _static_data_barrier(what: str):
+    """The conv / activation kernels are launched with programmatic dependent launch and read their STATIC inputs
+    (packed weights, bias, alpha/beta) BEFORE ``griddepcontrol.wait``, i.e. possibly while the kernel launched just
+    before them on the stream is still running.  Kernels that PRODUCE static data (weight fold / pack: once per
+    checkpoint and n_tile) therefore end with a stream synchronisation, so that nothing launched later can overlap
+    them.  They cannot run inside a CUDA-graph capture (warm up once before capturing: CudaGraphRunner does)."""
+    if torch.cuda.is_current_stream_capturing():
+        raise RuntimeError(f"{what}: weights are being folded / packed inside a CUDA-graph capture; run one eager "
+                           "forward first (weights are static data of the PDL-launched kernels)")
+    torch.cuda.current_stream().synchronize()
+
+
 def weight_norm_fold(v: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
     """w = v * g/||v|| (norm over all dims but 0) == torch._weight_norm(v, g, 0)."""
     _req(v, "weight_v"); _req(g, "weight_g")
@@ -208,6 +220,7 @@ def weight_norm_fold(v: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
     w = torch.empty_like(v)
     lib = _lib.load()
     _lib.check(lib.hsv_weight_norm_fold(_p(v), _p(g), _p(w), n0, v.numel() // n0, _stream()), "hsv_weight_norm_fold")
+    _static_data_barrier("weight_norm_fold")
     return w
 
 
@@ -238,6 +251,7 @@ def pack_conv_weight(w: torch.Tensor, n_tile: int) -> torch.Tensor:
     out = torch.empty(cout * cin * k, dtype=torch.float16, device=w.device)
     lib = _lib.load()
     _lib.check(lib.hsv_pack_conv_weight(_p(w), _p(out), cout, cin, k, n_tile, _stream()), "hsv_pack_conv_weight")
+    _static_data_barrier("pack_conv_weight")
     return out
 
 
@@ -316,6 +330,7 @@ def pack_convT_weight(w: torch.Tensor, u: int, n_tile: int) -> torch.Tensor:
     out = torch.empty(cout * cin * k, dtype=torch.float16, device=w.device)
     lib = _lib.load()
     _lib.check(lib.hsv_pack_convT_weight(_p(w), _p(out), cin, cout, k, u, n_tile, _stream()), "hsv_pack_convT_weight")
+    _static_data_barrier("pack_convT_weight")
     return out
 
 
@@ -452,6 +467,21 @@ def peak_norm_pcm16(x: torch.Tensor, s1: float = 32767.0, s2: float = 0.999, per
     _lib.check(lib.hsv_peak_norm_pcm16(_p(x), _p(out), _p(peaks), rows, L, float(s1), float(s2), int(per_row), _stream()),
                "hsv_peak_norm_pcm16")
     return out, (peaks if per_row else peaks[:1])
+
+
+def sinegen(f0: torch.Tensor, hop: int, sample_rate: float, harmonics: int = 8, amp: float = 0.1):
+    """Harmonic sine source from a frame-rate f0 track (Hz, <= 0 = unvoiced): returns (sines [B, harmonics, T*hop],
+    voiced mask [B, 1, T*hop]).  64-bit fixed-point phase accumulation: no drift over long utterances."""
+    _req(f0, "f0", ndim=2)
+    B, T = f0.shape
+    L = T * hop
+    out = torch.empty(B, harmonics, L, dtype=torch.float32, device=f0.device)
+    uv = torch.empty(B, 1, L, dtype=torch.float32, device=f0.device)
+    lib = _lib.load()
+    ws = torch.empty(max(1, int(lib.hsv_sinegen_workspace(B, T, hop)) // 8), dtype=torch.int64, device=f0.device)
+    _lib.check(lib.hsv_sinegen(_p(f0), _p(out), _p(uv), _p(ws), B, T, hop, float(sample_rate), harmonics, float(amp),
+                               _stream()), "hsv_sinegen")
+    return out, uv
 
 
 def set_act_variant(v: int):

@@ -173,3 +173,20 @@ def snr_db(ref, test) -> float:
     if den == 0.0:
         return float("inf")
     return 10.0 * math.log10(float(np.sum(ref * ref)) / den)
+
+
+# --------------------------------------------------------------------------
+# Harmonic sine source (BASELINE.json north_star item 3; no counterpart in the reference)
+# --------------------------------------------------------------------------
+def sinegen(f0: np.ndarray, hop: int, sample_rate: float, harmonics: int = 8, amp: float = 0.1):
+    """fp64 closed form: phase[n] = sum_{k<=n} f0_up[k]/sr (turns, unvoiced frames hold the phase),
+    out[h] = amp * voiced * sin(2 pi (h+1) phase).  f0 [B,T] Hz -> (out [B,H,T*hop] fp64, uv [B,1,T*hop])."""
+    f0 = np.asarray(f0, np.float32)
+    up = np.repeat(f0, hop, axis=1).astype(np.float64)
+    voiced = up > 0
+    inc = np.where(voiced, up / float(sample_rate), 0.0)
+    phase = np.cumsum(inc, axis=1)                       # fp64: 53 bits, error ~1e-10 turns over 5e5 samples
+    phase -= np.floor(phase)
+    h = np.arange(1, harmonics + 1, dtype=np.float64)[None, :, None]
+    out = amp * voiced[:, None, :] * np.sin(2.0 * np.pi * h * phase[:, None, :])
+    return out, voiced[:, None, :].astype(np.float32)

@@ -122,5 +122,5 @@ def test_bench_reference_arm_prints_contract_line():
     assert j["impl"] == "reference" and j["higher_is_better"] is True and j["unit"] == "audio-s/s"
     for key in ("metric", "value", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "config", "cpu_baseline", "e2e"):
         assert key in j, key
-    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1
+    assert j["cpu_baseline"]["kind"] in ("port", "reference") and j["cpu_baseline"]["cores"] >= 1
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0

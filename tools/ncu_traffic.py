@@ -55,6 +55,10 @@ def main(workload, path, nfwd=1):
         with open(dst) as f:
             allw = json.load(f)
     allw[workload] = out
+    import datetime
+    allw["_meta"] = {"head": os.environ.get("HSV_HEAD", "unknown"), "when": datetime.datetime.utcnow().isoformat() + "Z",
+                     "how": "ncu --clock-control none --metrics dram__bytes_read.sum,dram__bytes_write.sum (cold cache per "
+                            "kernel) over one eager forward; tools/ncu_traffic.py"}
     with open(dst, "w") as f:
         json.dump(allw, f, indent=1, sort_keys=True)
     print(json.dumps({workload: out}, indent=1))
