@@ -199,9 +199,11 @@ def gather_waveforms(local: Dict[int, torch.Tensor], dst: int = 0, sizes: Dict[i
         n = local[k].numel()
         flat[off:off + n].copy_(local[k].reshape(-1))
         off += n
+    # the payload travels as raw bytes: NCCL has no int16
+    wire = flat.view(torch.uint8)
     if rank == dst:
         recv = torch.empty(world, cap, dtype=dtype, device=dev)
-        dist.gather(flat, list(recv.unbind(0)), dst=dst)
+        dist.gather(wire, list(recv.view(torch.uint8).view(world, -1).unbind(0)), dst=dst)
         merged = {}
         for r, part in enumerate(layout):
             off = 0
@@ -209,7 +211,7 @@ def gather_waveforms(local: Dict[int, torch.Tensor], dst: int = 0, sizes: Dict[i
                 merged[k] = recv[r, off:off + n].view(shp)
                 off += n
         return merged
-    dist.gather(flat, None, dst=dst)
+    dist.gather(wire, None, dst=dst)
     return None
 
 
