@@ -157,6 +157,22 @@ def bucket_by_length(indices: Sequence[int], lengths: Sequence[int], max_batch: 
     return out
 
 
+def gather_packed(flat: torch.Tensor, dst: int = 0):
+    """The collective under ``gather_waveforms``: every rank contributes one 1-D buffer of the SAME size and dtype
+    (pad to the largest shard), rank ``dst`` gets a [world, n] tensor, the others None.  No metadata exchange, no
+    host synchronisation; the bytes travel as uint8 (NCCL has no int16)."""
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(), dist.get_rank()
+    wire = flat.contiguous().view(torch.uint8)
+    if rank == dst:
+        recv = torch.empty(world, flat.numel(), dtype=flat.dtype, device=flat.device)
+        dist.gather(wire, list(recv.view(torch.uint8).view(world, -1).unbind(0)), dst=dst)
+        return recv
+    dist.gather(wire, None, dst=dst)
+    return None
+
+
 def gather_waveforms(local: Dict[int, torch.Tensor], dst: int = 0, sizes: Dict[int, int] = None):
     """Final gather of {utterance index: waveform} onto rank ``dst`` -- the only collective of the job.
 
@@ -173,8 +189,11 @@ def gather_waveforms(local: Dict[int, torch.Tensor], dst: int = 0, sizes: Dict[i
         return dict(local)
     world, rank = dist.get_world_size(), dist.get_rank()
     mine = [(int(k), tuple(v.shape)) for k, v in sorted(local.items())]
-    layout = [None] * world
-    dist.all_gather_object(layout, mine)      # (index, shape) lists: a few bytes per utterance
+    any_t = next(iter(local.values())) if local else None
+    hello = [None] * world                    # (index, shape) lists + dtype/device: a few bytes per utterance
+    dist.all_gather_object(hello, (mine, None if any_t is None else (str(any_t.dtype), any_t.device.type)))
+    layout = [h[0] for h in hello]
+    meta = [h[1] for h in hello if h[1] is not None]
     if sizes is not None:
         for part in layout:
             for k, shp in part:
@@ -183,11 +202,6 @@ def gather_waveforms(local: Dict[int, torch.Tensor], dst: int = 0, sizes: Dict[i
     layout = [[(k, shp, int(torch.Size(shp).numel())) for k, shp in part] for part in layout]
     totals = [sum(n for _, _, n in part) for part in layout]
     cap = max(totals) if totals else 0
-    any_t = next(iter(local.values())) if local else None
-    # dtype / device must agree across ranks: take them from rank-local data, fall back to fp32 CPU for empty shards
-    meta = [None] * world
-    dist.all_gather_object(meta, None if any_t is None else (str(any_t.dtype), any_t.device.type))
-    meta = [m for m in meta if m is not None]
     if not meta or cap == 0:
         return {} if rank == dst else None
     dtype = getattr(torch, meta[0][0].split(".")[-1])

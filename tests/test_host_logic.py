@@ -124,3 +124,30 @@ def test_bench_reference_arm_prints_contract_line():
         assert key in j, key
     assert j["cpu_baseline"]["kind"] in ("port", "reference") and j["cpu_baseline"]["cores"] >= 1
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_two_rank_gloo_gather_packed(tmp_path):
+    """The metadata-free collective under gather_waveforms: equal-size int16 buffers, raw-byte transport."""
+    script = tmp_path / "job2.py"
+    script.write_text(
+        "import sys, torch, torch.distributed as dist\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "from megatts2_hierspeechpp_b200.runtime import gather_packed\n"
+        "dist.init_process_group('gloo')\n"
+        "r = dist.get_rank()\n"
+        "flat = (torch.arange(1000, dtype=torch.int32) * (r + 1) % 30000).to(torch.int16)\n"
+        "out = gather_packed(flat, dst=0)\n"
+        "if r == 0:\n"
+        "    assert out.shape == (2, 1000) and out.dtype == torch.int16\n"
+        "    for q in range(2):\n"
+        "        assert torch.equal(out[q], (torch.arange(1000, dtype=torch.int32) * (q + 1) % 30000).to(torch.int16))\n"
+        "    print('PACKED_OK')\n"
+        "else:\n"
+        "    assert out is None\n"
+        "dist.destroy_process_group()\n")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29619", str(script)],
+                       capture_output=True, text=True, env=env, timeout=240)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "PACKED_OK" in r.stdout
