@@ -57,6 +57,16 @@ def make_workload(args, rank):
                     sd=synth.vocoder_sd(1234), host_inputs=[z, g], audio_seconds=args.batch * T / 50.0,
                     data="synthetic z~N(0,1) [B,192,T], g~N(0,1) [B,256,1] (seed 1111+rank); "
                          "random-init weights (seed 1234, SnakeBeta alpha~U(-0.5,1), beta~U(-0.5,0.8))")
+    if args.workload == "chain24":
+        # config #4's timed stage: vocoder (random init) -> SpeechSR24 (bundled checkpoint), one CUDA graph
+        T = int(round(args.seconds * 50))
+        z, g = synth.vocoder_inputs(args.batch, T, seed=1111 + rank)
+        sd = {"vocoder." + k: v for k, v in synth.vocoder_sd(1234).items()}
+        gpath = os.path.join(ROOT, "tests", "golden", "speechsr24_state.npz")
+        sd.update({"sr." + k: torch.from_numpy(v.copy()) for k, v in np.load(gpath).items()})
+        return dict(name=f"config4_vocoder->speechsr24_B{args.batch}x{args.seconds:g}s", kind="chain24", sd=sd,
+                    host_inputs=[z, g], audio_seconds=args.batch * T / 50.0, which=24,
+                    data="synthetic z, g as config #2; vocoder random init (seed 1234) + bundled speechsr24k checkpoint")
     which = 48 if args.workload == "speechsr48" else 24
     L = int(round(args.seconds * 16000))
     x = synth.speechsr_input(args.batch, L, seed=1111 + rank)
@@ -75,6 +85,10 @@ def oracle_forward(wl, device="cpu"):
     ins = [t.to(device) for t in wl["host_inputs"]]
     if wl["kind"] == "vocoder":
         return lambda: OF.vocoder(sd, ins[0], ins[1])
+    if wl["kind"] == "chain24":
+        sv = {k[len("vocoder."):]: v for k, v in sd.items() if k.startswith("vocoder.")}
+        ss = {k[len("sr."):]: v for k, v in sd.items() if k.startswith("sr.")}
+        return lambda: OF.speechsr(ss, OF.vocoder(sv, ins[0], ins[1]), 24)
     return lambda: OF.speechsr(sd, ins[0], wl["which"])
 
 
@@ -85,6 +99,8 @@ def reference_forward(wl):
         from oracle import refload
         if refload.available():
             ref = refload.load()
+            if wl["kind"] == "chain24":
+                raise RuntimeError("chain workload: oracle port (the reference chains the two models in a script)")
             if wl["kind"] == "vocoder":
                 from megatts2_hierspeechpp_b200.config import HIER_CFG
                 G = ref.H.Generator(**HIER_CFG)
@@ -211,6 +227,8 @@ def build_model(wl, device):
 
     if wl["kind"] == "vocoder":
         m = hsv.Vocoder()
+    elif wl["kind"] == "chain24":
+        m = hsv.VocoderSR(24)
     else:
         m = (hsv.SpeechSR48 if wl["which"] == 48 else hsv.SpeechSR24)(100, 40, **hsv.SR_CFG)
     m.load_state_dict(wl["sd"], strict=True)
@@ -723,6 +741,20 @@ def run_b200(args):
             o = fwd(*static_in)
             host_out.copy_(o, non_blocking=True)
 
+        # the same end-to-end step with the step AFTER the path on the device: peak-normalise + int16
+        # inside the captured graph, 2 bytes per sample over PCIe
+        from megatts2_hierspeechpp_b200.runtime import to_pcm16
+        pcm_runner = hsv.CudaGraphRunner(lambda *a: to_pcm16(model(*a), per_utterance=True)) if not args.no_graph else None
+        pcm_out = pcm_runner(*dev_in) if pcm_runner else to_pcm16(model(*dev_in), per_utterance=True)
+        pcm_static_in = pcm_runner.static_inputs(*dev_in) if pcm_runner else dev_in
+        host_pcm = torch.empty(pcm_out.shape, dtype=torch.int16).pin_memory()
+
+        def e2e_pcm_step():
+            for s_, h in zip(pcm_static_in, host_in):
+                s_.copy_(h, non_blocking=True)
+            o = pcm_runner(*pcm_static_in) if pcm_runner else to_pcm16(model(*pcm_static_in), per_utterance=True)
+            host_pcm.copy_(o, non_blocking=True)
+
         def timed_block(step):
             """EXACTLY args.steps steps, CUDA events around each (L2 flushed before each, outside the events)."""
             evs = []
@@ -745,12 +777,16 @@ def run_b200(args):
         barrier()
         sampler.start()
         t_start = time.perf_counter()
-        dev_blocks, e2e_blocks = [], []
+        dev_blocks, e2e_blocks, pcm_blocks = [], [], []
+        for _ in range(3):
+            e2e_pcm_step()
         while True:
             barrier()
             dev_blocks.append(timed_block(dev_step))
             barrier()
             e2e_blocks.append(timed_block(e2e_step))
+            barrier()
+            pcm_blocks.append(timed_block(e2e_pcm_step))
             barrier()
             enough = time.perf_counter() - t_start >= args.min_seconds or len(dev_blocks) >= args.max_blocks
             flag = torch.tensor([1.0 if enough else 0.0], device=dev)
@@ -760,11 +796,13 @@ def run_b200(args):
                 break
         clocks = sampler.stop()
         nb = len(dev_blocks)
-        sums = torch.tensor([[sum(b) for b in dev_blocks], [sum(b) for b in e2e_blocks]], dtype=torch.float64, device=dev)
+        sums = torch.tensor([[sum(b) for b in dev_blocks], [sum(b) for b in e2e_blocks], [sum(b) for b in pcm_blocks]],
+                            dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(sums, op=dist.ReduceOp.MAX)     # max over ranks, block by block
         dev_ms = float(sums[0].median())
         e2e_ms = float(sums[1].median())
+        pcm_ms = float(sums[2].median())
         step_ms = sorted(x for b in dev_blocks for x in b)
 
         roof = extra = shares = step_roof = cpu = sat = eager = None
@@ -798,7 +836,7 @@ def run_b200(args):
                 cpu = {"value": cwl["audio_seconds"] / min(ts), "unit": "audio-s/s", "cores": cores, "kind": kind,
                        "sample": sample + (", the reference's own modules (baseline/_ref)" if kind == "reference" else
                                            ", oracle port of the reference's CPU path") + ", 1 warm-up + best of 3"}
-        del runner
+        del runner, pcm_runner
         c5 = None
         if not args.no_config5:
             try:
@@ -828,6 +866,10 @@ def run_b200(args):
                                    "(need_pred=False) while the reference arm's sn(z, g) computes it"},
         "e2e": {"value": total_audio / (e2e_ms / 1e3), "unit": "audio-s/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
+        "e2e_pcm16": {"value": total_audio / (pcm_ms / 1e3), "unit": "audio-s/s", "h2d_bytes_per_step": h2d,
+                      "d2h_bytes_per_step": int(host_pcm.numel() * 2), "ms_per_step": pcm_ms / args.steps,
+                      "what": "e2e with the step after the path on the device: peak-normalised int16 PCM "
+                              "(inference_plm.py:183-188) inside the graph, int16 D2H"},
         "gpu_launches": launches_per_step * args.steps,
         "launches_per_step": launches_per_step,
         "clocks": clocks, "roofline": roof, "roofline_other": extra, "step_roofline": step_roof,
@@ -844,7 +886,7 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="vocoder", choices=["vocoder", "speechsr48", "speechsr24"])
+    ap.add_argument("--workload", default="vocoder", choices=["vocoder", "speechsr48", "speechsr24", "chain24"])
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--seconds", type=float, default=10.0)
     ap.add_argument("--no-graph", action="store_true")

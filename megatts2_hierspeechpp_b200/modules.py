@@ -713,3 +713,31 @@ class Vocoder(nn.Module):
     def forward(self, z, g):
         e, _ = self.sn(z, g, need_pred=False)
         return self.dec(z, e, g=g)
+
+
+class VocoderSR(nn.Module):
+    """Config #4's timed stage as ONE callable: ``sn`` -> ``dec`` -> SpeechSR (inference_plm.py:176-181) -> optional
+    peak-normalised int16 PCM (:183-188), everything enqueued on one stream with no host round trip, so a
+    ``CudaGraphRunner`` replays the whole hand-off as one graph and the host only ever sees 2 bytes per output sample.
+
+    The 16 kHz fp32 waveform between the two models is 4 bytes per sample (0.02 % of the stage's traffic) and stays
+    in L2; a kernel-level fusion of ``conv_post+tanh`` into SpeechSR's ``conv_pre+interpolate`` would recompute every
+    16 kHz sample ~14x (7 taps x 2 source positions) to save that round trip, so the hand-off is fused at the graph
+    level, not the kernel level."""
+
+    def __init__(self, which: int = 24, **cfg):
+        super().__init__()
+        from .config import SR_CFG
+        if which not in (24, 48):
+            raise ValueError("which must be 24 or 48")
+        self.vocoder = Vocoder(**cfg)
+        self.sr = (SpeechSR24 if which == 24 else SpeechSR48)(100, 40, **SR_CFG)
+        self.which = which
+
+    def forward(self, z, g, pcm16: bool = False):
+        wav16 = self.vocoder(z, g)
+        out = self.sr(wav16)
+        if pcm16:
+            from .runtime import to_pcm16
+            return to_pcm16(out, per_utterance=True)
+        return out

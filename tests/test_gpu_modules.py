@@ -273,6 +273,18 @@ def test_config4_vocoder_then_speechsr24(hsv, vocoder):
     ref16 = OF.vocoder(synth.vocoder_sd(1234), z, gg)
     ref24 = OF.speechsr(sd_sr, ref16, 24)
     _check("vocoder -> SpeechSR24 chain", wav24, ref24)
+    # the same hand-off as ONE module / one CUDA graph, PCM on the device (inference_plm.py:176-188)
+    chain = hsv.VocoderSR(24)
+    sdc = {"vocoder." + k: v for k, v in synth.vocoder_sd(1234).items()}
+    sdc.update({"sr." + k: v for k, v in sd_sr.items()})
+    chain.load_state_dict(sdc, strict=True)
+    chain.to(DEV).eval()
+    runner = hsv.CudaGraphRunner(lambda a, b: chain(a, b, pcm16=True))
+    pcm = runner(z.to(DEV), gg.to(DEV))
+    assert pcm.dtype == torch.int16 and pcm.shape == (1, 1, 24000)
+    assert torch.equal(chain(z.to(DEV), gg.to(DEV)), wav24)
+    want = OF.peak_norm_pcm16(wav24.cpu())                     # the reference's expression on the same fp32 samples
+    assert np.array_equal(pcm.cpu().numpy().reshape(-1), want.reshape(-1))
 
 
 def test_fused_half_layers_are_bit_identical(hsv, vocoder):
