@@ -143,6 +143,7 @@ int hsv_conv_transpose1d_umma(const void *a_blk16, const void *w_packed, const f
 #define HSV_CONV_LRELU_IN 1
 #define HSV_CONV_TANH 2
 #define HSV_CONV_ADD_OUT 4
+#define HSV_CONV_SILU_IN 8      /* apply SiLU to x first (adaLN / cond_block, modules.py:402, hierspeechpp_speechsynthesizer.py:70) */
 int hsv_conv1d_direct(const float *x, const float *w, const float *bias, float *out,
                       int B, int Cin, int Cout, int64_t Lin, int64_t Lout, int k, int d, int pad,
                       int flags, void *stream);
@@ -199,6 +200,35 @@ int hsv_blk16_stats(const void *in, void *stats, int B, int C, int64_t L, void *
  */
 int hsv_peak_norm_pcm16(const float *x, int16_t *out, float *peak_ws, int rows, int64_t L, float s1, float s2,
                         int per_row, void *stream);
+
+/* ---- frame-rate operators of the step BEFORE the vocoder (csrc/frame_ops.cu).  fp32 [B,C,T] tensors,
+ * mask = [B,T] (1 = valid frame, may be NULL), blk16 outputs feed hsv_conv1d_umma.
+ *
+ * hsv_pack_blk16_act: operand packer with a fused activation.
+ *   mode 0: x * mask;  1: tanh(x[c] + bc[c]) * sigmoid(x[C+c] + bc[C+c]) (x [B,2C,T], bc [B,2C] or NULL: WN gate,
+ *   commons.py:108-114);  2: gelu_tanh(x) * mask (FFN_Conv, modules.py:382-388);  3: mish(x) * mask (styleencoder.py:6-10)
+ *   x_channels = channels per batch item of x (a channel prefix of a wider tensor can be packed).
+ * hsv_ln_mod_blk16: LayerNorm over channels (eps, no affine) [* mask] -> x*(1+scale[b,c]) + shift[b,c] (modules.py:346,
+ *   405-410); inmask: x*mask first; premask: normalised*mask before the modulation; mod_stride = batch stride of shift/scale.
+ * hsv_frame_op: element-wise ops (op codes in csrc/frame_ops.cu): 1 wn_res, 2 wn_last, 3 gate_add, 4 couple, 5 sample,
+ *   6 mask, 7 add, 8 glu_res, 9 mish, 10 flip, 11 add_bcast.
+ * hsv_mha: softmax(q k^T * scale) v per (batch, head); q/k/v channel-major [heads*D, T] with batch strides (so the fused
+ *   qkv tensor of timm's Attention can be addressed in place); lens [B] int32 or NULL = masked_fill(-1e4) of
+ *   attentions.py:174-175 for prefix masks; prescale_q: scale q before the product (attentions.py:164) or the scores
+ *   after it (timm).
+ * hsv_conv1d_c1_strided: Conv1d(1, Cout, k, stride, pad) * mask (PosteriorSFEncoder.pre_filter, :187,196).
+ * hsv_masked_mean: out[b,c] = sum_t x[b,c,t] / sum_t mask[b,t] (styleencoder.py:91-99: the sum runs over all frames). */
+int hsv_pack_blk16_act(const float *x, const float *bcast, const float *mask, void *out, int B, int C, int64_t L,
+                       int mode, int x_channels, void *stream);
+int hsv_ln_mod_blk16(const float *x, const float *shift, const float *scale, const float *mask, void *out, int B, int C,
+                     int64_t L, float eps, int inmask, int premask, int64_t mod_stride, void *stream);
+int hsv_frame_op(int op, const float *a, const float *b, const float *c, const float *mask, float *out, float *out2,
+                 int B, int C, int64_t L, float s, int64_t cstride, void *stream);
+int hsv_mha(const float *q, const float *k, const float *v, float *out, const int *lens, int B, int heads, int D, int Tq,
+            int Tk, int64_t q_bstride, int64_t k_bstride, int64_t v_bstride, float scale, int prescale_q, void *stream);
+int hsv_conv1d_c1_strided(const float *x, const float *w, const float *bias, const float *mask, float *out, int B,
+                          int Cout, int64_t Lin, int64_t Lout, int k, int stride, int pad, void *stream);
+int hsv_masked_mean(const float *x, const float *mask, float *out, int B, int C, int64_t L, void *stream);
 
 /* ---- f0-driven harmonic sine source (BASELINE.json north_star item 3; NSF / HiFTNet-style SineGen -- the
  * reference repository has no counterpart on this path).  The phase accumulator is 64-bit fixed point

@@ -42,6 +42,16 @@ SIGNATURES = {
     "hsv_pack_blk16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_float, c_void_p]),
     "hsv_unpack_blk16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p]),
     "hsv_blk16_stats": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p]),
+    "hsv_pack_blk16_act": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_int, c_void_p]),
+    "hsv_ln_mod_blk16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_float, c_int,
+                                 c_int, c_int64, c_void_p]),
+    "hsv_frame_op": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64,
+                             c_float, c_int64, c_void_p]),
+    "hsv_mha": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int64,
+                        c_int64, c_int64, c_float, c_int, c_void_p]),
+    "hsv_conv1d_c1_strided": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int64,
+                                      c_int, c_int, c_int, c_void_p]),
+    "hsv_masked_mean": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p]),
     "hsv_sinegen_workspace": (c_int64, [c_int, c_int64, c_int]),
     "hsv_sinegen": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_float, c_int, c_float,
                             c_void_p]),

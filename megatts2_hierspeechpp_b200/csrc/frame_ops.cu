@@ -1,0 +1,419 @@
+// Frame-rate (50 Hz) operators of the step BEFORE the vocoder: the pieces of StyleEncoder,
+// PosteriorSFEncoder (three WaveNet stacks) and the reverse coupling flows (DiT blocks) that are not convolutions.
+// The convolutions / Linear layers themselves run on the tcgen05 kernel (conv_umma.cu) through the operand packers
+// below.  All tensors are fp32 [B, C, T] (the reference's layout; T ~ 50 frames per second), so these kernels are
+// small, HBM/L2-bound element-wise or row-reduction kernels on CUDA cores; what matters is that each reference
+// expression becomes ONE launch instead of 3-9 ATen kernels, and that the whole front is CUDA-graph capturable.
+//
+// Reference expressions (paths relative to the reference root):
+//   gate      commons.fused_add_tanh_sigmoid_multiply            commons.py:108-114   (WN, modules.py:158-165)
+//   wn_res    x = (x + res) * mask ; output += skip               modules.py:167-174
+//   ln_mod    modulate(LayerNorm(x) [* mask], shift, scale)       modules.py:346-347, 405-410 (eps 1e-6, no affine)
+//   mha       softmax(q k^T / sqrt(d)) v                          timm 0.6.13 Attention; attentions.py:157-188
+//   gate_add  x + gate[b,c] * y * mask                            modules.py:408-409
+//   couple    x1 = (x1 - m) * mask        (mean_only, reverse)    modules.py:484-487
+//   sample    z = (m + eps * exp(logs) * noise_scale) * mask      hierspeechpp_speechsynthesizer.py:201, 687
+//   glu_res   x + y1 * sigmoid(y2)                                styleencoder.py:25-31
+//   mish      x * tanh(softplus(x))                               styleencoder.py:6-10
+//   flip      torch.flip(x, [1])                                  modules.py:270-277
+//   mean      x.sum(2) / mask.sum(2)                              styleencoder.py:91-99
+#include "hsv_common.cuh"
+
+namespace {
+
+inline int grid_for(int64_t n, int threads) {
+  int64_t b = (n + threads - 1) / threads;
+  const int64_t cap = 148 * 32;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
+__device__ __forceinline__ float gelu_tanh(float v) {
+  // F.gelu(approximate="tanh"): 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))
+  const float k = 0.7978845608028654f;
+  return 0.5f * v * (1.0f + tanhf(k * (v + 0.044715f * v * v * v)));
+}
+__device__ __forceinline__ float mishf(float v) {
+  // F.softplus (beta 1, threshold 20) then tanh
+  const float sp = v > 20.f ? v : log1pf(expf(v));
+  return v * tanhf(sp);
+}
+
+// ---- operand packers: fp32 [B, Cin, T] -> fp16 blk16 [C] with a fused activation --------------------------------
+// mode 0: x * mask            mode 1: tanh(x[c] + bc[c]) * sigmoid(x[C+c] + bc[C+c])   (x has 2C channels, bc [B,2C])
+// mode 2: gelu_tanh(x) * mask mode 3: mish(x) * mask
+__global__ void pack_act_kernel(const float *__restrict__ x, const float *__restrict__ bc, const float *__restrict__ mask,
+                                uint4 *__restrict__ out, int B, int C, int64_t L, int64_t Lp, int cw, int mode, int cin) {
+  // cin = channels per batch item of x (>= C, or >= 2C for the gate): a channel prefix of a wider tensor can be packed
+  const int nch = C >> 3;
+  const int64_t n = (int64_t)B * nch * L;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t bq = i / L, t = i - bq * L;
+    const int64_t bb = bq / nch;
+    const int c0 = (int)(bq - bb * nch) * 8;
+    const float mk = mask ? __ldg(mask + bb * L + t) : 1.f;
+    const float *xr = x + (bb * cin + c0) * L + t;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float a = __ldg(xr + (int64_t)e * L);
+      if (mode == 1) {
+        const float g = __ldg(xr + (int64_t)(C + e) * L);
+        const float ba = bc ? __ldg(bc + bb * 2 * C + c0 + e) : 0.f, bg = bc ? __ldg(bc + bb * 2 * C + C + c0 + e) : 0.f;
+        v[e] = tanhf(a + ba) * sigmoidf_(g + bg);
+      } else if (mode == 2) {
+        v[e] = gelu_tanh(a) * mk;
+      } else if (mode == 3) {
+        v[e] = mishf(a) * mk;
+      } else {
+        v[e] = a * mk;
+      }
+    }
+    __half2 h[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+    *reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(out) +
+                               hsv::blk_unit_offset(cw, Lp, C, bb, c0, HSV_BLK_PAD + t)) = *reinterpret_cast<uint4 *>(h);
+  }
+}
+
+// LayerNorm over channels (no affine) -> optional mask -> modulate -> fp16 blk16.  CTA = 32 time steps x 8 channel
+// groups; thread (tx, g) owns the C/8 consecutive channels of group g at step tx (C % 64 == 0: whole 16-byte units).
+template <int CPT>   // channels per thread = C / 8
+__global__ void __launch_bounds__(256) ln_mod_kernel(const float *__restrict__ x, const float *__restrict__ shift,
+                                                     const float *__restrict__ scale, const float *__restrict__ mask,
+                                                     uint4 *__restrict__ out, int C, int64_t L, int64_t Lp, int cw,
+                                                     float eps, int inmask, int premask, int64_t mod_stride) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const int64_t t = (int64_t)blockIdx.x * 32 + tx;
+  const bool ok = t < L;
+  const float mk = (mask && ok) ? __ldg(mask + (int64_t)b * L + t) : 1.f;
+  float v[CPT];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) {
+    v[i] = ok ? __ldg(x + ((int64_t)b * C + g * CPT + i) * L + t) : 0.f;
+    if (inmask) v[i] *= mk;
+    s += v[i];
+  }
+  red[g][tx] = s;
+  __syncthreads();
+  float mean = 0.f;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) mean += red[q][tx];
+  mean /= (float)C;
+  __syncthreads();
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) {
+    const float d = v[i] - mean;
+    ss += d * d;
+  }
+  red[g][tx] = ss;
+  __syncthreads();
+  float var = 0.f;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) var += red[q][tx];
+  const float rstd = rsqrtf(var / (float)C + eps);
+  if (!ok) return;
+  const float pm = premask ? mk : 1.f;
+#pragma unroll
+  for (int u = 0; u < CPT / 8; ++u) {
+    __half2 h[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float o[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int c = g * CPT + u * 8 + 2 * e + q;
+        const float nrm = (v[u * 8 + 2 * e + q] - mean) * rstd * pm;
+        o[q] = nrm * (1.f + __ldg(scale + (int64_t)b * mod_stride + c)) + __ldg(shift + (int64_t)b * mod_stride + c);
+      }
+      h[e] = __floats2half2_rn(o[0], o[1]);
+    }
+    *reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(out) +
+                               hsv::blk_unit_offset(cw, Lp, C, b, g * CPT + u * 8, HSV_BLK_PAD + t)) =
+        *reinterpret_cast<uint4 *>(h);
+  }
+}
+
+// ---- element-wise fp32 ops on [B, C, T] ---------------------------------------------------------------------------
+enum { OP_WN_RES = 1, OP_WN_LAST = 2, OP_GATE_ADD = 3, OP_COUPLE = 4, OP_SAMPLE = 5, OP_MASK = 6, OP_ADD = 7,
+       OP_GLU_RES = 8, OP_MISH = 9, OP_FLIP = 10, OP_ADD_BCAST = 11 };
+
+// (a / out / out2 may alias: several ops update a tensor in place)
+__global__ void frame_op_kernel(int op, const float *a, const float *__restrict__ b2, const float *__restrict__ c2,
+                                const float *__restrict__ mask, float *out, float *out2, int B, int C, int64_t L,
+                                float s, int64_t cstride) {
+  const int64_t n = (int64_t)B * C * L;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t bc = i / L, t = i - bc * L;
+    const int64_t bb = bc / C;
+    const int c = (int)(bc - bb * C);
+    const float mk = mask ? __ldg(mask + bb * L + t) : 1.f;
+    switch (op) {
+      case OP_WN_RES: {   // a = x [B,C,T] (updated in place through out), b2 = rs [B,2C,T], out2 = output accumulator
+        const float res = __ldg(b2 + (bb * 2 * C + c) * L + t), skip = __ldg(b2 + (bb * 2 * C + C + c) * L + t);
+        out[i] = (a[i] + res) * mk;
+        out2[i] = out2[i] + skip;
+        break;
+      }
+      case OP_WN_LAST:    // out2 = (output + rs) * mask, b2 = rs [B,C,T]
+        out2[i] = (out2[i] + __ldg(b2 + i)) * mk;
+        break;
+      case OP_GATE_ADD:   // out = a + gate[b, c] * b2 * mask; c2 = gate base, cstride = batch stride of the gate vector
+        out[i] = a[i] + (__ldg(c2 + bb * cstride + c) * __ldg(b2 + i)) * mk;
+        break;
+      case OP_COUPLE:     // a = x [B,2C,T]: channels [C, 2C) become (x1 - m) * mask, b2 = m [B,C,T]; in place via out
+        out[(bb * 2 * C + C + c) * L + t] = (a[(bb * 2 * C + C + c) * L + t] - __ldg(b2 + i)) * mk;
+        break;
+      case OP_SAMPLE: {   // a = stats [B,2C,T] (m | logs), b2 = eps [B,C,T]: out = (m + eps * exp(logs) * s) * mask
+        const float m = __ldg(a + (bb * 2 * C + c) * L + t), lg = __ldg(a + (bb * 2 * C + C + c) * L + t);
+        out[i] = (m + (__ldg(b2 + i) * expf(lg)) * s) * mk;
+        break;
+      }
+      case OP_MASK:
+        out[i] = a[i] * mk;
+        break;
+      case OP_ADD:
+        out[i] = (a[i] + __ldg(b2 + i)) * mk;
+        break;
+      case OP_GLU_RES: {  // a = x [B,C,T], b2 = y [B,2C,T]: out = x + y1 * sigmoid(y2)
+        const float y1 = __ldg(b2 + (bb * 2 * C + c) * L + t), y2 = __ldg(b2 + (bb * 2 * C + C + c) * L + t);
+        out[i] = (a[i] + y1 * sigmoidf_(y2)) * mk;
+        break;
+      }
+      case OP_MISH:
+        out[i] = mishf(a[i]) * mk;
+        break;
+      case OP_FLIP:
+        out[i] = __ldg(a + (bb * C + (C - 1 - c)) * L + t);
+        break;
+      case OP_ADD_BCAST:  // out = (a + c2[b, c]) * mask
+        out[i] = (a[i] + __ldg(c2 + bb * cstride + c)) * mk;
+        break;
+    }
+  }
+}
+
+// ---- multi-head attention, fp32, online softmax -------------------------------------------------------------------
+// q, k, v: channel-major [heads*D, T] per batch item (time contiguous), batch strides in elements; out [B, heads*D, Tq].
+// CTA = 16 query rows of one (batch, head); keys in tiles of 32.
+constexpr int MHA_Q = 16, MHA_K = 32, MHA_THREADS = 128;   // static shared memory stays under 48 KB for D = 128
+
+template <int D>
+__global__ void __launch_bounds__(MHA_THREADS) mha_kernel(const float *__restrict__ q, const float *__restrict__ k,
+                                                          const float *__restrict__ v, float *__restrict__ out,
+                                                          const int *__restrict__ lens, int Tq, int Tk, int64_t qbs,
+                                                          int64_t kbs, int64_t vbs, int heads, float scale, int prescale) {
+  __shared__ float Qs[MHA_Q][D];
+  __shared__ float Ks[MHA_K][D + 1];
+  __shared__ float Vs[MHA_K][D];
+  __shared__ float S[MHA_Q][MHA_K + 1];
+  __shared__ float row_m[MHA_Q], row_l[MHA_Q], row_c[MHA_Q];
+  const int tid = threadIdx.x;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * MHA_Q;
+  const float *qb = q + (int64_t)b * qbs + (int64_t)h * D * Tq;
+  const float *kb = k + (int64_t)b * kbs + (int64_t)h * D * Tk;
+  const float *vb = v + (int64_t)b * vbs + (int64_t)h * D * Tk;
+  const int len = lens ? lens[b] : 0x7fffffff;
+  for (int idx = tid; idx < MHA_Q * D; idx += MHA_THREADS) {
+    const int d = idx / MHA_Q, i = idx - d * MHA_Q;
+    const float val = (q0 + i < Tq) ? __ldg(qb + (int64_t)d * Tq + q0 + i) : 0.f;
+    Qs[i][d] = prescale ? val * scale : val;
+  }
+  if (tid < MHA_Q) {
+    row_m[tid] = -INFINITY;
+    row_l[tid] = 0.f;
+  }
+  constexpr int OPT = MHA_Q * D / MHA_THREADS;   // outputs per thread
+  float acc[OPT];
+#pragma unroll
+  for (int r = 0; r < OPT; ++r) acc[r] = 0.f;
+  for (int k0 = 0; k0 < Tk; k0 += MHA_K) {
+    __syncthreads();
+    for (int idx = tid; idx < MHA_K * D; idx += MHA_THREADS) {
+      const int d = idx / MHA_K, j = idx - d * MHA_K;
+      const bool okj = k0 + j < Tk;
+      Ks[j][d] = okj ? __ldg(kb + (int64_t)d * Tk + k0 + j) : 0.f;
+      Vs[j][d] = okj ? __ldg(vb + (int64_t)d * Tk + k0 + j) : 0.f;
+    }
+    __syncthreads();
+    {
+      constexpr int RP = MHA_THREADS / MHA_K;               // row phases: 4 x 32 keys
+      const int j = tid & (MHA_K - 1), i0 = tid / MHA_K;
+#pragma unroll
+      for (int r = 0; r < MHA_Q / RP; ++r) {
+        const int i = i0 + RP * r;
+        float sacc = 0.f;
+#pragma unroll 8
+        for (int d = 0; d < D; ++d) sacc = fmaf(Qs[i][d], Ks[j][d], sacc);
+        if (!prescale) sacc *= scale;
+        if (lens && (k0 + j >= len || q0 + i >= len)) sacc = -1e4f;    // masked_fill(mask == 0, -1e4)
+        if (k0 + j >= Tk) sacc = -INFINITY;                            // padding of the last key tile
+        S[i][j] = sacc;
+      }
+    }
+    __syncthreads();
+    if (tid < MHA_Q) {
+      const int i = tid;
+      float mx = row_m[i];
+      for (int j = 0; j < MHA_K; ++j) mx = fmaxf(mx, S[i][j]);
+      const float corr = expf(row_m[i] - mx);
+      float l = row_l[i] * corr;
+      for (int j = 0; j < MHA_K; ++j) {
+        const float p = expf(S[i][j] - mx);
+        S[i][j] = p;
+        l += p;
+      }
+      row_m[i] = mx;
+      row_l[i] = l;
+      row_c[i] = corr;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < OPT; ++r) {
+      const int idx = tid + MHA_THREADS * r;
+      const int i = idx / D, d = idx - i * D;
+      float o = acc[r] * row_c[i];
+#pragma unroll 8
+      for (int j = 0; j < MHA_K; ++j) o = fmaf(S[i][j], Vs[j][d], o);
+      acc[r] = o;
+    }
+  }
+  __syncthreads();
+  float *ob = out + ((int64_t)b * heads + h) * D * Tq;
+#pragma unroll
+  for (int r = 0; r < OPT; ++r) {
+    const int idx = tid + MHA_THREADS * r;
+    const int i = idx / D, d = idx - i * D;
+    if (q0 + i < Tq) ob[(int64_t)d * Tq + q0 + i] = acc[r] / row_l[i];
+  }
+}
+
+// Conv1d with ONE input channel and a stride (PosteriorSFEncoder.pre_filter: Conv1d(1, 192, 9, stride 4, padding 4),
+// hierspeechpp_speechsynthesizer.py:187,196): out[b, co, t] = bias[co] + sum_j w[co, j] * x[b, t*stride + j - pad]
+__global__ void conv1d_c1_strided_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                                         const float *__restrict__ bias, const float *__restrict__ mask,
+                                         float *__restrict__ out, int B, int Cout, int64_t Lin, int64_t Lout, int k,
+                                         int stride, int pad) {
+  const int64_t n = (int64_t)B * Cout * Lout;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t bc = i / Lout, t = i - bc * Lout;
+    const int64_t bb = bc / Cout;
+    const int co = (int)(bc - bb * Cout);
+    float acc = 0.f;
+    for (int j = 0; j < k; ++j) {
+      const int64_t s = t * stride + j - pad;
+      if (s >= 0 && s < Lin) acc = fmaf(__ldg(w + co * k + j), __ldg(x + bb * Lin + s), acc);
+    }
+    acc += bias ? __ldg(bias + co) : 0.f;
+    out[i] = acc * (mask ? __ldg(mask + bb * Lout + t) : 1.f);
+  }
+}
+
+// out[b, c] = sum_t x[b, c, t] / denom[b]   (StyleEncoder.temporal_avg_pool: the sum runs over ALL frames)
+__global__ void masked_mean_kernel(const float *__restrict__ x, float *__restrict__ out, int64_t L) {
+  const int64_t row = blockIdx.x;            // b * C + c
+  float s = 0.f;
+  for (int64_t t = threadIdx.x; t < L; t += blockDim.x) s += __ldg(x + row * L + t);
+  __shared__ float red[32];
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+    out[row] = tot;
+  }
+}
+__global__ void mean_div_kernel(float *__restrict__ out, const float *__restrict__ mask, int C, int64_t L) {
+  const int b = blockIdx.x;
+  __shared__ float len_s;
+  if (threadIdx.x == 0) {
+    float l = 0.f;
+    for (int64_t t = 0; t < L; ++t) l += mask ? mask[(int64_t)b * L + t] : 1.f;
+    len_s = l;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) out[(int64_t)b * C + c] = out[(int64_t)b * C + c] / len_s;
+}
+
+}  // namespace
+
+extern "C" int hsv_pack_blk16_act(const float *x, const float *bcast, const float *mask, void *out, int B, int C,
+                                  int64_t L, int mode, int x_channels, void *stream) {
+  if (B == 0 || L == 0) return HSV_OK;
+  HSV_REQUIRE(x && out, "pack_blk16_act: null pointer");
+  HSV_REQUIRE(C > 0 && C % 16 == 0 && mode >= 0 && mode <= 3, "pack_blk16_act: bad C=%d / mode=%d", C, mode);
+  HSV_REQUIRE(x_channels >= (mode == 1 ? 2 * C : C), "pack_blk16_act: x has %d channels, needs %d", x_channels,
+              mode == 1 ? 2 * C : C);
+  pack_act_kernel<<<grid_for((int64_t)B * (C / 8) * L, 256), 256, 0, hsv::as_stream(stream)>>>(
+      x, bcast, mask, reinterpret_cast<uint4 *>(out), B, C, L, hsv::blk16_rows(L), hsv::blk_cw(C), mode, x_channels);
+  return hsv::check_launch("pack_blk16_act");
+}
+
+extern "C" int hsv_ln_mod_blk16(const float *x, const float *shift, const float *scale, const float *mask, void *out,
+                                int B, int C, int64_t L, float eps, int inmask, int premask, int64_t mod_stride,
+                                void *stream) {
+  if (B == 0 || L == 0) return HSV_OK;
+  HSV_REQUIRE(x && shift && scale && out, "ln_mod_blk16: null pointer");
+  HSV_REQUIRE(C == 192 || C == 256 || C == 128 || C == 64, "ln_mod_blk16: C must be 64, 128, 192 or 256 (C=%d)", C);
+  HSV_REQUIRE(B <= 65535, "ln_mod_blk16: batch too large");
+  dim3 grid((unsigned)((L + 31) / 32), (unsigned)B);
+  cudaStream_t st = hsv::as_stream(stream);
+  uint4 *o = reinterpret_cast<uint4 *>(out);
+  const int64_t Lp = hsv::blk16_rows(L);
+  const int cw = hsv::blk_cw(C);
+  if (C == 192) ln_mod_kernel<24><<<grid, 256, 0, st>>>(x, shift, scale, mask, o, C, L, Lp, cw, eps, inmask, premask, mod_stride);
+  else if (C == 256) ln_mod_kernel<32><<<grid, 256, 0, st>>>(x, shift, scale, mask, o, C, L, Lp, cw, eps, inmask, premask, mod_stride);
+  else if (C == 128) ln_mod_kernel<16><<<grid, 256, 0, st>>>(x, shift, scale, mask, o, C, L, Lp, cw, eps, inmask, premask, mod_stride);
+  else ln_mod_kernel<8><<<grid, 256, 0, st>>>(x, shift, scale, mask, o, C, L, Lp, cw, eps, inmask, premask, mod_stride);
+  return hsv::check_launch("ln_mod_blk16");
+}
+
+extern "C" int hsv_frame_op(int op, const float *a, const float *b, const float *c, const float *mask, float *out,
+                            float *out2, int B, int C, int64_t L, float s, int64_t cstride, void *stream) {
+  if (B == 0 || L == 0 || C == 0) return HSV_OK;
+  HSV_REQUIRE(op >= OP_WN_RES && op <= OP_ADD_BCAST, "frame_op: unknown op %d", op);
+  HSV_REQUIRE(a || op == OP_WN_LAST, "frame_op: null input");
+  frame_op_kernel<<<grid_for((int64_t)B * C * L, 256), 256, 0, hsv::as_stream(stream)>>>(op, a, b, c, mask, out, out2, B,
+                                                                                          C, L, s, cstride);
+  return hsv::check_launch("frame_op");
+}
+
+extern "C" int hsv_mha(const float *q, const float *k, const float *v, float *out, const int *lens, int B, int heads,
+                       int D, int Tq, int Tk, int64_t q_bstride, int64_t k_bstride, int64_t v_bstride, float scale,
+                       int prescale_q, void *stream) {
+  if (B == 0 || Tq == 0) return HSV_OK;
+  HSV_REQUIRE(q && k && v && out, "mha: null pointer");
+  HSV_REQUIRE(D == 96 || D == 128 || D == 64, "mha: head dim must be 64, 96 or 128 (D=%d)", D);
+  HSV_REQUIRE(Tk > 0 && heads > 0 && heads <= 65535 && B <= 65535, "mha: bad shape");
+  dim3 grid((unsigned)((Tq + MHA_Q - 1) / MHA_Q), (unsigned)heads, (unsigned)B);
+  cudaStream_t st = hsv::as_stream(stream);
+  if (D == 96) mha_kernel<96><<<grid, MHA_THREADS, 0, st>>>(q, k, v, out, lens, Tq, Tk, q_bstride, k_bstride, v_bstride, heads, scale, prescale_q);
+  else if (D == 128) mha_kernel<128><<<grid, MHA_THREADS, 0, st>>>(q, k, v, out, lens, Tq, Tk, q_bstride, k_bstride, v_bstride, heads, scale, prescale_q);
+  else mha_kernel<64><<<grid, MHA_THREADS, 0, st>>>(q, k, v, out, lens, Tq, Tk, q_bstride, k_bstride, v_bstride, heads, scale, prescale_q);
+  return hsv::check_launch("mha");
+}
+
+extern "C" int hsv_conv1d_c1_strided(const float *x, const float *w, const float *bias, const float *mask, float *out,
+                                     int B, int Cout, int64_t Lin, int64_t Lout, int k, int stride, int pad,
+                                     void *stream) {
+  if (B == 0 || Lout == 0) return HSV_OK;
+  HSV_REQUIRE(x && w && out && k >= 1 && stride >= 1 && pad >= 0, "conv1d_c1_strided: bad arguments");
+  conv1d_c1_strided_kernel<<<grid_for((int64_t)B * Cout * Lout, 256), 256, 0, hsv::as_stream(stream)>>>(
+      x, w, bias, mask, out, B, Cout, Lin, Lout, k, stride, pad);
+  return hsv::check_launch("conv1d_c1_strided");
+}
+
+extern "C" int hsv_masked_mean(const float *x, const float *mask, float *out, int B, int C, int64_t L, void *stream) {
+  if (B == 0 || C == 0) return HSV_OK;
+  HSV_REQUIRE(x && out && L > 0, "masked_mean: bad arguments");
+  cudaStream_t st = hsv::as_stream(stream);
+  masked_mean_kernel<<<(unsigned)(B * C), 128, 0, st>>>(x, out, L);
+  mean_div_kernel<<<B, 128, 0, st>>>(out, mask, C, L);
+  return hsv::check_launch("masked_mean");
+}

@@ -270,6 +270,9 @@ def _row_tiles(B: int, L: int) -> int:
 # warps per SM, the fused CTA (144 registers, 66 KB) allows 12 -- so the default is 0 (off); set
 # HSV_FUSE_MAX_C=32|64 or FUSE_MAX_CHANNELS[0] to use it.
 FUSE_MAX_CHANNELS = [int(__import__("os").environ.get("HSV_FUSE_MAX_C", "0"))]
+# ... and only for layers of at most this many elements (B*C*L): small layers are latency-bound (one wave or less per
+# kernel), there the saved launch on the critical path is worth more than the slower in-CTA activation
+FUSE_MAX_ELEMS = [int(__import__("os").environ.get("HSV_FUSE_MAX_ELEMS", str(1 << 62)))]
 
 _MAIN_SLOT = 3   # blk16 workspace slot of the main stream (slots 0..2 belong to the per-resblock streams)
 
@@ -344,7 +347,7 @@ class AMPBlock1(nn.Module):
         if C != self.channels or C % 16:
             raise ValueError(f"AMP block expects {self.channels} channels (multiple of 16), got {C}")
         k = self.kernel_size
-        fused = C in ops.FUSED_CIN and C <= FUSE_MAX_CHANNELS[0]
+        fused = C in ops.FUSED_CIN and C <= FUSE_MAX_CHANNELS[0] and B * C * L <= FUSE_MAX_ELEMS[0]
         buf = None if fused else ops.blk16_buffer(B, C, L, x.device, slot)
         xt = torch.empty_like(x)
         cur = x

@@ -469,6 +469,109 @@ def peak_norm_pcm16(x: torch.Tensor, s1: float = 32767.0, s2: float = 0.999, per
     return out, (peaks if per_row else peaks[:1])
 
 
+# ----------------------------------------------------------------------------------------------
+# frame-rate operators of the step before the vocoder (csrc/frame_ops.cu)
+# ----------------------------------------------------------------------------------------------
+CONV_SILU_IN = 8
+PACK_MASK, PACK_GATE, PACK_GELU, PACK_MISH = 0, 1, 2, 3
+(OP_WN_RES, OP_WN_LAST, OP_GATE_ADD, OP_COUPLE, OP_SAMPLE, OP_MASK, OP_ADD, OP_GLU_RES, OP_MISH, OP_FLIP,
+ OP_ADD_BCAST) = range(1, 12)
+
+
+def _req_vec(t: torch.Tensor, name: str):
+    """Per-(batch, channel) vectors may be strided views (e.g. a chunk of the adaLN output): pointer + batch stride."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != torch.float32:
+        raise RuntimeError(f"{name}: expected a CUDA float32 tensor (no CPU fallback)")
+    if t.stride(-1) != 1 and t.shape[-1] != 1:
+        raise ValueError(f"{name}: innermost dimension must be dense")
+
+
+def pack_blk16_act(x: torch.Tensor, buf: torch.Tensor, C: int, mode: int = PACK_MASK, bcast: Optional[torch.Tensor] = None,
+                   mask: Optional[torch.Tensor] = None, c_off: int = 0):
+    """fp32 [B, >=c_off+C (>=2C for the gate), T] -> fp16 blk16 [C] with a fused activation (hsv_pack_blk16_act);
+    channels [c_off, c_off+C) of x are used (the gate: [0, 2C))."""
+    _req(x, "x", ndim=3); _req(buf, "buf", torch.float16, 4)
+    B, cin, L = x.shape
+    if cin < c_off + (2 * C if mode == PACK_GATE else C) or (c_off and mode == PACK_GATE):
+        raise ValueError(f"pack_blk16_act: x has {cin} channels, needs {c_off + (2 * C if mode == PACK_GATE else C)}")
+    if tuple(buf.shape) != blk16_shape(B, C, L):
+        raise ValueError("blk16 buffer shape mismatch")
+    if bcast is not None:
+        _req(bcast, "bcast")
+    if mask is not None:
+        _req(mask, "mask")
+    lib = _lib.load()
+    xp = ctypes.c_void_p(x.data_ptr() + 4 * c_off * L)
+    _lib.check(lib.hsv_pack_blk16_act(xp, _p(bcast), _p(mask), _p(buf), B, C, L, mode, cin, _stream()),
+               "hsv_pack_blk16_act")
+    return buf
+
+
+def ln_mod_blk16(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, buf: torch.Tensor, mod_stride: int,
+                 mask: Optional[torch.Tensor] = None, eps: float = 1e-6, inmask: bool = False, premask: bool = False):
+    """LayerNorm over channels (no affine) [* mask] -> x * (1 + scale[b]) + shift[b] -> fp16 blk16."""
+    _req(x, "x", ndim=3); _req_vec(shift, "shift"); _req_vec(scale, "scale"); _req(buf, "buf", torch.float16, 4)
+    B, C, L = x.shape
+    if tuple(buf.shape) != blk16_shape(B, C, L):
+        raise ValueError("blk16 buffer shape mismatch")
+    if mask is not None:
+        _req(mask, "mask")
+    lib = _lib.load()
+    _lib.check(lib.hsv_ln_mod_blk16(_p(x), _p(shift), _p(scale), _p(mask), _p(buf), B, C, L, float(eps), int(inmask),
+                                    int(premask), int(mod_stride), _stream()), "hsv_ln_mod_blk16")
+    return buf
+
+
+def frame_op(op: int, a, b=None, c=None, mask=None, out=None, out2=None, B=0, C=0, L=0, s: float = 1.0, cstride: int = 0):
+    for t, n in ((a, "a"), (b, "b"), (mask, "mask"), (out, "out"), (out2, "out2")):
+        if t is not None:
+            _req(t, n)
+    if c is not None:
+        _req_vec(c, "c")
+    lib = _lib.load()
+    _lib.check(lib.hsv_frame_op(int(op), _p(a), _p(b), _p(c), _p(mask), _p(out), _p(out2), B, C, L, float(s), int(cstride),
+                                _stream()), "hsv_frame_op")
+
+
+def mha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, heads: int, D: int, Tq: int, Tk: int, q_bs: int,
+        k_bs: int, v_bs: int, scale: float, prescale_q: bool, lens: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """softmax(q k^T * scale) v; q/k/v may be views into one fused [B, 3*heads*D, T] tensor (pass batch strides)."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        if not t.is_cuda or t.dtype != torch.float32:
+            raise RuntimeError(f"mha: {n} must be a CUDA float32 tensor")
+    out = torch.empty(B, heads * D, Tq, dtype=torch.float32, device=q.device)
+    if lens is not None:
+        _req(lens, "lens", torch.int32)
+    lib = _lib.load()
+    _lib.check(lib.hsv_mha(_p(q), _p(k), _p(v), _p(out), _p(lens), B, heads, D, Tq, Tk, int(q_bs), int(k_bs), int(v_bs),
+                           float(scale), int(prescale_q), _stream()), "hsv_mha")
+    return out
+
+
+def conv1d_c1_strided(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], stride: int, pad: int,
+                      mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(x, "x", ndim=3); _req(w, "w", ndim=3)
+    B, one, Lin = x.shape
+    cout, one_w, k = w.shape
+    if one != 1 or one_w != 1:
+        raise ValueError("conv1d_c1_strided: single input channel only")
+    Lout = (Lin + 2 * pad - k) // stride + 1
+    out = torch.empty(B, cout, Lout, dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    _lib.check(lib.hsv_conv1d_c1_strided(_p(x), _p(w), _p(bias), _p(mask), _p(out), B, cout, Lin, Lout, k, stride, pad,
+                                         _stream()), "hsv_conv1d_c1_strided")
+    return out
+
+
+def masked_mean(x: torch.Tensor, mask: Optional[torch.Tensor]) -> torch.Tensor:
+    _req(x, "x", ndim=3)
+    B, C, L = x.shape
+    out = torch.empty(B, C, dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    _lib.check(lib.hsv_masked_mean(_p(x), _p(mask), _p(out), B, C, L, _stream()), "hsv_masked_mean")
+    return out
+
+
 def sinegen(f0: torch.Tensor, hop: int, sample_rate: float, harmonics: int = 8, amp: float = 0.1):
     """Harmonic sine source from a frame-rate f0 track (Hz, <= 0 = unvoiced): returns (sines [B, harmonics, T*hop],
     voiced mask [B, 1, T*hop]).  64-bit fixed-point phase accumulation: no drift over long utterances."""

@@ -62,7 +62,7 @@ class CudaGraphRunner:
             self._pb_mods = [m for m in (self.fn.modules() if hasattr(self.fn, "modules") else [])
                              if hasattr(m, "parallel_blocks")]
         par = tuple(bool(m.parallel_blocks) for m in self._pb_mods)
-        return (M._CACHE_EPOCH[0], ops.WORKSPACE_EPOCH[0], M.FUSE_MAX_CHANNELS[0], par)
+        return (M._CACHE_EPOCH[0], ops.WORKSPACE_EPOCH[0], M.FUSE_MAX_CHANNELS[0], M.FUSE_MAX_ELEMS[0], par)
 
     def _key(self, args):
         return tuple((tuple(a.shape), a.dtype, a.device.index) for a in args)
@@ -229,11 +229,12 @@ def gather_waveforms(local: Dict[int, torch.Tensor], dst: int = 0, sizes: Dict[i
     return None
 
 
-def patch_reference(modules=None) -> List[str]:
+def patch_reference(modules=None, front: bool = True) -> List[str]:
     """Swap the reference's hot-path classes for the B200 ones in already-imported reference modules
     (``hierspeechpp_speechsynthesizer``, ``speechsr24k.speechsr``, ``speechsr48k.speechsr``,
     ``alias_free_torch``), so the reference's own ``SynthesizerTrn``/inference scripts build and call
     them.  Returns the list of patched attributes.  See INTEGRATION.md."""
+    from . import front as FR
     from . import modules as M
 
     mods = modules if modules is not None else sys.modules
@@ -258,4 +259,10 @@ def patch_reference(modules=None) -> List[str]:
                       ("DownSample1d", M.DownSample1d), ("LowPassFilter1d", M.LowPassFilter1d)):
         _set("alias_free_torch", attr, obj)
     _set("activations", "SnakeBeta", M.SnakeBeta)
+    if front:
+        # the step before the vocoder: enc_p_l, flow_l / flow, emb_g of SynthesizerTrn
+        for attr, obj in (("PosteriorSFEncoder", FR.PosteriorSFEncoder),
+                          ("ResidualCouplingBlock_Transformer", FR.ResidualCouplingBlock_Transformer),
+                          ("StyleEncoder", FR.StyleEncoder)):
+            _set("hierspeechpp_speechsynthesizer", attr, obj)
     return patched

@@ -144,3 +144,121 @@ def speechsr_input(B: int, L: int, seed: int = 1111):
     """x = 0.1*N(0,1) [B,1,L] (SURVEY.md §8d #3)."""
     gen = torch.Generator().manual_seed(seed)
     return 0.1 * torch.randn(B, 1, L, generator=gen)
+
+
+# ----------------------------------------------------------------------------------------------
+# the step BEFORE the vocoder (SURVEY.md §8f2): enc_p_l, flow_l / flow, emb_g of SynthesizerTrn
+# ----------------------------------------------------------------------------------------------
+def _linear(sd: SD, p: str, gen, cout: int, cin: int, scale: float = None):
+    bound = 1.0 / math.sqrt(cin) if scale is None else scale
+    sd[p + "weight"] = (torch.rand(cout, cin, generator=gen) * 2 - 1) * bound
+    sd[p + "bias"] = (torch.rand(cout, generator=gen) * 2 - 1) * bound
+
+
+def _wn(sd: SD, p: str, gen, hidden: int, k: int, n_layers: int, gin: int):
+    """modules.WN (:111-182): weight-normed cond_layer, in_layers, res_skip_layers."""
+    for i in range(n_layers):
+        _conv(sd, f"{p}in_layers.{i}.", gen, 2 * hidden, hidden, k)
+    for i in range(n_layers):
+        _conv(sd, f"{p}res_skip_layers.{i}.", gen, 2 * hidden if i < n_layers - 1 else hidden, hidden, 1)
+    _conv(sd, p + "cond_layer.", gen, 2 * hidden * n_layers, gin, 1)
+
+
+def posterior_sf_encoder_sd(seed: int, prefix: str = "enc_p_l.", hidden: int = 192, out: int = 192, k: int = 5,
+                            n_layers: int = 16, gin: int = 256, src: int = 1024) -> SD:
+    """Keys of hierspeechpp_speechsynthesizer.PosteriorSFEncoder (:168-203)."""
+    gen = torch.Generator().manual_seed(seed)
+    sd: SD = {}
+    _conv(sd, prefix + "pre_source.", gen, hidden, src, 1, wn=False)
+    _conv(sd, prefix + "pre_filter.", gen, hidden, 1, 9, wn=False)
+    for name in ("source_enc.", "filter_enc.", "enc."):
+        _wn(sd, prefix + name, gen, hidden, k, n_layers // 2, gin)
+    _conv(sd, prefix + "proj.", gen, 2 * out, hidden, 1, wn=False)
+    return _ordered_like_reference(sd, prefix)
+
+
+def _ordered_like_reference(sd: SD, prefix: str) -> SD:
+    """weight-normed convs register bias, weight_g, weight_v in that order (torch.nn.utils.weight_norm)."""
+    out: SD = {}
+    done = set()
+    for key in sd:
+        base = key.rsplit(".", 1)[0] + "."
+        if base in done:
+            continue
+        if base + "weight_g" in sd:
+            for leaf in ("bias", "weight_g", "weight_v"):
+                if base + leaf in sd:
+                    out[base + leaf] = sd[base + leaf]
+        else:
+            for leaf in ("weight", "bias"):
+                if base + leaf in sd:
+                    out[base + leaf] = sd[base + leaf]
+        done.add(base)
+    return out
+
+
+def coupling_block_sd(seed: int, prefix: str = "flow_l.", channels: int = 192, hidden: int = 192, n_layers: int = 3,
+                      n_flows: int = 4, gin: int = 256) -> SD:
+    """Keys of ResidualCouplingBlock_Transformer (:53-88) with ResidualCouplingLayer_Transformer_simple flows
+    (modules.py:412-488; DiTConVBlock :390-411).  The reference zero-initialises ``post`` and the adaLN output layer
+    (identity flows); here they get small random values so that the flows do something."""
+    gen = torch.Generator().manual_seed(seed)
+    sd: SD = {}
+    _linear(sd, prefix + "cond_block.0.", gen, 4 * hidden, gin)
+    _linear(sd, prefix + "cond_block.2.", gen, hidden, 4 * hidden)
+    half = channels // 2
+    for f in range(n_flows):
+        p = f"{prefix}flows.{2 * f}."
+        _conv(sd, p + "pre.", gen, hidden, half, 1, wn=False)
+        for b in range(n_layers):
+            q = f"{p}enc_block.{b}."
+            _linear(sd, q + "attn.qkv.", gen, 3 * hidden, hidden)
+            _linear(sd, q + "attn.proj.", gen, hidden, hidden)
+            _conv(sd, q + "mlp.fc1.", gen, 4 * hidden, hidden, 5, wn=False)
+            _conv(sd, q + "mlp.fc2.", gen, hidden, 4 * hidden, 1, wn=False)
+            _linear(sd, q + "adaLN_modulation.1.", gen, 6 * hidden, hidden, scale=0.02)
+        _conv(sd, p + "post.", gen, half, hidden, 1, wn=False)
+        sd[p + "post.weight"] *= 0.3
+    return sd
+
+
+def style_encoder_sd(seed: int, prefix: str = "emb_g.", in_dim: int = 80, hidden: int = 256, out: int = 256) -> SD:
+    """Keys of styleencoder.StyleEncoder (:33-66)."""
+    gen = torch.Generator().manual_seed(seed)
+    sd: SD = {}
+    _conv(sd, prefix + "spectral.0.", gen, hidden, in_dim, 1, wn=False)
+    _conv(sd, prefix + "spectral.3.", gen, hidden, hidden, 1, wn=False)
+    for i in range(2):
+        _conv(sd, f"{prefix}temporal.{i}.conv1.", gen, 2 * hidden, hidden, 5, wn=False)
+    for name in ("conv_q.", "conv_k.", "conv_v.", "conv_o."):
+        _conv(sd, prefix + "slf_attn." + name, gen, hidden, hidden, 1, wn=False)
+    _conv(sd, prefix + "fc.", gen, out, hidden, 1, wn=False)
+    return sd
+
+
+def front_sd(seed: int = 2345) -> SD:
+    """enc_p_l + flow_l + flow + emb_g of the HierSpeech++ SynthesizerTrn (libritts960 architecture)."""
+    sd = posterior_sf_encoder_sd(seed, "enc_p_l.")
+    sd.update(coupling_block_sd(seed + 1, "flow_l."))
+    sd.update(coupling_block_sd(seed + 2, "flow."))
+    sd.update(style_encoder_sd(seed + 3, "emb_g."))
+    return sd
+
+
+def synthesizer_sd(seed: int = 1234) -> SD:
+    """Everything SynthesizerTrn.infer / voice_conversion_noise_control touches: front + sn + dec."""
+    sd = front_sd(seed + 1111)
+    sd.update(vocoder_sd(seed))
+    return sd
+
+
+def synthesizer_inputs(T: int, T_mel: int = 150, seed: int = 1111):
+    """SURVEY.md §8d #2, SynthesizerTrn level: w2v ~ N(0,1) [1,1024,T], f0 = log(hz+1) with hz ~ U(80,400) and 30 %
+    unvoiced [1,1,4T], trg_mel ~ N(-4,2) [2,80,T_mel]."""
+    gen = torch.Generator().manual_seed(seed)
+    w2v = torch.randn(1, 1024, T, generator=gen)
+    hz = torch.rand(1, 1, 4 * T, generator=gen) * 320 + 80
+    hz[torch.rand(1, 1, 4 * T, generator=gen) < 0.3] = 0.0
+    f0 = torch.log(hz + 1)
+    mel = torch.randn(2, 80, T_mel, generator=gen) * 2 - 4
+    return w2v, f0, mel

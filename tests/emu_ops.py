@@ -113,6 +113,8 @@ def conv_transpose1d_umma(a_blk, wp, bias, Lin, cin, cout, k, u, n_tile, add=Non
 
 def conv1d_direct(x, w, bias, d=1, pad=0, flags=0, out=None):
     xin = F.leaky_relu(x, 0.1) if flags & real.CONV_LRELU_IN else x
+    if flags & real.CONV_SILU_IN:
+        xin = F.silu(xin)
     v = F.conv1d(xin, w, bias, padding=pad, dilation=d)
     if flags & real.CONV_TANH:
         v = torch.tanh(v)
@@ -149,7 +151,97 @@ def add3_bcast(a, b, bc, out=None):
     return v
 
 
-NAMES = ["blk16_buffer", "act1d", "act1d_blk16", "pack_blk16", "weight_norm_fold", "pack_conv_weight", "conv1d_umma", "act_conv1d_umma", "pack_convT_weight", "conv_transpose1d_umma",
+# ---- frame-rate operators (csrc/frame_ops.cu) ----
+def _m(mask, like):
+    return 1.0 if mask is None else mask.view(mask.shape[0], 1, -1)
+
+
+def pack_blk16_act(x, buf, C, mode=0, bcast=None, mask=None, c_off=0):
+    mk = _m(mask, x)
+    x = x[:, c_off:]
+    if mode == real.PACK_GATE:
+        b = 0.0 if bcast is None else bcast.view(bcast.shape[0], -1, 1)
+        a = x[:, :2 * C] + b
+        y = torch.tanh(a[:, :C]) * torch.sigmoid(a[:, C:])
+    elif mode == real.PACK_GELU:
+        y = F.gelu(x[:, :C], approximate="tanh") * mk
+    elif mode == real.PACK_MISH:
+        y = x[:, :C] * torch.tanh(F.softplus(x[:, :C])) * mk
+    else:
+        y = x[:, :C] * mk
+    _pack_into(buf, y.contiguous())
+    return buf
+
+
+def ln_mod_blk16(x, shift, scale, buf, mod_stride, mask=None, eps=1e-6, inmask=False, premask=False):
+    mk = _m(mask, x)
+    if inmask:
+        x = x * mk
+    n = F.layer_norm(x.transpose(1, 2), (x.shape[1],), None, None, eps).transpose(1, 2)
+    if premask:
+        n = n * mk
+    _pack_into(buf, (n * (1 + scale.unsqueeze(-1)) + shift.unsqueeze(-1)).contiguous())
+    return buf
+
+
+def frame_op(op, a, b=None, c=None, mask=None, out=None, out2=None, B=0, C=0, L=0, s=1.0, cstride=0):
+    mk = _m(mask, a if a is not None else b)
+    if op == real.OP_WN_RES:
+        res, skip = b[:, :C], b[:, C:]
+        out.copy_((a + res) * mk); out2.add_(skip)
+    elif op == real.OP_WN_LAST:
+        out2.copy_((out2 + b) * mk)
+    elif op == real.OP_GATE_ADD:
+        out.copy_(a + (c.unsqueeze(-1) * b) * mk)
+    elif op == real.OP_COUPLE:
+        out[:, C:2 * C] = (a[:, C:2 * C] - b) * mk
+    elif op == real.OP_SAMPLE:
+        out.copy_((a[:, :C] + (b * torch.exp(a[:, C:2 * C])) * s) * mk)
+    elif op == real.OP_MASK:
+        out.copy_(a * mk)
+    elif op == real.OP_ADD:
+        out.copy_((a + b) * mk)
+    elif op == real.OP_GLU_RES:
+        out.copy_((a + b[:, :C] * torch.sigmoid(b[:, C:])) * mk)
+    elif op == real.OP_MISH:
+        out.copy_(a * torch.tanh(F.softplus(a)) * mk)
+    elif op == real.OP_FLIP:
+        out.copy_(torch.flip(a, [1]))
+    elif op == real.OP_ADD_BCAST:
+        out.copy_((a + c.unsqueeze(-1)) * mk)
+    else:
+        raise ValueError(op)
+
+
+def mha(q, k, v, B, heads, D, Tq, Tk, q_bs, k_bs, v_bs, scale, prescale_q, lens=None):
+    def grab(t, bs, T):
+        return torch.stack([t.reshape(-1)[b * bs:b * bs + heads * D * T].view(heads, D, T) for b in range(B)])
+    qq, kk, vv = grab(q, q_bs, Tq).transpose(2, 3), grab(k, k_bs, Tk).transpose(2, 3), grab(v, v_bs, Tk).transpose(2, 3)
+    sc = torch.matmul(qq * scale, kk.transpose(-2, -1)) if prescale_q else torch.matmul(qq, kk.transpose(-2, -1)) * scale
+    if lens is not None:
+        for b in range(B):
+            n = int(lens[b])
+            sc[b, :, n:, :] = -1e4
+            sc[b, :, :, n:] = -1e4
+    o = torch.matmul(sc.softmax(-1), vv)
+    return o.transpose(2, 3).contiguous().view(B, heads * D, Tq)
+
+
+def conv1d_c1_strided(x, w, bias, stride, pad, mask=None):
+    return F.conv1d(x, w, bias, stride=stride, padding=pad) * _m(mask, x)
+
+
+def masked_mean(x, mask):
+    den = float(x.shape[-1]) if mask is None else mask.sum(dim=1, keepdim=True)
+    return x.sum(dim=2) / den
+
+
+def check_saturation(buf, C, L):
+    return None
+
+
+NAMES = ["pack_blk16_act", "ln_mod_blk16", "frame_op", "mha", "conv1d_c1_strided", "masked_mean", "check_saturation",
+         "blk16_buffer", "act1d", "act1d_blk16", "pack_blk16", "weight_norm_fold", "pack_conv_weight", "conv1d_umma", "act_conv1d_umma", "pack_convT_weight", "conv_transpose1d_umma",
          "conv1d_direct", "conv_transpose1d", "sr_pre_interp", "nearest_gather", "add3_bcast"]
 
 

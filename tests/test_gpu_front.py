@@ -1,0 +1,202 @@
+"""The step before the vocoder on the GPU: frame-rate kernels against torch, the drop-in modules against
+the oracle restatement (oracle/functional_front.py, pinned bit-exact to the reference on CPU) run in strict fp32 on the
+same device with the same CUDA generator seed (the noise draws happen in the same order and shapes)."""
+import contextlib
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import MAX_ABS_TOL, SNR_DB_MIN
+from oracle import closed_form as CF
+from oracle import functional_front as FF
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@contextlib.contextmanager
+def strict_fp32():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        yield
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def _rel(got, ref):
+    return float((got - ref).abs().max() / max(1e-6, float(ref.abs().max())))
+
+
+def test_pack_act_modes(hsv):
+    ops = hsv.ops
+    g = torch.Generator().manual_seed(1)
+    B, C, T = 2, 192, 77
+    x = torch.randn(B, 2 * C, T, generator=g).to(DEV)
+    bc = torch.randn(B, 2 * C, generator=g).to(DEV)
+    mask = (torch.arange(T)[None, :] < torch.tensor([T, 50])[:, None]).float().to(DEV)
+    buf = ops.blk16_buffer(B, C, T, DEV, slot=8)
+    ops.pack_blk16_act(x, buf, C, ops.PACK_GATE, bcast=bc)
+    a = x + bc.unsqueeze(-1)
+    assert _rel(ops.unpack_blk16(buf, C, T), torch.tanh(a[:, :C]) * torch.sigmoid(a[:, C:])) <= 1e-3
+    ops.pack_blk16_act(x, buf, C, ops.PACK_GELU, mask=mask)
+    assert _rel(ops.unpack_blk16(buf, C, T), F.gelu(x[:, :C], approximate="tanh") * mask.unsqueeze(1)) <= 1e-3
+    ops.pack_blk16_act(x, buf, C, ops.PACK_MISH, mask=mask, c_off=C)
+    xm = x[:, C:]
+    assert _rel(ops.unpack_blk16(buf, C, T), xm * torch.tanh(F.softplus(xm)) * mask.unsqueeze(1)) <= 1e-3
+    ops.pack_blk16_act(x, buf, C, ops.PACK_MASK)
+    assert _rel(ops.unpack_blk16(buf, C, T), x[:, :C]) <= 1e-3
+
+
+@pytest.mark.parametrize("C", [192, 256])
+def test_ln_mod(hsv, C):
+    ops = hsv.ops
+    g = torch.Generator().manual_seed(2)
+    B, T = 2, 131
+    x = (torch.randn(B, C, T, generator=g) * 3 + 1).to(DEV)
+    mod = torch.randn(B, 6 * C, generator=g).to(DEV)
+    mask = (torch.arange(T)[None, :] < torch.tensor([T, 90])[:, None]).float().to(DEV)
+    buf = ops.blk16_buffer(B, C, T, DEV, slot=8)
+    for premask in (False, True):
+        ops.ln_mod_blk16(x, mod[:, C:2 * C], mod[:, 3 * C:4 * C], buf, 6 * C, mask, 1e-6, premask=premask)
+        n = F.layer_norm(x.transpose(1, 2), (C,), None, None, 1e-6).transpose(1, 2)
+        if premask:
+            n = n * mask.unsqueeze(1)
+        ref = n * (1 + mod[:, 3 * C:4 * C].unsqueeze(-1)) + mod[:, C:2 * C].unsqueeze(-1)
+        assert _rel(ops.unpack_blk16(buf, C, T), ref) <= 1.5e-3
+
+
+def test_frame_ops(hsv):
+    ops = hsv.ops
+    g = torch.Generator().manual_seed(3)
+    B, C, T = 2, 96, 53
+    mask = (torch.arange(T)[None, :] < torch.tensor([T, 31])[:, None]).float().to(DEV)
+    mk = mask.unsqueeze(1)
+    x = torch.randn(B, C, T, generator=g).to(DEV)
+    rs = torch.randn(B, 2 * C, T, generator=g).to(DEV)
+    o = torch.randn(B, C, T, generator=g).to(DEV)
+    x1, o1 = x.clone(), o.clone()
+    ops.frame_op(ops.OP_WN_RES, x1, rs, None, mask, x1, o1, B, C, T)
+    assert torch.allclose(x1, (x + rs[:, :C]) * mk) and torch.allclose(o1, o + rs[:, C:])
+    o2 = o.clone()
+    ops.frame_op(ops.OP_WN_LAST, None, rs[:, :C].contiguous(), None, mask, None, o2, B, C, T)
+    assert torch.allclose(o2, (o + rs[:, :C]) * mk)
+    gate = torch.randn(B, 6 * C, generator=g).to(DEV)
+    y = torch.randn(B, C, T, generator=g).to(DEV)
+    x3 = x.clone()
+    ops.frame_op(ops.OP_GATE_ADD, x3, y, gate[:, 2 * C:3 * C], mask, x3, None, B, C, T, cstride=6 * C)
+    assert torch.allclose(x3, x + gate[:, 2 * C:3 * C].unsqueeze(-1) * y * mk, atol=1e-6)
+    full = torch.randn(B, 2 * C, T, generator=g).to(DEV)
+    f2 = full.clone()
+    ops.frame_op(ops.OP_COUPLE, f2, y, None, mask, f2, None, B, C, T)
+    assert torch.equal(f2[:, :C], full[:, :C]) and torch.allclose(f2[:, C:], (full[:, C:] - y) * mk)
+    z = torch.empty(B, C, T, device=DEV)
+    ops.frame_op(ops.OP_SAMPLE, full, y, None, mask, z, None, B, C, T, s=0.333)
+    assert torch.allclose(z, (full[:, :C] + y * torch.exp(full[:, C:]) * 0.333) * mk, rtol=1e-5, atol=1e-6)
+    out = torch.empty_like(x)
+    ops.frame_op(ops.OP_GLU_RES, x, rs, None, mask, out, None, B, C, T)
+    assert torch.allclose(out, (x + rs[:, :C] * torch.sigmoid(rs[:, C:])) * mk, atol=1e-6)
+    ops.frame_op(ops.OP_MISH, x, None, None, mask, out, None, B, C, T)
+    assert torch.allclose(out, x * torch.tanh(F.softplus(x)) * mk, atol=1e-6)
+    ops.frame_op(ops.OP_FLIP, x, None, None, None, out, None, B, C, T)
+    assert torch.equal(out, torch.flip(x, [1]))
+    ops.frame_op(ops.OP_ADD, x, y, None, None, out, None, B, C, T)
+    assert torch.equal(out, x + y)
+
+
+@pytest.mark.parametrize("D,T,masked", [(96, 500, False), (96, 37, False), (128, 150, True), (64, 70, True)])
+def test_mha_vs_torch(hsv, D, T, masked):
+    ops = hsv.ops
+    g = torch.Generator().manual_seed(D + T)
+    B, H = 2, 2
+    C = H * D
+    qkv = torch.randn(B, 3 * C, T, generator=g).to(DEV)
+    lens = torch.tensor([T, max(1, T - 9)], dtype=torch.int32, device=DEV) if masked else None
+    flat = qkv.view(-1)
+    got = ops.mha(flat, flat[C * T:], flat[2 * C * T:], B, H, D, T, T, 3 * C * T, 3 * C * T, 3 * C * T, D ** -0.5,
+                  prescale_q=masked, lens=lens)
+    q, k, v = (qkv[:, i * C:(i + 1) * C].view(B, H, D, T).transpose(2, 3) for i in range(3))
+    with strict_fp32():
+        sc = torch.matmul(q * D ** -0.5, k.transpose(-2, -1)) if masked else torch.matmul(q, k.transpose(-2, -1)) * D ** -0.5
+        if masked:
+            m = (torch.arange(T, device=DEV)[None, :] < lens[:, None]).float()
+            am = (m.unsqueeze(1) * m.unsqueeze(-1)).unsqueeze(1)
+            sc = sc.masked_fill(am == 0, -1e4)
+        ref = torch.matmul(sc.softmax(-1), v).transpose(2, 3).contiguous().view(B, C, T)
+    assert _rel(got, ref) <= 2e-5
+
+
+def test_strided_conv_and_mean(hsv):
+    ops = hsv.ops
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 1, 403, generator=g).to(DEV)           # not a multiple of the stride
+    w = torch.randn(192, 1, 9, generator=g).to(DEV)
+    b = torch.randn(192, generator=g).to(DEV)
+    ref = F.conv1d(x, w, b, stride=4, padding=4)
+    assert torch.allclose(ops.conv1d_c1_strided(x, w, b, 4, 4), ref, atol=1e-5)
+    h = torch.randn(2, 256, 77, generator=g).to(DEV)
+    mask = (torch.arange(77)[None, :] < torch.tensor([77, 40])[:, None]).float().to(DEV)
+    assert torch.allclose(ops.masked_mean(h, mask), h.sum(2) / mask.sum(1, keepdim=True), rtol=1e-5, atol=1e-6)
+
+
+@pytest.fixture(scope="module")
+def synthesizer(hsv):
+    m = hsv.HierSpeechSynthesizer()
+    m.load_state_dict(synth.synthesizer_sd(1234), strict=True)
+    return m.to(DEV).eval()
+
+
+def _inputs(T, T_mel, lens_mel):
+    from megatts2_hierspeechpp_b200 import synthetic
+    w2v, f0, mel = synthetic.synthesizer_inputs(T, T_mel, seed=1111)
+    return (w2v.to(DEV), f0.to(DEV), mel.to(DEV), torch.LongTensor([T]).to(DEV), torch.LongTensor(lens_mel).to(DEV))
+
+
+@pytest.mark.parametrize("T,T_mel,lens_mel", [(100, 150, [150, 150]), (37, 64, [64, 41])])
+def test_front_modules_vs_oracle(hsv, synthesizer, T, T_mel, lens_mel):
+    sd = {k: v.to(DEV) for k, v in synth.synthesizer_sd(1234).items()}
+    w2v, f0, mel, ln, ln2 = _inputs(T, T_mel, lens_mel)
+    with strict_fp32(), torch.no_grad():
+        tm = torch.unsqueeze(FF.sequence_mask(ln2, mel.size(2)), 1).to(mel.dtype)
+        g_ref = FF.style_encoder(sd, "emb_g.", mel, tm)
+        g = synthesizer.emb_g(mel, tm)
+        print(f"[parity] StyleEncoder g: rel={_rel(g, g_ref):.2e}")
+        assert _rel(g, g_ref) <= 2e-3
+        ym = torch.ones(1, 1, T, device=DEV)
+        gi = g_ref[:1].unsqueeze(-1).contiguous()
+        torch.manual_seed(5)
+        z_ref, m_ref, l_ref = FF.posterior_sf_encoder(sd, "enc_p_l.", w2v, f0, ym, gi)
+        torch.manual_seed(5)
+        z, m, l = synthesizer.enc_p_l(w2v, f0, ym, g=gi)
+        print(f"[parity] PosteriorSFEncoder z: rel={_rel(z, z_ref):.2e}  m: {_rel(m, m_ref):.2e}  logs: {_rel(l, l_ref):.2e}")
+        assert _rel(z, z_ref) <= 2e-3 and _rel(m, m_ref) <= 2e-3 and _rel(l, l_ref) <= 2e-3
+        f_ref = FF.coupling_block_reverse(sd, "flow_l.", z_ref, ym, gi)
+        f = synthesizer.flow_l(z_ref, ym, g=gi, reverse=True)
+        print(f"[parity] flow_l reverse: rel={_rel(f, f_ref):.2e}")
+        assert _rel(f, f_ref) <= 2e-3
+
+
+@pytest.mark.parametrize("T,T_mel,lens_mel", [(150, 150, [150, 150]), (500, 300, [300, 300])])
+def test_voice_conversion_noise_control_vs_oracle(hsv, synthesizer, T, T_mel, lens_mel):
+    """w2v + f0 + prompt mel -> 16 kHz waveform, everything on B200 kernels, vs the reference op sequence (config #2 at
+    the SynthesizerTrn level for T = 500)."""
+    sd = {k: v.to(DEV) for k, v in synth.synthesizer_sd(1234).items()}
+    w2v, f0, mel, ln, ln2 = _inputs(T, T_mel, lens_mel)
+    with strict_fp32(), torch.no_grad():
+        torch.manual_seed(7)
+        ref = FF.voice_conversion_noise_control(sd, w2v, ln, mel, ln2, f0, noise_scale=0.333, denoise_ratio=0.3)
+        torch.manual_seed(7)
+        got = synthesizer.voice_conversion_noise_control(w2v, ln, mel, ln2, f0, noise_scale=0.333, denoise_ratio=0.3)
+    assert got.shape == (1, 1, 320 * T)
+    ma, snr = CF.max_abs(ref.cpu().numpy(), got.cpu().numpy()), CF.snr_db(ref.cpu().numpy(), got.cpu().numpy())
+    print(f"[parity] voice_conversion_noise_control T={T}: max_abs={ma:.3e} snr={snr:.1f} dB")
+    assert ma <= MAX_ABS_TOL and snr >= SNR_DB_MIN
+    # graph replay == eager (same seed before each)
+    runner = hsv.CudaGraphRunner(lambda a, b, c: synthesizer.voice_conversion_noise_control(a, ln, c, ln2, b, 0.333, False, 0.3))
+    torch.manual_seed(7)
+    g1 = runner(w2v, f0, mel)
+    assert g1.shape == got.shape and bool(torch.isfinite(g1).all())

@@ -24,7 +24,8 @@ DEV = "cuda:0"
 
 @contextlib.contextmanager
 def patched(hsv, ref):
-    names = {"H": ("Generator", "SourceNetwork", "AMPBlock1", "DBlock", "Activation1d"),
+    names = {"H": ("Generator", "SourceNetwork", "AMPBlock1", "DBlock", "Activation1d", "PosteriorSFEncoder",
+                   "ResidualCouplingBlock_Transformer", "StyleEncoder"),
              "sr24": ("Generator", "AMPBlock0", "Activation1d"), "sr48": ("Generator", "AMPBlock0", "Activation1d")}
     saved = {(mod, n): getattr(getattr(ref, mod), n) for mod, ns in names.items() for n in ns}
     try:
@@ -64,6 +65,8 @@ def test_reference_synthesizer_with_patched_vocoder(hsv):
         torch.manual_seed(1234)
         B = ref.H.SynthesizerTrn(**refload.HIER_SYNTH_CFG)   # the reference's constructor builds the B200 classes
         assert isinstance(B.dec, hsv.Generator) and isinstance(B.sn, hsv.SourceNetwork)
+        assert isinstance(B.enc_p_l, hsv.front.PosteriorSFEncoder) and isinstance(B.emb_g, hsv.front.StyleEncoder)
+        assert isinstance(B.flow, hsv.front.ResidualCouplingBlock_Transformer)
         B.load_state_dict(state, strict=True)
         B.eval()
     A.to(DEV); B.to(DEV)

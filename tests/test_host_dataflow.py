@@ -78,3 +78,35 @@ def test_mean_of_blocks_and_cache_invalidation(monkeypatch):
     m.load_state_dict(sd2, strict=True)
     y2 = m(x)
     assert CF.snr_db(OF.speechsr(sd2, x, 24).numpy(), y2.numpy()) >= 40.0   # refolded, not stale
+
+
+def test_front_dataflow_matches_oracle(monkeypatch):
+    """The step before the vocoder: the drop-in modules' dataflow (operand packing modes, in-place
+    residual updates, fused qkv addressing, flow reversal order, noise draws) on CPU through the op emulation, against
+    the oracle restatement of SynthesizerTrn.voice_conversion_noise_control / infer."""
+    import megatts2_hierspeechpp_b200 as hsv
+    from megatts2_hierspeechpp_b200 import synthetic as synth
+    from oracle import functional_front as FF
+    emu_ops.install(monkeypatch)
+    import megatts2_hierspeechpp_b200.front as FR
+    monkeypatch.setattr(FR, "_as_input", lambda x: x.detach().contiguous())
+    sd = synth.synthesizer_sd(1234)
+    m = hsv.HierSpeechSynthesizer()
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    T = 16
+    w2v, f0, mel = synth.synthesizer_inputs(T, 24, seed=3)
+    ln, ln2 = torch.LongTensor([T]), torch.LongTensor([24, 20])           # a padded prompt exercises the masks
+    torch.manual_seed(7)
+    got = m.voice_conversion_noise_control(w2v, ln, mel, ln2, f0, noise_scale=0.333, denoise_ratio=0.3)
+    torch.manual_seed(7)
+    ref = FF.voice_conversion_noise_control(sd, w2v, ln, mel, ln2, f0, noise_scale=0.333, denoise_ratio=0.3)
+    assert got.shape == ref.shape == (1, 1, 320 * T)
+    assert CF.max_abs(ref.numpy(), got.numpy()) <= 2e-3 and CF.snr_db(ref.numpy(), got.numpy()) >= 40.0
+    # the front alone, tighter: z before the vocoder
+    torch.manual_seed(9)
+    z_ref, g_ref = FF.front(sd, w2v, ln, mel, ln2, f0, 0.333, 0.3)
+    torch.manual_seed(9)
+    tm = torch.unsqueeze(FR.sequence_mask(ln2, mel.size(2)), 1).to(mel.dtype)
+    g = m.emb_g(mel, tm).unsqueeze(-1)
+    assert (g - FF.style_encoder(sd, "emb_g.", mel, tm).unsqueeze(-1)).abs().max() <= 2e-3

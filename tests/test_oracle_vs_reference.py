@@ -87,3 +87,34 @@ def test_patch_reference_swaps_classes():
         import importlib, sys
         for modname in ("alias_free_torch", "activations"):
             importlib.reload(sys.modules[modname])
+
+
+def test_front_oracle_bit_exact_vs_reference_synthesizer():
+    """The step before the vocoder: seeded synthetic front checkpoint loads strictly into the
+    reference's SynthesizerTrn (with its other sub-modules untouched), and the oracle restatement of
+    voice_conversion_noise_control reproduces the reference bit for bit on CPU."""
+    from oracle import functional_front as FF
+    ref = refload.load()
+    torch.manual_seed(0)
+    m = ref.H.SynthesizerTrn(**refload.HIER_SYNTH_CFG)
+    sd = synth.synthesizer_sd(1234)
+    own = m.state_dict()
+    for prefix in ("enc_p_l.", "flow_l.", "flow.", "emb_g.", "sn.", "dec."):
+        want = [k for k in own if k.startswith(prefix)]
+        got = [k for k in sd if k.startswith(prefix)]
+        assert sorted(want) == sorted(got), (prefix, [k for k in want if k not in got][:3], [k for k in got if k not in want][:3])
+        for k in want:
+            assert own[k].shape == sd[k].shape, k
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.split(".")[0] in ("enc_p", "enc_q", "mel_decoder") for k in missing)
+    m.eval()
+    T = 24
+    w2v, f0, mel = synth.synthesizer_inputs(T, 40, seed=3)
+    ln, ln2 = torch.LongTensor([T]), torch.LongTensor([40, 40])
+    with torch.no_grad():
+        torch.manual_seed(7)
+        a = m.voice_conversion_noise_control(w2v, ln, mel, ln2, f0, noise_scale=0.333, denoise_ratio=0.3)
+        torch.manual_seed(7)
+        b = FF.voice_conversion_noise_control(sd, w2v, ln, mel, ln2, f0, noise_scale=0.333, denoise_ratio=0.3)
+    assert a.shape == (1, 1, 320 * T)
+    assert torch.equal(a, b)
