@@ -67,13 +67,15 @@ def test_b200_modules_are_drop_in_for_reference_state_dicts():
 def test_patch_reference_swaps_classes():
     import megatts2_hierspeechpp_b200 as hsv
     ref = refload.load()
-    saved = {n: getattr(ref.H, n) for n in ("Generator", "SourceNetwork", "AMPBlock1", "DBlock", "Activation1d")}
+    saved = {n: getattr(ref.H, n) for n in ("Generator", "SourceNetwork", "AMPBlock1", "DBlock", "Activation1d",
+                                            "PosteriorSFEncoder", "ResidualCouplingBlock_Transformer", "StyleEncoder")}
     saved_sr = {n: getattr(ref.sr24, n) for n in ("Generator", "AMPBlock0", "Activation1d")}
     saved_sr48 = {n: getattr(ref.sr48, n) for n in ("Generator", "AMPBlock0", "Activation1d")}
     try:
         patched = hsv.patch_reference()
         assert "hierspeechpp_speechsynthesizer.Generator" in patched
         assert ref.H.Generator is hsv.Generator and ref.sr24.Generator is hsv.SpeechSR24Generator
+        assert ref.H.PosteriorSFEncoder is hsv.front.PosteriorSFEncoder and ref.H.StyleEncoder is hsv.front.StyleEncoder
         m = ref.sr24.SynthesizerTrn(100, 40, **synth.SR_CFG)          # the reference's own SynthesizerTrn
         assert isinstance(m.dec, hsv.SpeechSR24Generator)
         m.load_state_dict(refload.load_speechsr(24).state_dict(), strict=True)
