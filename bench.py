@@ -67,6 +67,17 @@ def make_workload(args, rank):
         return dict(name=f"config4_vocoder->speechsr24_B{args.batch}x{args.seconds:g}s", kind="chain24", sd=sd,
                     host_inputs=[z, g], audio_seconds=args.batch * T / 50.0, which=24,
                     data="synthetic z, g as config #2; vocoder random init (seed 1234) + bundled speechsr24k checkpoint")
+    if args.workload == "synth":
+        # config #2 at the SynthesizerTrn level: w2v + f0 + prompt mel -> 16 kHz wav through
+        # voice_conversion_noise_control: StyleEncoder, PosteriorSFEncoder, both reverse flows, sn, dec
+        if args.batch != 1:
+            raise SystemExit("the synth workload is the reference's single-utterance call (B = 1)")
+        T = int(round(args.seconds * 50))
+        w2v, f0, mel = synth.synthesizer_inputs(T, 150, seed=1111 + rank)
+        return dict(name=f"hierspeechpp_synthesizer_vc_noise_control_B1x{args.seconds:g}s", kind="synth",
+                    sd=synth.synthesizer_sd(1234), host_inputs=[w2v, f0, mel], audio_seconds=T / 50.0, T=T,
+                    data="synthetic w2v~N(0,1) [1,1024,T], f0=log(hz+1) 30 % unvoiced [1,1,4T], prompt mel~N(-4,2) [2,80,150]; "
+                         "random-init weights (seed 1234; flows' post / adaLN small random instead of zero)")
     which = 48 if args.workload == "speechsr48" else 24
     L = int(round(args.seconds * 16000))
     x = synth.speechsr_input(args.batch, L, seed=1111 + rank)
@@ -85,6 +96,11 @@ def oracle_forward(wl, device="cpu"):
     ins = [t.to(device) for t in wl["host_inputs"]]
     if wl["kind"] == "vocoder":
         return lambda: OF.vocoder(sd, ins[0], ins[1])
+    if wl["kind"] == "synth":
+        from oracle import functional_front as FF
+        T = wl["T"]
+        ln, ln2 = torch.LongTensor([T]).to(device), torch.LongTensor([150, 150]).to(device)
+        return lambda: FF.voice_conversion_noise_control(sd, ins[0], ln, ins[2], ln2, ins[1], 0.333, 0.3)
     if wl["kind"] == "chain24":
         sv = {k[len("vocoder."):]: v for k, v in sd.items() if k.startswith("vocoder.")}
         ss = {k[len("sr."):]: v for k, v in sd.items() if k.startswith("sr.")}
@@ -101,6 +117,13 @@ def reference_forward(wl):
             ref = refload.load()
             if wl["kind"] == "chain24":
                 raise RuntimeError("chain workload: oracle port (the reference chains the two models in a script)")
+            if wl["kind"] == "synth":
+                m = ref.H.SynthesizerTrn(**refload.HIER_SYNTH_CFG)
+                m.load_state_dict(wl["sd"], strict=False)
+                m.eval()
+                w2v, f0, mel = wl["host_inputs"]
+                ln, ln2 = torch.LongTensor([wl["T"]]), torch.LongTensor([150, 150])
+                return (lambda: m.voice_conversion_noise_control(w2v, ln, mel, ln2, f0, 0.333, False, 0.3)), "reference"
             if wl["kind"] == "vocoder":
                 from megatts2_hierspeechpp_b200.config import HIER_CFG
                 G = ref.H.Generator(**HIER_CFG)
@@ -229,6 +252,24 @@ def build_model(wl, device):
         m = hsv.Vocoder()
     elif wl["kind"] == "chain24":
         m = hsv.VocoderSR(24)
+    elif wl["kind"] == "synth":
+        class SynthStep(torch.nn.Module):
+            """voice_conversion_noise_control(w2v, [T], mel, [150, 150], f0, 0.333, denoise_ratio 0.3) as a tensor->tensor
+            callable (lengths are host constants, as in inference_plm.py:166-173)."""
+
+            def __init__(self, T):
+                super().__init__()
+                self.net = hsv.HierSpeechSynthesizer()
+                self.T = T
+
+            def load_state_dict(self, sd, strict=True):
+                return self.net.load_state_dict(sd, strict=strict)
+
+            def forward(self, w2v, f0, mel):
+                ln = torch.full((1,), self.T, dtype=torch.long, device=w2v.device)
+                ln2 = torch.full((2,), mel.shape[-1], dtype=torch.long, device=w2v.device)
+                return self.net.voice_conversion_noise_control(w2v, ln, mel, ln2, f0, 0.333, False, 0.3)
+        m = SynthStep(wl["T"])
     else:
         m = (hsv.SpeechSR48 if wl["which"] == 48 else hsv.SpeechSR24)(100, 40, **hsv.SR_CFG)
     m.load_state_dict(wl["sd"], strict=True)
@@ -241,6 +282,9 @@ FAMILIES = (
     ("conv_umma", ("conv_umma",), ("conv1d_umma", "conv_transpose1d_umma", "act_conv1d_umma")),
     ("act1d", ("act1d_kernel", "act1d_mma_kernel"), ("act1d", "act1d_blk16")),
     ("pack_blk16", ("pack_blk16_kernel",), ("pack_blk16",)),
+    ("frame_ops", ("pack_act_kernel", "ln_mod_kernel", "frame_op_kernel", "mha_kernel", "conv1d_c1_strided",
+                   "masked_mean_kernel", "mean_div_kernel", "absmax_kernel", "pcm16_kernel", "rowmax_kernel"),
+     ("pack_blk16_act", "ln_mod_blk16", "frame_op", "mha", "conv1d_c1_strided", "masked_mean")),
     ("small_fp32", ("conv1d_thin", "conv1d_rowdot", "conv1d_tiled", "conv_transpose1d_kernel", "add3_bcast",
                     "nearest_gather", "sr_pre_interp", "weight_norm_fold", "pack_weight"),
      ("conv1d_direct", "conv_transpose1d", "add3_bcast", "nearest_gather", "sr_pre_interp")),
@@ -359,6 +403,14 @@ def cupti_step_profile(step_fn, flush, reps=3):
             for e in prof.events():
                 if "cuda" in str(getattr(e, "device_type", "")).lower():
                     evs.append((e.name, float(e.time_range.start), float(e.time_range.end - e.time_range.start)))
+        if os.environ.get("BENCH_DUMP_KERNELS"):          # debugging aid: every device kernel of the profiled replays
+            agg = {}
+            for n, st, du in evs:
+                a = agg.setdefault(n[:90], [0, 0.0])
+                a[0] += 1; a[1] += du
+            with open(os.environ["BENCH_DUMP_KERNELS"], "w") as f:
+                for n, (c, du) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                    f.write(f"{du / reps:10.1f} us/step  n={c / reps:7.1f}  avg={du / c:7.2f} us  {n}\n")
         evs = sorted((n, st, du) for n, st, du in evs if family_of_kernel(n) is not None)
         if not evs:
             return None
@@ -886,7 +938,7 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="vocoder", choices=["vocoder", "speechsr48", "speechsr24", "chain24"])
+    ap.add_argument("--workload", default="vocoder", choices=["vocoder", "speechsr48", "speechsr24", "chain24", "synth"])
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--seconds", type=float, default=10.0)
     ap.add_argument("--no-graph", action="store_true")

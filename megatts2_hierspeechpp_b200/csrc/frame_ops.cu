@@ -200,97 +200,193 @@ __global__ void frame_op_kernel(int op, const float *a, const float *__restrict_
 
 // ---- multi-head attention, fp32, online softmax -------------------------------------------------------------------
 // q, k, v: channel-major [heads*D, T] per batch item (time contiguous), batch strides in elements; out [B, heads*D, Tq].
-// CTA = 16 query rows of one (batch, head); keys in tiles of 32.
-constexpr int MHA_Q = 16, MHA_K = 32, MHA_THREADS = 128;   // static shared memory stays under 48 KB for D = 128
+// CTA = 4 warps, each warp owns RW query rows of one (batch, head) outright (no cross-warp traffic); keys in tiles of
+// 64, double-buffered with cp.async (16-byte copies: the channel-major layout IS the [d][t] layout both products
+// want, so a tile is 2*D row segments of 256 bytes).
+//   S = Q K^T : lane = 2 keys, RW rows -> per d one broadcast LDS of the rows + one LDS.64 of the keys, 2*RW FMAs
+//   softmax   : a row's 64 scores live in the 32 lanes of its warp -> shuffles
+//   O += P V  : lane = dims {lane, lane+32, ...}, four keys per step: one LDS.128 of V per dim (16-byte chunks of a
+//               V row XOR-swizzled with d, so the 8 lanes of a quarter-warp hit 8 different chunks) and 4*RW
+//               broadcast P values -> 4*RW*D/32 FMAs per 3-4 shared loads
+constexpr int MHA_K = 64, MHA_THREADS = 128;
 
-template <int D>
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int D, int RW>
 __global__ void __launch_bounds__(MHA_THREADS) mha_kernel(const float *__restrict__ q, const float *__restrict__ k,
                                                           const float *__restrict__ v, float *__restrict__ out,
                                                           const int *__restrict__ lens, int Tq, int Tk, int64_t qbs,
-                                                          int64_t kbs, int64_t vbs, int heads, float scale, int prescale) {
-  __shared__ float Qs[MHA_Q][D];
-  __shared__ float Ks[MHA_K][D + 1];
-  __shared__ float Vs[MHA_K][D];
-  __shared__ float S[MHA_Q][MHA_K + 1];
-  __shared__ float row_m[MHA_Q], row_l[MHA_Q], row_c[MHA_Q];
-  const int tid = threadIdx.x;
-  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * MHA_Q;
+                                                          int64_t kbs, int64_t vbs, int heads, float scale, int prescale,
+                                                          int fast) {
+  constexpr int QT = 4 * RW;            // query rows per CTA
+  constexpr int DL = D / 32;            // output dims per lane
+  constexpr int TILE = D * MHA_K;       // floats per K (or V) tile
+  extern __shared__ __align__(16) float sm[];
+  float *Qs = sm;                       // [D][QT]
+  float *KV = Qs + D * QT;              // 2 stages x (K tile [D][64], V tile [D][64] chunk-swizzled)
+  float *Ps = KV + 4 * TILE;            // [4 warps][MHA_K][RW]
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * QT;
   const float *qb = q + (int64_t)b * qbs + (int64_t)h * D * Tq;
   const float *kb = k + (int64_t)b * kbs + (int64_t)h * D * Tk;
   const float *vb = v + (int64_t)b * vbs + (int64_t)h * D * Tk;
   const int len = lens ? lens[b] : 0x7fffffff;
-  for (int idx = tid; idx < MHA_Q * D; idx += MHA_THREADS) {
-    const int d = idx / MHA_Q, i = idx - d * MHA_Q;
+  const int ntiles = (Tk + MHA_K - 1) / MHA_K;
+
+  auto load_tile = [&](int t, int stage) {
+    float *Kd = KV + stage * 2 * TILE, *Vd = Kd + TILE;
+    const int k0 = t * MHA_K;
+    if (fast && k0 + MHA_K <= Tk) {
+      for (int c = tid; c < D * 16; c += MHA_THREADS) {          // 16-byte chunks: 16 per row
+        const int d = c >> 4, ch = c & 15;
+        cp_async16(Kd + d * MHA_K + ch * 4, kb + (int64_t)d * Tk + k0 + ch * 4);
+        cp_async16(Vd + d * MHA_K + ((ch ^ (d & 15)) << 2), vb + (int64_t)d * Tk + k0 + ch * 4);
+      }
+    } else {                                                     // ragged last tile / unaligned tensors
+      for (int idx = tid; idx < TILE; idx += MHA_THREADS) {
+        const int d = idx / MHA_K, j = idx - d * MHA_K;
+        const bool okj = k0 + j < Tk;
+        Kd[idx] = okj ? __ldg(kb + (int64_t)d * Tk + k0 + j) : 0.f;
+        Vd[d * MHA_K + ((((j >> 2) ^ (d & 15)) << 2) | (j & 3))] = okj ? __ldg(vb + (int64_t)d * Tk + k0 + j) : 0.f;
+      }
+    }
+    cp_async_commit();
+  };
+
+  load_tile(0, 0);
+  for (int idx = tid; idx < D * QT; idx += MHA_THREADS) {
+    const int d = idx / QT, i = idx - d * QT;
     const float val = (q0 + i < Tq) ? __ldg(qb + (int64_t)d * Tq + q0 + i) : 0.f;
-    Qs[i][d] = prescale ? val * scale : val;
+    Qs[idx] = prescale ? val * scale : val;
   }
-  if (tid < MHA_Q) {
-    row_m[tid] = -INFINITY;
-    row_l[tid] = 0.f;
-  }
-  constexpr int OPT = MHA_Q * D / MHA_THREADS;   // outputs per thread
-  float acc[OPT];
+  float m_run[RW], l_run[RW], acc[RW][DL];
 #pragma unroll
-  for (int r = 0; r < OPT; ++r) acc[r] = 0.f;
-  for (int k0 = 0; k0 < Tk; k0 += MHA_K) {
-    __syncthreads();
-    for (int idx = tid; idx < MHA_K * D; idx += MHA_THREADS) {
-      const int d = idx / MHA_K, j = idx - d * MHA_K;
-      const bool okj = k0 + j < Tk;
-      Ks[j][d] = okj ? __ldg(kb + (int64_t)d * Tk + k0 + j) : 0.f;
-      Vs[j][d] = okj ? __ldg(vb + (int64_t)d * Tk + k0 + j) : 0.f;
+  for (int r = 0; r < RW; ++r) {
+    m_run[r] = -INFINITY;
+    l_run[r] = 0.f;
+#pragma unroll
+    for (int j = 0; j < DL; ++j) acc[r][j] = 0.f;
+  }
+  float *Pw = Ps + w * MHA_K * RW;
+  for (int t = 0; t < ntiles; ++t) {
+    const int k0 = t * MHA_K;
+    if (t + 1 < ntiles) {
+      load_tile(t + 1, (t + 1) & 1);     // its buffer was released by the barrier at the end of iteration t - 1
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
-    {
-      constexpr int RP = MHA_THREADS / MHA_K;               // row phases: 4 x 32 keys
-      const int j = tid & (MHA_K - 1), i0 = tid / MHA_K;
+    const float *Ks = KV + (t & 1) * 2 * TILE, *Vs = Ks + TILE;
+    // ---- S: RW rows x 2 keys per lane ----
+    float s0[RW], s1[RW];
 #pragma unroll
-      for (int r = 0; r < MHA_Q / RP; ++r) {
-        const int i = i0 + RP * r;
-        float sacc = 0.f;
+    for (int r = 0; r < RW; ++r) s0[r] = s1[r] = 0.f;
 #pragma unroll 8
-        for (int d = 0; d < D; ++d) sacc = fmaf(Qs[i][d], Ks[j][d], sacc);
-        if (!prescale) sacc *= scale;
-        if (lens && (k0 + j >= len || q0 + i >= len)) sacc = -1e4f;    // masked_fill(mask == 0, -1e4)
-        if (k0 + j >= Tk) sacc = -INFINITY;                            // padding of the last key tile
-        S[i][j] = sacc;
+    for (int d = 0; d < D; ++d) {
+      const float2 kk = *reinterpret_cast<const float2 *>(Ks + d * MHA_K + 2 * lane);
+      float qq[RW];
+      if (RW == 4) {
+        const float4 tq = *reinterpret_cast<const float4 *>(Qs + d * QT + 4 * w);
+        qq[0] = tq.x; qq[1] = tq.y; qq[2 % RW] = tq.z; qq[3 % RW] = tq.w;
+      } else {
+        const float2 tq = *reinterpret_cast<const float2 *>(Qs + d * QT + 2 * w);
+        qq[0] = tq.x; qq[1 % RW] = tq.y;
+      }
+#pragma unroll
+      for (int r = 0; r < RW; ++r) {
+        s0[r] = fmaf(qq[r], kk.x, s0[r]);
+        s1[r] = fmaf(qq[r], kk.y, s1[r]);
       }
     }
-    __syncthreads();
-    if (tid < MHA_Q) {
-      const int i = tid;
-      float mx = row_m[i];
-      for (int j = 0; j < MHA_K; ++j) mx = fmaxf(mx, S[i][j]);
-      const float corr = expf(row_m[i] - mx);
-      float l = row_l[i] * corr;
-      for (int j = 0; j < MHA_K; ++j) {
-        const float p = expf(S[i][j] - mx);
-        S[i][j] = p;
-        l += p;
-      }
-      row_m[i] = mx;
-      row_l[i] = l;
-      row_c[i] = corr;
-    }
-    __syncthreads();
+    // ---- online softmax per row (a row = one warp's 64 values) ----
+    const int j0 = k0 + 2 * lane, j1 = j0 + 1;
 #pragma unroll
-    for (int r = 0; r < OPT; ++r) {
-      const int idx = tid + MHA_THREADS * r;
-      const int i = idx / D, d = idx - i * D;
-      float o = acc[r] * row_c[i];
-#pragma unroll 8
-      for (int j = 0; j < MHA_K; ++j) o = fmaf(S[i][j], Vs[j][d], o);
-      acc[r] = o;
+    for (int r = 0; r < RW; ++r) {
+      const int qi = q0 + RW * w + r;
+      float a = prescale ? s0[r] : s0[r] * scale, c = prescale ? s1[r] : s1[r] * scale;
+      if (lens && (qi >= len || j0 >= len)) a = -1e4f;     // masked_fill(mask == 0, -1e4)
+      if (lens && (qi >= len || j1 >= len)) c = -1e4f;
+      if (j0 >= Tk) a = -INFINITY;                         // padding of the last key tile
+      if (j1 >= Tk) c = -INFINITY;
+      float mx = fmaxf(a, c);
+#pragma unroll
+      for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const float m_new = fmaxf(m_run[r], mx);
+      const float corr = expf(m_run[r] - m_new);
+      const float p0 = expf(a - m_new), p1 = expf(c - m_new);
+      float sum = p0 + p1;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      l_run[r] = l_run[r] * corr + sum;
+      m_run[r] = m_new;
+#pragma unroll
+      for (int j = 0; j < DL; ++j) acc[r][j] *= corr;
+      *reinterpret_cast<float2 *>(Pw + r * MHA_K + 2 * lane) = make_float2(p0, p1);      // Pw[r][key]
     }
+    __syncwarp();
+    // ---- O += P V, four keys per step ----
+#pragma unroll 2
+    for (int j4 = 0; j4 < MHA_K / 4; ++j4) {
+      float4 pp[RW];
+#pragma unroll
+      for (int r = 0; r < RW; ++r) pp[r] = *reinterpret_cast<const float4 *>(Pw + r * MHA_K + 4 * j4);   // broadcast
+#pragma unroll
+      for (int e = 0; e < DL; ++e) {
+        const int d = lane + 32 * e;
+        const float4 vv = *reinterpret_cast<const float4 *>(Vs + d * MHA_K + ((j4 ^ (d & 15)) << 2));
+#pragma unroll
+        for (int r = 0; r < RW; ++r) {
+          acc[r][e] = fmaf(pp[r].x, vv.x, acc[r][e]);
+          acc[r][e] = fmaf(pp[r].y, vv.y, acc[r][e]);
+          acc[r][e] = fmaf(pp[r].z, vv.z, acc[r][e]);
+          acc[r][e] = fmaf(pp[r].w, vv.w, acc[r][e]);
+        }
+      }
+    }
+    __syncthreads();     // this stage's K / V may be overwritten by the load issued in the next iteration
   }
-  __syncthreads();
   float *ob = out + ((int64_t)b * heads + h) * D * Tq;
 #pragma unroll
-  for (int r = 0; r < OPT; ++r) {
-    const int idx = tid + MHA_THREADS * r;
-    const int i = idx / D, d = idx - i * D;
-    if (q0 + i < Tq) ob[(int64_t)d * Tq + q0 + i] = acc[r] / row_l[i];
+  for (int r = 0; r < RW; ++r) {
+    const int qi = q0 + RW * w + r;
+    if (qi < Tq) {
+      const float inv = 1.0f / l_run[r];
+#pragma unroll
+      for (int e = 0; e < DL; ++e) ob[(int64_t)(lane + 32 * e) * Tq + qi] = acc[r][e] * inv;
+    }
   }
+}
+
+template <int D, int RW>
+int mha_launch(const float *q, const float *k, const float *v, float *out, const int *lens, int B, int heads, int Tq,
+               int Tk, int64_t qbs, int64_t kbs, int64_t vbs, float scale, int prescale, cudaStream_t st) {
+  constexpr int QT = 4 * RW;
+  const size_t smem = sizeof(float) * (D * QT + 4 * D * MHA_K + 4 * MHA_K * RW);
+  static bool done = false;
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(mha_kernel<D, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      hsv::set_error("mha: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+      return HSV_ERR_CUDA;
+    }
+    done = true;
+  }
+  // 16-byte cp.async needs every K / V row segment aligned: Tk % 4 == 0, aligned bases and batch strides
+  auto al = [](const void *p_) { return (reinterpret_cast<uintptr_t>(p_) & 15) == 0; };
+  const int fast = (Tk % 4 == 0) && al(k) && al(v) && (kbs % 4 == 0) && (vbs % 4 == 0);
+  dim3 grid((unsigned)((Tq + QT - 1) / QT), (unsigned)heads, (unsigned)B);
+  mha_kernel<D, RW><<<grid, MHA_THREADS, smem, st>>>(q, k, v, out, lens, Tq, Tk, qbs, kbs, vbs, heads, scale, prescale, fast);
+  return hsv::check_launch("mha");
 }
 
 // Conv1d with ONE input channel and a stride (PosteriorSFEncoder.pre_filter: Conv1d(1, 192, 9, stride 4, padding 4),
@@ -391,12 +487,18 @@ extern "C" int hsv_mha(const float *q, const float *k, const float *v, float *ou
   HSV_REQUIRE(q && k && v && out, "mha: null pointer");
   HSV_REQUIRE(D == 96 || D == 128 || D == 64, "mha: head dim must be 64, 96 or 128 (D=%d)", D);
   HSV_REQUIRE(Tk > 0 && heads > 0 && heads <= 65535 && B <= 65535, "mha: bad shape");
-  dim3 grid((unsigned)((Tq + MHA_Q - 1) / MHA_Q), (unsigned)heads, (unsigned)B);
   cudaStream_t st = hsv::as_stream(stream);
-  if (D == 96) mha_kernel<96><<<grid, MHA_THREADS, 0, st>>>(q, k, v, out, lens, Tq, Tk, q_bstride, k_bstride, v_bstride, heads, scale, prescale_q);
-  else if (D == 128) mha_kernel<128><<<grid, MHA_THREADS, 0, st>>>(q, k, v, out, lens, Tq, Tk, q_bstride, k_bstride, v_bstride, heads, scale, prescale_q);
-  else mha_kernel<64><<<grid, MHA_THREADS, 0, st>>>(q, k, v, out, lens, Tq, Tk, q_bstride, k_bstride, v_bstride, heads, scale, prescale_q);
-  return hsv::check_launch("mha");
+  // few (batch, head, query tile) items: 8-row tiles spread the work over more SMs
+  const bool small = (int64_t)B * heads * ((Tq + 15) / 16) < 148;
+#define HSV_MHA(DD)                                                                                               \
+  return small ? mha_launch<DD, 2>(q, k, v, out, lens, B, heads, Tq, Tk, q_bstride, k_bstride, v_bstride, scale, \
+                                   prescale_q, st)                                                                 \
+               : mha_launch<DD, 4>(q, k, v, out, lens, B, heads, Tq, Tk, q_bstride, k_bstride, v_bstride, scale, \
+                                   prescale_q, st)
+  if (D == 96) { HSV_MHA(96); }
+  if (D == 128) { HSV_MHA(128); }
+  HSV_MHA(64);
+#undef HSV_MHA
 }
 
 extern "C" int hsv_conv1d_c1_strided(const float *x, const float *w, const float *bias, const float *mask, float *out,
