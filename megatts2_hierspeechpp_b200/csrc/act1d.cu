@@ -233,14 +233,33 @@ extern "C" int hsv_act1d_snakebeta(const float *x, void *out, const float *alpha
   HSV_REQUIRE(out_mode == 0 || out_mode == 1, "act1d: out_mode must be 0 (fp32 NCL) or 1 (fp16 blk16)");
   if (B == 0 || L == 0) return HSV_OK;
   cudaStream_t st = hsv::as_stream(stream);
-  // run length per thread: 25 outputs (5 halo steps per 25: 1.2x redundant 2x-rate work, 66 registers -> 7 CTAs
-  // per SM; measured 3.97 TB/s vs 3.85 for 33 and 3.06 for 17 on [16,32,480000]) when the tensor is large enough
-  // to still fill the GPU with the bigger tiles, else 17 (1.29x) for more CTAs (batch-1 layers: 17 beats 9/25/33)
+  // Run length per thread R (a CTA covers 8 rows x 16 R steps; every thread also evaluates a 5-step halo): longer runs
+  // waste less on the halo (R = 25: 1.2x redundant 2x-rate work, 3.97 TB/s on [16,32,480000] vs 3.06 for R = 17), shorter
+  // runs give more CTAs.  Seven CTAs fit an SM (66 registers), so the launch runs in ceil(CTAs / (148 x 7)) waves of
+  // ~(R + 5) steps each: pick the R that minimises waves x (R + 5).  This matters at batch 1: the three late stages of
+  // the vocoder are 2.56 M elements each = 1180 CTAs at R = 17, i.e. 1.14 waves (7.6 us); R = 21 fits one wave.
   const int64_t groups = ((int64_t)B * C + ROWS - 1) / ROWS;
-  const bool big = g_act_run ? g_act_run == 25 : (groups * ((L + 25 * RUNS - 1) / (25 * RUNS)) >= 16 * 148);
+  int R = 17;
+  if (g_act_run) {
+    R = g_act_run;
+  } else {
+    int64_t best = -1;
+    for (int cand : {17, 21, 25}) {
+      const int64_t ctas = groups * ((L + cand * RUNS - 1) / (cand * RUNS));
+      const int64_t waves = (ctas + 148 * 7 - 1) / (148 * 7);
+      // many waves: the halo overhead decides (cost per element ~ (R + 5) / R); few: the wave count does
+      const int64_t cost = waves * (cand + 5) * 1000 / (waves >= 4 ? cand : 1) / (waves >= 4 ? waves : 1);
+      if (best < 0 || cost < best) {
+        best = cost;
+        R = cand;
+      }
+    }
+  }
+  HSV_REQUIRE(R == 17 || R == 21 || R == 25, "act1d: run length must be 17, 21 or 25");
   if (out_mode == 0)
-    return big ? launch<25, 0>(x, out, alpha, beta, B, C, L, in_scale, st)
-               : launch<17, 0>(x, out, alpha, beta, B, C, L, in_scale, st);
+    return R == 25 ? launch<25, 0>(x, out, alpha, beta, B, C, L, in_scale, st)
+                   : (R == 21 ? launch<21, 0>(x, out, alpha, beta, B, C, L, in_scale, st)
+                              : launch<17, 0>(x, out, alpha, beta, B, C, L, in_scale, st));
   HSV_REQUIRE(C % 16 == 0, "act1d: blk16 output needs C %% 16 == 0 (C=%d)", C);
   // tensor-core FIR variant (act1d_mma.cu): every shape with at least half a tile of work per row; the CUDA-core
   // kernel keeps the tiny sequences (its tiles are 8 x 272 instead of 8 x 512)
@@ -249,6 +268,7 @@ extern "C" int hsv_act1d_snakebeta(const float *x, void *out, const float *alpha
     if (rc != 1) return rc;
     HSV_REQUIRE(g_act_mma != 2, "act1d: shape not eligible for the forced tensor-core variant");
   }
-  return big ? launch<25, 1>(x, out, alpha, beta, B, C, L, in_scale, st)
-             : launch<17, 1>(x, out, alpha, beta, B, C, L, in_scale, st);
+  return R == 25 ? launch<25, 1>(x, out, alpha, beta, B, C, L, in_scale, st)
+                 : (R == 21 ? launch<21, 1>(x, out, alpha, beta, B, C, L, in_scale, st)
+                            : launch<17, 1>(x, out, alpha, beta, B, C, L, in_scale, st));
 }

@@ -1,0 +1,34 @@
+#!/bin/bash
+# Round-2 artifacts (1 GPU): tests, smoke, default bench (+CPU reference arm), side workloads, ncu launch list of the
+# bench command, DRAM traffic of the hot kernels (stamped with HSV_HEAD), full captures of the hot kernels, sanitizer.
+mkdir -p gpurun_out
+P=gpurun_out/r02
+nvidia-smi --query-gpu=name,driver_version,clocks.max.sm,clocks.max.mem,power.limit --format=csv > ${P}_env.txt 2>&1
+timeout 1500 python -m pytest tests -q -m gpu -s > ${P}_t_all.log 2>&1; echo "tests rc=$?"; tail -3 ${P}_t_all.log; grep "\[parity\]" ${P}_t_all.log > ${P}_parity.log
+timeout 200 python __graft_entry__.py --smoke > ${P}_smoke.log 2>&1; tail -1 ${P}_smoke.log
+NCU="ncu --clock-control none"
+$NCU --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --csv --log-file ${P}_traffic_vocoder.csv python tools/profile_kernels.py forward > ${P}_p_forward.log 2>&1
+python tools/ncu_traffic.py hierspeechpp_vocoder_sn+dec_B1x10s ${P}_traffic_vocoder.csv 3 > ${P}_traffic.log 2>&1
+$NCU --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --csv --log-file ${P}_traffic_sr48.csv python tools/profile_kernels.py sr48 16 > ${P}_p_sr48.log 2>&1
+python tools/ncu_traffic.py speechsr48_B16x10s ${P}_traffic_sr48.csv 2 >> ${P}_traffic.log 2>&1
+cp profiles/ncu_traffic.json ${P}_ncu_traffic.json
+timeout 900 python bench.py > ${P}_bench.log 2> ${P}_bench.err; echo "bench rc=$?"
+timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > ${P}_bench_ref.log 2>&1; echo "ref rc=$?"
+timeout 600 python bench.py --steps 5 --warmup 3 --workload speechsr48 --batch 16 --no-cpu-baseline --no-config5 > ${P}_bench_sr48_b16.log 2>&1
+timeout 600 python bench.py --steps 5 --warmup 3 --batch 16 --no-cpu-baseline --no-config5 > ${P}_bench_voc_b16.log 2>&1
+timeout 900 python bench.py --steps 3 --warmup 3 --workload speechsr48 --batch 64 --no-cpu-baseline --no-config5 --no-gpu-eager > ${P}_bench_sr48_b64.log 2>&1
+timeout 600 python bench.py --steps 20 --warmup 5 --workload chain24 --no-config5 > ${P}_bench_chain24.log 2>&1
+timeout 600 python bench.py --steps 20 --warmup 5 --workload synth --no-config5 > ${P}_bench_synth.log 2>&1
+timeout 600 python bench.py --steps 20 --warmup 5 --workload speechsr24 --seconds 3 --no-config5 > ${P}_bench_sr24_3s.log 2>&1
+$NCU --metrics gpu__time_duration.sum --csv --log-file ${P}_launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-config5 --no-gpu-eager --no-cupti --min-seconds 0 --max-blocks 1 > ${P}_p_bench.log 2>&1
+$NCU --set full --import-source on -k regex:act1d_kernel -s 2 -c 1 -o ${P}_prof_act_sat -f python tools/profile_kernels.py act 16 32 480000 1 > ${P}_p_act.log 2>&1
+HSV_ACT_VARIANT=2 $NCU --set full --import-source on -k regex:act1d_mma -s 2 -c 1 -o ${P}_prof_actmma_sat -f python tools/profile_kernels.py act 16 32 480000 1 > ${P}_p_actmma.log 2>&1
+$NCU --set full --import-source on -k regex:conv_umma -s 2 -c 1 -o ${P}_prof_umma_c32_b16 -f python tools/profile_kernels.py umma 16 32 480000 7 3 > ${P}_p_umma1.log 2>&1
+$NCU --set full --import-source on -k regex:conv_umma -s 2 -c 1 -o ${P}_prof_umma_c128_b16 -f python tools/profile_kernels.py umma 16 128 10000 11 5 > ${P}_p_umma2.log 2>&1
+$NCU --set full --import-source on -k regex:conv_umma -s 2 -c 1 -o ${P}_prof_umma_c256_b16 -f python tools/profile_kernels.py umma 16 256 2000 11 5 > ${P}_p_umma4.log 2>&1
+$NCU --set full --import-source on -k regex:conv_umma -s 2 -c 1 -o ${P}_prof_umma_c16_b1 -f python tools/profile_kernels.py umma 1 16 160000 11 5 > ${P}_p_umma3.log 2>&1
+for tool in memcheck racecheck synccheck; do
+  timeout 900 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_target.py > ${P}_sanitize_$tool.log 2>&1
+  echo "== $tool: rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|sanitize target ok" ${P}_sanitize_$tool.log | head -4
+done
+tail -c 300 ${P}_bench.log; echo; tail -c 200 ${P}_bench_ref.log
