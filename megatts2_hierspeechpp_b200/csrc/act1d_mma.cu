@@ -85,6 +85,24 @@ __device__ __forceinline__ void block_of(int j, int &shift_rows, int &ks) {
   ks = j < 0 ? 3 : (j > 3 ? 0 : j);
 }
 
+// mbarrier wait that lets the hardware park the warp (suspend-time hint) instead of spinning through the issue slots
+// the other warps need; the iteration bound turns a protocol bug into a trap
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (uint32_t it = 0; !ok; ++it) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(100000u)
+        : "memory");
+    if (it > (1u << 22)) __trap();
+  }
+}
+
 __device__ __forceinline__ uint32_t split_pack(float v) {
   // hi = the top 11 significant bits (exact in fp16), lo = the remainder rounded to fp16; K order (hi, lo)
   const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
@@ -242,6 +260,32 @@ __global__ void __launch_bounds__(A_NT, A_CTAS_PER_SM) act1d_mma_kernel(const __
     for (int r = 0; r < A_CH; ++r) bulk_g2s(smem_u32(x_s + r * A_XP), xg + r * p.L + tw, A_WIN * 4, bar_x);
   };
 
+  // ---- tile-invariant addresses of P5 / copy-out (a warp copies out exactly the staging rows it wrote) ----
+  // staging write: lane pairs (channels c, c^1) exchange packed halves so that every lane stores (even channel, odd
+  // channel) words; even lanes take the even time steps, odd lanes the odd ones
+  const bool odd = (c & 1) != 0;
+  const uint32_t perm_sel = odd ? 0x3276u : 0x5410u;
+  const uint32_t stg_w = base + A_OFF_STG + (uint32_t)run * A_STG_RUN + (uint32_t)(half * 16) * 16u +
+                         (uint32_t)(c >> 1) * 4u + (odd ? 16u : 0u);
+  // copy-out: idx = lane + 32 k -> run r_k, step tl_k of the window.  The swizzle term of the blk16 address only
+  // depends on (row mod 8) and the tile stride (448 rows) is a multiple of 8: it is a per-thread constant.
+  uint32_t stg_r[2];
+  uint8_t *gp[2];
+  int64_t t_rel[2];      // t - 448 * tile
+  bool keep[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int idx = lane + 32 * k;
+    const int r = 4 * (warp & 3) + (idx >> 4), tl = r * A_RT + half * 16 + (idx & 15);
+    keep[k] = r != 0 && r != A_RUNS - 1;                 // runs 0 and 15 are the recomputed halo of the tile
+    stg_r[k] = A_OFF_STG + (uint32_t)r * A_STG_RUN + (uint32_t)(tl & 31) * 16u;
+    t_rel[k] = (int64_t)tl - A_RT;
+    const uint64_t row = (uint64_t)(HSV_BLK_PAD + t_rel[k] + (int64_t)A_VALID * blockIdx.x);
+    const uint64_t lin = (row << p.lg) + ub;
+    gp[k] = ob + (lin ^ (((lin >> 7) & mask) << 4));
+  }
+  const int64_t g_step = ((int64_t)A_VALID * gridDim.x) << p.lg;
+
   uint32_t ph = 0, xph = 0;
   bool have_x = false;
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
@@ -251,8 +295,8 @@ __global__ void __launch_bounds__(A_NT, A_CTAS_PER_SM) act1d_mma_kernel(const __
 
     // ---- x window -> shared (the stage aliases the XA tile, free since the previous tile's P2 completed) ----
     if (fast) {
-      if (!have_x && tid == 32) issue_x(tile);
-      mbar_wait(bar_x, xph);
+      if (!have_x && tid == A_NT - 32) issue_x(tile);
+      mbar_wait_sleep(bar_x, xph);
       xph ^= 1u;
     } else {
       // tiles touching either end of the sequence (or unaligned tensors): replicate-clamped loads, all issued
@@ -297,7 +341,7 @@ __global__ void __launch_bounds__(A_NT, A_CTAS_PER_SM) act1d_mma_kernel(const __
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();  // XA complete; every thread is done with the previous tile's TMEM reads
-    if (warp == 0) {
+    if (warp == A_NT / 32 - 1) {
       // ---- P2: Y = XA * U.  Blocks j = 0 and j = 3 first (disjoint windows covering every used column) ----
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t bh = desc_lo(tab + HSV_TOEP_UP_HI), bl = desc_lo(tab + HSV_TOEP_UP_LO);
@@ -337,20 +381,20 @@ __global__ void __launch_bounds__(A_NT, A_CTAS_PER_SM) act1d_mma_kernel(const __
       lo = lo64 < 0 ? 0 : (lo64 > 64 ? 64 : (int)lo64);
       hi = hi64 < 0 ? 0 : (hi64 > 64 ? 64 : (int)hi64);
     }
-    mbar_wait(bar_y, ph);
+    mbar_wait_sleep(bar_y, ph);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     // the XA tile is free: stage the next tile's x window behind the rest of this tile
     {
       const int tn = tile + (int)gridDim.x;
       have_x = tn < p.ntiles && is_fast(tn);
-      if (have_x && tid == 32) issue_x(tn);
+      if (have_x && tid == A_NT - 32) issue_x(tn);
     }
     if (interior) snake_half_row<false>(trow + 32u + 32u * (uint32_t)half, z_row, swz, half, a2, ib2, 0, 64, 0.f, 0.f);
     else snake_half_row<true>(trow + 32u + 32u * (uint32_t)half, z_row, swz, half, a2, ib2, lo, hi, zL, zR);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();  // Z complete; Y fully read (O aliases its columns)
-    if (warp == 0) {
+    if (warp == A_NT / 32 - 1) {
       // ---- P4: O = Z * D.  Blocks j = -1 and j = 3 first (disjoint windows covering every used column) ----
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t bo = desc_lo(tab + HSV_TOEP_DN_ODD), bev = desc_lo(tab + HSV_TOEP_DN_EVEN);
@@ -369,40 +413,30 @@ __global__ void __launch_bounds__(A_NT, A_CTAS_PER_SM) act1d_mma_kernel(const __
     }
 
     // ---- P5: 16 outputs of this half row -> fp16 -> staging [t][8 channels] -> 16-byte units of the blk16 layout ----
-    mbar_wait(bar_o, ph);
+    mbar_wait_sleep(bar_o, ph);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     {
       uint32_t ra[16];
       tmem_ld16_nowait(trow + 16u + 16u * (uint32_t)half, ra);
       tmem_ld_wait(ra);
-      // lane pairs (channels c, c^1) exchange every other value so that each lane stores packed (even channel, odd
-      // channel) words: even lanes take the even time steps, odd lanes the odd ones
-      const bool odd = (c & 1) != 0;
-      const uint32_t stg = base + A_OFF_STG + (uint32_t)run * A_STG_RUN + (uint32_t)(half * 16) * 16u +
-                           (uint32_t)(c >> 1) * 4u + (odd ? 16u : 0u);
 #pragma unroll
       for (int i = 0; i < 16; i += 2) {
-        const float v0 = __uint_as_float(ra[i]), v1 = __uint_as_float(ra[i + 1]);
-        const float got = __shfl_xor_sync(0xffffffffu, odd ? v0 : v1, 1);
-        const __half2 h = odd ? __floats2half2_rn(got, v1) : __floats2half2_rn(v0, got);
-        asm volatile("st.shared.b32 [%0], %1;" ::"r"(stg + (uint32_t)i * 16u), "r"(*reinterpret_cast<const uint32_t *>(&h))
+        const __half2 mine = __floats2half2_rn(__uint_as_float(ra[i]), __uint_as_float(ra[i + 1]));   // steps i, i+1
+        const uint32_t mb = *reinterpret_cast<const uint32_t *>(&mine);
+        const uint32_t th = __shfl_xor_sync(0xffffffffu, mb, 1);
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(stg_w + (uint32_t)i * 16u), "r"(__byte_perm(mb, th, perm_sel))
                      : "memory");
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncwarp();  // a warp copies out exactly the staging rows it wrote: 4 runs x 16 steps
+    __syncwarp();
     {
+      const int64_t t0 = (int64_t)A_VALID * tile;
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
-        const int idx = lane + 32 * k;
-        const int r = 4 * (warp & 3) + (idx >> 4), tl = r * A_RT + half * 16 + (idx & 15);
-        const int64_t t = tw + tl;
-        if (r != 0 && r != A_RUNS - 1 && t < p.L) {   // runs 0 and 15 are the recomputed halo of the tile
-          const uint4 v = *reinterpret_cast<const uint4 *>(gbase + A_OFF_STG + (uint32_t)r * A_STG_RUN +
-                                                           (uint32_t)(tl & 31) * 16u);
-          const uint64_t lin = ((uint64_t)(HSV_BLK_PAD + t) << p.lg) + ub;
-          *reinterpret_cast<uint4 *>(ob + (lin ^ (((lin >> 7) & mask) << 4))) = v;
-        }
+        if (keep[k] && t0 + t_rel[k] < p.L)
+          *reinterpret_cast<uint4 *>(gp[k]) = *reinterpret_cast<const uint4 *>(gbase + stg_r[k]);
+        gp[k] += g_step;
       }
     }
     __syncwarp();
