@@ -78,6 +78,20 @@ def make_workload(args, rank):
                     sd=synth.synthesizer_sd(1234), host_inputs=[w2v, f0, mel], audio_seconds=T / 50.0, T=T,
                     data="synthetic w2v~N(0,1) [1,1024,T], f0=log(hz+1) 30 % unvoiced [1,1,4T], prompt mel~N(-4,2) [2,80,150]; "
                          "random-init weights (seed 1234; flows' post / adaLN small random instead of zero)")
+    if args.workload == "tts":
+        # the device-resident tail of text-to-speech (inference.py:158-167): the text-to-vec model's flow output z ->
+        # W2VDecoder -> PitchPredictor -> voice_conversion_noise_control -> 16 kHz wav (SURVEY.md §8f4 partial + f2 + a)
+        if args.batch != 1:
+            raise SystemExit("the tts workload is the reference's single-utterance call (B = 1)")
+        T = int(round(args.seconds * 50))
+        z, mask, g = synth.ttv_tail_inputs(1, T, seed=1111 + rank)
+        _, _, mel = synth.synthesizer_inputs(T, 150, seed=1111 + rank)
+        sd = {"syn." + k: v for k, v in synth.synthesizer_sd(1234).items()}
+        sd.update({"tail." + k: v for k, v in synth.ttv_tail_sd(3456).items()})
+        return dict(name=f"ttv_tail->synthesizer_vc_noise_control_B1x{args.seconds:g}s", kind="tts", sd=sd,
+                    host_inputs=[z, g, mel], audio_seconds=T / 50.0, T=T,
+                    data="synthetic z~N(0,1) [1,256,T], g~0.5*N(0,1) [1,256,1], prompt mel~N(-4,2) [2,80,150]; random-init "
+                         "weights (seeds 1234 / 3456)")
     which = 48 if args.workload == "speechsr48" else 24
     L = int(round(args.seconds * 16000))
     x = synth.speechsr_input(args.batch, L, seed=1111 + rank)
@@ -101,6 +115,19 @@ def oracle_forward(wl, device="cpu"):
         T = wl["T"]
         ln, ln2 = torch.LongTensor([T]).to(device), torch.LongTensor([150, 150]).to(device)
         return lambda: FF.voice_conversion_noise_control(sd, ins[0], ln, ins[2], ln2, ins[1], 0.333, 0.3)
+    if wl["kind"] == "tts":
+        from oracle import functional_front as FF
+        from oracle import functional_ttv as FT
+        T = wl["T"]
+        st = {k[len("tail."):]: v for k, v in sd.items() if k.startswith("tail.")}
+        sy = {k[len("syn."):]: v for k, v in sd.items() if k.startswith("syn.")}
+        ln, ln2 = torch.LongTensor([T]).to(device), torch.LongTensor([150, 150]).to(device)
+        mask = torch.ones(1, 1, T, device=device)
+
+        def fwd():
+            w2v, pitch = FT.ttv_tail(st, ins[0], mask, ins[1])
+            return FF.voice_conversion_noise_control(sy, w2v, ln, ins[2], ln2, pitch, 0.333, 0.3)
+        return fwd
     if wl["kind"] == "chain24":
         sv = {k[len("vocoder."):]: v for k, v in sd.items() if k.startswith("vocoder.")}
         ss = {k[len("sr."):]: v for k, v in sd.items() if k.startswith("sr.")}
@@ -117,6 +144,24 @@ def reference_forward(wl):
             ref = refload.load()
             if wl["kind"] == "chain24":
                 raise RuntimeError("chain workload: oracle port (the reference chains the two models in a script)")
+            if wl["kind"] == "tts":
+                TT = refload.load_ttv()
+                m = ref.H.SynthesizerTrn(**refload.HIER_SYNTH_CFG)
+                m.load_state_dict({k[4:]: v for k, v in wl["sd"].items() if k.startswith("syn.")}, strict=False)
+                wd, pp = TT.W2VDecoder(**refload.W2V_DECODER_CFG), TT.PitchPredictor()
+                wd.load_state_dict({k[len("tail.w2v_decoder."):]: v for k, v in wl["sd"].items()
+                                    if k.startswith("tail.w2v_decoder.")}, strict=True)
+                pp.load_state_dict({k[len("tail.pp."):]: v for k, v in wl["sd"].items() if k.startswith("tail.pp.")},
+                                   strict=True)
+                m.eval(); wd.eval(); pp.eval()
+                z, g, mel = wl["host_inputs"]
+                ln, ln2 = torch.LongTensor([wl["T"]]), torch.LongTensor([150, 150])
+                mask = torch.ones(1, 1, wl["T"])
+
+                def fwd():
+                    w2v = wd(z, mask, g=g)
+                    return m.voice_conversion_noise_control(w2v, ln, mel, ln2, pp(w2v, g), 0.333, False, 0.3)
+                return fwd, "reference"
             if wl["kind"] == "synth":
                 m = ref.H.SynthesizerTrn(**refload.HIER_SYNTH_CFG)
                 m.load_state_dict(wl["sd"], strict=False)
@@ -270,6 +315,23 @@ def build_model(wl, device):
                 ln2 = torch.full((2,), mel.shape[-1], dtype=torch.long, device=w2v.device)
                 return self.net.voice_conversion_noise_control(w2v, ln, mel, ln2, f0, 0.333, False, 0.3)
         m = SynthStep(wl["T"])
+    elif wl["kind"] == "tts":
+        class TTSStep(torch.nn.Module):
+            """(z, g, prompt mel) -> wav: TTVTail -> voice_conversion_noise_control, lengths are host constants."""
+
+            def __init__(self, T):
+                super().__init__()
+                self.tail = hsv.TTVTail()
+                self.syn = hsv.HierSpeechSynthesizer()
+                self.T = T
+
+            def forward(self, z, g, mel):
+                mask = torch.ones(1, 1, self.T, dtype=torch.float32, device=z.device)
+                w2v, pitch = self.tail(z, mask, g)
+                ln = torch.full((1,), self.T, dtype=torch.long, device=z.device)
+                ln2 = torch.full((2,), mel.shape[-1], dtype=torch.long, device=z.device)
+                return self.syn.voice_conversion_noise_control(w2v, ln, mel, ln2, pitch, 0.333, False, 0.3)
+        m = TTSStep(wl["T"])
     else:
         m = (hsv.SpeechSR48 if wl["which"] == 48 else hsv.SpeechSR24)(100, 40, **hsv.SR_CFG)
     m.load_state_dict(wl["sd"], strict=True)
@@ -938,7 +1000,7 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="vocoder", choices=["vocoder", "speechsr48", "speechsr24", "chain24", "synth"])
+    ap.add_argument("--workload", default="vocoder", choices=["vocoder", "speechsr48", "speechsr24", "chain24", "synth", "tts"])
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--seconds", type=float, default=10.0)
     ap.add_argument("--no-graph", action="store_true")

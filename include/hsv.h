@@ -144,6 +144,7 @@ int hsv_conv_transpose1d_umma(const void *a_blk16, const void *w_packed, const f
 #define HSV_CONV_TANH 2
 #define HSV_CONV_ADD_OUT 4
 #define HSV_CONV_SILU_IN 8      /* apply SiLU to x first (adaLN / cond_block, modules.py:402, hierspeechpp_speechsynthesizer.py:70) */
+#define HSV_CONV_LRELU001_IN 16 /* apply leaky_relu(0.01) to x first (PitchPredictor, ttv_v1/t2w2v_transformer.py:456) */
 int hsv_conv1d_direct(const float *x, const float *w, const float *bias, float *out,
                       int B, int Cin, int Cout, int64_t Lin, int64_t Lout, int k, int d, int pad,
                       int flags, void *stream);

@@ -47,7 +47,7 @@ conv1d_tiled_kernel(const float *__restrict__ x, const float *__restrict__ w, co
       if (ci0 + ci < Cin && t >= 0 && t < Lin) {
         v = __ldg(x + ((int64_t)b * Cin + ci0 + ci) * Lin + t);
         if (flags & HSV_CONV_LRELU_IN) v = v > 0.f ? v : 0.1f * v;
-      if (flags & HSV_CONV_SILU_IN) v = v / (1.f + expf(-v));
+        if (flags & HSV_CONV_LRELU001_IN) v = v > 0.f ? v : 0.01f * v;
         if (flags & HSV_CONV_SILU_IN) v = v / (1.f + expf(-v));
       }
       x_s[ci][pp] = v;
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256) conv1d_thin4_kernel(const float *__restri
         const int64_t ts = t0 - pad + j;
         float v = (ts >= 0 && ts < Lin) ? __ldg(xr + ts) : 0.f;
         if (flags & HSV_CONV_LRELU_IN) v = v > 0.f ? v : 0.1f * v;
-      if (flags & HSV_CONV_SILU_IN) v = v / (1.f + expf(-v));
+        if (flags & HSV_CONV_LRELU001_IN) v = v > 0.f ? v : 0.01f * v;
         if (flags & HSV_CONV_SILU_IN) v = v / (1.f + expf(-v));
         xv[j] = v;
       }
@@ -162,9 +162,8 @@ __global__ void conv1d_thin_kernel(const float *__restrict__ x, const float *__r
           if (ts >= 0 && ts < Lin) {
             float v = __ldg(xr + ts);
             if (flags & HSV_CONV_LRELU_IN) v = v > 0.f ? v : 0.1f * v;
-      if (flags & HSV_CONV_SILU_IN) v = v / (1.f + expf(-v));
+            if (flags & HSV_CONV_LRELU001_IN) v = v > 0.f ? v : 0.01f * v;
             if (flags & HSV_CONV_SILU_IN) v = v / (1.f + expf(-v));
-        if (flags & HSV_CONV_SILU_IN) v = v / (1.f + expf(-v));
             acc = fmaf(__ldg(wr + j), v, acc);
           }
         }
@@ -197,6 +196,7 @@ __global__ void conv1d_rowdot_kernel(const float *__restrict__ x, const float *_
     if (ts >= 0 && ts < Lin) {
       float v = __ldg(x + ((int64_t)b * Cin + ci) * Lin + ts);
       if (flags & HSV_CONV_LRELU_IN) v = v > 0.f ? v : 0.1f * v;
+      if (flags & HSV_CONV_LRELU001_IN) v = v > 0.f ? v : 0.01f * v;
       if (flags & HSV_CONV_SILU_IN) v = v / (1.f + expf(-v));
       acc = fmaf(__ldg(w + (int64_t)co * Cin * k + r), v, acc);
     }

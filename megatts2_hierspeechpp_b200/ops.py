@@ -473,6 +473,7 @@ def peak_norm_pcm16(x: torch.Tensor, s1: float = 32767.0, s2: float = 0.999, per
 # frame-rate operators of the step before the vocoder (csrc/frame_ops.cu)
 # ----------------------------------------------------------------------------------------------
 CONV_SILU_IN = 8
+CONV_LRELU001_IN = 16
 PACK_MASK, PACK_GATE, PACK_GELU, PACK_MISH = 0, 1, 2, 3
 (OP_WN_RES, OP_WN_LAST, OP_GATE_ADD, OP_COUPLE, OP_SAMPLE, OP_MASK, OP_ADD, OP_GLU_RES, OP_MISH, OP_FLIP,
  OP_ADD_BCAST) = range(1, 12)

@@ -265,4 +265,9 @@ def patch_reference(modules=None, front: bool = True) -> List[str]:
                           ("ResidualCouplingBlock_Transformer", FR.ResidualCouplingBlock_Transformer),
                           ("StyleEncoder", FR.StyleEncoder)):
             _set("hierspeechpp_speechsynthesizer", attr, obj)
+        # ... and the tail of the text-to-vec model that feeds it (partial); only when the caller has
+        # imported ttv_v1.t2w2v_transformer (its SynthesizerTrn builds self.w2v_decoder / self.pp from these names)
+        from . import ttv as TV
+        _set("ttv_v1.t2w2v_transformer", "W2VDecoder", TV.W2VDecoder)
+        _set("ttv_v1.t2w2v_transformer", "PitchPredictor", TV.PitchPredictor)
     return patched

@@ -262,3 +262,53 @@ def synthesizer_inputs(T: int, T_mel: int = 150, seed: int = 1111):
     f0 = torch.log(hz + 1)
     mel = torch.randn(2, 80, T_mel, generator=gen) * 2 - 4
     return w2v, f0, mel
+
+
+# ----------------------------------------------------------------------------------------------
+# the tail of the text-to-vec model (partial): W2VDecoder + PitchPredictor
+# ----------------------------------------------------------------------------------------------
+def w2v_decoder_sd(seed: int = 3456, prefix: str = "w2v_decoder.", cin: int = 256, hidden: int = 512, k: int = 5,
+                   n_layers: int = 8, out: int = 1024, gin: int = 256) -> SD:
+    """Keys of ttv_v1/t2w2v_transformer.W2VDecoder (:377-405) as instantiated at :779."""
+    gen = torch.Generator().manual_seed(seed)
+    sd: SD = {}
+    _conv(sd, prefix + "pre.", gen, hidden, cin, 1, wn=False)
+    _wn(sd, prefix + "enc.", gen, hidden, k, n_layers, gin)
+    _conv(sd, prefix + "proj.", gen, out, hidden, 1, wn=False)
+    return _ordered_like_reference(sd, prefix)
+
+
+def pitch_predictor_sd(seed: int = 3457, prefix: str = "pp.", cin: int = 1024, c0: int = 256, gin: int = 256,
+                       kernels=(3, 5, 7)) -> SD:
+    """Keys of ttv_v1/t2w2v_transformer.PitchPredictor (:408-438): conv_pre, 2 weight-normed ConvTranspose1d(k4, u2),
+    2 x 3 ResBlock1, conv_post (no bias), cond."""
+    gen = torch.Generator().manual_seed(seed)
+    sd: SD = {}
+    _conv(sd, prefix + "conv_pre.", gen, c0, cin, 7, wn=False)
+    for i in range(2):
+        _conv(sd, f"{prefix}ups.{i}.", gen, c0 >> (i + 1), c0 >> i, 4, transposed=True)
+    for i in range(2):
+        ch = c0 >> (i + 1)
+        for j, k in enumerate(kernels):
+            for grp in ("convs1", "convs2"):
+                for l in range(3):
+                    _conv(sd, f"{prefix}resblocks.{i * len(kernels) + j}.{grp}.{l}.", gen, ch, ch, k)
+    _conv(sd, prefix + "conv_post.", gen, 1, c0 >> 2, 7, wn=False, bias=False)
+    _conv(sd, prefix + "cond.", gen, c0, gin, 1, wn=False)
+    return _ordered_like_reference(sd, prefix)
+
+
+def ttv_tail_sd(seed: int = 3456) -> SD:
+    sd = w2v_decoder_sd(seed)
+    sd.update(pitch_predictor_sd(seed + 1))
+    return sd
+
+
+def ttv_tail_inputs(B: int, T: int, seed: int = 1111, lengths=None):
+    """(z [B,256,T], y_mask [B,1,T], g [B,256,1]): the flow output, its frame mask and the style vector."""
+    gen = torch.Generator().manual_seed(seed)
+    z = torch.randn(B, 256, T, generator=gen)
+    g = torch.randn(B, 256, 1, generator=gen) * 0.5
+    ln = torch.full((B,), T, dtype=torch.long) if lengths is None else torch.as_tensor(lengths, dtype=torch.long)
+    mask = (torch.arange(T)[None, :] < ln[:, None]).unsqueeze(1).to(torch.float32)
+    return z, mask, g

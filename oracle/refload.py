@@ -110,6 +110,34 @@ def load():
     return types.SimpleNamespace(**_loaded)
 
 
+def load_ttv():
+    """The reference's text-to-vec module (``ttv_v1/t2w2v_transformer.py``) -- used for ``W2VDecoder`` (:377-405) and
+    ``PitchPredictor`` (:408-463).  Its import chain pulls training-only packages that this image lacks
+    (``torchmetrics``, ``matplotlib``); they are stubbed, none of them is on the inference path of the two classes."""
+    load()
+    if "ttv" in _loaded:
+        return _loaded["ttv"]
+
+    class _Unused:
+        def __init__(self, *a, **k):
+            pass
+
+    _stub("torchmetrics")
+    _stub("torchmetrics.classification", MulticlassAccuracy=_Unused)
+    _stub("matplotlib")
+    _stub("matplotlib.pyplot", Figure=_Unused)      # only a type annotation in ttv_v1/utils_mega.py:41
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    ma = sys.modules["monotonic_align"]
+    if not hasattr(ma, "mask_from_lens") or ma.mask_from_lens is None:
+        ma.mask_from_lens = _Unused
+    _loaded["ttv"] = importlib.import_module("ttv_v1.t2w2v_transformer")
+    return _loaded["ttv"]
+
+
+W2V_DECODER_CFG = dict(in_channels=256, hidden_channels=512, kernel_size=5, dilation_rate=1, n_layers=8,
+                       output_size=1024, p_dropout=0.1, gin_channels=256)   # ttv_v1/t2w2v_transformer.py (TTV decoder)
+
+
 HIER_SYNTH_CFG = dict(spec_channels=513, segment_size=30, inter_channels=192, hidden_channels=192,
                       filter_channels=768, n_heads=2, n_layers=6, kernel_size=3, p_dropout=0.1, resblock="1",
                       resblock_kernel_sizes=[3, 7, 11], resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5], [1, 3, 5]],

@@ -113,6 +113,8 @@ def conv_transpose1d_umma(a_blk, wp, bias, Lin, cin, cout, k, u, n_tile, add=Non
 
 def conv1d_direct(x, w, bias, d=1, pad=0, flags=0, out=None):
     xin = F.leaky_relu(x, 0.1) if flags & real.CONV_LRELU_IN else x
+    if flags & real.CONV_LRELU001_IN:
+        xin = F.leaky_relu(xin, 0.01)
     if flags & real.CONV_SILU_IN:
         xin = F.silu(xin)
     v = F.conv1d(xin, w, bias, padding=pad, dilation=d)

@@ -110,3 +110,31 @@ def test_front_dataflow_matches_oracle(monkeypatch):
     tm = torch.unsqueeze(FR.sequence_mask(ln2, mel.size(2)), 1).to(mel.dtype)
     g = m.emb_g(mel, tm).unsqueeze(-1)
     assert (g - FF.style_encoder(sd, "emb_g.", mel, tm).unsqueeze(-1)).abs().max() <= 2e-3
+
+
+def test_ttv_tail_dataflow_matches_oracle(monkeypatch):
+    """W2VDecoder + PitchPredictor (partial) on CPU through the op emulation: split-K conv_pre, the
+    leaky_relu packs, the 1/3 of the resblock mean carried into the next pack / the conv_post weight, the accumulating
+    resblock epilogues -- against the oracle restatement, with a padded batch."""
+    import megatts2_hierspeechpp_b200 as hsv
+    from megatts2_hierspeechpp_b200 import synthetic as synth
+    from oracle import functional_ttv as FT
+    emu_ops.install(monkeypatch)
+    import megatts2_hierspeechpp_b200.front as FR
+    import megatts2_hierspeechpp_b200.ttv as TV
+    for mod in (FR, TV):
+        monkeypatch.setattr(mod, "_as_input", lambda x: x.detach().contiguous())
+    monkeypatch.setattr(TV.PitchPredictor, "parallel_blocks", False)
+    sd = synth.ttv_tail_sd(3456)
+    m = hsv.TTVTail()
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    z, mask, g = synth.ttv_tail_inputs(2, 40, lengths=[40, 31])
+    w2v, pitch = m(z, mask, g)
+    w2v_ref, pitch_ref = FT.ttv_tail(sd, z, mask, g)
+    assert w2v.shape == (2, 1024, 40) and pitch.shape == (2, 1, 160)
+    assert CF.snr_db(w2v_ref.numpy(), w2v.numpy()) >= 55.0 and CF.snr_db(pitch_ref.numpy(), pitch.numpy()) >= 55.0
+    assert (w2v[1, :, 31:] == 0).all()                                   # masked frames stay exactly zero
+    # the pitch predictor alone on the oracle's w2v: isolates it from the decoder's rounding
+    p2 = m.pp(w2v_ref, g)
+    assert CF.max_abs(pitch_ref.numpy(), p2.numpy()) <= 2e-4

@@ -120,3 +120,55 @@ def test_front_oracle_bit_exact_vs_reference_synthesizer():
         b = FF.voice_conversion_noise_control(sd, w2v, ln, mel, ln2, f0, noise_scale=0.333, denoise_ratio=0.3)
     assert a.shape == (1, 1, 320 * T)
     assert torch.equal(a, b)
+
+
+def test_ttv_tail_oracle_bit_exact_vs_reference_and_drop_in():
+    """The tail of the text-to-vec model (partial): the synthetic W2VDecoder / PitchPredictor
+    checkpoints load strictly into the reference's classes, the oracle restatement reproduces them bit for bit on CPU,
+    the B200 classes have the same state_dict keys and shapes, and patch_reference() swaps them in."""
+    import megatts2_hierspeechpp_b200 as hsv
+    from oracle import functional_ttv as FT
+    T = refload.load_ttv()
+    w = T.W2VDecoder(**refload.W2V_DECODER_CFG).eval()
+    p = T.PitchPredictor().eval()
+    sd = synth.ttv_tail_sd(3456)
+    sdw = {k[len("w2v_decoder."):]: v for k, v in sd.items() if k.startswith("w2v_decoder.")}
+    sdp = {k[len("pp."):]: v for k, v in sd.items() if k.startswith("pp.")}
+    w.load_state_dict(sdw, strict=True)
+    p.load_state_dict(sdp, strict=True)
+    z, mask, g = synth.ttv_tail_inputs(2, 40, lengths=[40, 31])
+    with torch.no_grad():
+        a = w(z, mask, g=g)
+        b = p(a, g)
+    a2, b2 = FT.ttv_tail(sd, z, mask, g)
+    assert a.shape == (2, 1024, 40) and b.shape == (2, 1, 160)
+    assert torch.equal(a, a2) and torch.equal(b, b2)
+    # drop-in: same keys, same order, same shapes
+    mine = hsv.TTVTail()
+    for r, m in ((w, mine.w2v_decoder), (p, mine.pp)):
+        rs, ms = r.state_dict(), m.state_dict()
+        assert list(rs.keys()) == list(ms.keys()), type(r).__name__
+        for k in rs:
+            assert rs[k].shape == ms[k].shape, k
+    mine.load_state_dict(sd, strict=True)
+    saved = (T.W2VDecoder, T.PitchPredictor)
+    ref = refload.load()
+    saved_h = {n: getattr(ref.H, n) for n in ("Generator", "SourceNetwork", "AMPBlock1", "DBlock", "Activation1d",
+                                              "PosteriorSFEncoder", "ResidualCouplingBlock_Transformer", "StyleEncoder")}
+    saved_sr = {n: getattr(ref.sr24, n) for n in ("Generator", "AMPBlock0", "Activation1d")}
+    saved_sr48 = {n: getattr(ref.sr48, n) for n in ("Generator", "AMPBlock0", "Activation1d")}
+    try:
+        patched = hsv.patch_reference()
+        assert "ttv_v1.t2w2v_transformer.PitchPredictor" in patched
+        assert T.W2VDecoder is hsv.W2VDecoder and T.PitchPredictor is hsv.PitchPredictor
+    finally:
+        T.W2VDecoder, T.PitchPredictor = saved
+        for n, v in saved_h.items():
+            setattr(ref.H, n, v)
+        for n, v in saved_sr.items():
+            setattr(ref.sr24, n, v)
+        for n, v in saved_sr48.items():
+            setattr(ref.sr48, n, v)
+        import importlib, sys
+        for modname in ("alias_free_torch", "activations"):
+            importlib.reload(sys.modules[modname])
