@@ -384,7 +384,8 @@ def algorithmic_work(model, dev_inputs):
 
     wrap("act1d", bytes_fn=lambda x, *a, **k: 8.0 * x.numel())                 # fp32 in + fp32 out
     wrap("act1d_blk16", bytes_fn=lambda x, *a, **k: 6.0 * x.numel())           # fp32 in + fp16 out
-    wrap("pack_blk16", bytes_fn=lambda x, *a, **k: 6.0 * x.numel())
+    wrap("pack_blk16", bytes_fn=lambda x, *a, **k: (4.0 * len(x) + 2.0) * x[0].numel() if isinstance(x, (list, tuple))
+         else 6.0 * x.numel())                                                 # fp32 addend(s) in + fp16 out
 
     def umma_bytes(a_blk, w, bias, L, cin, cout, k, d, n_tile, residual=None, out=None, acc=None, acc_mode=0, **kw):
         B = a_blk.shape[0]

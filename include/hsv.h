@@ -182,6 +182,10 @@ int hsv_add3_bcast(const float *a, const float *b, const float *bc, float *out,
 
 /* fp32 [B,C,L] * in_scale -> fp16 blk16 (optional leaky_relu(0.1) first); C % 16 == 0. */
 int hsv_pack_blk16(const float *x, void *out, int B, int C, int64_t L, int lrelu, float in_scale, void *stream);
+/* the same with the operand = ((x1 + x2) + x3) * in_scale (x2, x3 nullable): the sum over the resblocks of a stage
+ * (hierspeechpp_speechsynthesizer.py:440-446) taken by the consumer, each resblock writing its own tensor. */
+int hsv_pack_blk16_sum3(const float *x1, const float *x2, const float *x3, void *out, int B, int C, int64_t L,
+                        int lrelu, float in_scale, void *stream);
 /* inverse (tests / debugging): fp16 blk16 -> fp32 [B,C,L]. */
 int hsv_unpack_blk16(const void *in, float *x, int B, int C, int64_t L, void *stream);
 /* operand health (debugging aid; the reference keeps fp32 everywhere, the tensor-core operands here are fp16):

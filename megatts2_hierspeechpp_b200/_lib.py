@@ -40,6 +40,8 @@ SIGNATURES = {
     "hsv_nearest_gather": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p]),
     "hsv_add3_bcast": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p]),
     "hsv_pack_blk16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_float, c_void_p]),
+    "hsv_pack_blk16_sum3": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_float,
+                                    c_void_p]),
     "hsv_unpack_blk16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p]),
     "hsv_blk16_stats": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p]),
     "hsv_pack_blk16_act": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_int, c_void_p]),

@@ -95,47 +95,72 @@ conv1d_tiled_kernel(const float *__restrict__ x, const float *__restrict__ w, co
   }
 }
 
-// thin conv for Cout <= 4 and d == 1 (conv_post 16|32|64 -> 1, k=7): each thread produces 4 consecutive
-// outputs of one (b, co) from a register window of k+3 inputs per input channel; weights are uniform loads.
+// thin conv for Cout <= 4 and d == 1 (conv_post 16|32|64 -> 1, k=7).  CTA = TT consecutive outputs of one batch
+// row: the input window of CC channels is staged in shared memory with coalesced, independent loads (the previous
+// version walked the channels serially from global memory: 20 us for the [16,160000] conv_post of the batch-1
+// vocoder, a dependent-load chain), then every thread produces 2 outputs per output channel from a register window
+// of K+1 samples per input channel.  Accumulation order (ci outer, tap inner, fmaf) as before.
 template <int K>
-__global__ void __launch_bounds__(256) conv1d_thin4_kernel(const float *__restrict__ x, const float *__restrict__ w,
-                                                           const float *__restrict__ bias, float *__restrict__ out,
-                                                           int B, int Cin, int Cout, int64_t Lin, int64_t Lout,
-                                                           int pad, int flags) {
-  const int64_t nq = (Lout + 3) / 4;
-  const int64_t n = (int64_t)B * Cout * nq;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t q = i % nq;
-    const int co = (int)((i / nq) % Cout);
-    const int b = (int)(i / (nq * Cout));
-    const int64_t t0 = q * 4;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int ci = 0; ci < Cin; ++ci) {
-      const float *xr = x + ((int64_t)b * Cin + ci) * Lin;
-      const float *wr = w + ((int64_t)co * Cin + ci) * K;
-      float xv[K + 3];
+__global__ void __launch_bounds__(256) conv1d_thin_smem_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                                                               const float *__restrict__ bias, float *__restrict__ out,
+                                                               int Cin, int Cout, int64_t Lin, int64_t Lout, int pad,
+                                                               int flags) {
+  constexpr int TT = 512, CC = 16, W = TT + K - 1, WP = (W + 3) & ~3;
+  __shared__ __align__(16) float xs[CC][WP];
+  __shared__ float ws[4][CC * K];
+  const int tid = threadIdx.x;
+  const int b = blockIdx.y;
+  const int64_t t0 = (int64_t)blockIdx.x * TT;
+  float acc[4][2];
 #pragma unroll
-      for (int j = 0; j < K + 3; ++j) {
-        const int64_t ts = t0 - pad + j;
-        float v = (ts >= 0 && ts < Lin) ? __ldg(xr + ts) : 0.f;
-        if (flags & HSV_CONV_LRELU_IN) v = v > 0.f ? v : 0.1f * v;
-        if (flags & HSV_CONV_LRELU001_IN) v = v > 0.f ? v : 0.01f * v;
-        if (flags & HSV_CONV_SILU_IN) v = v / (1.f + expf(-v));
-        xv[j] = v;
+  for (int co = 0; co < 4; ++co) acc[co][0] = acc[co][1] = 0.f;
+  for (int c0 = 0; c0 < Cin; c0 += CC) {
+    const int nc = min(CC, Cin - c0);
+    if (c0) __syncthreads();
+    for (int idx = tid; idx < nc * W; idx += 256) {
+      const int c = idx / W, pp = idx - c * W;
+      const int64_t ts = t0 - pad + pp;
+      float v = (ts >= 0 && ts < Lin) ? __ldg(x + ((int64_t)b * Cin + c0 + c) * Lin + ts) : 0.f;
+      if (flags & HSV_CONV_LRELU_IN) v = v > 0.f ? v : 0.1f * v;
+      if (flags & HSV_CONV_LRELU001_IN) v = v > 0.f ? v : 0.01f * v;
+      if (flags & HSV_CONV_SILU_IN) v = v / (1.f + expf(-v));
+      xs[c][pp] = v;
+    }
+    for (int idx = tid; idx < Cout * nc * K; idx += 256) {
+      const int co = idx / (nc * K), r = idx - co * (nc * K);
+      ws[co][r] = __ldg(w + ((int64_t)co * Cin + c0) * K + r);
+    }
+    __syncthreads();
+    for (int c = 0; c < nc; ++c) {
+      float xv[K + 1];
+#pragma unroll
+      for (int j = 0; j < K + 1; j += 2) {
+        const float2 v2 = *reinterpret_cast<const float2 *>(&xs[c][2 * tid + j]);
+        xv[j] = v2.x;
+        if (j + 1 < K + 1) xv[j + 1] = v2.y;
       }
 #pragma unroll
-      for (int j = 0; j < K; ++j) {
-        const float wj = __ldg(wr + j);
+      for (int co = 0; co < 4; ++co) {
+        if (co < Cout) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) acc[r] = fmaf(wj, xv[j + r], acc[r]);
+          for (int j = 0; j < K; ++j) {
+            const float wj = ws[co][c * K + j];
+            acc[co][0] = fmaf(wj, xv[j], acc[co][0]);
+            acc[co][1] = fmaf(wj, xv[j + 1], acc[co][1]);
+          }
+        }
       }
     }
-    const float bv = bias ? __ldg(bias + co) : 0.f;
-    float *o = out + ((int64_t)b * Cout + co) * Lout + t0;
+  }
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      if (t0 + r < Lout) {
-        float v = acc[r] + bv;
+  for (int co = 0; co < 4; ++co) {
+    if (co >= Cout) break;
+    const float bv = bias ? __ldg(bias + co) : 0.f;
+    float *o = out + ((int64_t)b * Cout + co) * Lout + t0 + 2 * tid;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      if (t0 + 2 * tid + r < Lout) {
+        float v = acc[co][r] + bv;
         if (flags & HSV_CONV_TANH) v = tanhf(v);
         if (flags & HSV_CONV_ADD_OUT) v += o[r];
         o[r] = v;
@@ -206,6 +231,52 @@ __global__ void conv1d_rowdot_kernel(const float *__restrict__ x, const float *_
     if (bias) acc += __ldg(bias + co);
     if (flags & HSV_CONV_TANH) acc = tanhf(acc);
     float *o = out + ((int64_t)b * Cout + co) * Lout + t;
+    if (flags & HSV_CONV_ADD_OUT) acc += *o;
+    *o = acc;
+  }
+}
+
+// the same for a per-utterance vector (k == 1, Lin == Lout == 1, Cin % 4 == 0: cond(g), adaLN, cond_layer): float4
+// loads, all of a lane's weight loads issued before the first FMA (the scalar loop above is a chain of dependent
+// DRAM round trips when the weights are cold: 9 us for 512 x 256)
+__global__ void conv1d_vecdot_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                                     const float *__restrict__ bias, float *__restrict__ out, int B, int Cin,
+                                     int Cout, int flags) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (wid >= (int64_t)B * Cout) return;
+  const int co = (int)(wid % Cout);
+  const int b = (int)(wid / Cout);
+  const float4 *w4 = reinterpret_cast<const float4 *>(w + (int64_t)co * Cin);
+  const float4 *x4 = reinterpret_cast<const float4 *>(x + (int64_t)b * Cin);
+  const int n4 = Cin >> 2;
+  float acc = 0.f;
+  for (int r0 = lane; r0 < n4; r0 += 128) {
+    float4 wv[4], xv[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int r = r0 + 32 * q;
+      wv[q] = r < n4 ? __ldg(w4 + r) : make_float4(0.f, 0.f, 0.f, 0.f);
+      xv[q] = r < n4 ? __ldg(x4 + r) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float v[4] = {xv[q].x, xv[q].y, xv[q].z, xv[q].w};
+      const float ww[4] = {wv[q].x, wv[q].y, wv[q].z, wv[q].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (flags & HSV_CONV_LRELU_IN) v[e] = v[e] > 0.f ? v[e] : 0.1f * v[e];
+        if (flags & HSV_CONV_LRELU001_IN) v[e] = v[e] > 0.f ? v[e] : 0.01f * v[e];
+        if (flags & HSV_CONV_SILU_IN) v[e] = v[e] / (1.f + expf(-v[e]));
+        acc = fmaf(ww[e], v[e], acc);
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    if (bias) acc += __ldg(bias + co);
+    if (flags & HSV_CONV_TANH) acc = tanhf(acc);
+    float *o = out + (int64_t)b * Cout + co;
     if (flags & HSV_CONV_ADD_OUT) acc += *o;
     *o = acc;
   }
@@ -405,17 +476,31 @@ __global__ void weight_norm_fold_kernel(const float *__restrict__ v, const float
 }
 
 // fp32 [B,C,L] -> fp16 blk16; one thread per (b, chunk, t)
-__global__ void pack_blk16_kernel(const float *__restrict__ x, uint4 *__restrict__ out, int B, int C, int64_t L,
+// x2 / x3 (nullable): further addends, summed in the fixed order (x + x2) + x3 before the scale -- the consumer-side
+// sum over the resblocks of a stage (each resblock stream writes its own tensor; no chained accumulation)
+__global__ void pack_blk16_kernel(const float *__restrict__ x, const float *__restrict__ x2,
+                                  const float *__restrict__ x3, uint4 *__restrict__ out, int B, int C, int64_t L,
                                   int64_t Lp, int lrelu, float sc, int cw) {
   const int nch = C >> 3;
   const int64_t n = (int64_t)B * nch * L;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t bq = i / L, t = i - bq * L;
-    const float *xr = x + bq * 8 * L + t;  // (b*C + 8q) * L + t
+    const int64_t off = bq * 8 * L + t;  // (b*C + 8q) * L + t
+    const float *xr = x + off;
     __half2 h[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      float v0 = __ldg(xr + (2 * e) * L) * sc, v1 = __ldg(xr + (2 * e + 1) * L) * sc;
+      float v0 = __ldg(xr + (2 * e) * L), v1 = __ldg(xr + (2 * e + 1) * L);
+      if (x2) {
+        v0 += __ldg(x2 + off + (2 * e) * L);
+        v1 += __ldg(x2 + off + (2 * e + 1) * L);
+      }
+      if (x3) {
+        v0 += __ldg(x3 + off + (2 * e) * L);
+        v1 += __ldg(x3 + off + (2 * e + 1) * L);
+      }
+      v0 *= sc;
+      v1 *= sc;
       if (lrelu) {
         v0 = v0 > 0.f ? v0 : 0.1f * v0;
         v1 = v1 > 0.f ? v1 : 0.1f * v1;
@@ -497,14 +582,19 @@ extern "C" int hsv_conv1d_direct(const float *x, const float *w, const float *bi
   HSV_REQUIRE(Lout == Lin + 2 * (int64_t)pad - (int64_t)d * (k - 1), "conv1d_direct: Lout mismatch");
   if (B == 0 || Lout <= 0) return HSV_OK;
   cudaStream_t st = hsv::as_stream(stream);
-  if (Lout <= 8) {
+  if (k == 1 && Lin == 1 && pad == 0 && (Cin & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w)) & 15) == 0) {
+    const int64_t nwarps = (int64_t)B * Cout;
+    HSV_REQUIRE(nwarps * 32 / 256 + 1 < (1ll << 31), "conv1d_direct: grid too large");
+    conv1d_vecdot_kernel<<<(unsigned)((nwarps * 32 + 255) / 256), 256, 0, st>>>(x, w, bias, out, B, Cin, Cout, flags);
+  } else if (Lout <= 8) {
     const int64_t nwarps = (int64_t)B * Cout * Lout;
     HSV_REQUIRE(nwarps * 32 / 256 + 1 < (1ll << 31), "conv1d_direct: grid too large");
     conv1d_rowdot_kernel<<<(unsigned)((nwarps * 32 + 255) / 256), 256, 0, st>>>(x, w, bias, out, B, Cin, Cout, Lin,
                                                                                Lout, k, d, pad, flags);
   } else if (Cout <= 4 && d == 1 && k == 7) {
-    conv1d_thin4_kernel<7><<<grid_for((int64_t)B * Cout * ((Lout + 3) / 4), 256), 256, 0, st>>>(
-        x, w, bias, out, B, Cin, Cout, Lin, Lout, pad, flags);
+    HSV_REQUIRE(B <= 65535, "conv1d_direct: grid too large");
+    dim3 grid((unsigned)((Lout + 511) / 512), (unsigned)B);
+    conv1d_thin_smem_kernel<7><<<grid, 256, 0, st>>>(x, w, bias, out, Cin, Cout, Lin, Lout, pad, flags);
   } else if (Cout <= 4) {
     conv1d_thin_kernel<<<grid_for((int64_t)B * Lout, 256), 256, 0, st>>>(x, w, bias, out, B, Cin, Cout, Lin,
                                                                         Lout, k, d, pad, flags);
@@ -588,8 +678,19 @@ extern "C" int hsv_pack_blk16(const float *x, void *out, int B, int C, int64_t L
   HSV_REQUIRE(x && out, "pack_blk16: null pointer");
   HSV_REQUIRE(C > 0 && C % 16 == 0, "pack_blk16: C %% 16 != 0 (C=%d)", C);
   pack_blk16_kernel<<<grid_for((int64_t)B * (C / 8) * L, 256), 256, 0, hsv::as_stream(stream)>>>(
-      x, reinterpret_cast<uint4 *>(out), B, C, L, hsv::blk16_rows(L), lrelu, in_scale, hsv::blk_cw(C));
+      x, nullptr, nullptr, reinterpret_cast<uint4 *>(out), B, C, L, hsv::blk16_rows(L), lrelu, in_scale, hsv::blk_cw(C));
   return hsv::check_launch("pack_blk16");
+}
+
+extern "C" int hsv_pack_blk16_sum3(const float *x1, const float *x2, const float *x3, void *out, int B, int C,
+                                   int64_t L, int lrelu, float in_scale, void *stream) {
+  if (B == 0 || L == 0) return HSV_OK;
+  HSV_REQUIRE(x1 && out, "pack_blk16_sum3: null pointer");
+  HSV_REQUIRE(x2 || !x3, "pack_blk16_sum3: x3 without x2");
+  HSV_REQUIRE(C > 0 && C % 16 == 0, "pack_blk16_sum3: C %% 16 != 0 (C=%d)", C);
+  pack_blk16_kernel<<<grid_for((int64_t)B * (C / 8) * L, 256), 256, 0, hsv::as_stream(stream)>>>(
+      x1, x2, x3, reinterpret_cast<uint4 *>(out), B, C, L, hsv::blk16_rows(L), lrelu, in_scale, hsv::blk_cw(C));
+  return hsv::check_launch("pack_blk16_sum3");
 }
 
 extern "C" int hsv_unpack_blk16(const void *in, float *x, int B, int C, int64_t L, void *stream) {

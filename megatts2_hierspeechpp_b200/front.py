@@ -22,7 +22,7 @@ from torch import nn
 from torch.nn import Conv1d
 
 from . import ops
-from .modules import (_Folded, _as_input, _bump_on_load, _row_tiles, _weight_norm, Generator, SourceNetwork)
+from .modules import (_Folded, _as_input, _bump_on_load, _row_tiles, _weight_norm, Generator, SourceNetwork, vocode)
 
 _S_X, _S_G, _S_W = 4, 5, 6      # blk16 workspace slots of this module family (0..3 belong to the vocoder)
 
@@ -510,8 +510,7 @@ class HierSpeechSynthesizer(nn.Module):
         z, _, _ = self.enc_p_l(w2v, f0, x_mask, g=g)
         z = self.flow_l(z, x_mask, g=g, reverse=True)
         z = self.flow(z, x_mask, g=g, reverse=True)
-        e, e_ = self.sn(z, g)
-        return self.dec(z, e, g=g), e_
+        return vocode(self.sn, self.dec, z, g, need_pred=True)
 
     @torch.no_grad()
     def voice_conversion_noise_control(self, src, src_length, trg_mel, trg_length, f0, noise_scale=0.333, uncond=False,
@@ -530,8 +529,7 @@ class HierSpeechSynthesizer(nn.Module):
         ops.frame_op(ops.OP_SAMPLE, stats, eps.contiguous(), None, _mask2d(y_mask), z, None, B, C, T, s=float(noise_scale))
         z = self.flow_l(z, y_mask, g=g_interpolation, reverse=True)
         z = self.flow(z, y_mask, g=g_interpolation, reverse=True)
-        e, _ = self.sn(z, g_interpolation)
-        return self.dec(z, e, g=g_interpolation)
+        return vocode(self.sn, self.dec, z, g_interpolation)[0]
 
     @torch.no_grad()
     def voice_conversion(self, src, src_length, trg_mel, trg_length, f0, noise_scale=0.333, uncond=False):
@@ -547,5 +545,4 @@ class HierSpeechSynthesizer(nn.Module):
         ops.frame_op(ops.OP_SAMPLE, stats, eps.contiguous(), None, _mask2d(y_mask), z, None, B, C, T, s=float(noise_scale))
         z = self.flow_l(z, y_mask, g=g, reverse=True)
         z = self.flow(z, y_mask, g=g, reverse=True)
-        e, _ = self.sn(z, g)
-        return self.dec(z, e, g=g)
+        return vocode(self.sn, self.dec, z, g)[0]

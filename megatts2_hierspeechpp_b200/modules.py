@@ -275,41 +275,48 @@ FUSE_MAX_CHANNELS = [int(__import__("os").environ.get("HSV_FUSE_MAX_C", "0"))]
 FUSE_MAX_ELEMS = [int(__import__("os").environ.get("HSV_FUSE_MAX_ELEMS", str(1 << 62)))]
 
 _MAIN_SLOT = 3   # blk16 workspace slot of the main stream (slots 0..2 belong to the per-resblock streams)
+_PRE_SLOT = 7    # ... of Generator.pre when Vocoder runs it beside the SourceNetwork (4..6: front.py, 8+: tests)
 
 
 def _dense_conv(x: torch.Tensor, f: _Folded, k: int, d: int = 1, lrelu: bool = False,
-                residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+                residual: Optional[torch.Tensor] = None, slot: Optional[int] = None,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """'same' Conv1d of an fp32 [B,C,L] tensor: tcgen05 path when both channel counts are multiples of
     16 (pack to the fp16 operand layout, optional leaky_relu(0.1) fused into the pack), fp32 direct
     kernel otherwise."""
     B, C, L = x.shape
     cout = f.conv.out_channels
     if C % 16 == 0 and cout % 16 == 0 and ((k - 1) // 2) * d <= ops.BLK_PAD:
-        buf = ops.blk16_buffer(B, C, L, x.device, _MAIN_SLOT)
+        buf = ops.blk16_buffer(B, C, L, x.device, _MAIN_SLOT if slot is None else slot)
         ops.pack_blk16(x, buf, lrelu)
         ops.check_saturation(buf, C, L)
         wp, nt = f.packed_weight(_row_tiles(B, L))
-        return ops.conv1d_umma(buf, wp, f.bias(), L, C, cout, k, d, nt, residual=residual)
+        return ops.conv1d_umma(buf, wp, f.bias(), L, C, cout, k, d, nt, residual=residual, out=out)
     pad = ((k - 1) // 2) * d
     if residual is not None:
-        out = residual.clone()
+        if out is None:
+            out = residual.clone()
+        else:
+            out.copy_(residual)
         return ops.conv1d_direct(x, f.weight(), f.bias(), d=d, pad=pad,
                                  flags=(ops.CONV_LRELU_IN if lrelu else 0) | ops.CONV_ADD_OUT, out=out)
-    return ops.conv1d_direct(x, f.weight(), f.bias(), d=d, pad=pad, flags=ops.CONV_LRELU_IN if lrelu else 0)
+    return ops.conv1d_direct(x, f.weight(), f.bias(), d=d, pad=pad, flags=ops.CONV_LRELU_IN if lrelu else 0, out=out)
 
 
 def _dense_convT(x: torch.Tensor, f: _Folded, k: int, u: int, add: Optional[torch.Tensor] = None,
                  scale: float = 1.0) -> torch.Tensor:
-    """ConvTranspose1d(k, stride u, padding (k-u)//2) of the fp32 [B,C,L] tensor ``x * scale`` (+ optional add)."""
-    B, C, L = x.shape
+    """ConvTranspose1d(k, stride u, padding (k-u)//2) of the fp32 [B,C,L] tensor ``x * scale`` (+ optional add).
+    ``x`` may be the list of per-resblock outputs of the previous stage (``sum_of_blocks(..., separate=True)``): their
+    sum is taken inside the operand pack."""
+    B, C, L = (x[0] if isinstance(x, (list, tuple)) else x).shape
     cout = f.conv.out_channels
     if C % 16 == 0 and cout % 16 == 0:
-        buf = ops.blk16_buffer(B, C, L, x.device, _MAIN_SLOT)
+        buf = ops.blk16_buffer(B, C, L, f.weight().device, _MAIN_SLOT)
         ops.pack_blk16(x, buf, scale=scale)
         ops.check_saturation(buf, C, L)
         wp, nt = f.packedT_weight(u, _row_tiles(B, L))
         return ops.conv_transpose1d_umma(buf, wp, f.bias(), L, C, cout, k, u, nt, add=add)
-    if scale != 1.0:
+    if scale != 1.0 or isinstance(x, (list, tuple)):
         raise NotImplementedError("channel counts that are not multiples of 16 are not supported on this path")
     return ops.conv_transpose1d(x, f.weight(), f.bias(), u, add=add)
 
@@ -402,14 +409,34 @@ class AMPBlock1(nn.Module):
 AMPBlock0 = AMPBlock1
 
 
-def sum_of_blocks(x: torch.Tensor, blocks: Sequence[AMPBlock1], parallel: bool = False):
+def sum_of_blocks(x: torch.Tensor, blocks: Sequence[AMPBlock1], parallel: bool = False, separate: bool = False):
     """(xs, scale) with xs = sum_j resblock_j(x) and scale = 1/num_kernels
     (hierspeechpp_speechsynthesizer.py:440-446).  The sum is accumulated in the epilogue of each block's
     last conv (store, then red.add in stream order: deterministic); the division is applied by the
-    consumer of xs (``in_scale`` of the next activation / operand pack), so xs is never re-read."""
+    consumer of xs (``in_scale`` of the next activation / operand pack), so xs is never re-read.
+
+    ``separate=True`` (multi-stream mode only, up to three blocks): every block writes its own tensor and the LIST is
+    returned; the consumer's operand pack adds them in the same fixed order ((x1 + x2) + x3, bit-identical to the
+    chained accumulation, same bytes moved).  The last convs of the blocks then run concurrently instead of one
+    after the other: at batch 1 that chain was ~10 us at the end of every stage."""
     nk = len(blocks)
     if nk == 1:
         return blocks[0].run(x), 1.0
+    if separate and parallel and nk <= 3:
+        main = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(main)
+        streams = _side_streams(x.device, nk)
+        outs = []
+        for j, blk in enumerate(blocks):
+            s = streams[j]
+            s.wait_event(fork)
+            with torch.cuda.stream(s):
+                outs.append(blk.run(x, slot=j))
+                ev = torch.cuda.Event()
+                ev.record(s)
+            main.wait_event(ev)
+        return outs, 1.0 / nk
     xs = torch.empty_like(x)
     modes = [ops.ACC_SET] + [ops.ACC_ADD] * (nk - 1)
     if not parallel:
@@ -488,9 +515,11 @@ class _VocoderBase(nn.Module):
         super().__init__()
         _bump_on_load(self)
 
-    def _stage(self, x, i):
+    def _stage(self, x, i, separate: bool = False):
+        """``separate``: the consumer of this stage is an operand pack (the next stage's ConvTranspose1d), which can
+        take the per-resblock tensors as a list."""
         nk = self.num_kernels
-        return sum_of_blocks(x, [self.resblocks[i * nk + j] for j in range(nk)], self.parallel_blocks)
+        return sum_of_blocks(x, [self.resblocks[i * nk + j] for j in range(nk)], self.parallel_blocks, separate)
 
 
 class SourceNetwork(_VocoderBase):
@@ -536,7 +565,7 @@ class SourceNetwork(_VocoderBase):
         sc = 1.0
         for i in range(self.num_upsamples):
             x = _dense_convT(x, self._f_ups[i], self.ups[i].kernel_size[0], self.upsample_rates[i], scale=sc)
-            x, sc = self._stage(x, i)
+            x, sc = self._stage(x, i, separate=i < self.num_upsamples - 1)
         self.activation_post.check_filters()
         x = ops.act1d(x, *self.activation_post.params(), scale=sc)
         x_ = ops.conv1d_direct(x, self._f_post.weight(), None, pad=3) if need_pred else None
@@ -576,14 +605,21 @@ class Generator(_VocoderBase):
         self._f_cond = _Folded(self.cond) if gin_channels != 0 else None
         self._f_proj = _Folded(self.proj)
 
-    def forward(self, x, pitch, g=None):
+    def pre(self, x, g, out=None, slot: Optional[int] = None):
+        """``conv_pre(x)`` and ``cond(g)`` (:428, :430): the part of forward that does not need the pitch hidden state,
+        so ``Vocoder`` can run it beside the SourceNetwork.  ``out`` = (xp, cg) preallocated by the caller."""
+        x, g = _as_input(x), _as_input(g)
+        xp = _dense_conv(x, self._f_pre, 7, slot=slot, out=None if out is None else out[0])
+        cg = ops.conv1d_direct(g, self._f_cond.weight(), self._f_cond.bias(), out=None if out is None else out[1])
+        return xp, cg
+
+    def forward(self, x, pitch, g=None, _pre=None):
         x, pitch = _as_input(x), _as_input(pitch)
-        xp = _dense_conv(x, self._f_pre, 7)
-        dn = self.downs(pitch)
         if g is None:
             # the reference evaluates self.cond(g) unconditionally (:430) and fails on g=None
             raise ValueError("Generator.forward needs the speaker embedding g")
-        cg = ops.conv1d_direct(_as_input(g), self._f_cond.weight(), self._f_cond.bias())
+        xp, cg = self.pre(x, g) if _pre is None else _pre
+        dn = self.downs(pitch)
         x = ops.add3_bcast(xp, dn, cg, out=xp)
         sc = 1.0
         for i in range(self.num_upsamples):
@@ -592,7 +628,7 @@ class Generator(_VocoderBase):
                 add = _dense_conv(pitch, self._f_proj, 7)
             x = _dense_convT(x, self._f_ups[i], self.ups[i].kernel_size[0], self.upsample_rates[i], add=add,
                              scale=sc)
-            x, sc = self._stage(x, i)
+            x, sc = self._stage(x, i, separate=i < self.num_upsamples - 1)
         self.activation_post.check_filters()
         x = ops.act1d(x, *self.activation_post.params(), scale=sc)
         return ops.conv1d_direct(x, self._f_post.weight(), None, pad=3, flags=ops.CONV_TANH)
@@ -701,6 +737,33 @@ class SpeechSR48(_SpeechSRSynthesizer):
     _gen_cls = SpeechSR48Generator
 
 
+def vocode(sn: "SourceNetwork", dec: "Generator", z, g, need_pred: bool = False):
+    """``e, e_ = sn(z, g); return dec(z, e, g), e_`` (hierspeechpp_speechsynthesizer.py:648-649, :697-698).
+
+    In multi-stream mode (``dec.parallel_blocks``) ``dec.conv_pre(z)`` and ``dec.cond(g)``, which do not depend on the
+    SourceNetwork, run beside it on their own stream and operand workspace slot; their outputs are allocated on the
+    caller's stream."""
+    if not (dec.parallel_blocks and z.is_cuda):
+        e, e_ = sn(z, g, need_pred=need_pred)
+        return dec(z, e, g=g), e_
+    z_, g_ = _as_input(z), _as_input(g)
+    B, _, T = z_.shape
+    c0 = dec.conv_pre.out_channels
+    xp = torch.empty(B, c0, T, dtype=torch.float32, device=z_.device)
+    cg = torch.empty(B, c0, 1, dtype=torch.float32, device=z_.device)
+    main = torch.cuda.current_stream()
+    side = _side_streams(z_.device, 1)[0]
+    fork, done = torch.cuda.Event(), torch.cuda.Event()
+    fork.record(main)
+    side.wait_event(fork)
+    with torch.cuda.stream(side):
+        dec.pre(z_, g_, out=(xp, cg), slot=_PRE_SLOT)
+        done.record(side)
+    e, e_ = sn(z_, g_, need_pred=need_pred)
+    main.wait_event(done)
+    return dec(z_, e, g=g_, _pre=(xp, cg)), e_
+
+
 class Vocoder(nn.Module):
     """The ``sn`` -> ``dec`` pair as ``SynthesizerTrn`` owns it (hierspeechpp_speechsynthesizer.py:624-625,
     648-649): ``forward(z, g)`` returns the 16 kHz waveform [B,1,320*T]."""
@@ -714,8 +777,7 @@ class Vocoder(nn.Module):
         self.sn = SourceNetwork(c["upsample_initial_channel"] // 2)
 
     def forward(self, z, g):
-        e, _ = self.sn(z, g, need_pred=False)
-        return self.dec(z, e, g=g)
+        return vocode(self.sn, self.dec, z, g)[0]
 
 
 class VocoderSR(nn.Module):

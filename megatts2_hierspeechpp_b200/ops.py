@@ -137,13 +137,27 @@ def act1d_blk16(x: torch.Tensor, alpha: torch.Tensor, beta: torch.Tensor, buf: t
     return buf
 
 
-def pack_blk16(x: torch.Tensor, buf: torch.Tensor, lrelu: bool = False, scale: float = 1.0):
-    _req(x, "x", ndim=3); _req(buf, "buf", torch.float16, 4)
-    B, C, L = x.shape
+def pack_blk16(x, buf: torch.Tensor, lrelu: bool = False, scale: float = 1.0):
+    """fp32 [B,C,L] -> fp16 blk16 operand of ``x * scale`` (optionally leaky_relu(0.1) of it).  ``x`` may be a list of up
+    to three equally shaped tensors: the operand is then ``((x1 + x2) + x3) * scale`` (the sum over a stage's resblocks
+    taken by the consumer, ``modules.sum_of_blocks(..., separate=True)``)."""
+    xs = list(x) if isinstance(x, (list, tuple)) else [x]
+    if not 1 <= len(xs) <= 3:
+        raise ValueError("pack_blk16: one to three addends")
+    for t in xs:
+        _req(t, "x", ndim=3)
+        if t.shape != xs[0].shape:
+            raise ValueError("pack_blk16: addend shapes differ")
+    _req(buf, "buf", torch.float16, 4)
+    B, C, L = xs[0].shape
     if tuple(buf.shape) != blk16_shape(B, C, L):
         raise ValueError("blk16 buffer shape mismatch")
     lib = _lib.load()
-    _lib.check(lib.hsv_pack_blk16(_p(x), _p(buf), B, C, L, int(lrelu), float(scale), _stream()), "hsv_pack_blk16")
+    if len(xs) == 1:
+        _lib.check(lib.hsv_pack_blk16(_p(xs[0]), _p(buf), B, C, L, int(lrelu), float(scale), _stream()), "hsv_pack_blk16")
+    else:
+        _lib.check(lib.hsv_pack_blk16_sum3(_p(xs[0]), _p(xs[1]), _p(xs[2]) if len(xs) == 3 else None, _p(buf), B, C, L,
+                                           int(lrelu), float(scale), _stream()), "hsv_pack_blk16_sum3")
     return buf
 
 

@@ -178,9 +178,9 @@ class PitchPredictor(nn.Module):
         sc = 1.0
         L = T
         for i in range(self.num_upsamples):
-            cin = h.shape[1]
+            cin = (h[0] if isinstance(h, list) else h).shape[1]
             f = self._f_ups[i]
-            buf = ops.blk16_buffer(B, cin, L, h.device, _MAIN_SLOT)
+            buf = ops.blk16_buffer(B, cin, L, x.device, _MAIN_SLOT)
             ops.pack_blk16(h, buf, True, scale=sc)                            # leaky_relu(x / num_kernels, 0.1)
             ops.check_saturation(buf, cin, L)
             wp, nt = f.packedT_weight(self.upsample_rates[i], _row_tiles(B, L))
@@ -188,7 +188,7 @@ class PitchPredictor(nn.Module):
                                           self.ups[i].kernel_size[0], self.upsample_rates[i], nt)
             L *= self.upsample_rates[i]
             blocks: Sequence[ResBlock1] = self.resblocks[i * self.num_kernels:(i + 1) * self.num_kernels]
-            h, sc = sum_of_blocks(h, blocks, parallel=self.parallel_blocks)
+            h, sc = sum_of_blocks(h, blocks, parallel=self.parallel_blocks, separate=i < self.num_upsamples - 1)
         return ops.conv1d_direct(h, self._post_weight(sc), None, pad=3, flags=ops.CONV_LRELU001_IN)
 
     def remove_weight_norm(self):

@@ -50,6 +50,11 @@ def act1d_blk16(x, a, b, buf, scale=1.0):
 
 
 def pack_blk16(x, buf, lrelu=False, scale=1.0):
+    if isinstance(x, (list, tuple)):
+        xs = list(x)
+        x = xs[0]
+        for t in xs[1:]:
+            x = x + t
     x = x * scale
     _pack_into(buf, F.leaky_relu(x, 0.1) if lrelu else x)
     return buf

@@ -123,19 +123,40 @@ def test_weight_norm_fold(hsv, shape):
 
 @pytest.mark.parametrize("cin,cout,k,d,pad,L,flags", [
     (192, 512, 7, 1, 3, 50, 0), (64, 512, 3, 1, 1, 33, 1), (512, 512, 3, 4, 4, 61, 1), (64, 256, 7, 1, 3, 200, 0),
-    (16, 1, 7, 1, 3, 1000, 2), (32, 1, 7, 1, 3, 999, 2), (256, 512, 1, 1, 0, 1, 0), (5, 9, 5, 2, 4, 77, 0)])
+    (16, 1, 7, 1, 3, 1000, 2), (32, 1, 7, 1, 3, 999, 2), (256, 512, 1, 1, 0, 1, 0), (5, 9, 5, 2, 4, 77, 0),
+    (40, 3, 7, 1, 3, 1541, 3), (64, 1, 7, 1, 3, 511, 0), (7, 4, 7, 1, 3, 513, 2),      # smem-staged thin conv: ragged
+    (1024, 768, 1, 1, 0, 1, 8), (6, 10, 1, 1, 0, 1, 0)])                                # vector dot (float4) / row dot
 def test_conv1d_direct(hsv, cin, cout, k, d, pad, L, flags):
     gen = torch.Generator().manual_seed(cin + cout + k + L)
     x = torch.randn(2, cin, L, generator=gen)
     w = torch.randn(cout, cin, k, generator=gen) / (cin * k) ** 0.5
     b = torch.randn(cout, generator=gen)
     xin = F.leaky_relu(x, 0.1) if flags & 1 else x
+    xin = F.silu(xin) if flags & 8 else xin
     ref = F.conv1d(xin, w, b, padding=pad, dilation=d)
     if flags & 2:
         ref = torch.tanh(ref)
     y = hsv.ops.conv1d_direct(x.to(DEV), w.to(DEV), b.to(DEV), d=d, pad=pad, flags=flags).cpu()
     assert y.shape == ref.shape
     assert (y - ref).abs().max() <= 2e-5 * max(1.0, ref.abs().max().item())
+
+
+def test_pack_blk16_sum_of_addends(hsv):
+    """The consumer-side sum over a stage's resblocks: ((x1 + x2) + x3) * scale, bit-identical to packing the
+    pre-summed tensor."""
+    ops = hsv.ops
+    gen = torch.Generator().manual_seed(9)
+    B, C, L = 2, 32, 333
+    xs = [torch.randn(B, C, L, generator=gen).to(DEV) for _ in range(3)]
+    a, b = ops.blk16_buffer(B, C, L, DEV, slot=8), ops.blk16_buffer(B, C, L, DEV, slot=9)
+    for n in (2, 3):
+        for lrelu in (False, True):
+            pre = xs[0] + xs[1] if n == 2 else (xs[0] + xs[1]) + xs[2]
+            ops.pack_blk16(xs[:n], a, lrelu, scale=1.0 / 3)
+            ops.pack_blk16(pre, b, lrelu, scale=1.0 / 3)
+            assert torch.equal(ops.unpack_blk16(a, C, L), ops.unpack_blk16(b, C, L))
+    with pytest.raises(ValueError):
+        ops.pack_blk16(xs + xs[:1], a)
 
 
 def test_conv1d_direct_add_out(hsv):
