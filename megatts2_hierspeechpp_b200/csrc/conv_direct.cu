@@ -117,14 +117,27 @@ __global__ void __launch_bounds__(256) conv1d_thin_smem_kernel(const float *__re
   for (int c0 = 0; c0 < Cin; c0 += CC) {
     const int nc = min(CC, Cin - c0);
     if (c0) __syncthreads();
-    for (int idx = tid; idx < nc * W; idx += 256) {
-      const int c = idx / W, pp = idx - c * W;
-      const int64_t ts = t0 - pad + pp;
-      float v = (ts >= 0 && ts < Lin) ? __ldg(x + ((int64_t)b * Cin + c0 + c) * Lin + ts) : 0.f;
-      if (flags & HSV_CONV_LRELU_IN) v = v > 0.f ? v : 0.1f * v;
-      if (flags & HSV_CONV_LRELU001_IN) v = v > 0.f ? v : 0.01f * v;
-      if (flags & HSV_CONV_SILU_IN) v = v / (1.f + expf(-v));
-      xs[c][pp] = v;
+    // all loads of a batch are issued before the first store (independent L2 round trips, not a chain)
+    constexpr int NB = 11;
+    for (int i0 = tid; i0 < nc * W; i0 += 256 * NB) {
+      float v[NB];
+#pragma unroll
+      for (int q = 0; q < NB; ++q) {
+        const int idx = i0 + 256 * q;
+        const int c = idx / W, pp = idx - c * W;
+        const int64_t ts = t0 - pad + pp;
+        v[q] = (idx < nc * W && ts >= 0 && ts < Lin) ? __ldg(x + ((int64_t)b * Cin + c0 + c) * Lin + ts) : 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < NB; ++q) {
+        const int idx = i0 + 256 * q;
+        const int c = idx / W, pp = idx - c * W;
+        float u = v[q];
+        if (flags & HSV_CONV_LRELU_IN) u = u > 0.f ? u : 0.1f * u;
+        if (flags & HSV_CONV_LRELU001_IN) u = u > 0.f ? u : 0.01f * u;
+        if (flags & HSV_CONV_SILU_IN) u = u / (1.f + expf(-u));
+        if (idx < nc * W) xs[c][pp] = u;
+      }
     }
     for (int idx = tid; idx < Cout * nc * K; idx += 256) {
       const int co = idx / (nc * K), r = idx - co * (nc * K);

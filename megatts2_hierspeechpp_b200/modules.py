@@ -491,14 +491,30 @@ class DBlock(nn.Module):
         self._fc = [_Folded(c) for c in self.conv]
         _bump_on_load(self)
 
-    def forward(self, x):
+    def forward(self, x, side=None):
+        """``side`` = (stream, workspace slot): run the residual 1x1 conv there, beside the first two convs of the
+        main branch (it is only needed by the third)."""
         x = _as_input(x)
         size = x.shape[-1] // self.factor
         # nearest down-sampling commutes with the 1x1 conv: gather first (4x less work, same values)
         xd = ops.nearest_gather(x, size)
-        res = _dense_conv(xd, self._fr, 1)
+        if side is None:
+            res = _dense_conv(xd, self._fr, 1)
+            ready = None
+        else:
+            st, slot = side
+            main = torch.cuda.current_stream()
+            res = torch.empty(x.shape[0], self.residual_dense.out_channels, size, dtype=torch.float32, device=x.device)
+            fork, ready = torch.cuda.Event(), torch.cuda.Event()
+            fork.record(main)
+            st.wait_event(fork)
+            with torch.cuda.stream(st):
+                _dense_conv(xd, self._fr, 1, slot=slot, out=res)
+                ready.record(st)
         h = xd
         for i, d in enumerate((1, 2, 4)):
+            if i == 2 and ready is not None:
+                torch.cuda.current_stream().wait_event(ready)
             h = _dense_conv(h, self._fc[i], 3, d, lrelu=True, residual=res if i == 2 else None)
         return h
 
@@ -619,13 +635,32 @@ class Generator(_VocoderBase):
             # the reference evaluates self.cond(g) unconditionally (:430) and fails on g=None
             raise ValueError("Generator.forward needs the speaker embedding g")
         xp, cg = self.pre(x, g) if _pre is None else _pre
-        dn = self.downs(pitch)
+        proj = proj_ready = None
+        if self.parallel_blocks:
+            # multi-stream mode: proj(pitch) (:437) and the DBlock's residual conv run beside the DBlock's main branch
+            # on two of the (idle) resblock streams, each with its stream's workspace slot
+            main = torch.cuda.current_stream()
+            s0, s1 = _side_streams(x.device, 3)[:2]
+            proj = torch.empty(x.shape[0], self.proj.out_channels, pitch.shape[-1], dtype=torch.float32, device=x.device)
+            fork, proj_ready = torch.cuda.Event(), torch.cuda.Event()
+            fork.record(main)
+            s0.wait_event(fork)
+            with torch.cuda.stream(s0):
+                _dense_conv(pitch, self._f_proj, 7, slot=0, out=proj)
+                proj_ready.record(s0)
+            dn = self.downs(pitch, side=(s1, 1))
+        else:
+            dn = self.downs(pitch)
         x = ops.add3_bcast(xp, dn, cg, out=xp)
         sc = 1.0
         for i in range(self.num_upsamples):
             add = None
             if i == 0:
-                add = _dense_conv(pitch, self._f_proj, 7)
+                if proj is None:
+                    add = _dense_conv(pitch, self._f_proj, 7)
+                else:
+                    torch.cuda.current_stream().wait_event(proj_ready)
+                    add = proj
             x = _dense_convT(x, self._f_ups[i], self.ups[i].kernel_size[0], self.upsample_rates[i], add=add,
                              scale=sc)
             x, sc = self._stage(x, i, separate=i < self.num_upsamples - 1)
