@@ -225,12 +225,23 @@ int hsv_peak_norm_pcm16(const float *x, int16_t *out, float *peak_ws, int rows, 
  * hsv_masked_mean: out[b,c] = sum_t x[b,c,t] / sum_t mask[b,t] (styleencoder.py:91-99: the sum runs over all frames). */
 int hsv_pack_blk16_act(const float *x, const float *bcast, const float *mask, void *out, int B, int C, int64_t L,
                        int mode, int x_channels, void *stream);
+/* WN layer tail + the next layer's operand pack in one pass (modules.py:167-174): x = (x + rs[:, :C]) * mask in place,
+ * output += rs[:, C:], blk = fp16 blk16 operand of the new x.  rs is [B, 2C, T]. */
+int hsv_wn_res_pack(float *x, const float *rs, const float *mask, float *output, void *blk, int B, int C, int64_t L,
+                    void *stream);
 int hsv_ln_mod_blk16(const float *x, const float *shift, const float *scale, const float *mask, void *out, int B, int C,
                      int64_t L, float eps, int inmask, int premask, int64_t mod_stride, void *stream);
 int hsv_frame_op(int op, const float *a, const float *b, const float *c, const float *mask, float *out, float *out2,
                  int B, int C, int64_t L, float s, int64_t cstride, void *stream);
 int hsv_mha(const float *q, const float *k, const float *v, float *out, const int *lens, int B, int heads, int D, int Tq,
             int Tk, int64_t q_bstride, int64_t k_bstride, int64_t v_bstride, float scale, int prescale_q, void *stream);
+/* the same (tensor-core kernel only), the result written as the fp16 blk16 operand [heads*D channels, Tq rows] of the
+ * projection conv that follows (timm Attention.proj): saves the fp32 round trip and the pack launch. */
+int hsv_mha_blk16(const float *q, const float *k, const float *v, void *out_blk16, const int *lens, int B, int heads, int D,
+                  int Tq, int Tk, int64_t q_bstride, int64_t k_bstride, int64_t v_bstride, float scale, int prescale_q,
+                  void *stream);
+/* test hook: 0 = tensor-core attention (csrc/mha_mma.cu, default), 1 = the fp32 CUDA-core kernel. Process-global. */
+int hsv_set_mha_variant(int v);
 int hsv_conv1d_c1_strided(const float *x, const float *w, const float *bias, const float *mask, float *out, int B,
                           int Cout, int64_t Lin, int64_t Lout, int k, int stride, int pad, void *stream);
 int hsv_masked_mean(const float *x, const float *mask, float *out, int B, int C, int64_t L, void *stream);

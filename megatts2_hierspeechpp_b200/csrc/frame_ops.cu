@@ -77,6 +77,36 @@ __global__ void pack_act_kernel(const float *__restrict__ x, const float *__rest
   }
 }
 
+// WN layer tail fused with the next layer's operand pack (modules.py:167-174 + the PACK of in_layers[i+1]):
+//   x = (x + rs[:, :C]) * mask  (in place, fp32: the residual stream)   output += rs[:, C:]   blk = fp16(x)
+__global__ void wn_res_pack_kernel(float *__restrict__ x, const float *__restrict__ rs, const float *__restrict__ mask,
+                                   float *__restrict__ output, uint4 *__restrict__ blk, int B, int C, int64_t L,
+                                   int64_t Lp, int cw) {
+  const int nch = C >> 3;
+  const int64_t n = (int64_t)B * nch * L;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t bq = i / L, t = i - bq * L;
+    const int64_t bb = bq / nch;
+    const int c0 = (int)(bq - bb * nch) * 8;
+    const float mk = mask ? __ldg(mask + bb * L + t) : 1.f;
+    float *xr = x + (bb * C + c0) * L + t, *orow = output + (bb * C + c0) * L + t;
+    const float *rr = rs + (bb * 2 * C + c0) * L + t;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      v[e] = (xr[(int64_t)e * L] + __ldg(rr + (int64_t)e * L)) * mk;
+      const float skip = __ldg(rr + (int64_t)(C + e) * L);
+      xr[(int64_t)e * L] = v[e];
+      orow[(int64_t)e * L] = orow[(int64_t)e * L] + skip;
+    }
+    __half2 h[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+    *reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(blk) +
+                               hsv::blk_unit_offset(cw, Lp, C, bb, c0, HSV_BLK_PAD + t)) = *reinterpret_cast<uint4 *>(h);
+  }
+}
+
 // LayerNorm over channels (no affine) -> optional mask -> modulate -> fp16 blk16.  CTA = 32 time steps x 8 channel
 // groups; thread (tx, g) owns the C/8 consecutive channels of group g at step tx (C % 64 == 0: whole 16-byte units).
 template <int CPT>   // channels per thread = C / 8
@@ -451,6 +481,16 @@ extern "C" int hsv_pack_blk16_act(const float *x, const float *bcast, const floa
   return hsv::check_launch("pack_blk16_act");
 }
 
+extern "C" int hsv_wn_res_pack(float *x, const float *rs, const float *mask, float *output, void *blk, int B, int C,
+                               int64_t L, void *stream) {
+  if (B == 0 || L == 0) return HSV_OK;
+  HSV_REQUIRE(x && rs && output && blk, "wn_res_pack: null pointer");
+  HSV_REQUIRE(C > 0 && C % 16 == 0, "wn_res_pack: C %% 16 != 0 (C=%d)", C);
+  wn_res_pack_kernel<<<grid_for((int64_t)B * (C / 8) * L, 256), 256, 0, hsv::as_stream(stream)>>>(
+      x, rs, mask, output, reinterpret_cast<uint4 *>(blk), B, C, L, hsv::blk16_rows(L), hsv::blk_cw(C));
+  return hsv::check_launch("wn_res_pack");
+}
+
 extern "C" int hsv_ln_mod_blk16(const float *x, const float *shift, const float *scale, const float *mask, void *out,
                                 int B, int C, int64_t L, float eps, int inmask, int premask, int64_t mod_stride,
                                 void *stream) {
@@ -480,6 +520,17 @@ extern "C" int hsv_frame_op(int op, const float *a, const float *b, const float 
   return hsv::check_launch("frame_op");
 }
 
+namespace hsv {
+int mha_mma_launch(const float *q, const float *k, const float *v, void *out, int blk, const int *lens, int B, int heads,
+                   int D, int Tq, int Tk, int64_t qbs, int64_t kbs, int64_t vbs, float scale, int prescale,
+                   cudaStream_t st);
+}
+static int g_mha_variant = 0;   // 0: tensor cores (mha_mma.cu), 1: the fp32 CUDA-core kernel of this file (test hook)
+extern "C" int hsv_set_mha_variant(int v) {
+  g_mha_variant = v;
+  return HSV_OK;
+}
+
 extern "C" int hsv_mha(const float *q, const float *k, const float *v, float *out, const int *lens, int B, int heads,
                        int D, int Tq, int Tk, int64_t q_bstride, int64_t k_bstride, int64_t v_bstride, float scale,
                        int prescale_q, void *stream) {
@@ -488,6 +539,11 @@ extern "C" int hsv_mha(const float *q, const float *k, const float *v, float *ou
   HSV_REQUIRE(D == 96 || D == 128 || D == 64, "mha: head dim must be 64, 96 or 128 (D=%d)", D);
   HSV_REQUIRE(Tk > 0 && heads > 0 && heads <= 65535 && B <= 65535, "mha: bad shape");
   cudaStream_t st = hsv::as_stream(stream);
+  if (g_mha_variant == 0) {
+    const int rc = hsv::mha_mma_launch(q, k, v, out, 0, lens, B, heads, D, Tq, Tk, q_bstride, k_bstride, v_bstride, scale,
+                                       prescale_q, st);
+    if (rc != 1) return rc;
+  }
   // few (batch, head, query tile) items: 8-row tiles spread the work over more SMs
   const bool small = (int64_t)B * heads * ((Tq + 15) / 16) < 148;
 #define HSV_MHA(DD)                                                                                               \
@@ -499,6 +555,18 @@ extern "C" int hsv_mha(const float *q, const float *k, const float *v, float *ou
   if (D == 128) { HSV_MHA(128); }
   HSV_MHA(64);
 #undef HSV_MHA
+}
+
+extern "C" int hsv_mha_blk16(const float *q, const float *k, const float *v, void *out_blk16, const int *lens, int B,
+                             int heads, int D, int Tq, int Tk, int64_t q_bstride, int64_t k_bstride, int64_t v_bstride,
+                             float scale, int prescale_q, void *stream) {
+  if (B == 0 || Tq == 0) return HSV_OK;
+  HSV_REQUIRE(q && k && v && out_blk16, "mha_blk16: null pointer");
+  HSV_REQUIRE(Tk > 0 && heads > 0 && heads <= 32767 && B <= 65535 && (heads * D) % 16 == 0, "mha_blk16: bad shape");
+  const int rc = hsv::mha_mma_launch(q, k, v, out_blk16, 1, lens, B, heads, D, Tq, Tk, q_bstride, k_bstride, v_bstride,
+                                     scale, prescale_q, hsv::as_stream(stream));
+  HSV_REQUIRE(rc != 1, "mha_blk16: head dim must be 64, 96 or 128 (D=%d)", D);
+  return rc;
 }
 
 extern "C" int hsv_conv1d_c1_strided(const float *x, const float *w, const float *bias, const float *mask, float *out,

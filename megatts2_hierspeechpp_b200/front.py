@@ -22,9 +22,11 @@ from torch import nn
 from torch.nn import Conv1d
 
 from . import ops
-from .modules import (_Folded, _as_input, _bump_on_load, _row_tiles, _weight_norm, Generator, SourceNetwork, vocode)
+from .modules import (_Folded, _as_input, _bump_on_load, _row_tiles, _side_streams, _weight_norm, Generator,
+                      SourceNetwork, vocode)
 
-_S_X, _S_G, _S_W = 4, 5, 6      # blk16 workspace slots of this module family (0..3 belong to the vocoder)
+_S_X, _S_G, _S_W = 4, 5, 6      # blk16 workspace slots of this module family (0..3 and 7 belong to the vocoder)
+_S_X2, _S_G2 = 10, 11           # ... of the second WaveNet stack when two run side by side (8, 9: tests)
 
 
 class _FoldedLinear(_Folded):
@@ -46,6 +48,30 @@ class _FoldedLinear(_Folded):
 def _epoch():
     from . import modules as M
     return M._CACHE_EPOCH[0]
+
+
+class _FoldedCat:
+    """Several nn.Linear layers with the same input, concatenated along the output dimension (one launch for all)."""
+
+    def __init__(self, lins):
+        self.lins = list(lins)
+        self.key, self.w, self.b = None, None, None
+
+    def _refresh(self):
+        key = tuple((l.weight.data_ptr(), l.weight._version, l.bias.data_ptr(), l.bias._version) for l in self.lins) \
+            + (_epoch(),)
+        if key != self.key:
+            self.w = torch.cat([l.weight.detach() for l in self.lins], 0).unsqueeze(-1).contiguous()
+            self.b = torch.cat([l.bias.detach() for l in self.lins], 0).contiguous()
+            self.key = key
+
+    def weight(self):
+        self._refresh()
+        return self.w
+
+    def bias(self):
+        self._refresh()
+        return self.b
 
 
 def _mask2d(x_mask: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
@@ -103,10 +129,21 @@ def _conv(x: torch.Tensor, f: _Folded, k: int = 1, d: int = 1, mode: int = ops.P
     if not hasattr(f, "_slices") or f._slices[0] != (C, nsplit):
         f._slices = ((C, nsplit), [_FoldedSlice(f, i * per, (i + 1) * per) for i in range(nsplit)])
     out = None
+    whole = None
+    if B == 1 and per % ops.blk_cw(C) == 0 and ops.blk_cw(per) == ops.blk_cw(C):
+        # one batch item: the channel chunks of a blk16 buffer are its outermost dimension, so ONE pack of all C channels
+        # serves every pass as a dense sub-buffer
+        whole = ops.blk16_buffer(B, C, L, x.device, slot)
+        ops.pack_blk16_act(x, whole, C, mode, mask=mask)
+        ops.check_saturation(whole, C, L)
+        nchunk = whole.shape[1] * per // C            # channel chunks per pass
     for i, fs in enumerate(f._slices[1]):
-        buf = ops.blk16_buffer(B, per, L, x.device, slot)
-        ops.pack_blk16_act(x, buf, per, mode, mask=mask, c_off=i * per)
-        ops.check_saturation(buf, per, L)
+        if whole is not None:
+            buf = whole[:, i * nchunk:(i + 1) * nchunk]
+        else:
+            buf = ops.blk16_buffer(B, per, L, x.device, slot)
+            ops.pack_blk16_act(x, buf, per, mode, mask=mask, c_off=i * per)
+            ops.check_saturation(buf, per, L)
         wp, nt = fs.packed_weight(_row_tiles(B, L))
         out = ops.conv1d_umma(buf, wp, f.bias() if i == 0 else None, L, per, cout, k, d, nt, residual=out)
     return out
@@ -149,25 +186,32 @@ class WN(nn.Module):
         self._f_cond = _Folded(self.cond_layer) if gin_channels != 0 else None
         _bump_on_load(self)
 
-    def forward(self, x, x_mask, g=None, **kwargs):
+    def forward(self, x, x_mask, g=None, slots=(_S_X, _S_G), **kwargs):
+        """``slots``: the two operand workspace slots of this call (two WN stacks on two streams need two pairs)."""
         x = _as_input(x)
         mask = _mask2d(x_mask)
         B, H, T = x.shape
         k = self.kernel_size[0]
         n = self.n_layers
+        sx, sg = slots
         gl = None
         if g is not None:
             # cond_layer(g): [B, 2H*n, 1]; per layer slice, laid out [n, B, 2H] so every slice is dense
             gl = _vec(_as_input(g).reshape(B, -1), self._f_cond).view(B, n, 2 * H).transpose(0, 1).contiguous()
         x = x.clone()
         output = torch.zeros_like(x)
+        # the operand of in_layers[0]; every later layer's operand is written by the previous layer's fused tail
+        buf = ops.blk16_buffer(B, H, T, x.device, sx)
+        ops.pack_blk16_act(x, buf, H, ops.PACK_MASK)
+        ops.check_saturation(buf, H, T)
         for i in range(n):
             d = self.dilation_rate ** i
-            x_in = _conv(x, self._f_in[i], k, d, slot=_S_X)
-            acts_rs = _conv(x_in, self._f_rs[i], 1, 1, mode=ops.PACK_GATE, C=H, slot=_S_G,
+            x_in = _conv_buf(buf, self._f_in[i], T, H, 2 * H, k, d)
+            acts_rs = _conv(x_in, self._f_rs[i], 1, 1, mode=ops.PACK_GATE, C=H, slot=sg,
                             bcast=None if gl is None else gl[i])
             if i < n - 1:
-                ops.frame_op(ops.OP_WN_RES, x, acts_rs, None, mask, x, output, B, H, T)
+                ops.wn_res_pack(x, acts_rs, mask, output, buf)       # x, output updated in place; buf = fp16(x)
+                ops.check_saturation(buf, H, T)
             else:
                 ops.frame_op(ops.OP_WN_LAST, None, acts_rs, None, mask, None, output, B, H, T)
         return output
@@ -186,6 +230,8 @@ class WN(nn.Module):
 # PosteriorSFEncoder  (hierspeechpp_speechsynthesizer.py:168-203)
 # ----------------------------------------------------------------------------------------------
 class PosteriorSFEncoder(nn.Module):
+    parallel_blocks = False     # multi-stream mode (set together with the vocoder's switch)
+
     def __init__(self, src_channels, out_channels, hidden_channels, kernel_size, dilation_rate, n_layers,
                  gin_channels=0):
         super().__init__()
@@ -215,8 +261,21 @@ class PosteriorSFEncoder(nn.Module):
         xf = ops.conv1d_c1_strided(x_ftr, self.pre_filter.weight.detach(), self.pre_filter.bias.detach(), 4, 4, mask)
         if xf.shape[-1] != T:
             raise ValueError(f"f0 has {x_ftr.shape[-1]} frames, expected 4 x {T}")
-        xs = self.source_enc(xs, x_mask, g=g)
-        xf = self.filter_enc(xf, x_mask, g=g)
+        if self.parallel_blocks:
+            # the two WaveNet stacks are independent (:197-198): second stream, second pair of workspace slots
+            main = torch.cuda.current_stream()
+            side = _side_streams(xs.device, 3)[0]
+            fork, done = torch.cuda.Event(), torch.cuda.Event()
+            fork.record(main)
+            side.wait_event(fork)
+            with torch.cuda.stream(side):
+                xf = self.filter_enc(xf, x_mask, g=g, slots=(_S_X2, _S_G2))
+                done.record(side)
+            xs = self.source_enc(xs, x_mask, g=g)
+            main.wait_event(done)
+        else:
+            xs = self.source_enc(xs, x_mask, g=g)
+            xf = self.filter_enc(xf, x_mask, g=g)
         ops.frame_op(ops.OP_ADD, xs, xf, None, None, xs, None, B, H, T)
         x = self.enc(xs, x_mask, g=g)
         stats = _conv(x, self._f_proj)
@@ -253,6 +312,12 @@ class Attention(nn.Module):
         qkv = _conv_buf(buf, self._f_qkv, T, C, 3 * C)
         D = C // self.num_heads
         flat = qkv.view(-1)
+        if ops.MHA_VARIANT[0] == 0 and D in (64, 96, 128):
+            # the tensor-core attention writes the proj conv's fp16 operand directly
+            ab = ops.mha(flat, flat[C * T:], flat[2 * C * T:], B, self.num_heads, D, T, T, 3 * C * T, 3 * C * T, 3 * C * T,
+                         self.scale, prescale_q=False, out_blk=ops.blk16_buffer(B, C, T, qkv.device, _S_G))
+            ops.check_saturation(ab, C, T)
+            return _conv_buf(ab, self._f_proj, T, C, C)
         att = ops.mha(flat, flat[C * T:], flat[2 * C * T:], B, self.num_heads, D, T, T, 3 * C * T, 3 * C * T, 3 * C * T,
                       self.scale, prescale_q=False)
         return _conv(att, self._f_proj, slot=_S_G)
@@ -290,19 +355,27 @@ class DiTConVBlock(nn.Module):
         self.adaLN_modulation = nn.Sequential(nn.SiLU(), nn.Linear(hidden_size, 6 * hidden_size, bias=True))
         self._f_ada = _FoldedLinear(self.adaLN_modulation[1])
 
-    def run(self, x: torch.Tensor, c: torch.Tensor, mask) -> torch.Tensor:
-        """x fp32 [B, C, T] (updated in place), c [B, C] conditioning, mask [B, T] or None."""
+    def run(self, x: torch.Tensor, c: torch.Tensor, mask, mod: Optional[torch.Tensor] = None,
+            masked_input: bool = False) -> torch.Tensor:
+        """x fp32 [B, C, T] (updated in place), c [B, C] conditioning, mask [B, T] or None.
+
+        ``mod``: this block's adaLN vector [B, 6C] (rows may be strided) when the caller evaluated all blocks'
+        modulations in one launch; ``masked_input``: x is already x * mask (the output of a previous block:
+        x*m + g*y*m re-masked is the same bits), so the leading mask pass is skipped."""
         B, C, T = x.shape
-        ops.frame_op(ops.OP_MASK, x, None, None, mask, x, None, B, C, T)
-        mod = _vec(c, self._f_ada, silu=True)                      # [B, 6C]: shift/scale/gate msa, shift/scale/gate mlp
+        if mask is not None and not masked_input:
+            ops.frame_op(ops.OP_MASK, x, None, None, mask, x, None, B, C, T)
+        if mod is None:
+            mod = _vec(c, self._f_ada, silu=True)                  # [B, 6C]: shift/scale/gate msa, shift/scale/gate mlp
+        ms = mod.stride(0)
         sh1, sc1, g1, sh2, sc2, g2 = (mod[:, i * C:(i + 1) * C] for i in range(6))
         buf = ops.blk16_buffer(B, C, T, x.device, _S_X)
-        ops.ln_mod_blk16(x, sh1, sc1, buf, 6 * C, mask, 1e-6, premask=True)
+        ops.ln_mod_blk16(x, sh1, sc1, buf, ms, mask, 1e-6, premask=True)
         y = self.attn.run(buf, C, T)
-        ops.frame_op(ops.OP_GATE_ADD, x, y, g1, mask, x, None, B, C, T, cstride=6 * C)
-        ops.ln_mod_blk16(x, sh2, sc2, buf, 6 * C, mask, 1e-6, premask=False)
+        ops.frame_op(ops.OP_GATE_ADD, x, y, g1, mask, x, None, B, C, T, cstride=ms)
+        ops.ln_mod_blk16(x, sh2, sc2, buf, ms, mask, 1e-6, premask=False)
         y = self.mlp.run(buf, C, T, mask)
-        ops.frame_op(ops.OP_GATE_ADD, x, y, g2, mask, x, None, B, C, T, cstride=6 * C)
+        ops.frame_op(ops.OP_GATE_ADD, x, y, g2, mask, x, None, B, C, T, cstride=ms)
         return x
 
 
@@ -327,7 +400,9 @@ class ResidualCouplingLayer_Transformer_simple(nn.Module):
         self._f_pre, self._f_post = _Folded(self.pre), _Folded(self.post)
         _bump_on_load(self)
 
-    def forward(self, x, x_mask, g=None, reverse=False):
+    def forward(self, x, x_mask, g=None, reverse=False, mods=None):
+        """``mods``: [B, n_layers, 6H] adaLN vectors of this layer's blocks, when the owning
+        ``ResidualCouplingBlock_Transformer`` evaluated them for all its flows at once."""
         if not reverse:
             raise NotImplementedError("inference path: reverse=True only")
         x = _as_input(x)
@@ -335,8 +410,8 @@ class ResidualCouplingLayer_Transformer_simple(nn.Module):
         B, C, T = x.shape
         half, H = self.half_channels, self.hidden_channels
         h = _conv(x, self._f_pre, C=half)                                   # pre(x0): the first half of the channels
-        for blk in self.enc_block:
-            h = blk.run(h, g, mask)                                         # the first op of a block masks h
+        for j, blk in enumerate(self.enc_block):
+            h = blk.run(h, g, mask, None if mods is None else mods[:, j], masked_input=j > 0)
         m = _conv(h, self._f_post)
         out = x.clone()
         ops.frame_op(ops.OP_COUPLE, out, m, None, mask, out, None, B, half, T)   # x1 = (x1 - m) * mask
@@ -370,6 +445,8 @@ class ResidualCouplingBlock_Transformer(nn.Module):
                                                                        dilation_rate, n_layers, mean_only=True))
             self.flows.append(Flip())
         self._f_c0, self._f_c2 = _FoldedLinear(self.cond_block[0]), _FoldedLinear(self.cond_block[2])
+        self._f_ada_all = _FoldedCat([blk.adaLN_modulation[1] for i in range(0, 2 * n_flows, 2)
+                                      for blk in self.flows[i].enc_block])
         _bump_on_load(self)
 
     def forward(self, x, x_mask, g=None, reverse=False):
@@ -377,8 +454,16 @@ class ResidualCouplingBlock_Transformer(nn.Module):
             raise NotImplementedError("inference path: reverse=True only")
         B = x.shape[0]
         c = _vec(_vec(_as_input(g).reshape(B, -1), self._f_c0), self._f_c2, silu=True)
-        for flow in reversed(self.flows):
-            x = flow(x, x_mask, g=c, reverse=True)
+        # every DiT block's adaLN modulation depends on c only: ONE launch for all n_flows * n_layers blocks
+        # (concatenated weights, cached per checkpoint) instead of one per block on the critical path
+        nl, H = self.n_layers, self.hidden_channels
+        mods = _vec(c, self._f_ada_all, silu=True).view(B, self.n_flows, nl, 6 * H)
+        for idx in reversed(range(len(self.flows))):
+            flow = self.flows[idx]
+            if idx % 2 == 0:
+                x = flow(x, x_mask, g=c, reverse=True, mods=mods[:, idx // 2])
+            else:
+                x = flow(x, x_mask, g=c, reverse=True)
         return x
 
 

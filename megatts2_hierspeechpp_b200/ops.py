@@ -522,6 +522,22 @@ def pack_blk16_act(x: torch.Tensor, buf: torch.Tensor, C: int, mode: int = PACK_
     return buf
 
 
+def wn_res_pack(x: torch.Tensor, rs: torch.Tensor, mask: Optional[torch.Tensor], output: torch.Tensor, buf: torch.Tensor):
+    """WN layer tail fused with the next layer's operand pack: x = (x + rs[:, :C]) * mask (in place), output += rs[:, C:],
+    buf = fp16 blk16 operand of the new x."""
+    _req(x, "x", ndim=3); _req(rs, "rs", ndim=3); _req(output, "output", ndim=3); _req(buf, "buf", torch.float16, 4)
+    B, C, L = x.shape
+    if tuple(rs.shape) != (B, 2 * C, L) or tuple(output.shape) != (B, C, L):
+        raise ValueError("wn_res_pack: shape mismatch")
+    if tuple(buf.shape) != blk16_shape(B, C, L):
+        raise ValueError("blk16 buffer shape mismatch")
+    if mask is not None:
+        _req(mask, "mask")
+    _lib.check(_lib.load().hsv_wn_res_pack(_p(x), _p(rs), _p(mask), _p(output), _p(buf), B, C, L, _stream()),
+               "hsv_wn_res_pack")
+    return buf
+
+
 def ln_mod_blk16(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, buf: torch.Tensor, mod_stride: int,
                  mask: Optional[torch.Tensor] = None, eps: float = 1e-6, inmask: bool = False, premask: bool = False):
     """LayerNorm over channels (no affine) [* mask] -> x * (1 + scale[b]) + shift[b] -> fp16 blk16."""
@@ -549,15 +565,25 @@ def frame_op(op: int, a, b=None, c=None, mask=None, out=None, out2=None, B=0, C=
 
 
 def mha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, heads: int, D: int, Tq: int, Tk: int, q_bs: int,
-        k_bs: int, v_bs: int, scale: float, prescale_q: bool, lens: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """softmax(q k^T * scale) v; q/k/v may be views into one fused [B, 3*heads*D, T] tensor (pass batch strides)."""
+        k_bs: int, v_bs: int, scale: float, prescale_q: bool, lens: Optional[torch.Tensor] = None,
+        out_blk: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """softmax(q k^T * scale) v; q/k/v may be views into one fused [B, 3*heads*D, T] tensor (pass batch strides).
+    ``out_blk``: write the result as the fp16 blk16 operand of the conv that follows (tensor-core kernel only) and
+    return that buffer instead of a fp32 tensor."""
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
         if not t.is_cuda or t.dtype != torch.float32:
             raise RuntimeError(f"mha: {n} must be a CUDA float32 tensor")
-    out = torch.empty(B, heads * D, Tq, dtype=torch.float32, device=q.device)
     if lens is not None:
         _req(lens, "lens", torch.int32)
     lib = _lib.load()
+    if out_blk is not None:
+        _req(out_blk, "out_blk", torch.float16, 4)
+        if tuple(out_blk.shape) != blk16_shape(B, heads * D, Tq):
+            raise ValueError("mha: blk16 buffer shape mismatch")
+        _lib.check(lib.hsv_mha_blk16(_p(q), _p(k), _p(v), _p(out_blk), _p(lens), B, heads, D, Tq, Tk, int(q_bs), int(k_bs),
+                                     int(v_bs), float(scale), int(prescale_q), _stream()), "hsv_mha_blk16")
+        return out_blk
+    out = torch.empty(B, heads * D, Tq, dtype=torch.float32, device=q.device)
     _lib.check(lib.hsv_mha(_p(q), _p(k), _p(v), _p(out), _p(lens), B, heads, D, Tq, Tk, int(q_bs), int(k_bs), int(v_bs),
                            float(scale), int(prescale_q), _stream()), "hsv_mha")
     return out
@@ -600,6 +626,15 @@ def sinegen(f0: torch.Tensor, hop: int, sample_rate: float, harmonics: int = 8, 
     _lib.check(lib.hsv_sinegen(_p(f0), _p(out), _p(uv), _p(ws), B, T, hop, float(sample_rate), harmonics, float(amp),
                                _stream()), "hsv_sinegen")
     return out, uv
+
+
+MHA_VARIANT = [0]
+
+
+def set_mha_variant(v: int):
+    """Test hook: 0 = tensor-core attention (default), 1 = the fp32 CUDA-core kernel."""
+    _lib.check(_lib.load().hsv_set_mha_variant(int(v)), "hsv_set_mha_variant")
+    MHA_VARIANT[0] = int(v)
 
 
 def set_act_variant(v: int):

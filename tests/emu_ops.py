@@ -180,6 +180,14 @@ def pack_blk16_act(x, buf, C, mode=0, bcast=None, mask=None, c_off=0):
     return buf
 
 
+def wn_res_pack(x, rs, mask, output, buf):
+    C = x.shape[1]
+    x.copy_((x + rs[:, :C]) * _m(mask, x))
+    output.add_(rs[:, C:])
+    _pack_into(buf, x)
+    return buf
+
+
 def ln_mod_blk16(x, shift, scale, buf, mod_stride, mask=None, eps=1e-6, inmask=False, premask=False):
     mk = _m(mask, x)
     if inmask:
@@ -220,7 +228,7 @@ def frame_op(op, a, b=None, c=None, mask=None, out=None, out2=None, B=0, C=0, L=
         raise ValueError(op)
 
 
-def mha(q, k, v, B, heads, D, Tq, Tk, q_bs, k_bs, v_bs, scale, prescale_q, lens=None):
+def mha(q, k, v, B, heads, D, Tq, Tk, q_bs, k_bs, v_bs, scale, prescale_q, lens=None, out_blk=None):
     def grab(t, bs, T):
         return torch.stack([t.reshape(-1)[b * bs:b * bs + heads * D * T].view(heads, D, T) for b in range(B)])
     qq, kk, vv = grab(q, q_bs, Tq).transpose(2, 3), grab(k, k_bs, Tk).transpose(2, 3), grab(v, v_bs, Tk).transpose(2, 3)
@@ -231,7 +239,11 @@ def mha(q, k, v, B, heads, D, Tq, Tk, q_bs, k_bs, v_bs, scale, prescale_q, lens=
             sc[b, :, n:, :] = -1e4
             sc[b, :, :, n:] = -1e4
     o = torch.matmul(sc.softmax(-1), vv)
-    return o.transpose(2, 3).contiguous().view(B, heads * D, Tq)
+    o = o.transpose(2, 3).contiguous().view(B, heads * D, Tq)
+    if out_blk is not None:
+        _pack_into(out_blk, o)
+        return out_blk
+    return o
 
 
 def conv1d_c1_strided(x, w, bias, stride, pad, mask=None):
@@ -247,7 +259,7 @@ def check_saturation(buf, C, L):
     return None
 
 
-NAMES = ["pack_blk16_act", "ln_mod_blk16", "frame_op", "mha", "conv1d_c1_strided", "masked_mean", "check_saturation",
+NAMES = ["pack_blk16_act", "wn_res_pack", "ln_mod_blk16", "frame_op", "mha", "conv1d_c1_strided", "masked_mean", "check_saturation",
          "blk16_buffer", "act1d", "act1d_blk16", "pack_blk16", "weight_norm_fold", "pack_conv_weight", "conv1d_umma", "act_conv1d_umma", "pack_convT_weight", "conv_transpose1d_umma",
          "conv1d_direct", "conv_transpose1d", "sr_pre_interp", "nearest_gather", "add3_bcast"]
 
