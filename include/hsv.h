@@ -103,6 +103,17 @@ int hsv_conv1d_umma(const void *a_blk16, const void *w_packed, const float *bias
                     const float *residual, float *out, float *acc, int acc_mode, float acc_div,
                     int B, int Cin, int Cout, int64_t L, int k, int d, int n_tile, void *stream);
 
+/* hsv_conv1d_umma_blk16: the same convolution with an OPERAND-WRITING epilogue: (conv + bias + bc[b]) -> activation ->
+ * * mask -> fp16 blk16 buffer that the next hsv_conv1d_umma reads (no fp32 round trip, no pack launch).
+ *   mode 0: none;  2: gelu_tanh (FFN_Conv, modules.py:382-388);  3: leaky_relu(0.1);
+ *   mode 1: the WN gate tanh(a) * sigmoid(b) (commons.py:108-114): the caller packs the weights / bias / bc with the
+ *           output channels ordered as groups of [8 tanh | 8 sigmoid] (channels 8j..8j+7 then H+8j..H+8j+7), the
+ *           output buffer has Cout / 2 channels.
+ *   bc: [B][Cout] (batch stride bc_stride) added before the activation, or NULL; mask: [B][L] or NULL. */
+int hsv_conv1d_umma_blk16(const void *a_blk16, const void *w_packed, const float *bias, void *out_blk16, int mode,
+                          const float *bc, int64_t bc_stride, const float *mask, int B, int Cin, int Cout, int64_t L, int k,
+                          int d, int n_tile, void *stream);
+
 /* ---- whole AMP half-layer: Activation1d(SnakeBeta) followed by the dilated Conv1d,
  *   xt = conv(Activation1d(x * in_scale))            (hierspeechpp_speechsynthesizer.py:380-384)
  * in ONE kernel: the CTA evaluates the fused activation on the fp32 input and writes the fp16 operand

@@ -80,6 +80,13 @@ struct Params {
   const float *beta;
   float in_scale;
   uint32_t x_off;      // byte offset (from the aligned shared base) of the two fp32 staging buffers
+  // operand-writing epilogue (hsv_conv1d_umma_blk16): the result goes out as the fp16 blk16 operand of the NEXT conv
+  void *out_blk;          // nullptr = the fp32 epilogues below
+  int blk_mode;           // 0 none, 1 WN gate (column pairs), 2 gelu_tanh, 3 leaky_relu(0.1)
+  int blk_C;              // channels of the output buffer (Cout; Cout / 2 for the gate)
+  const float *blk_bc;    // [B][Cout] vector added before the activation (batch stride blk_bcs), or nullptr
+  int64_t blk_bcs;
+  const float *blk_mask;  // [B][L] frame mask applied to the result, or nullptr
   int debug;
   long long *trace;  // bring-up: clock64 stamps of CTA (0,0,0) (hsv_set_umma_trace), else nullptr
   TapTable tt;
@@ -523,7 +530,63 @@ __global__ void __launch_bounds__(32 * NW, MINB) conv_umma_kernel(const __grid_c
   for (int q = 0; q < NBR; ++q) bias_s[threadIdx.x + 32 * NW * q] = bias_r[q];
   if (threadIdx.x == 0) stamp(p, 6);
   const uint32_t trow = tmem + ((uint32_t)(wq * 32) << 16);
-  if (p.vec_epi) {
+  if (p.out_blk) {
+    // Operand-writing epilogue.  tcgen05.ld gives a lane one time row x 16 consecutive output channels: exactly two
+    // 16-byte units of the blk16 layout ([row][8 channels]) -- no transpose.  The WN gate pairs columns: the host packs
+    // in_layers' output channels as [8 tanh | 8 sigmoid] groups, so a 16-column unit yields 8 gate outputs = one unit.
+    const int64_t row_base = (int64_t)tile * MSUB * TILE_M + wq * 32 + lane;
+    const int cwo = hsv::blk_cw(p.blk_C);
+    uint8_t *ob = reinterpret_cast<uint8_t *>(p.out_blk);
+    const float *bcv = p.blk_bc ? p.blk_bc + (int64_t)b * p.blk_bcs + co0 : nullptr;
+    __syncthreads();  // bias_s complete
+    mbar_wait(bar_acc, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    __syncwarp();
+#pragma unroll 1
+    for (int u = half ? nunits : 0; u < nunits; ++u) {   // warps 4..7 (NW = 8) sit this path out
+      const int sub = u / nchk, c0 = (u - sub * nchk) << 4;
+      const int64_t t = row_base + (int64_t)sub * TILE_M;
+      uint32_t r[16];
+      tmem_ld16(trow + (uint32_t)(sub * p.n_tile + c0), r);
+      if (t < p.L) {
+        const float mk = p.blk_mask ? __ldg(p.blk_mask + (int64_t)b * p.L + t) : 1.f;
+        float v[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) v[c] = __uint_as_float(r[c]) + bias_s[c0 + c] + (bcv ? __ldg(bcv + c0 + c) : 0.f);
+        if (p.blk_mode == 1) {
+          __half2 hh[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float g0 = tanhf(v[2 * e]) * (1.0f / (1.0f + expf(-v[8 + 2 * e])));
+            const float g1 = tanhf(v[2 * e + 1]) * (1.0f / (1.0f + expf(-v[9 + 2 * e])));
+            hh[e] = __floats2half2_rn(g0 * mk, g1 * mk);
+          }
+          *reinterpret_cast<uint4 *>(ob + hsv::blk_unit_offset(cwo, p.Lp, p.blk_C, b, (co0 + c0) >> 1, HSV_BLK_PAD + t)) =
+              *reinterpret_cast<uint4 *>(hh);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            float a = v[c];
+            if (p.blk_mode == 2) {
+              const float kk = 0.7978845608028654f;
+              a = 0.5f * a * (1.0f + tanhf(kk * (a + 0.044715f * a * a * a)));
+            } else if (p.blk_mode == 3) {
+              a = a > 0.f ? a : 0.1f * a;
+            }
+            v[c] = a * mk;
+          }
+#pragma unroll
+          for (int q8 = 0; q8 < 2; ++q8) {
+            __half2 hh[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) hh[e] = __floats2half2_rn(v[8 * q8 + 2 * e], v[8 * q8 + 2 * e + 1]);
+            *reinterpret_cast<uint4 *>(ob + hsv::blk_unit_offset(cwo, p.Lp, p.blk_C, b, co0 + c0 + 8 * q8, HSV_BLK_PAD + t)) =
+                *reinterpret_cast<uint4 *>(hh);
+          }
+        }
+      }
+    }
+  } else if (p.vec_epi) {
     // the A tile / weight ring are idle once the accumulator is complete: reuse 2 KB per warp as staging
     const uint32_t stg = a_s + (uint32_t)warp * 2048u;
     const uint32_t stg_w = stg + (uint32_t)lane * 4u;                       // [c][lane]
@@ -1117,10 +1180,25 @@ struct FusedAct {  // activation-producing variant: fp32 input of Activation1d i
   float in_scale;
 };
 
+struct BlkOut {    // operand-writing epilogue (see Params)
+  void *out;
+  int mode, C;
+  const float *bc;
+  int64_t bcs;
+  const float *mask;
+};
+
 int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const float *bias,
            const float *residual, float *out, float *acc, int acc_mode, int B, int Cin, int Cout, int64_t L,
-           int64_t Lout, int n_tile, cudaStream_t st, const char *what, const FusedAct *fa = nullptr) {
+           int64_t Lout, int n_tile, cudaStream_t st, const char *what, const FusedAct *fa = nullptr,
+           const BlkOut *bo = nullptr) {
   Params p;
+  p.out_blk = bo ? bo->out : nullptr;
+  p.blk_mode = bo ? bo->mode : 0;
+  p.blk_C = bo ? bo->C : 0;
+  p.blk_bc = bo ? bo->bc : nullptr;
+  p.blk_bcs = bo ? bo->bcs : 0;
+  p.blk_mask = bo ? bo->mask : nullptr;
   p.fx = fa ? fa->x : nullptr;
   p.alpha = fa ? fa->alpha : nullptr;
   p.beta = fa ? fa->beta : nullptr;
@@ -1164,7 +1242,7 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
   // persistent variant (opt-in): one 128-row tile at a time per CTA, roles overlapped across tiles
   auto al16e = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   const bool force_persist = (g_host_debug & 128) != 0;  // tests: any size / tile width
-  const bool want_persist = g_persist && !fa && tt.nphase == 1 && tt.out_stride == 1 &&
+  const bool want_persist = g_persist && !fa && !bo && tt.nphase == 1 && tt.out_stride == 1 &&
                             (force_persist || (n_tile >= 128 && ctas1 >= 2 * 148) || (n_tile == 64 && Cout == 64 && ctas1 >= 4 * 148)) &&
                             (Lout % 4) == 0 && al16e(residual) && al16e(out) && al16e(acc) &&
                             ((out != nullptr) != (acc_mode != 0));
@@ -1334,6 +1412,23 @@ extern "C" int hsv_conv1d_umma(const void *a_blk16, const void *w_packed, const 
   HSV_REQUIRE(out || acc_mode, "conv1d_umma: no output");
   return launch(conv_taps(k, d), a_blk16, w_packed, bias, residual, out, acc, acc_mode, B, Cin, Cout, L, L, n_tile,
                 hsv::as_stream(stream), "conv1d_umma");
+}
+
+extern "C" int hsv_conv1d_umma_blk16(const void *a_blk16, const void *w_packed, const float *bias, void *out_blk16, int mode,
+                                     const float *bc, int64_t bc_stride, const float *mask, int B, int Cin, int Cout,
+                                     int64_t L, int k, int d, int n_tile, void *stream) {
+  if (B == 0 || L == 0) return HSV_OK;  // empty batch / sequence
+  if (int rc = check_common("conv1d_umma_blk16", a_blk16, w_packed, Cin, Cout, n_tile)) return rc;
+  HSV_REQUIRE(out_blk16 && out_blk16 != a_blk16, "conv1d_umma_blk16: bad output buffer");
+  HSV_REQUIRE(mode >= 0 && mode <= 3, "conv1d_umma_blk16: mode %d", mode);
+  HSV_REQUIRE(mode != 1 || Cout % 32 == 0, "conv1d_umma_blk16: the gate needs Cout %% 32 == 0 (Cout=%d)", Cout);
+  HSV_REQUIRE(k >= 1 && k <= MAX_TAPS && (k & 1) && d >= 1, "conv1d_umma_blk16: k must be odd and <= %d (k=%d d=%d)",
+              MAX_TAPS, k, d);
+  HSV_REQUIRE(((k - 1) / 2) * d <= HSV_BLK_PAD, "conv1d_umma_blk16: halo %d exceeds blk16 padding %d", ((k - 1) / 2) * d,
+              HSV_BLK_PAD);
+  const BlkOut bo = {out_blk16, mode, mode == 1 ? Cout / 2 : Cout, bc, bc_stride, mask};
+  return launch(conv_taps(k, d), a_blk16, w_packed, bias, nullptr, nullptr, nullptr, 0, B, Cin, Cout, L, L, n_tile,
+                hsv::as_stream(stream), "conv1d_umma_blk16", nullptr, &bo);
 }
 
 extern "C" int hsv_act_conv1d_umma(const float *x, const float *alpha, const float *beta, float in_scale,

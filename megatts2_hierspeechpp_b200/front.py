@@ -50,6 +50,37 @@ def _epoch():
     return M._CACHE_EPOCH[0]
 
 
+class _FoldedGate(_Folded):
+    """A WN in_layer (2H output channels: tanh half | sigmoid half) with its output channels in the order the
+    operand-writing gate epilogue wants (``ops.gate_permutation``): weight, bias and packed operand all permuted."""
+
+    def __init__(self, conv, blocks: int = 1):
+        super().__init__(conv)
+        self.blocks = blocks            # cond_layer: n_layers blocks of 2H channels, each permuted on its own
+        self._pkey, self._wperm, self._bperm = None, None, None
+
+    def _perm(self, cout, device):
+        per = cout // self.blocks
+        base = ops.gate_permutation(per, device)
+        return torch.cat([base + i * per for i in range(self.blocks)])
+
+    def weight(self):
+        w = _Folded.weight(self)
+        if self._pkey != self.key:
+            perm = self._perm(w.shape[0], w.device)
+            self._wperm = w[perm].contiguous()
+            b = _Folded.bias(self)
+            self._bperm = None if b is None else b[perm].contiguous()
+            self._pkey = self.key
+            if w.is_cuda:
+                ops._static_data_barrier("WN gate-order weights")
+        return self._wperm
+
+    def bias(self):
+        self.weight()
+        return self._bperm
+
+
 class _FoldedCat:
     """Several nn.Linear layers with the same input, concatenated along the output dimension (one launch for all)."""
 
@@ -149,6 +180,35 @@ def _conv(x: torch.Tensor, f: _Folded, k: int = 1, d: int = 1, mode: int = ops.P
     return out
 
 
+def _slices_of(f: _Folded, C: int):
+    nsplit = (C + 511) // 512
+    per = C // nsplit
+    if per * nsplit != C or per % 16:
+        raise NotImplementedError(f"split-K: Cin={C} does not split into equal multiples of 16")
+    if not hasattr(f, "_slices") or f._slices[0] != (C, nsplit):
+        f._slices = ((C, nsplit), [_FoldedSlice(f, i * per, (i + 1) * per) for i in range(nsplit)])
+    return per, f._slices[1]
+
+
+def _conv_packed(buf: torch.Tensor, f: _Folded, C: int, L: int, k: int = 1, d: int = 1) -> torch.Tensor:
+    """tcgen05 conv of an already packed operand of C channels; wider than 512: split-K over channel sub-buffers
+    (batch 1 only: the channel chunks are the outermost dimension of the buffer)."""
+    B = buf.shape[0]
+    cout = f.conv.out_channels if hasattr(f.conv, "out_channels") else f.conv.out_features
+    if C <= 512:
+        return _conv_buf(buf, f, L, C, cout, k, d)
+    if B != 1:
+        raise NotImplementedError("split-K over a packed buffer needs batch 1")
+    per, slices = _slices_of(f, C)
+    nchunk = buf.shape[1] * per // C
+    out = None
+    for i, fs in enumerate(slices):
+        wp, nt = fs.packed_weight(_row_tiles(B, L))
+        out = ops.conv1d_umma(buf[:, i * nchunk:(i + 1) * nchunk], wp, f.bias() if i == 0 else None, L, per, cout, k, d, nt,
+                              residual=out)
+    return out
+
+
 def _vec(x: torch.Tensor, f: _Folded, silu: bool = False) -> torch.Tensor:
     """Linear / 1x1 conv on a per-utterance vector [B, Cin] -> [B, Cout] (fp32 warp-per-output dot products)."""
     B = x.shape[0]
@@ -181,10 +241,15 @@ class WN(nn.Module):
                                                       dilation=dilation, padding=padding)))
             rs = 2 * hidden_channels if i < n_layers - 1 else hidden_channels
             self.res_skip_layers.append(_weight_norm(Conv1d(hidden_channels, rs, 1)))
-        self._f_in = [_Folded(c) for c in self.in_layers]
-        self._f_rs = [_Folded(c) for c in self.res_skip_layers]
-        self._f_cond = _Folded(self.cond_layer) if gin_channels != 0 else None
+        self._refold()
         _bump_on_load(self)
+
+    def _refold(self):
+        # in_layers / cond_layer in gate order: the in_layer conv's epilogue evaluates the gate and writes the
+        # res_skip conv's fp16 operand directly (csrc/conv_umma.cu, hsv_conv1d_umma_blk16)
+        self._f_in = [_FoldedGate(c) for c in self.in_layers]
+        self._f_rs = [_Folded(c) for c in self.res_skip_layers]
+        self._f_cond = _FoldedGate(self.cond_layer, blocks=self.n_layers) if self.gin_channels != 0 else None
 
     def forward(self, x, x_mask, g=None, slots=(_S_X, _S_G), **kwargs):
         """``slots``: the two operand workspace slots of this call (two WN stacks on two streams need two pairs)."""
@@ -196,19 +261,24 @@ class WN(nn.Module):
         sx, sg = slots
         gl = None
         if g is not None:
-            # cond_layer(g): [B, 2H*n, 1]; per layer slice, laid out [n, B, 2H] so every slice is dense
-            gl = _vec(_as_input(g).reshape(B, -1), self._f_cond).view(B, n, 2 * H).transpose(0, 1).contiguous()
+            # cond_layer(g): [B, n, 2H] (each layer's 2H block in gate order); a layer's slice is a strided row view
+            gl = _vec(_as_input(g).reshape(B, -1), self._f_cond).view(B, n, 2 * H)
         x = x.clone()
         output = torch.zeros_like(x)
         # the operand of in_layers[0]; every later layer's operand is written by the previous layer's fused tail
         buf = ops.blk16_buffer(B, H, T, x.device, sx)
+        gbuf = ops.blk16_buffer(B, H, T, x.device, sg)
         ops.pack_blk16_act(x, buf, H, ops.PACK_MASK)
         ops.check_saturation(buf, H, T)
+        rt = _row_tiles(B, T)
         for i in range(n):
             d = self.dilation_rate ** i
-            x_in = _conv_buf(buf, self._f_in[i], T, H, 2 * H, k, d)
-            acts_rs = _conv(x_in, self._f_rs[i], 1, 1, mode=ops.PACK_GATE, C=H, slot=sg,
-                            bcast=None if gl is None else gl[i])
+            # in_layers[i] -> + cond -> tanh * sigmoid, straight into the res_skip conv's operand
+            wp, nt = self._f_in[i].packed_weight(rt)
+            ops.conv1d_umma_blk(buf, wp, self._f_in[i].bias(), T, H, 2 * H, k, d, nt, gbuf, ops.BLK_GATE,
+                                bc=None if gl is None else gl[:, i])
+            ops.check_saturation(gbuf, H, T)
+            acts_rs = _conv_buf(gbuf, self._f_rs[i], T, H, 2 * H if i < n - 1 else H)
             if i < n - 1:
                 ops.wn_res_pack(x, acts_rs, mask, output, buf)       # x, output updated in place; buf = fp16(x)
                 ops.check_saturation(buf, H, T)
@@ -219,11 +289,9 @@ class WN(nn.Module):
     def remove_weight_norm(self):
         if self.gin_channels != 0:
             torch.nn.utils.remove_weight_norm(self.cond_layer)
-            self._f_cond = _Folded(self.cond_layer)
         for l in list(self.in_layers) + list(self.res_skip_layers):
             torch.nn.utils.remove_weight_norm(l)
-        self._f_in = [_Folded(c) for c in self.in_layers]
-        self._f_rs = [_Folded(c) for c in self.res_skip_layers]
+        self._refold()
 
 
 # ----------------------------------------------------------------------------------------------
@@ -339,8 +407,19 @@ class FFN_Conv(nn.Module):
         self._f1, self._f2 = _Folded(self.fc1), _Folded(self.fc2)
 
     def run(self, buf: torch.Tensor, C: int, T: int, mask) -> torch.Tensor:
-        h = _conv_buf(buf, self._f1, T, C, self.fc1.out_channels, self.kernel, 1)
-        return _conv(h, self._f2, mode=ops.PACK_GELU, slot=_S_W, mask=mask)       # fc2(gelu(h) * mask); * mask by the caller
+        """fc2(gelu(fc1(buf)) * mask); the trailing * mask is the caller's."""
+        B = buf.shape[0]
+        Hh = self.fc1.out_channels
+        if B == 1 or Hh <= 512:
+            # fc1's epilogue applies GELU * mask and writes fc2's fp16 operand; fc2 wider than 512 input channels runs as
+            # split-K passes over channel sub-buffers (dense at batch 1)
+            hb = ops.blk16_buffer(B, Hh, T, buf.device, _S_W)
+            wp, nt = self._f1.packed_weight(_row_tiles(B, T))
+            ops.conv1d_umma_blk(buf, wp, self._f1.bias(), T, C, Hh, self.kernel, 1, nt, hb, ops.BLK_GELU, mask=mask)
+            ops.check_saturation(hb, Hh, T)
+            return _conv_packed(hb, self._f2, Hh, T)
+        h = _conv_buf(buf, self._f1, T, C, Hh, self.kernel, 1)
+        return _conv(h, self._f2, mode=ops.PACK_GELU, slot=_S_W, mask=mask)
 
 
 class DiTConVBlock(nn.Module):

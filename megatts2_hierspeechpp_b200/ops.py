@@ -297,6 +297,52 @@ def conv1d_umma(a_blk: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torc
     return out
 
 
+BLK_NONE, BLK_GATE, BLK_GELU, BLK_LRELU = 0, 1, 2, 3
+
+
+def gate_permutation(two_h: int, device=None) -> torch.Tensor:
+    """Output-channel order the operand-writing gate epilogue expects of a WN in_layer (2H channels: tanh half, sigmoid
+    half): groups of [8 tanh | 8 sigmoid] = channels 8j..8j+7 then H+8j..H+8j+7."""
+    H = two_h // 2
+    if H % 8:
+        raise ValueError("gate_permutation: H % 8 != 0")
+    j = torch.arange(H // 8).view(-1, 1) * 8
+    e = torch.arange(8).view(1, -1)
+    return torch.cat([j + e, H + j + e], 1).reshape(-1).to(device)
+
+
+def conv1d_umma_blk(a_blk: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], L: int, cin: int, cout: int,
+                    k: int, d: int, n_tile: int, out_blk: torch.Tensor, mode: int = BLK_NONE,
+                    bc: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """tcgen05 Conv1d whose epilogue writes the NEXT conv's fp16 blk16 operand: act(conv + bias + bc[b]) * mask.
+    ``bc``: [B, cout] rows (dense innermost dimension, any batch stride); BLK_GATE: weights / bias / bc in
+    ``gate_permutation`` order, ``out_blk`` has cout // 2 channels."""
+    _req(a_blk, "a_blk16", torch.float16, 4); _req(w_packed, "w_packed", torch.float16)
+    _req(out_blk, "out_blk16", torch.float16, 4)
+    B = a_blk.shape[0]
+    if tuple(a_blk.shape) != blk16_shape(B, cin, L):
+        raise ValueError(f"a_blk16 shape {tuple(a_blk.shape)} does not match Cin={cin}, L={L}")
+    co = cout // 2 if mode == BLK_GATE else cout
+    if tuple(out_blk.shape) != blk16_shape(B, co, L):
+        raise ValueError(f"out_blk16 shape {tuple(out_blk.shape)} does not match C={co}, L={L}")
+    if w_packed.numel() < cout * cin * k:
+        raise ValueError("w_packed size mismatch")
+    if bias is not None:
+        _req(bias, "bias")
+    bcs = 0
+    if bc is not None:
+        _req_vec(bc, "bc")
+        if tuple(bc.shape) != (B, cout):
+            raise ValueError("bc shape mismatch")
+        bcs = bc.stride(0)
+    if mask is not None:
+        _req(mask, "mask")
+    _lib.check(_lib.load().hsv_conv1d_umma_blk16(_p(a_blk), _p(w_packed), _p(bias), _p(out_blk), int(mode), _p(bc), int(bcs),
+                                                 _p(mask), B, cin, cout, L, k, d, n_tile, _stream()),
+               "hsv_conv1d_umma_blk16")
+    return out_blk
+
+
 def act_conv1d_umma(x: torch.Tensor, alpha: torch.Tensor, beta: torch.Tensor, w_packed: torch.Tensor,
                     bias: Optional[torch.Tensor], cout: int, k: int, d: int, residual: Optional[torch.Tensor] = None,
                     out: Optional[torch.Tensor] = None, acc: Optional[torch.Tensor] = None, acc_mode: int = ACC_NONE,

@@ -24,6 +24,7 @@ from .modules import (_Folded, _MAIN_SLOT, _as_input, _bump_on_load, _row_tiles,
                       sum_of_blocks)
 
 LRELU_SLOPE = 0.1
+_SLOT2 = 12       # second operand workspace of a resblock stream (slots 0..2 -> 12..14)
 
 
 class W2VDecoder(nn.Module):
@@ -84,7 +85,7 @@ class ResBlock1(nn.Module):
             raise ValueError(f"ResBlock1 expects {self.channels} channels (multiple of 16), got {C}")
         k = self.kernel_size
         buf = ops.blk16_buffer(B, C, L, x.device, slot)
-        xt = torch.empty_like(x)
+        buf2 = ops.blk16_buffer(B, C, L, x.device, slot + _SLOT2)
         cur = x
         nl = len(self.dilation)
         rt = _row_tiles(B, L)
@@ -94,9 +95,10 @@ class ResBlock1(nn.Module):
             w2, nt2 = self._f2[i].packed_weight(rt)
             ops.pack_blk16(cur, buf, True)
             ops.check_saturation(buf, C, L)
-            ops.conv1d_umma(buf, w1, self._f1[i].bias(), L, C, C, k, d, nt1, out=xt)
-            ops.pack_blk16(xt, buf, True)
-            ops.check_saturation(buf, C, L)
+            # c1's epilogue applies the second leaky_relu and writes c2's fp16 operand (no fp32 round trip, no pack)
+            ops.conv1d_umma_blk(buf, w1, self._f1[i].bias(), L, C, C, k, d, nt1, buf2, ops.BLK_LRELU)
+            ops.check_saturation(buf2, C, L)
+            buf, buf2 = buf2, buf
             if last and before_final is not None:
                 before_final()
             if last and acc_mode != ops.ACC_NONE:

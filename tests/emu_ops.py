@@ -87,6 +87,24 @@ def conv1d_umma(a_blk, wp, bias, L, cin, cout, k, d, n_tile, residual=None, out=
     return v if want_out else None
 
 
+def conv1d_umma_blk(a_blk, wp, bias, L, cin, cout, k, d, n_tile, out_blk, mode=0, bc=None, mask=None):
+    x = _unpack(a_blk, L)
+    w = wp.float().view(cout, cin, k)
+    v = F.conv1d(x, w, bias, padding=(k - 1) // 2 * d, dilation=d)
+    if bc is not None:
+        v = v + bc.unsqueeze(-1)
+    if mode == real.BLK_GATE:
+        B = v.shape[0]
+        g = v.view(B, cout // 16, 2, 8, L)
+        v = (torch.tanh(g[:, :, 0]) * torch.sigmoid(g[:, :, 1])).reshape(B, cout // 2, L)
+    elif mode == real.BLK_GELU:
+        v = F.gelu(v, approximate="tanh")
+    elif mode == real.BLK_LRELU:
+        v = F.leaky_relu(v, 0.1)
+    _pack_into(out_blk, v * _m(mask, v))
+    return out_blk
+
+
 def act_conv1d_umma(x, alpha, beta, wp, bias, cout, k, d, residual=None, out=None, acc=None, acc_mode=0, scale=1.0,
                     want_out=True):
     B, cin, L = x.shape
@@ -260,7 +278,7 @@ def check_saturation(buf, C, L):
 
 
 NAMES = ["pack_blk16_act", "wn_res_pack", "ln_mod_blk16", "frame_op", "mha", "conv1d_c1_strided", "masked_mean", "check_saturation",
-         "blk16_buffer", "act1d", "act1d_blk16", "pack_blk16", "weight_norm_fold", "pack_conv_weight", "conv1d_umma", "act_conv1d_umma", "pack_convT_weight", "conv_transpose1d_umma",
+         "blk16_buffer", "act1d", "act1d_blk16", "pack_blk16", "weight_norm_fold", "pack_conv_weight", "conv1d_umma", "conv1d_umma_blk", "act_conv1d_umma", "pack_convT_weight", "conv_transpose1d_umma",
          "conv1d_direct", "conv_transpose1d", "sr_pre_interp", "nearest_gather", "add3_bcast"]
 
 

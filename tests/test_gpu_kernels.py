@@ -449,3 +449,45 @@ def test_conv1d_umma_persistent_variant(hsv):
             assert torch.equal(acc, ref)
     finally:
         hsv.ops.set_umma_debug(0)
+
+
+@pytest.mark.parametrize("mode", ["none", "gelu", "lrelu", "gate"])
+@pytest.mark.parametrize("B,cin,cout,k,d,L", [(1, 192, 384, 5, 1, 500), (2, 192, 768, 5, 1, 77), (2, 64, 64, 7, 3, 333),
+                                              (1, 512, 1024, 5, 1, 150)])
+def test_conv1d_umma_operand_writing_epilogue(hsv, mode, B, cin, cout, k, d, L):
+    """hsv_conv1d_umma_blk16 (act(conv + bias + bc) * mask written as the next conv's fp16 operand) against the fp32
+    epilogue followed by the stand-alone packers; a differing value may only be the neighbouring fp16 number."""
+    ops = hsv.ops
+    gen = torch.Generator().manual_seed(cin + cout + L)
+    x = torch.randn(B, cin, L, generator=gen).to(DEV)
+    w = (torch.randn(cout, cin, k, generator=gen) / (cin * k) ** 0.5).to(DEV)
+    bias = torch.randn(cout, generator=gen).to(DEV)
+    bc = torch.randn(B, 3, cout, generator=gen).to(DEV)[:, 1]            # strided rows
+    mask = (torch.arange(L)[None, :] < torch.tensor([L, max(1, L - 20)][:B])[:, None]).float().to(DEV)
+    a = ops.blk16_buffer(B, cin, L, DEV, slot=8)
+    ops.pack_blk16(x, a)
+    nt = ops.pick_n_tile(cout, B * ((L + 127) // 128), cin * k)
+    co = cout // 2 if mode == "gate" else cout
+    got = ops.blk16_buffer(B, co, L, DEV, slot=9)
+    ref = ops.blk16_buffer(B, co, L, DEV, slot=10)
+    if mode == "gate":
+        perm = ops.gate_permutation(cout, DEV)
+        wp = ops.pack_conv_weight(w[perm].contiguous(), nt)
+        ops.conv1d_umma_blk(a, wp, bias[perm].contiguous(), L, cin, cout, k, d, nt, got, ops.BLK_GATE,
+                            bc=bc[:, perm].contiguous())
+        y = ops.conv1d_umma(a, ops.pack_conv_weight(w, nt), bias, L, cin, cout, k, d, nt)
+        ops.pack_blk16_act(y, ref, co, ops.PACK_GATE, bcast=bc.contiguous())
+    else:
+        m = {"none": ops.BLK_NONE, "gelu": ops.BLK_GELU, "lrelu": ops.BLK_LRELU}[mode]
+        wp = ops.pack_conv_weight(w, nt)
+        ops.conv1d_umma_blk(a, wp, bias, L, cin, cout, k, d, nt, got, m, bc=bc, mask=mask)
+        y = ops.conv1d_umma(a, wp, bias, L, cin, cout, k, d, nt) + bc.unsqueeze(-1)
+        y = {"none": lambda t: t, "gelu": lambda t: F.gelu(t, approximate="tanh"), "lrelu": lambda t: F.leaky_relu(t, 0.1)}[mode](y)
+        ops.pack_blk16(y * mask.unsqueeze(1), ref)
+    g, r = ops.unpack_blk16(got, co, L), ops.unpack_blk16(ref, co, L)
+    assert torch.isfinite(g).all()
+    assert ((g - r).abs() <= 1.1e-3 * r.abs() + 1e-6).all()
+    assert float((g != r).float().mean()) < 0.02          # ... and that only rarely
+    # the padding rows of the operand layout stay zero (the next conv's zero padding)
+    raw = got.view(-1, got.shape[-2], got.shape[-1])
+    assert float(raw[:, :ops.BLK_PAD].abs().max()) == 0.0 and float(raw[:, ops.BLK_PAD + L:].abs().max()) == 0.0
