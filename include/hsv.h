@@ -242,6 +242,11 @@ int hsv_wn_res_pack(float *x, const float *rs, const float *mask, float *output,
                     void *stream);
 int hsv_ln_mod_blk16(const float *x, const float *shift, const float *scale, const float *mask, void *out, int B, int C,
                      int64_t L, float eps, int inmask, int premask, int64_t mod_stride, void *stream);
+/* hsv_gate_ln_mod_blk16: x = x + gate[b,c] * y * mask (in place, modules.py:408-409) fused with hsv_ln_mod_blk16 of the new x:
+ * the gated residual update of a DiT block and the LayerNorm/modulate/pack that follows it, one pass. */
+int hsv_gate_ln_mod_blk16(float *x, const float *y, const float *gate, int64_t gate_stride, const float *shift,
+                          const float *scale, const float *mask, void *out, int B, int C, int64_t L, float eps, int premask,
+                          int64_t mod_stride, void *stream);
 int hsv_frame_op(int op, const float *a, const float *b, const float *c, const float *mask, float *out, float *out2,
                  int B, int C, int64_t L, float s, int64_t cstride, void *stream);
 int hsv_mha(const float *q, const float *k, const float *v, float *out, const int *lens, int B, int heads, int D, int Tq,

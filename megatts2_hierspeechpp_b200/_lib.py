@@ -50,6 +50,8 @@ SIGNATURES = {
     "hsv_wn_res_pack": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p]),
     "hsv_ln_mod_blk16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_float, c_int,
                                  c_int, c_int64, c_void_p]),
+    "hsv_gate_ln_mod_blk16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                      c_int, c_int64, c_float, c_int, c_int64, c_void_p]),
     "hsv_frame_op": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64,
                              c_float, c_int64, c_void_p]),
     "hsv_mha_blk16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int64,

@@ -91,13 +91,21 @@ __global__ void wn_res_pack_kernel(float *__restrict__ x, const float *__restric
     const float mk = mask ? __ldg(mask + bb * L + t) : 1.f;
     float *xr = x + (bb * C + c0) * L + t, *orow = output + (bb * C + c0) * L + t;
     const float *rr = rs + (bb * 2 * C + c0) * L + t;
-    float v[8];
+    // all 32 loads first (x and output are updated in place: interleaved with the stores the compiler must keep them in
+    // program order, a chain of 8 dependent round trips)
+    float xv[8], ov[8], rv[8], sv[8], v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      v[e] = (xr[(int64_t)e * L] + __ldg(rr + (int64_t)e * L)) * mk;
-      const float skip = __ldg(rr + (int64_t)(C + e) * L);
+      xv[e] = xr[(int64_t)e * L];
+      ov[e] = orow[(int64_t)e * L];
+      rv[e] = __ldg(rr + (int64_t)e * L);
+      sv[e] = __ldg(rr + (int64_t)(C + e) * L);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      v[e] = (xv[e] + rv[e]) * mk;
       xr[(int64_t)e * L] = v[e];
-      orow[(int64_t)e * L] = orow[(int64_t)e * L] + skip;
+      orow[(int64_t)e * L] = ov[e] + sv[e];
     }
     __half2 h[4];
 #pragma unroll
@@ -109,8 +117,11 @@ __global__ void wn_res_pack_kernel(float *__restrict__ x, const float *__restric
 
 // LayerNorm over channels (no affine) -> optional mask -> modulate -> fp16 blk16.  CTA = 32 time steps x 8 channel
 // groups; thread (tx, g) owns the C/8 consecutive channels of group g at step tx (C % 64 == 0: whole 16-byte units).
+// With y != nullptr the preceding gated residual update is fused in (modules.py:408-409): x = x + gate[b,c] * y * mask is
+// written back to x (fp32, in place) and the normalisation runs on the new x.
 template <int CPT>   // channels per thread = C / 8
-__global__ void __launch_bounds__(256) ln_mod_kernel(const float *__restrict__ x, const float *__restrict__ shift,
+__global__ void __launch_bounds__(256) ln_mod_kernel(float *x, const float *__restrict__ y, const float *__restrict__ gate,
+                                                     int64_t gate_stride, const float *__restrict__ shift,
                                                      const float *__restrict__ scale, const float *__restrict__ mask,
                                                      uint4 *__restrict__ out, int C, int64_t L, int64_t Lp, int cw,
                                                      float eps, int inmask, int premask, int64_t mod_stride) {
@@ -123,8 +134,19 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(const float *__restrict__ x
   float v[CPT];
   float s = 0.f;
 #pragma unroll
+  for (int i = 0; i < CPT; ++i) v[i] = ok ? x[((int64_t)b * C + g * CPT + i) * L + t] : 0.f;
+  if (y) {
+    float yv[CPT];
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) yv[i] = ok ? __ldg(y + ((int64_t)b * C + g * CPT + i) * L + t) : 0.f;
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+      v[i] = v[i] + (__ldg(gate + (int64_t)b * gate_stride + g * CPT + i) * yv[i]) * mk;
+      if (ok) x[((int64_t)b * C + g * CPT + i) * L + t] = v[i];
+    }
+  }
+#pragma unroll
   for (int i = 0; i < CPT; ++i) {
-    v[i] = ok ? __ldg(x + ((int64_t)b * C + g * CPT + i) * L + t) : 0.f;
     if (inmask) v[i] *= mk;
     s += v[i];
   }
@@ -491,23 +513,41 @@ extern "C" int hsv_wn_res_pack(float *x, const float *rs, const float *mask, flo
   return hsv::check_launch("wn_res_pack");
 }
 
-extern "C" int hsv_ln_mod_blk16(const float *x, const float *shift, const float *scale, const float *mask, void *out,
-                                int B, int C, int64_t L, float eps, int inmask, int premask, int64_t mod_stride,
-                                void *stream) {
+static int ln_mod_launch(float *x, const float *y, const float *gate, int64_t gate_stride, const float *shift,
+                         const float *scale, const float *mask, void *out, int B, int C, int64_t L, float eps, int inmask,
+                         int premask, int64_t mod_stride, void *stream, const char *what) {
   if (B == 0 || L == 0) return HSV_OK;
-  HSV_REQUIRE(x && shift && scale && out, "ln_mod_blk16: null pointer");
-  HSV_REQUIRE(C == 192 || C == 256 || C == 128 || C == 64, "ln_mod_blk16: C must be 64, 128, 192 or 256 (C=%d)", C);
-  HSV_REQUIRE(B <= 65535, "ln_mod_blk16: batch too large");
+  HSV_REQUIRE(x && shift && scale && out, "%s: null pointer", what);
+  HSV_REQUIRE(C == 192 || C == 256 || C == 128 || C == 64, "%s: C must be 64, 128, 192 or 256 (C=%d)", what, C);
+  HSV_REQUIRE(B <= 65535, "%s: batch too large", what);
   dim3 grid((unsigned)((L + 31) / 32), (unsigned)B);
   cudaStream_t st = hsv::as_stream(stream);
   uint4 *o = reinterpret_cast<uint4 *>(out);
   const int64_t Lp = hsv::blk16_rows(L);
   const int cw = hsv::blk_cw(C);
-  if (C == 192) ln_mod_kernel<24><<<grid, 256, 0, st>>>(x, shift, scale, mask, o, C, L, Lp, cw, eps, inmask, premask, mod_stride);
-  else if (C == 256) ln_mod_kernel<32><<<grid, 256, 0, st>>>(x, shift, scale, mask, o, C, L, Lp, cw, eps, inmask, premask, mod_stride);
-  else if (C == 128) ln_mod_kernel<16><<<grid, 256, 0, st>>>(x, shift, scale, mask, o, C, L, Lp, cw, eps, inmask, premask, mod_stride);
-  else ln_mod_kernel<8><<<grid, 256, 0, st>>>(x, shift, scale, mask, o, C, L, Lp, cw, eps, inmask, premask, mod_stride);
-  return hsv::check_launch("ln_mod_blk16");
+#define HSV_LN(CPT) \
+  ln_mod_kernel<CPT><<<grid, 256, 0, st>>>(x, y, gate, gate_stride, shift, scale, mask, o, C, L, Lp, cw, eps, inmask, premask, mod_stride)
+  if (C == 192) HSV_LN(24);
+  else if (C == 256) HSV_LN(32);
+  else if (C == 128) HSV_LN(16);
+  else HSV_LN(8);
+#undef HSV_LN
+  return hsv::check_launch(what);
+}
+
+extern "C" int hsv_ln_mod_blk16(const float *x, const float *shift, const float *scale, const float *mask, void *out,
+                                int B, int C, int64_t L, float eps, int inmask, int premask, int64_t mod_stride,
+                                void *stream) {
+  return ln_mod_launch(const_cast<float *>(x), nullptr, nullptr, 0, shift, scale, mask, out, B, C, L, eps, inmask, premask,
+                       mod_stride, stream, "ln_mod_blk16");   // y == nullptr: x is only read
+}
+
+extern "C" int hsv_gate_ln_mod_blk16(float *x, const float *y, const float *gate, int64_t gate_stride, const float *shift,
+                                     const float *scale, const float *mask, void *out, int B, int C, int64_t L, float eps,
+                                     int premask, int64_t mod_stride, void *stream) {
+  HSV_REQUIRE(y && gate, "gate_ln_mod_blk16: null pointer");
+  return ln_mod_launch(x, y, gate, gate_stride, shift, scale, mask, out, B, C, L, eps, 0, premask, mod_stride, stream,
+                       "gate_ln_mod_blk16");
 }
 
 extern "C" int hsv_frame_op(int op, const float *a, const float *b, const float *c, const float *mask, float *out,

@@ -435,12 +435,15 @@ class DiTConVBlock(nn.Module):
         self._f_ada = _FoldedLinear(self.adaLN_modulation[1])
 
     def run(self, x: torch.Tensor, c: torch.Tensor, mask, mod: Optional[torch.Tensor] = None,
-            masked_input: bool = False) -> torch.Tensor:
-        """x fp32 [B, C, T] (updated in place), c [B, C] conditioning, mask [B, T] or None.
+            masked_input: bool = False, pending=None, defer: bool = False):
+        """x fp32 [B, C, T] (updated in place), c [B, C] conditioning, mask [B, T] or None.  Returns (x, pending).
 
         ``mod``: this block's adaLN vector [B, 6C] (rows may be strided) when the caller evaluated all blocks'
         modulations in one launch; ``masked_input``: x is already x * mask (the output of a previous block:
-        x*m + g*y*m re-masked is the same bits), so the leading mask pass is skipped."""
+        x*m + g*y*m re-masked is the same bits), so the leading mask pass is skipped.  Every gated residual update
+        ``x += gate * y * mask`` (:408-409) is fused into the LayerNorm/modulate/pack launch that follows it:
+        ``pending`` = the (y, gate) of the previous block's MLP branch still to be applied, ``defer`` = hand this block's
+        own last update to the next block the same way instead of applying it here."""
         B, C, T = x.shape
         if mask is not None and not masked_input:
             ops.frame_op(ops.OP_MASK, x, None, None, mask, x, None, B, C, T)
@@ -449,13 +452,19 @@ class DiTConVBlock(nn.Module):
         ms = mod.stride(0)
         sh1, sc1, g1, sh2, sc2, g2 = (mod[:, i * C:(i + 1) * C] for i in range(6))
         buf = ops.blk16_buffer(B, C, T, x.device, _S_X)
-        ops.ln_mod_blk16(x, sh1, sc1, buf, ms, mask, 1e-6, premask=True)
+        if pending is None:
+            ops.ln_mod_blk16(x, sh1, sc1, buf, ms, mask, 1e-6, premask=True)
+        else:
+            if pending[1].stride(0) != ms:
+                raise RuntimeError("DiTConVBlock: pending gate and this block's modulation must share a batch stride")
+            ops.gate_ln_mod_blk16(x, pending[0], pending[1], sh1, sc1, buf, ms, mask, 1e-6, premask=True)
         y = self.attn.run(buf, C, T)
-        ops.frame_op(ops.OP_GATE_ADD, x, y, g1, mask, x, None, B, C, T, cstride=ms)
-        ops.ln_mod_blk16(x, sh2, sc2, buf, ms, mask, 1e-6, premask=False)
+        ops.gate_ln_mod_blk16(x, y, g1, sh2, sc2, buf, ms, mask, 1e-6, premask=False)
         y = self.mlp.run(buf, C, T, mask)
+        if defer:
+            return x, (y, g2)
         ops.frame_op(ops.OP_GATE_ADD, x, y, g2, mask, x, None, B, C, T, cstride=ms)
-        return x
+        return x, None
 
 
 class ResidualCouplingLayer_Transformer_simple(nn.Module):
@@ -489,8 +498,11 @@ class ResidualCouplingLayer_Transformer_simple(nn.Module):
         B, C, T = x.shape
         half, H = self.half_channels, self.hidden_channels
         h = _conv(x, self._f_pre, C=half)                                   # pre(x0): the first half of the channels
+        pending = None
+        nb = len(self.enc_block)
         for j, blk in enumerate(self.enc_block):
-            h = blk.run(h, g, mask, None if mods is None else mods[:, j], masked_input=j > 0)
+            h, pending = blk.run(h, g, mask, None if mods is None else mods[:, j], masked_input=j > 0, pending=pending,
+                                 defer=j < nb - 1)
         m = _conv(h, self._f_post)
         out = x.clone()
         ops.frame_op(ops.OP_COUPLE, out, m, None, mask, out, None, B, half, T)   # x1 = (x1 - m) * mask

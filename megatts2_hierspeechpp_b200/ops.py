@@ -599,6 +599,24 @@ def ln_mod_blk16(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, buf:
     return buf
 
 
+def gate_ln_mod_blk16(x: torch.Tensor, y: torch.Tensor, gate: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor,
+                      buf: torch.Tensor, mod_stride: int, mask: Optional[torch.Tensor] = None, eps: float = 1e-6,
+                      premask: bool = False):
+    """x += gate[b] * y * mask (in place), then ``ln_mod_blk16`` of the new x: one launch.  gate/shift/scale are row views
+    of one modulation tensor (batch stride ``mod_stride``)."""
+    _req(x, "x", ndim=3); _req(y, "y", ndim=3); _req_vec(gate, "gate"); _req_vec(shift, "shift"); _req_vec(scale, "scale")
+    _req(buf, "buf", torch.float16, 4)
+    B, C, L = x.shape
+    if tuple(y.shape) != (B, C, L) or tuple(buf.shape) != blk16_shape(B, C, L):
+        raise ValueError("gate_ln_mod_blk16: shape mismatch")
+    if mask is not None:
+        _req(mask, "mask")
+    _lib.check(_lib.load().hsv_gate_ln_mod_blk16(_p(x), _p(y), _p(gate), int(mod_stride), _p(shift), _p(scale), _p(mask),
+                                                 _p(buf), B, C, L, float(eps), int(premask), int(mod_stride), _stream()),
+               "hsv_gate_ln_mod_blk16")
+    return buf
+
+
 def frame_op(op: int, a, b=None, c=None, mask=None, out=None, out2=None, B=0, C=0, L=0, s: float = 1.0, cstride: int = 0):
     for t, n in ((a, "a"), (b, "b"), (mask, "mask"), (out, "out"), (out2, "out2")):
         if t is not None:

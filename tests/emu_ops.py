@@ -217,6 +217,11 @@ def ln_mod_blk16(x, shift, scale, buf, mod_stride, mask=None, eps=1e-6, inmask=F
     return buf
 
 
+def gate_ln_mod_blk16(x, y, gate, shift, scale, buf, mod_stride, mask=None, eps=1e-6, premask=False):
+    x.add_(gate.unsqueeze(-1) * y * _m(mask, x))
+    return ln_mod_blk16(x, shift, scale, buf, mod_stride, mask, eps, premask=premask)
+
+
 def frame_op(op, a, b=None, c=None, mask=None, out=None, out2=None, B=0, C=0, L=0, s=1.0, cstride=0):
     mk = _m(mask, a if a is not None else b)
     if op == real.OP_WN_RES:
@@ -277,7 +282,7 @@ def check_saturation(buf, C, L):
     return None
 
 
-NAMES = ["pack_blk16_act", "wn_res_pack", "ln_mod_blk16", "frame_op", "mha", "conv1d_c1_strided", "masked_mean", "check_saturation",
+NAMES = ["pack_blk16_act", "wn_res_pack", "ln_mod_blk16", "gate_ln_mod_blk16", "frame_op", "mha", "conv1d_c1_strided", "masked_mean", "check_saturation",
          "blk16_buffer", "act1d", "act1d_blk16", "pack_blk16", "weight_norm_fold", "pack_conv_weight", "conv1d_umma", "conv1d_umma_blk", "act_conv1d_umma", "pack_convT_weight", "conv_transpose1d_umma",
          "conv1d_direct", "conv_transpose1d", "sr_pre_interp", "nearest_gather", "add3_bcast"]
 

@@ -70,6 +70,26 @@ def test_ln_mod(hsv, C):
         assert _rel(ops.unpack_blk16(buf, C, T), ref) <= 1.5e-3
 
 
+def test_gate_ln_mod_equals_two_launches(hsv):
+    """x += gate * y * mask fused into the LayerNorm / modulate / pack launch == gate_add then ln_mod, bit for bit."""
+    ops = hsv.ops
+    g = torch.Generator().manual_seed(12)
+    B, C, T = 2, 192, 131
+    x = (torch.randn(B, C, T, generator=g) * 2).to(DEV)
+    y = torch.randn(B, C, T, generator=g).to(DEV)
+    mod = torch.randn(B, 3, 6 * C, generator=g).to(DEV)[:, 1]            # strided rows, as the batched adaLN gives them
+    ms = mod.stride(0)
+    mask = (torch.arange(T)[None, :] < torch.tensor([T, 90])[:, None]).float().to(DEV)
+    a, b = ops.blk16_buffer(B, C, T, DEV, slot=8), ops.blk16_buffer(B, C, T, DEV, slot=9)
+    for premask in (False, True):
+        x1, x2 = x.clone(), x.clone()
+        ops.frame_op(ops.OP_GATE_ADD, x1, y, mod[:, 2 * C:3 * C], mask, x1, None, B, C, T, cstride=ms)
+        ops.ln_mod_blk16(x1, mod[:, :C], mod[:, C:2 * C], a, ms, mask, 1e-6, premask=premask)
+        ops.gate_ln_mod_blk16(x2, y, mod[:, 2 * C:3 * C], mod[:, :C], mod[:, C:2 * C], b, ms, mask, 1e-6, premask=premask)
+        assert torch.equal(x1, x2)
+        assert torch.equal(ops.unpack_blk16(a, C, T), ops.unpack_blk16(b, C, T))
+
+
 def test_frame_ops(hsv):
     ops = hsv.ops
     g = torch.Generator().manual_seed(3)

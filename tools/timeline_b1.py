@@ -56,7 +56,7 @@ def main():
     ks = [e for e in tr["traceEvents"] if e.get("cat") == "kernel"]
     ks.sort(key=lambda e: e["ts"])
     # last replay = kernels after the last flush fill
-    idx = [i for i, e in enumerate(ks) if "fill" in e["name"].lower() or "vectorized_elementwise" in e["name"]]
+    idx = [i for i, e in enumerate(ks) if "FillFunctor" in e["name"] and e["dur"] > 20]   # the 256 MB L2 flush
     ks = ks[idx[-1] + 1:] if idx else ks
     t0 = ks[0]["ts"]
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
