@@ -275,6 +275,7 @@ FUSE_MAX_CHANNELS = [int(__import__("os").environ.get("HSV_FUSE_MAX_C", "0"))]
 FUSE_MAX_ELEMS = [int(__import__("os").environ.get("HSV_FUSE_MAX_ELEMS", str(1 << 62)))]
 
 _MAIN_SLOT = 3   # blk16 workspace slot of the main stream (slots 0..2 belong to the per-resblock streams)
+_DB_SLOT = 15   # second operand workspace of the DBlock's conv chain
 _PRE_SLOT = 7    # ... of Generator.pre when Vocoder runs it beside the SourceNetwork (4..6: front.py, 8+: tests)
 
 
@@ -511,6 +512,26 @@ class DBlock(nn.Module):
             with torch.cuda.stream(st):
                 _dense_conv(xd, self._fr, 1, slot=slot, out=res)
                 ready.record(st)
+        B, cin, L = xd.shape
+        hid = self.conv[0].out_channels
+        if cin % 16 == 0 and hid % 16 == 0:
+            # leaky_relu -> conv chain with operand-writing epilogues: one pack, then every conv hands the next one its
+            # fp16 operand (leaky_relu applied in the epilogue)
+            rt = _row_tiles(B, L)
+            b0 = ops.blk16_buffer(B, cin, L, xd.device, _MAIN_SLOT)
+            ops.pack_blk16(xd, b0, True)
+            ops.check_saturation(b0, cin, L)
+            b1 = ops.blk16_buffer(B, hid, L, xd.device, _MAIN_SLOT)
+            b2 = ops.blk16_buffer(B, hid, L, xd.device, _DB_SLOT)
+            w0, n0 = self._fc[0].packed_weight(rt)
+            ops.conv1d_umma_blk(b0, w0, self._fc[0].bias(), L, cin, hid, 3, 1, n0, b1, ops.BLK_LRELU)
+            w1, n1 = self._fc[1].packed_weight(rt)
+            ops.conv1d_umma_blk(b1, w1, self._fc[1].bias(), L, hid, hid, 3, 2, n1, b2, ops.BLK_LRELU)
+            ops.check_saturation(b2, hid, L)
+            if ready is not None:
+                torch.cuda.current_stream().wait_event(ready)
+            w2, n2 = self._fc[2].packed_weight(rt)
+            return ops.conv1d_umma(b2, w2, self._fc[2].bias(), L, hid, hid, 3, 4, n2, residual=res)
         h = xd
         for i, d in enumerate((1, 2, 4)):
             if i == 2 and ready is not None:

@@ -20,6 +20,12 @@ timeout 900 python bench.py --steps 3 --warmup 3 --workload speechsr48 --batch 6
 timeout 600 python bench.py --steps 20 --warmup 5 --workload chain24 --no-config5 > ${P}_bench_chain24.log 2>&1
 timeout 600 python bench.py --steps 20 --warmup 5 --workload synth --no-config5 > ${P}_bench_synth.log 2>&1
 timeout 600 python bench.py --steps 20 --warmup 5 --workload speechsr24 --seconds 3 --no-config5 > ${P}_bench_sr24_3s.log 2>&1
+timeout 600 python bench.py --steps 20 --warmup 5 --workload tts --no-config5 > ${P}_bench_tts.log 2>&1
+timeout 200 python tools/timeline_b1.py --out ${P}_timeline_vocoder_b1.txt > /dev/null 2>&1
+timeout 200 python tools/timeline_b1.py --parallel-blocks 0 --pdl 0 --out ${P}_timeline_vocoder_b1_serial.txt > /dev/null 2>&1
+timeout 200 python tools/timeline_b1.py --workload synth --out ${P}_timeline_synth.txt > /dev/null 2>&1
+python tools/prof_mha.py > ${P}_microbench_mha.txt 2>&1
+$NCU --set full --import-source on -k regex:mha_mma -s 2 -c 1 -o ${P}_prof_mha -f python tools/prof_mha.py 0 > /dev/null 2>&1
 $NCU --metrics gpu__time_duration.sum --csv --log-file ${P}_launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-config5 --no-gpu-eager --no-cupti --min-seconds 0 --max-blocks 1 > ${P}_p_bench.log 2>&1
 $NCU --set full --import-source on -k regex:act1d_kernel -s 2 -c 1 -o ${P}_prof_act_sat -f python tools/profile_kernels.py act 16 32 480000 1 > ${P}_p_act.log 2>&1
 HSV_ACT_VARIANT=2 $NCU --set full --import-source on -k regex:act1d_mma -s 2 -c 1 -o ${P}_prof_actmma_sat -f python tools/profile_kernels.py act 16 32 480000 1 > ${P}_p_actmma.log 2>&1
