@@ -107,13 +107,20 @@ mha_mma_kernel(const float *__restrict__ q, const float *__restrict__ k, const f
         gk += ld_step;
         gv += ld_step;
       }
-    } else {                                                     // ragged last tile / unaligned tensors: zero fill
-      float *Kd = my + stage * STAGE, *Vd = Kd + D * KP;
-      for (int idx = lane; idx < D * KT; idx += 32) {
-        const int d = idx / KT, j = idx - d * KT;
-        const bool ok = k0 + j < Tk;
-        Kd[d * KP + j] = ok ? __ldg(kb + (int64_t)d * Tk + k0 + j) : 0.f;
-        Vd[d * VP + j] = ok ? __ldg(vb + (int64_t)d * Tk + k0 + j) : 0.f;
+    } else {
+      // ragged last tile / Tk % 4 != 0 / unaligned tensors: 4-byte cp.async with zero fill past Tk (src-size 0) -- still
+      // asynchronous (a plain load -> store loop here was a chain of L2 round trips: 29 us for the StyleEncoder's T = 150)
+      const uint32_t sk0 = (uint32_t)__cvta_generic_to_shared(my + stage * STAGE);
+      const uint32_t sv0 = sk0 + D * KP * 4;
+      const int j = lane & (KT - 1), dq = lane / KT;             // 16 keys x 2 rows per warp step
+      const int ok = (k0 + j < Tk) ? 4 : 0;
+      const int64_t col = ok ? k0 + j : 0;                       // keep the (unused) source address in bounds
+#pragma unroll 8
+      for (int d = dq; d < D; d += 32 / KT) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sk0 + (d * KP + j) * 4),
+                     "l"(kb + (int64_t)d * Tk + col), "r"(ok) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sv0 + (d * VP + j) * 4),
+                     "l"(vb + (int64_t)d * Tk + col), "r"(ok) : "memory");
       }
     }
     cp_commit();
@@ -128,11 +135,15 @@ mha_mma_kernel(const float *__restrict__ q, const float *__restrict__ k, const f
         const int d = ch >> 2, x4 = (ch & 3) * 4;
         cp16(Qs + d * KP + x4, qb + (int64_t)d * Tq + q0 + x4);
       }
-    } else {
-      for (int idx = tid; idx < D * QT; idx += 32 * NWARP) {
-        const int d = idx / QT, r = idx - d * QT;
-        Qs[d * KP + r] = q0 + r < Tq ? __ldg(qb + (int64_t)d * Tq + q0 + r) : 0.f;
-      }
+    } else {                                                     // ragged / unaligned: 4-byte copies, zero fill past Tq
+      const uint32_t sq0 = (uint32_t)__cvta_generic_to_shared(Qs);
+      const int r = tid & (QT - 1);
+      const int ok = (q0 + r < Tq) ? 4 : 0;
+      const int64_t col = ok ? q0 + r : 0;
+#pragma unroll 4
+      for (int d = tid / QT; d < D; d += 32 * NWARP / QT)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sq0 + (d * KP + r) * 4),
+                     "l"(qb + (int64_t)d * Tq + col), "r"(ok) : "memory");
     }
     cp_commit();
   }
