@@ -114,6 +114,12 @@ int hsv_conv1d_umma_blk16(const void *a_blk16, const void *w_packed, const float
                           const float *bc, int64_t bc_stride, const float *mask, int B, int Cin, int Cout, int64_t L, int k,
                           int d, int n_tile, void *stream);
 
+/* hsv_conv1d_umma_wn_tail: a WN layer's res_skip 1x1 conv (Cin -> 2H) with the layer tail in its epilogue (modules.py:167-174):
+ * x = (x + rs[:, :H]) * mask in place, output += rs[:, H:] in place, and the new x written as the next in_layer's fp16
+ * blk16 operand.  H must be a multiple of n_tile. */
+int hsv_conv1d_umma_wn_tail(const void *a_blk16, const void *w_packed, const float *bias, float *x, float *output,
+                            const float *mask, void *next_blk16, int B, int Cin, int H, int64_t L, int n_tile, void *stream);
+
 /* ---- whole AMP half-layer: Activation1d(SnakeBeta) followed by the dilated Conv1d,
  *   xt = conv(Activation1d(x * in_scale))            (hierspeechpp_speechsynthesizer.py:380-384)
  * in ONE kernel: the CTA evaluates the fused activation on the fp32 input and writes the fp16 operand

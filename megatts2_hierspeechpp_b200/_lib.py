@@ -28,6 +28,8 @@ SIGNATURES = {
                                 c_int, c_int, c_int, c_int64, c_int, c_int, c_int, c_void_p]),
     "hsv_conv1d_umma_blk16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int, c_int,
                                       c_int, c_int64, c_int, c_int, c_int, c_void_p]),
+    "hsv_conv1d_umma_wn_tail": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                        c_int, c_int64, c_int, c_void_p]),
     "hsv_act_conv1d_umma": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_int, c_int, c_int, c_int, c_int64, c_int, c_int, c_void_p]),
     "hsv_pack_convT_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),

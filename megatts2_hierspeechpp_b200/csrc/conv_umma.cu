@@ -82,11 +82,13 @@ struct Params {
   uint32_t x_off;      // byte offset (from the aligned shared base) of the two fp32 staging buffers
   // operand-writing epilogue (hsv_conv1d_umma_blk16): the result goes out as the fp16 blk16 operand of the NEXT conv
   void *out_blk;          // nullptr = the fp32 epilogues below
-  int blk_mode;           // 0 none, 1 WN gate (column pairs), 2 gelu_tanh, 3 leaky_relu(0.1)
-  int blk_C;              // channels of the output buffer (Cout; Cout / 2 for the gate)
+  int blk_mode;           // 0 none, 1 WN gate (column pairs), 2 gelu_tanh, 3 leaky_relu(0.1), 4 WN layer tail
+  int blk_C;              // channels of the output buffer (Cout; Cout / 2 for the gate and the WN tail)
   const float *blk_bc;    // [B][Cout] vector added before the activation (batch stride blk_bcs), or nullptr
   int64_t blk_bcs;
   const float *blk_mask;  // [B][L] frame mask applied to the result, or nullptr
+  float *blk_x;           // mode 4 (WN layer tail): residual stream [B][Cout/2][L], updated in place
+  float *blk_acc;         // mode 4: skip accumulator [B][Cout/2][L], updated in place
   int debug;
   long long *trace;  // bring-up: clock64 stamps of CTA (0,0,0) (hsv_set_umma_trace), else nullptr
   TapTable tt;
@@ -553,7 +555,39 @@ __global__ void __launch_bounds__(32 * NW, MINB) conv_umma_kernel(const __grid_c
         float v[16];
 #pragma unroll
         for (int c = 0; c < 16; ++c) v[c] = __uint_as_float(r[c]) + bias_s[c0 + c] + (bcv ? __ldg(bcv + c0 + c) : 0.f);
-        if (p.blk_mode == 1) {
+        if (p.blk_mode == 4) {
+          // WN layer tail (modules.py:167-174): columns [0, H) are the residual branch: x = (x + rs) * mask in place, and
+          // the new x IS the next in_layer's operand; columns [H, 2H) are the skip branch: output += rs.  H % n_tile == 0,
+          // so a CTA is entirely on one side.  For a fixed channel consecutive lanes are consecutive frames: coalesced.
+          const int H = p.blk_C;
+          const int cb = co0 + c0;
+          if (cb < H) {
+            float *xp = p.blk_x + ((int64_t)b * H + cb) * p.L + t;
+            float xv[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) xv[c] = xp[(int64_t)c * p.L];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              xv[c] = (xv[c] + v[c]) * mk;
+              xp[(int64_t)c * p.L] = xv[c];
+            }
+#pragma unroll
+            for (int q8 = 0; q8 < 2; ++q8) {
+              __half2 hh[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) hh[e] = __floats2half2_rn(xv[8 * q8 + 2 * e], xv[8 * q8 + 2 * e + 1]);
+              *reinterpret_cast<uint4 *>(ob + hsv::blk_unit_offset(cwo, p.Lp, H, b, cb + 8 * q8, HSV_BLK_PAD + t)) =
+                  *reinterpret_cast<uint4 *>(hh);
+            }
+          } else {
+            float *op = p.blk_acc + ((int64_t)b * H + (cb - H)) * p.L + t;
+            float ov[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) ov[c] = op[(int64_t)c * p.L];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) op[(int64_t)c * p.L] = ov[c] + v[c];
+          }
+        } else if (p.blk_mode == 1) {
           __half2 hh[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -1186,6 +1220,7 @@ struct BlkOut {    // operand-writing epilogue (see Params)
   const float *bc;
   int64_t bcs;
   const float *mask;
+  float *x, *acc;  // mode 4
 };
 
 int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const float *bias,
@@ -1199,6 +1234,8 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
   p.blk_bc = bo ? bo->bc : nullptr;
   p.blk_bcs = bo ? bo->bcs : 0;
   p.blk_mask = bo ? bo->mask : nullptr;
+  p.blk_x = bo ? bo->x : nullptr;
+  p.blk_acc = bo ? bo->acc : nullptr;
   p.fx = fa ? fa->x : nullptr;
   p.alpha = fa ? fa->alpha : nullptr;
   p.beta = fa ? fa->beta : nullptr;
@@ -1426,9 +1463,21 @@ extern "C" int hsv_conv1d_umma_blk16(const void *a_blk16, const void *w_packed, 
               MAX_TAPS, k, d);
   HSV_REQUIRE(((k - 1) / 2) * d <= HSV_BLK_PAD, "conv1d_umma_blk16: halo %d exceeds blk16 padding %d", ((k - 1) / 2) * d,
               HSV_BLK_PAD);
-  const BlkOut bo = {out_blk16, mode, mode == 1 ? Cout / 2 : Cout, bc, bc_stride, mask};
+  const BlkOut bo = {out_blk16, mode, mode == 1 ? Cout / 2 : Cout, bc, bc_stride, mask, nullptr, nullptr};
   return launch(conv_taps(k, d), a_blk16, w_packed, bias, nullptr, nullptr, nullptr, 0, B, Cin, Cout, L, L, n_tile,
                 hsv::as_stream(stream), "conv1d_umma_blk16", nullptr, &bo);
+}
+
+extern "C" int hsv_conv1d_umma_wn_tail(const void *a_blk16, const void *w_packed, const float *bias, float *x, float *output,
+                                       const float *mask, void *next_blk16, int B, int Cin, int H, int64_t L, int n_tile,
+                                       void *stream) {
+  if (B == 0 || L == 0) return HSV_OK;
+  if (int rc = check_common("conv1d_umma_wn_tail", a_blk16, w_packed, Cin, 2 * H, n_tile)) return rc;
+  HSV_REQUIRE(x && output && next_blk16 && next_blk16 != a_blk16, "conv1d_umma_wn_tail: null / aliased buffer");
+  HSV_REQUIRE(H % n_tile == 0, "conv1d_umma_wn_tail: H=%d must be a multiple of n_tile=%d", H, n_tile);
+  const BlkOut bo = {next_blk16, 4, H, nullptr, 0, mask, x, output};
+  return launch(conv_taps(1, 1), a_blk16, w_packed, bias, nullptr, nullptr, nullptr, 0, B, Cin, 2 * H, L, L, n_tile,
+                hsv::as_stream(stream), "conv1d_umma_wn_tail", nullptr, &bo);
 }
 
 extern "C" int hsv_act_conv1d_umma(const float *x, const float *alpha, const float *beta, float in_scale,

@@ -26,6 +26,7 @@ from .modules import (_Folded, _as_input, _bump_on_load, _row_tiles, _side_strea
                       SourceNetwork, vocode)
 
 _S_X, _S_G, _S_W = 4, 5, 6      # blk16 workspace slots of this module family (0..3 and 7 belong to the vocoder)
+_WN_TAIL = __import__("os").environ.get("HSV_WN_TAIL", "1") != "0"   # A/B switch: WN layer tail in the res_skip conv's epilogue
 _S_X2, _S_G2 = 10, 11           # ... of the second WaveNet stack when two run side by side (8, 9: tests)
 
 
@@ -278,11 +279,18 @@ class WN(nn.Module):
             ops.conv1d_umma_blk(buf, wp, self._f_in[i].bias(), T, H, 2 * H, k, d, nt, gbuf, ops.BLK_GATE,
                                 bc=None if gl is None else gl[:, i])
             ops.check_saturation(gbuf, H, T)
-            acts_rs = _conv_buf(gbuf, self._f_rs[i], T, H, 2 * H if i < n - 1 else H)
             if i < n - 1:
-                ops.wn_res_pack(x, acts_rs, mask, output, buf)       # x, output updated in place; buf = fp16(x)
+                # res_skip conv with the layer tail in its epilogue: x = (x + res) * mask, output += skip (both in place),
+                # buf = fp16(x) = the next in_layer's operand
+                wr, ntr = self._f_rs[i].packed_weight(rt)
+                if H % ntr == 0 and _WN_TAIL:
+                    ops.conv1d_umma_wn_tail(gbuf, wr, self._f_rs[i].bias(), x, output, mask, buf, ntr)
+                else:
+                    acts_rs = ops.conv1d_umma(gbuf, wr, self._f_rs[i].bias(), T, H, 2 * H, 1, 1, ntr)
+                    ops.wn_res_pack(x, acts_rs, mask, output, buf)
                 ops.check_saturation(buf, H, T)
             else:
+                acts_rs = _conv_buf(gbuf, self._f_rs[i], T, H, H)
                 ops.frame_op(ops.OP_WN_LAST, None, acts_rs, None, mask, None, output, B, H, T)
         return output
 

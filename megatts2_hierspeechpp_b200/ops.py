@@ -343,6 +343,27 @@ def conv1d_umma_blk(a_blk: torch.Tensor, w_packed: torch.Tensor, bias: Optional[
     return out_blk
 
 
+def conv1d_umma_wn_tail(a_blk: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], x: torch.Tensor,
+                        output: torch.Tensor, mask: Optional[torch.Tensor], next_blk: torch.Tensor, n_tile: int):
+    """A WN layer's res_skip conv (1x1, Cin -> 2H) with the layer tail in its epilogue: x = (x + rs[:, :H]) * mask and
+    output += rs[:, H:] in place, the new x also written as the next in_layer's fp16 operand ``next_blk``."""
+    _req(a_blk, "a_blk16", torch.float16, 4); _req(w_packed, "w_packed", torch.float16)
+    _req(next_blk, "next_blk16", torch.float16, 4); _req(x, "x", ndim=3); _req(output, "output", ndim=3)
+    B, H, L = x.shape
+    cin = a_blk.shape[1] * a_blk.shape[3]
+    if tuple(a_blk.shape) != blk16_shape(B, cin, L) or tuple(next_blk.shape) != blk16_shape(B, H, L):
+        raise ValueError("conv1d_umma_wn_tail: operand buffer shape mismatch")
+    if tuple(output.shape) != (B, H, L) or H % n_tile:
+        raise ValueError("conv1d_umma_wn_tail: output shape / n_tile mismatch")
+    if bias is not None:
+        _req(bias, "bias")
+    if mask is not None:
+        _req(mask, "mask")
+    _lib.check(_lib.load().hsv_conv1d_umma_wn_tail(_p(a_blk), _p(w_packed), _p(bias), _p(x), _p(output), _p(mask),
+                                                   _p(next_blk), B, cin, H, L, n_tile, _stream()), "hsv_conv1d_umma_wn_tail")
+    return next_blk
+
+
 def act_conv1d_umma(x: torch.Tensor, alpha: torch.Tensor, beta: torch.Tensor, w_packed: torch.Tensor,
                     bias: Optional[torch.Tensor], cout: int, k: int, d: int, residual: Optional[torch.Tensor] = None,
                     out: Optional[torch.Tensor] = None, acc: Optional[torch.Tensor] = None, acc_mode: int = ACC_NONE,

@@ -105,6 +105,13 @@ def conv1d_umma_blk(a_blk, wp, bias, L, cin, cout, k, d, n_tile, out_blk, mode=0
     return out_blk
 
 
+def conv1d_umma_wn_tail(a_blk, wp, bias, x, output, mask, next_blk, n_tile):
+    B, H, L = x.shape
+    cin = a_blk.shape[1] * a_blk.shape[3]
+    rs = F.conv1d(_unpack(a_blk, L), wp.float().view(2 * H, cin, 1), bias)
+    return wn_res_pack(x, rs, mask, output, next_blk)
+
+
 def act_conv1d_umma(x, alpha, beta, wp, bias, cout, k, d, residual=None, out=None, acc=None, acc_mode=0, scale=1.0,
                     want_out=True):
     B, cin, L = x.shape
@@ -283,7 +290,7 @@ def check_saturation(buf, C, L):
 
 
 NAMES = ["pack_blk16_act", "wn_res_pack", "ln_mod_blk16", "gate_ln_mod_blk16", "frame_op", "mha", "conv1d_c1_strided", "masked_mean", "check_saturation",
-         "blk16_buffer", "act1d", "act1d_blk16", "pack_blk16", "weight_norm_fold", "pack_conv_weight", "conv1d_umma", "conv1d_umma_blk", "act_conv1d_umma", "pack_convT_weight", "conv_transpose1d_umma",
+         "blk16_buffer", "act1d", "act1d_blk16", "pack_blk16", "weight_norm_fold", "pack_conv_weight", "conv1d_umma", "conv1d_umma_blk", "conv1d_umma_wn_tail", "act_conv1d_umma", "pack_convT_weight", "conv_transpose1d_umma",
          "conv1d_direct", "conv_transpose1d", "sr_pre_interp", "nearest_gather", "add3_bcast"]
 
 

@@ -282,3 +282,28 @@ def test_voice_conversion_noise_control_vs_oracle(hsv, synthesizer, T, T_mel, le
     torch.manual_seed(7)
     g1 = runner(w2v, f0, mel)
     assert g1.shape == got.shape and bool(torch.isfinite(g1).all())
+
+
+@pytest.mark.parametrize("B,H,T", [(1, 192, 500), (2, 192, 77), (1, 512, 150)])
+def test_wn_tail_epilogue_equals_conv_then_wn_res_pack(hsv, B, H, T):
+    """The res_skip conv with the WN layer tail in its epilogue == the fp32 conv followed by wn_res_pack, bit for bit."""
+    ops = hsv.ops
+    g = torch.Generator().manual_seed(H + T)
+    acts = torch.randn(B, H, T, generator=g).to(DEV)
+    w = (torch.randn(2 * H, H, 1, generator=g) / H ** 0.5).to(DEV)
+    bias = torch.randn(2 * H, generator=g).to(DEV)
+    x = torch.randn(B, H, T, generator=g).to(DEV)
+    out = torch.randn(B, H, T, generator=g).to(DEV)
+    mask = (torch.arange(T)[None, :] < torch.tensor([T, max(1, T - 20)][:B])[:, None]).float().to(DEV)
+    a = ops.blk16_buffer(B, H, T, DEV, slot=8)
+    ops.pack_blk16(acts, a)
+    nt = ops.pick_n_tile(2 * H, B * ((T + 127) // 128), H)
+    assert H % nt == 0
+    wp = ops.pack_conv_weight(w, nt)
+    x1, o1, x2, o2 = x.clone(), out.clone(), x.clone(), out.clone()
+    b1, b2 = ops.blk16_buffer(B, H, T, DEV, slot=9), ops.blk16_buffer(B, H, T, DEV, slot=10)
+    rs = ops.conv1d_umma(a, wp, bias, T, H, 2 * H, 1, 1, nt)
+    ops.wn_res_pack(x1, rs, mask, o1, b1)
+    ops.conv1d_umma_wn_tail(a, wp, bias, x2, o2, mask, b2, nt)
+    assert torch.equal(x1, x2) and torch.equal(o1, o2)
+    assert torch.equal(ops.unpack_blk16(b1, H, T), ops.unpack_blk16(b2, H, T))
