@@ -231,7 +231,9 @@ constexpr int BAR_A = 1, BAR_WF = 1 + MAX_CHUNKS, BAR_WE = BAR_WF + MAX_STAGES, 
 // NW = warps per CTA: 4, or 8 for the wide variants -- warps 4..7 only take part in the epilogue (two warps per
 // TMEM lane quarter, alternating 16-column units), which is a chain of ~180 dependent instructions per unit for
 // a lone warp per scheduler.
-template <int MSUB, int MINB, bool SMALLN, int RR, int NW>
+// BLK = the operand-writing epilogue is compiled in (its own instantiations: the fp32 variants of the vocoder's hot path
+// keep their register budget -- with the extra path in the same kernel the 80-register narrow variant spilled 52 bytes)
+template <int MSUB, int MINB, bool SMALLN, int RR, int NW, bool BLK = false>
 __global__ void __launch_bounds__(32 * NW, MINB) conv_umma_kernel(const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[NBARS + 2];
@@ -532,7 +534,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) conv_umma_kernel(const __grid_c
   for (int q = 0; q < NBR; ++q) bias_s[threadIdx.x + 32 * NW * q] = bias_r[q];
   if (threadIdx.x == 0) stamp(p, 6);
   const uint32_t trow = tmem + ((uint32_t)(wq * 32) << 16);
-  if (p.out_blk) {
+  if (BLK && p.out_blk) {
     // Operand-writing epilogue.  tcgen05.ld gives a lane one time row x 16 consecutive output channels: exactly two
     // 16-byte units of the blk16 layout ([row][8 channels]) -- no transpose.  The WN gate pairs columns: the host packs
     // in_layers' output channels as [8 tanh | 8 sigmoid] groups, so a 16-column unit yields 8 gate outputs = one unit.
@@ -1167,7 +1169,7 @@ TapTable convT_taps(int k, int u) {
 long long *g_trace = nullptr;
 int g_msub_override = 0;  // bring-up aid: force the sub-tiles per CTA (0 = automatic)
 
-template <int MSUB, int MINB, bool SMALLN, int RR = 0, int NW = 4>
+template <int MSUB, int MINB, bool SMALLN, int RR = 0, int NW = 4, bool BLK = false>
 int launch_variant(const Params &p, dim3 grid, size_t smem, cudaStream_t st, const char *what) {
   // opt-in dynamic shared memory: 227 KB per block minus the kernel's static shared memory
   static int max_dyn[64] = {0};
@@ -1176,11 +1178,11 @@ int launch_variant(const Params &p, dim3 grid, size_t smem, cudaStream_t st, con
   if (dev < 0 || dev >= 64) dev = 0;
   if (max_dyn[dev] == 0) {
     cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, conv_umma_kernel<MSUB, MINB, SMALLN, RR, NW>);
+    cudaError_t e = cudaFuncGetAttributes(&fa, conv_umma_kernel<MSUB, MINB, SMALLN, RR, NW, BLK>);
     int want = 227 * 1024 - (e == cudaSuccess ? (int)fa.sharedSizeBytes : 1024);
     want &= ~1023;
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_umma_kernel<MSUB, MINB, SMALLN, RR, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+      e = cudaFuncSetAttribute(conv_umma_kernel<MSUB, MINB, SMALLN, RR, NW, BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
     if (e != cudaSuccess) {
       cudaGetLastError();  // clear
       hsv::set_error("%s: cudaFuncSetAttribute(%d): %s", what, want, cudaGetErrorString(e));
@@ -1200,7 +1202,7 @@ int launch_variant(const Params &p, dim3 grid, size_t smem, cudaStream_t st, con
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = hsv::g_pdl ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<MSUB, MINB, SMALLN, RR, NW>, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_umma_kernel<MSUB, MINB, SMALLN, RR, NW, BLK>, p);
   if (e != cudaSuccess) {
     cudaGetLastError();
     hsv::set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
@@ -1283,7 +1285,7 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
                             (force_persist || (n_tile >= 128 && ctas1 >= 2 * 148) || (n_tile == 64 && Cout == 64 && ctas1 >= 4 * 148)) &&
                             (Lout % 4) == 0 && al16e(residual) && al16e(out) && al16e(acc) &&
                             ((out != nullptr) != (acc_mode != 0));
-  if (want_persist) msub = 1;
+  if (want_persist || bo) msub = 1;
   if (fa) msub = 2;  // 256-row tiles: the activation's 5-row run halo and the conv halo are amortised over more rows
   auto a_bytes_for = [&](int ms) {
     const size_t per = (((size_t)(TILE_M * ms + p.hlo8 + tt.h_hi) * rowbytes) + 1023) & ~(size_t)1023;
@@ -1334,7 +1336,7 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
   // 8-warp CTAs (two epilogue warps per TMEM lane quarter) for n_tile >= 128 only: measured +7 % on the C=128/256
   // layers at batch 16 (722 -> 770 TFLOP/s), but -20 % on n_tile = 64 (two CTAs per SM instead of four) and on
   // the 512-row C=16 tiles
-  const bool w8 = !(g_host_debug & 32) && !fa && n_tile >= 128;
+  const bool w8 = !(g_host_debug & 32) && !fa && !bo && n_tile >= 128;
   const int minb = n_tile <= 32 && msub == 1 ? 6 : (w8 ? 2 : (n_tile <= 64 ? 4 : 2));
   int want = (int)((total_ctas + 147) / 148);
   want = want < 1 ? 1 : (want > minb ? minb : want);
@@ -1367,6 +1369,12 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
   // small n_tile = HBM/latency-bound streaming layers: they want many co-resident CTAs (register cap 80);
   // large n_tile = few fat CTAs per SM anyway
   // wide tiles (>= 4 units of 16 columns per CTA) run 8 warps: two epilogue warps per TMEM lane quarter
+  if (bo) {   // operand-writing epilogue: 128-row tiles, 4 warps
+    HSV_REQUIRE(p.msub == 1, "%s: the operand-writing epilogue runs 128-row tiles", what);
+    if (n_tile <= 32) return launch_variant<1, 6, true, 0, 4, true>(p, grid, smem, st, what);
+    if (n_tile <= 64) return launch_variant<1, 4, false, 0, 4, true>(p, grid, smem, st, what);
+    return launch_variant<1, 2, false, 0, 4, true>(p, grid, smem, st, what);
+  }
   if (p.msub == 1) {
     if (n_tile <= 32) return launch_variant<1, 6, true>(p, grid, smem, st, what);
     if (w8) return launch_variant<1, 2, false, 0, 8>(p, grid, smem, st, what);

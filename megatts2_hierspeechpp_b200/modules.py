@@ -410,6 +410,13 @@ class AMPBlock1(nn.Module):
 AMPBlock0 = AMPBlock1
 
 
+_PRE_OVERLAP = [__import__("os").environ.get("HSV_PRE_OVERLAP", "1") != "0"]      # A/B switch of the pre-stage side streams
+# ... which pay while the kernels are short (batch 1: -4.7 % on the step); at batch 16 (40 M elements per late-stage tensor) the
+# chained epilogues are 0.5 % faster (A/B on one box), hence the size cut
+SEPARATE_MAX_ELEMS = [1 << 23]
+_SEPARATE = [__import__("os").environ.get("HSV_SEPARATE_SUMS", "1") != "0"]   # A/B switch of the consumer-side resblock sums
+
+
 def sum_of_blocks(x: torch.Tensor, blocks: Sequence[AMPBlock1], parallel: bool = False, separate: bool = False):
     """(xs, scale) with xs = sum_j resblock_j(x) and scale = 1/num_kernels
     (hierspeechpp_speechsynthesizer.py:440-446).  The sum is accumulated in the epilogue of each block's
@@ -423,7 +430,7 @@ def sum_of_blocks(x: torch.Tensor, blocks: Sequence[AMPBlock1], parallel: bool =
     nk = len(blocks)
     if nk == 1:
         return blocks[0].run(x), 1.0
-    if separate and parallel and nk <= 3:
+    if separate and parallel and nk <= 3 and _SEPARATE[0] and x.numel() <= SEPARATE_MAX_ELEMS[0]:
         main = torch.cuda.current_stream()
         fork = torch.cuda.Event()
         fork.record(main)
@@ -657,7 +664,7 @@ class Generator(_VocoderBase):
             raise ValueError("Generator.forward needs the speaker embedding g")
         xp, cg = self.pre(x, g) if _pre is None else _pre
         proj = proj_ready = None
-        if self.parallel_blocks:
+        if self.parallel_blocks and _PRE_OVERLAP[0]:
             # multi-stream mode: proj(pitch) (:437) and the DBlock's residual conv run beside the DBlock's main branch
             # on two of the (idle) resblock streams, each with its stream's workspace slot
             main = torch.cuda.current_stream()
@@ -799,7 +806,7 @@ def vocode(sn: "SourceNetwork", dec: "Generator", z, g, need_pred: bool = False)
     In multi-stream mode (``dec.parallel_blocks``) ``dec.conv_pre(z)`` and ``dec.cond(g)``, which do not depend on the
     SourceNetwork, run beside it on their own stream and operand workspace slot; their outputs are allocated on the
     caller's stream."""
-    if not (dec.parallel_blocks and z.is_cuda):
+    if not (dec.parallel_blocks and z.is_cuda and _PRE_OVERLAP[0]):
         e, e_ = sn(z, g, need_pred=need_pred)
         return dec(z, e, g=g), e_
     z_, g_ = _as_input(z), _as_input(g)
