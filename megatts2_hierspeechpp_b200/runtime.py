@@ -62,7 +62,8 @@ class CudaGraphRunner:
             self._pb_mods = [m for m in (self.fn.modules() if hasattr(self.fn, "modules") else [])
                              if hasattr(m, "parallel_blocks")]
         par = tuple(bool(m.parallel_blocks) for m in self._pb_mods)
-        return (M._CACHE_EPOCH[0], ops.WORKSPACE_EPOCH[0], M.FUSE_MAX_CHANNELS[0], M.FUSE_MAX_ELEMS[0], par)
+        return (M._CACHE_EPOCH[0], ops.WORKSPACE_EPOCH[0], M.FUSE_MAX_CHANNELS[0], M.FUSE_MAX_ELEMS[0],
+                M.SEPARATE_MAX_ELEMS[0], ops.MHA_VARIANT[0], par)
 
     def _key(self, args):
         return tuple((tuple(a.shape), a.dtype, a.device.index) for a in args)

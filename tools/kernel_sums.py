@@ -21,7 +21,7 @@ with torch.no_grad():
 agg = collections.OrderedDict(); rows = []
 for e in prof.events():
     if "cuda" in str(getattr(e, "device_type", "")).lower():
-        n = e.name.split("(")[0][-60:]
+        n = __import__("re").sub(r"\(anonymous namespace\)::|void |<unnamed>::", "", e.name).split("(")[0][:60]
         a = agg.setdefault(n, [0, 0.0]); a[0] += 1; a[1] += e.time_range.end - e.time_range.start
         rows.append((e.time_range.start, e.time_range.end - e.time_range.start, n))
 tot = sum(v[1] for v in agg.values())
