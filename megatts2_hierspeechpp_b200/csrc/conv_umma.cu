@@ -695,14 +695,24 @@ __global__ void __launch_bounds__(32 * NW, MINB) conv_umma_kernel(const __grid_c
       ok = t < p.L;
       off = chan_base + (int64_t)p.tt.out_stride * t + (int64_t)c0 * cs;
     };
+    // (addresses walk by pointer increments: `off + c * cs` per element was 16 64-bit multiply-adds per unit and made this
+    // path -- every ConvTranspose1d of the vocoder -- issue-bound: 1 575 instructions per warp for 32 outputs per lane)
     float res[PFG][16];
 #pragma unroll
-    for (int q = 0; q < PFG; ++q) {
-      int64_t off; bool ok;
-      unit_ptr(q < nunits ? q : 0, off, ok);
-      ok = ok && has_res && q < nunits && half == 0;
+    for (int q = 0; q < PFG; ++q)
 #pragma unroll
-      for (int c = 0; c < 16; ++c) res[q][c] = ok ? p.residual[off + c * cs] : 0.f;
+      for (int c = 0; c < 16; ++c) res[q][c] = 0.f;
+    if (has_res && half == 0) {
+#pragma unroll
+      for (int q = 0; q < PFG; ++q) {
+        int64_t off; bool ok;
+        unit_ptr(q < nunits ? q : 0, off, ok);
+        if (ok && q < nunits) {
+          const float *rp = p.residual + off;
+#pragma unroll
+          for (int c = 0; c < 16; ++c, rp += cs) res[q][c] = *rp;
+        }
+      }
     }
     __syncthreads();  // bias_s complete (every warp is past its role loop here; the MMAs are in flight)
     mbar_wait(bar_acc, 0);
@@ -723,24 +733,28 @@ __global__ void __launch_bounds__(32 * NW, MINB) conv_umma_kernel(const __grid_c
           float v[16];
 #pragma unroll
           for (int c = 0; c < 16; ++c) v[c] = (__uint_as_float(r[c]) + bias_s[c0 + c]) + res[q][c];  // reference order
-          {
+          if (has_res) {
             int64_t offn; bool okn;
             unit_ptr(u + PFG < nunits ? u + PFG : u, offn, okn);
-            okn = okn && has_res && u + PFG < nunits;
+            okn = okn && u + PFG < nunits;
+            const float *rp = p.residual + offn;
 #pragma unroll
-            for (int c = 0; c < 16; ++c) res[q][c] = okn ? p.residual[offn + c * cs] : 0.f;
+            for (int c = 0; c < 16; ++c, rp += cs) res[q][c] = okn ? *rp : 0.f;
           }
           if (valid) {
             if (p.acc_mode == 1) {
+              float *ap = p.acc + off;
 #pragma unroll
-              for (int c = 0; c < 16; ++c) p.acc[off + c * cs] = v[c];
+              for (int c = 0; c < 16; ++c, ap += cs) *ap = v[c];
             } else if (p.acc_mode == 2) {
+              float *ap = p.acc + off;
 #pragma unroll
-              for (int c = 0; c < 16; ++c) atomicAdd(p.acc + off + c * cs, v[c]);
+              for (int c = 0; c < 16; ++c, ap += cs) atomicAdd(ap, v[c]);
             }
             if (p.out) {
+              float *op = p.out + off;
 #pragma unroll
-              for (int c = 0; c < 16; ++c) p.out[off + c * cs] = v[c];
+              for (int c = 0; c < 16; ++c, op += cs) *op = v[c];
             }
           }
         }
