@@ -244,7 +244,12 @@ extern "C" int hsv_act1d_snakebeta(const float *x, void *out, const float *alpha
     R = g_act_run;
   } else {
     int64_t best = -1;
-    for (int cand : {17, 21, 25}) {
+    // R = 9: only for launches that leave most SMs empty at R = 17 (the SourceNetwork / early stages at batch 1: 64
+    // CTAs): twice the CTAs, half the serial work per thread
+    static const bool no_r9 = getenv("HSV_ACT_NO_R9") != nullptr;   // A/B switch
+    const bool tiny = !no_r9 && groups * ((L + 17 * RUNS - 1) / (17 * RUNS)) < 148;
+    for (int cand : {9, 17, 21, 25}) {
+      if (cand == 9 && !tiny) continue;
       const int64_t ctas = groups * ((L + cand * RUNS - 1) / (cand * RUNS));
       const int64_t waves = (ctas + 148 * 7 - 1) / (148 * 7);
       // many waves: the halo overhead decides (cost per element ~ (R + 5) / R); few: the wave count does
@@ -255,11 +260,12 @@ extern "C" int hsv_act1d_snakebeta(const float *x, void *out, const float *alpha
       }
     }
   }
-  HSV_REQUIRE(R == 17 || R == 21 || R == 25, "act1d: run length must be 17, 21 or 25");
+  HSV_REQUIRE(R == 9 || R == 17 || R == 21 || R == 25, "act1d: run length must be 9, 17, 21 or 25");
   if (out_mode == 0)
     return R == 25 ? launch<25, 0>(x, out, alpha, beta, B, C, L, in_scale, st)
                    : (R == 21 ? launch<21, 0>(x, out, alpha, beta, B, C, L, in_scale, st)
-                              : launch<17, 0>(x, out, alpha, beta, B, C, L, in_scale, st));
+                              : (R == 17 ? launch<17, 0>(x, out, alpha, beta, B, C, L, in_scale, st)
+                                         : launch<9, 0>(x, out, alpha, beta, B, C, L, in_scale, st)));
   HSV_REQUIRE(C % 16 == 0, "act1d: blk16 output needs C %% 16 == 0 (C=%d)", C);
   // tensor-core FIR variant (act1d_mma.cu): every shape with at least half a tile of work per row; the CUDA-core
   // kernel keeps the tiny sequences (its tiles are 8 x 272 instead of 8 x 512)
@@ -270,5 +276,6 @@ extern "C" int hsv_act1d_snakebeta(const float *x, void *out, const float *alpha
   }
   return R == 25 ? launch<25, 1>(x, out, alpha, beta, B, C, L, in_scale, st)
                  : (R == 21 ? launch<21, 1>(x, out, alpha, beta, B, C, L, in_scale, st)
-                            : launch<17, 1>(x, out, alpha, beta, B, C, L, in_scale, st));
+                            : (R == 17 ? launch<17, 1>(x, out, alpha, beta, B, C, L, in_scale, st)
+                                       : launch<9, 1>(x, out, alpha, beta, B, C, L, in_scale, st)));
 }
