@@ -8,6 +8,7 @@ for w in sr48_b16 voc_b16 sr48_b64 chain24 synth sr24_3s tts; do lastjson ${G}_b
 cp ${G}_parity.log ${P}_parity.log
 cp ${G}_env.txt ${P}_env.txt
 cp ${G}_microbench_mha.txt ${P}_microbench_mha.txt
+[ -f ${G}_microbench_convT.txt ] && cp ${G}_microbench_convT.txt ${P}_microbench_convT.txt
 cp ${G}_timeline_vocoder_b1.txt ${P}_timeline_vocoder_b1.txt
 cp ${G}_timeline_vocoder_b1_serial.txt ${P}_timeline_vocoder_b1_serial.txt
 cp ${G}_timeline_synth.txt ${P}_timeline_synth.txt
