@@ -590,40 +590,39 @@ __global__ void weight_norm_fold_kernel(const float *__restrict__ v, const float
 // fp32 [B,C,L] -> fp16 blk16; one thread per (b, chunk, t)
 // x2 / x3 (nullable): further addends, summed in the fixed order (x + x2) + x3 before the scale -- the consumer-side
 // sum over the resblocks of a stage (each resblock stream writes its own tensor; no chained accumulation)
-__global__ void pack_blk16_kernel(const float *__restrict__ x, const float *__restrict__ x2,
-                                  const float *__restrict__ x3, uint4 *__restrict__ out, int B, int C, int64_t L,
-                                  int64_t Lp, int lrelu, float sc, int cw) {
-  const int nch = C >> 3;
-  const int64_t n = (int64_t)B * nch * L;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t bq = i / L, t = i - bq * L;
-    const int64_t off = bq * 8 * L + t;  // (b*C + 8q) * L + t
-    const float *xr = x + off;
-    __half2 h[4];
+// grid = (time blocks, channel groups of 8, batch): no index division (a flat index cost two 64-bit divisions per thread,
+// as many instructions as the rest of the kernel)
+__global__ void __launch_bounds__(256) pack_blk16_kernel(const float *__restrict__ x, const float *__restrict__ x2,
+                                                         const float *__restrict__ x3, uint4 *__restrict__ out, int C,
+                                                         int64_t L, int64_t Lp, int lrelu, float sc, int cw) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= L) return;
+  const int q = blockIdx.y, bb = blockIdx.z;
+  const int64_t off = ((int64_t)bb * C + 8 * q) * L + t;
+  const float *xr = x + off;
+  float v[8];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float v0 = __ldg(xr + (2 * e) * L), v1 = __ldg(xr + (2 * e + 1) * L);
-      if (x2) {
-        v0 += __ldg(x2 + off + (2 * e) * L);
-        v1 += __ldg(x2 + off + (2 * e + 1) * L);
-      }
-      if (x3) {
-        v0 += __ldg(x3 + off + (2 * e) * L);
-        v1 += __ldg(x3 + off + (2 * e + 1) * L);
-      }
-      v0 *= sc;
-      v1 *= sc;
-      if (lrelu) {
-        v0 = v0 > 0.f ? v0 : 0.1f * v0;
-        v1 = v1 > 0.f ? v1 : 0.1f * v1;
-      }
-      h[e] = __floats2half2_rn(v0, v1);
-    }
-    const int64_t bb = bq / nch;
-    const int c0 = (int)(bq - bb * nch) * 8;
-    *reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(out) +
-                               hsv::blk_unit_offset(cw, Lp, C, bb, c0, HSV_BLK_PAD + t)) = *reinterpret_cast<uint4 *>(h);
+  for (int e = 0; e < 8; ++e) v[e] = __ldg(xr + e * L);
+  if (x2) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] += __ldg(x2 + off + e * L);
   }
+  if (x3) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] += __ldg(x3 + off + e * L);
+  }
+  __half2 h[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float v0 = v[2 * e] * sc, v1 = v[2 * e + 1] * sc;
+    if (lrelu) {
+      v0 = v0 > 0.f ? v0 : 0.1f * v0;
+      v1 = v1 > 0.f ? v1 : 0.1f * v1;
+    }
+    h[e] = __floats2half2_rn(v0, v1);
+  }
+  *reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(out) +
+                             hsv::blk_unit_offset(cw, Lp, C, bb, 8 * q, HSV_BLK_PAD + t)) = *reinterpret_cast<uint4 *>(h);
 }
 
 // inverse of pack_blk16 (test / debugging aid): blk16 -> fp32 [B,C,L]
@@ -792,8 +791,9 @@ extern "C" int hsv_pack_blk16(const float *x, void *out, int B, int C, int64_t L
   if (B == 0 || L == 0) return HSV_OK;
   HSV_REQUIRE(x && out, "pack_blk16: null pointer");
   HSV_REQUIRE(C > 0 && C % 16 == 0, "pack_blk16: C %% 16 != 0 (C=%d)", C);
-  pack_blk16_kernel<<<grid_for((int64_t)B * (C / 8) * L, 256), 256, 0, hsv::as_stream(stream)>>>(
-      x, nullptr, nullptr, reinterpret_cast<uint4 *>(out), B, C, L, hsv::blk16_rows(L), lrelu, in_scale, hsv::blk_cw(C));
+  HSV_REQUIRE(B <= 65535 && C / 8 <= 65535, "pack_blk16: grid too large");
+  pack_blk16_kernel<<<dim3((unsigned)((L + 255) / 256), (unsigned)(C / 8), (unsigned)B), 256, 0, hsv::as_stream(stream)>>>(
+      x, nullptr, nullptr, reinterpret_cast<uint4 *>(out), C, L, hsv::blk16_rows(L), lrelu, in_scale, hsv::blk_cw(C));
   return hsv::check_launch("pack_blk16");
 }
 
@@ -803,8 +803,9 @@ extern "C" int hsv_pack_blk16_sum3(const float *x1, const float *x2, const float
   HSV_REQUIRE(x1 && out, "pack_blk16_sum3: null pointer");
   HSV_REQUIRE(x2 || !x3, "pack_blk16_sum3: x3 without x2");
   HSV_REQUIRE(C > 0 && C % 16 == 0, "pack_blk16_sum3: C %% 16 != 0 (C=%d)", C);
-  pack_blk16_kernel<<<grid_for((int64_t)B * (C / 8) * L, 256), 256, 0, hsv::as_stream(stream)>>>(
-      x1, x2, x3, reinterpret_cast<uint4 *>(out), B, C, L, hsv::blk16_rows(L), lrelu, in_scale, hsv::blk_cw(C));
+  HSV_REQUIRE(B <= 65535 && C / 8 <= 65535, "pack_blk16_sum3: grid too large");
+  pack_blk16_kernel<<<dim3((unsigned)((L + 255) / 256), (unsigned)(C / 8), (unsigned)B), 256, 0, hsv::as_stream(stream)>>>(
+      x1, x2, x3, reinterpret_cast<uint4 *>(out), C, L, hsv::blk16_rows(L), lrelu, in_scale, hsv::blk_cw(C));
   return hsv::check_launch("pack_blk16_sum3");
 }
 
