@@ -45,12 +45,11 @@ __device__ __forceinline__ float mishf(float v) {
 __global__ void pack_act_kernel(const float *__restrict__ x, const float *__restrict__ bc, const float *__restrict__ mask,
                                 uint4 *__restrict__ out, int B, int C, int64_t L, int64_t Lp, int cw, int mode, int cin) {
   // cin = channels per batch item of x (>= C, or >= 2C for the gate): a channel prefix of a wider tensor can be packed
-  const int nch = C >> 3;
-  const int64_t n = (int64_t)B * nch * L;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t bq = i / L, t = i - bq * L;
-    const int64_t bb = bq / nch;
-    const int c0 = (int)(bq - bb * nch) * 8;
+  // grid = (time blocks, channel groups of 8, batch): no index division
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < L) {
+    const int64_t bb = blockIdx.z;
+    const int c0 = blockIdx.y * 8;
     const float mk = mask ? __ldg(mask + bb * L + t) : 1.f;
     const float *xr = x + (bb * cin + c0) * L + t;
     float v[8];
@@ -199,11 +198,12 @@ enum { OP_WN_RES = 1, OP_WN_LAST = 2, OP_GATE_ADD = 3, OP_COUPLE = 4, OP_SAMPLE 
 __global__ void frame_op_kernel(int op, const float *a, const float *__restrict__ b2, const float *__restrict__ c2,
                                 const float *__restrict__ mask, float *out, float *out2, int B, int C, int64_t L,
                                 float s, int64_t cstride) {
-  const int64_t n = (int64_t)B * C * L;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t bc = i / L, t = i - bc * L;
-    const int64_t bb = bc / C;
-    const int c = (int)(bc - bb * C);
+  // grid = (time blocks, channels, batch): no index division
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < L) {
+    const int c = blockIdx.y;
+    const int64_t bb = blockIdx.z;
+    const int64_t i = (bb * C + c) * L + t;
     const float mk = mask ? __ldg(mask + bb * L + t) : 1.f;
     switch (op) {
       case OP_WN_RES: {   // a = x [B,C,T] (updated in place through out), b2 = rs [B,2C,T], out2 = output accumulator
@@ -498,7 +498,8 @@ extern "C" int hsv_pack_blk16_act(const float *x, const float *bcast, const floa
   HSV_REQUIRE(C > 0 && C % 16 == 0 && mode >= 0 && mode <= 3, "pack_blk16_act: bad C=%d / mode=%d", C, mode);
   HSV_REQUIRE(x_channels >= (mode == 1 ? 2 * C : C), "pack_blk16_act: x has %d channels, needs %d", x_channels,
               mode == 1 ? 2 * C : C);
-  pack_act_kernel<<<grid_for((int64_t)B * (C / 8) * L, 256), 256, 0, hsv::as_stream(stream)>>>(
+  HSV_REQUIRE(B <= 65535 && C / 8 <= 65535, "pack_blk16_act: grid too large");
+  pack_act_kernel<<<dim3((unsigned)((L + 127) / 128), (unsigned)(C / 8), (unsigned)B), 128, 0, hsv::as_stream(stream)>>>(
       x, bcast, mask, reinterpret_cast<uint4 *>(out), B, C, L, hsv::blk16_rows(L), hsv::blk_cw(C), mode, x_channels);
   return hsv::check_launch("pack_blk16_act");
 }
@@ -555,8 +556,10 @@ extern "C" int hsv_frame_op(int op, const float *a, const float *b, const float 
   if (B == 0 || L == 0 || C == 0) return HSV_OK;
   HSV_REQUIRE(op >= OP_WN_RES && op <= OP_ADD_BCAST, "frame_op: unknown op %d", op);
   HSV_REQUIRE(a || op == OP_WN_LAST, "frame_op: null input");
-  frame_op_kernel<<<grid_for((int64_t)B * C * L, 256), 256, 0, hsv::as_stream(stream)>>>(op, a, b, c, mask, out, out2, B,
-                                                                                          C, L, s, cstride);
+  HSV_REQUIRE(B <= 65535 && C <= 65535, "frame_op: grid too large");
+  const int th = L >= 256 ? 256 : 128;
+  frame_op_kernel<<<dim3((unsigned)((L + th - 1) / th), (unsigned)C, (unsigned)B), th, 0, hsv::as_stream(stream)>>>(
+      op, a, b, c, mask, out, out2, B, C, L, s, cstride);
   return hsv::check_launch("frame_op");
 }
 
