@@ -70,6 +70,7 @@ struct Params {
   int hlo8;          // halo rows before the tile, rounded up to a multiple of 8 (swizzle phase alignment)
   uint32_t a_pitch;  // bytes between chunks of the shared A tile (multiple of 1024)
   int G;             // weight blocks ([chunk][tap] units) per ring stage
+  int nrounds_ph[MAX_PHASES];  // ceil(nchunks * ntaps[ph] / G) per phase
   int stages;
   uint32_t tmem_cols;
   int vec_epi;       // 1: float4 epilogue (stride-1 output, Lout % 4 == 0, 16-byte aligned tensors)
@@ -243,10 +244,22 @@ __global__ void __launch_bounds__(32 * NW, MINB) conv_umma_kernel(const __grid_c
   // canonical (shuffled) warp index: tells ptxas the role branches are warp-uniform
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int tile = blockIdx.x, b = blockIdx.z;
-  const int ph = blockIdx.y / p.nco_tiles, nt = blockIdx.y - ph * p.nco_tiles;
+  // (phase, n-tile) of this CTA and its ring rounds without integer divisions: both are host-known per launch / phase
+  // (the two divisions were 6 % of the instructions of a streaming C = 32 tile)
+  int ph, nt;
+  if (p.tt.nphase == 1) {
+    ph = 0;
+    nt = blockIdx.y;
+  } else if (p.nco_tiles == 1) {
+    ph = blockIdx.y;
+    nt = 0;
+  } else {
+    ph = blockIdx.y / p.nco_tiles;
+    nt = blockIdx.y - ph * p.nco_tiles;
+  }
   const int ntaps = p.tt.ntaps[ph];
   const int nblocks = p.nchunks * ntaps;          // [chunk][tap] weight blocks of this (phase, n-tile)
-  const int nrounds = (nblocks + p.G - 1) / p.G;  // ring rounds
+  const int nrounds = p.nrounds_ph[ph];           // ring rounds = ceil(nblocks / G)
   const uint32_t rowbytes = (uint32_t)p.cw * 2u;
   const uint32_t a_chunk_bytes = (uint32_t)p.R * rowbytes;
   const uint32_t blk_bytes = (uint32_t)p.n_tile * rowbytes;
@@ -1329,6 +1342,7 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
   if (G < 1) G = 1;
   if (G > max_blocks) G = max_blocks;
   p.G = G;
+  for (int q = 0; q < MAX_PHASES; ++q) p.nrounds_ph[q] = q < tt.nphase ? (p.nchunks * tt.ntaps[q] + G - 1) / G : 0;
   const int nrounds = (max_blocks + G - 1) / G;
   p.stages = nrounds < MAX_STAGES ? nrounds : MAX_STAGES;
   uint32_t cols = 32;
