@@ -359,11 +359,15 @@ __global__ void __launch_bounds__(32 * NW, MINB) conv_umma_kernel(const __grid_c
   auto advance = [&](int &u, int &sub, int &ch, int64_t &off, bool &ok) {
     ++u;
     off += unit_b;
-    if (++ch == nchk) {
-      ch = 0;
-      ++sub;
-      off += wrap_b;
-      ok = t_warp + (int64_t)sub * TILE_M < p.L;
+    if constexpr (MSUB == 1) {
+      ++ch;                      // one sub-tile: the units are the 16-column chunks, nothing wraps
+    } else {
+      if (++ch == nchk) {
+        ch = 0;
+        ++sub;
+        off += wrap_b;
+        ok = t_warp + (int64_t)sub * TILE_M < p.L;
+      }
     }
   };
   int nxt_sub = 0, nxt_ch = 0, nxt_u = 0;   // the unit being prefetched
