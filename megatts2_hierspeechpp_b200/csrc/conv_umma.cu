@@ -375,13 +375,20 @@ __global__ void __launch_bounds__(32 * NW, MINB) conv_umma_kernel(const __grid_c
   bool nxt_ok = t_warp < p.L;               // L % 4 == 0: a float4 is all-valid or all-invalid
   if (NH > 1 && half) advance(nxt_u, nxt_sub, nxt_ch, nxt_b, nxt_ok);
   float4 res[PF][4];
+#pragma unroll
+  for (int q = 0; q < PF; ++q)
+#pragma unroll
+    for (int ps = 0; ps < 4; ++ps) res[q][ps] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (p.vec_epi) {
 #pragma unroll
     for (int q = 0; q < PF; ++q) {
-      const bool ok = nxt_ok && has_res && nxt_u < nunits;
+      // warp-uniform guard: without a residual (every first conv of a half-layer) or past the last unit nothing is
+      // computed at all (the predicated form cost ~6 instructions per dead load)
+      if (has_res && nxt_u < nunits) {
 #pragma unroll
-      for (int ps = 0; ps < 4; ++ps)
-        res[q][ps] = ok ? *reinterpret_cast<const float4 *>(res_b + nxt_b + ps * cs4b) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int ps = 0; ps < 4; ++ps)
+          res[q][ps] = nxt_ok ? *reinterpret_cast<const float4 *>(res_b + nxt_b + ps * cs4b) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll
       for (int h = 0; h < NH; ++h) advance(nxt_u, nxt_sub, nxt_ch, nxt_b, nxt_ok);
     }
@@ -667,7 +674,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) conv_umma_kernel(const __grid_c
           for (int c = 0; c < 16; ++c)
             asm volatile("st.shared.b32 [%0], %1;" ::"r"(stg_w + (uint32_t)c * 128u), "r"(r[c]) : "memory");
           __syncwarp();
-          const bool okn = nxt_ok && has_res && nxt_u < nunits;
+          const bool refill = has_res && nxt_u < nunits;   // warp-uniform: is there a unit u + PF to prefetch for?
           const float *bias_u = bias_s + (cur_ch << 4) + cq;
 #pragma unroll
           for (int ps = 0; ps < 4; ++ps) {
@@ -683,7 +690,9 @@ __global__ void __launch_bounds__(32 * NW, MINB) conv_umma_kernel(const __grid_c
             a.z = (a.z + bch) + rr.z;
             a.w = (a.w + bch) + rr.w;
             // refill this ring slot (unit u + PF) before this unit's stores
-            res[q][ps] = okn ? *reinterpret_cast<const float4 *>(res_b + nxt_b + ps * cs4b) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (refill)
+              res[q][ps] = nxt_ok ? *reinterpret_cast<const float4 *>(res_b + nxt_b + ps * cs4b)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
             if (cur_ok) {
               char *o = dst_b + cur_b + ps * cs4b;
               // red.global.add: no read, one add per element per kernel -> deterministic given stream order
