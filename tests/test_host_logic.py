@@ -151,3 +151,39 @@ def test_two_rank_gloo_gather_packed(tmp_path):
                        capture_output=True, text=True, env=env, timeout=240)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "PACKED_OK" in r.stdout
+
+
+def test_gate_permutation_groups_tanh_and_sigmoid_halves():
+    """The channel order the operand-writing gate epilogue expects of a WN in_layer (2H outputs): consecutive groups of
+    [8 tanh | 8 sigmoid] channels, i.e. unit j of 16 columns holds channels 8j..8j+7 and H+8j..H+8j+7 -- a permutation."""
+    from megatts2_hierspeechpp_b200 import ops
+    for H in (192, 512, 8):
+        perm = ops.gate_permutation(2 * H)
+        assert sorted(perm.tolist()) == list(range(2 * H))
+        g = perm.view(H // 8, 2, 8)
+        assert torch.equal(g[:, 0], torch.arange(H).view(H // 8, 8))
+        assert torch.equal(g[:, 1], H + torch.arange(H).view(H // 8, 8))
+    with pytest.raises(ValueError):
+        ops.gate_permutation(2 * 12)
+
+
+def test_folded_gate_and_cat_weights_follow_their_layers():
+    """_FoldedGate permutes weight and bias together (and per layer block for cond_layer); _FoldedCat concatenates the
+    adaLN layers of a flow block in module order and refreshes when a parameter changes."""
+    import megatts2_hierspeechpp_b200.front as FR
+    from megatts2_hierspeechpp_b200 import ops
+    torch.manual_seed(0)
+    H, n = 16, 3
+    conv = torch.nn.Conv1d(8, 2 * H * n, 1)
+    fg = FR._FoldedGate(conv, blocks=n)
+    w, b = fg.weight(), fg.bias()
+    base = ops.gate_permutation(2 * H)
+    perm = torch.cat([base + i * 2 * H for i in range(n)])
+    assert torch.equal(w, conv.weight.detach()[perm]) and torch.equal(b, conv.bias.detach()[perm])
+    lins = [torch.nn.Linear(4, 6) for _ in range(3)]
+    fc = FR._FoldedCat(lins)
+    assert torch.equal(fc.weight()[:, :, 0], torch.cat([l.weight for l in lins]).detach())
+    assert torch.equal(fc.bias(), torch.cat([l.bias for l in lins]).detach())
+    with torch.no_grad():
+        lins[1].bias.add_(1.0)
+    assert torch.equal(fc.bias(), torch.cat([l.bias for l in lins]).detach())
