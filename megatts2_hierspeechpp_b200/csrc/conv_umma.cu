@@ -1316,6 +1316,10 @@ int launch(const TapTable &tt, const void *a_blk16, const void *w_packed, const 
   // C = 16 streaming layers: a 128-row tile moves only 20 KB, the per-CTA prologue dominates -> 512-row tiles
   // (3.5 -> 5.4 TB/s at batch 16, 8.7 -> 6.5 us at batch 1 on [16, 160000])
   if (n_tile <= 16 && ctas1 >= 2 * 148 * 2) msub = 4;
+  // C = 32 streaming layers at batch scale (SpeechSR48 batch 16: 60 000 128-row tiles): the ~1 800 set-up / addressing
+  // instructions of a tile are paid once per 512 rows instead of once per 128 -- 16.8 -> 16.0 ms per step (A/B on one box);
+  // small grids (batch 1: 625 tiles) keep 128-row tiles, there the CTA count matters more
+  if (n_tile <= 32 && ctas1 >= 16 * 148) msub = 4;
   if (g_msub_override > 0) msub = g_msub_override;
   if (msub == 3) msub = 2;
   // persistent variant (opt-in): one 128-row tile at a time per CTA, roles overlapped across tiles
